@@ -1,0 +1,147 @@
+/* libb200exec -- C ABI of the B200-native Ballista execution engine.
+ *
+ * The reference defines NO C ABI: its plug-in point is the Rust trait pair
+ *   ExecutionEngine::create_query_stage_exec   ballista/executor/src/execution_engine.rs:45-59
+ *   QueryStageExecutor::execute_query_stage /
+ *   QueryStageExecutor::collect_plan_metrics   ballista/executor/src/execution_engine.rs:67-81
+ * installed through ExecutorProcessConfig.override_execution_engine
+ *   (ballista/executor/src/executor_process.rs:158-160, consumed :341-351).
+ * Every entry point below names the reference interface it stands behind; INTEGRATION.md shows the
+ * Rust shim (`GpuExecutionEngine: ExecutionEngine`) that binds them with `extern "C"`.
+ *
+ * Conventions: opaque handles; every call returns 0 on success or a negative b200_status and
+ * records a message retrievable with b200_last_error() (thread-local); no exceptions, no
+ * callbacks, nothing unwinds across the boundary (reference rule: "the engine must never
+ * panic/abort", SURVEY.md 8(b) "Error convention").  Column data crosses as Arrow C Data
+ * Interface structs (include/b200_arrow_abi.h); the consumer releases what it receives.
+ */
+#ifndef B200EXEC_H
+#define B200EXEC_H
+#include <stdint.h>
+
+#include "b200_arrow_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum b200_status {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,       /* bad argument / malformed plan  -> DataFusionError::Plan           */
+  B200_ERR_UNSUPPORTED = -2,   /* operator/expr not lowered yet  -> DataFusionError::NotImplemented */
+  B200_ERR_EXECUTION = -3,     /* arithmetic overflow, div by 0  -> DataFusionError::Execution      */
+  B200_ERR_CUDA = -4,          /* CUDA runtime failure           -> DataFusionError::External       */
+  B200_ERR_NOT_FOUND = -5,     /* missing shuffle partition      -> BallistaError::FetchFailed      */
+  B200_ERR_CANCELLED = -6,     /* cancel flag observed           -> task aborted (executor.rs:217)  */
+  B200_ERR_OOM = -7            /* device pool exhausted          -> DataFusionError::ResourcesExhausted */
+} b200_status;
+
+typedef struct b200_engine b200_engine;  /* one per executor process == one per GPU */
+typedef struct b200_stage b200_stage;    /* one per task: Arc<dyn QueryStageExecutor> */
+
+/* Mirror of message ShuffleWritePartition, ballista/core/proto/ballista.proto:481-492.
+ * file_id < 0 encodes `None` (un-partitioned writer branch, shuffle_writer.rs:260-267). */
+typedef struct b200_shuffle_write_partition {
+  uint64_t partition_id;
+  uint64_t num_batches;
+  uint64_t num_rows;
+  uint64_t num_bytes;
+  int64_t file_id;
+  int32_t is_sort_shuffle;
+  int32_t _pad;
+} b200_shuffle_write_partition;
+
+/* One entry per operator of the stage plan (pre-order), the payload of
+ * QueryStageExecutor::collect_plan_metrics (execution_engine.rs:80; utils.rs:328-339). */
+typedef struct b200_operator_metrics {
+  char name[48];
+  uint64_t output_rows;
+  uint64_t input_rows;
+  uint64_t elapsed_compute_ns; /* device time, CUDA events */
+  uint64_t bytes_read;         /* algorithmic bytes */
+  uint64_t bytes_written;
+  uint64_t kernel_launches;
+} b200_operator_metrics;
+
+/* ---- engine lifecycle (Executor::new, ballista/executor/src/executor.rs:67-95) ------------- */
+/* device: CUDA ordinal; pool_bytes: device pool release threshold (0 = keep everything);
+ * rank/world: position of this executor among the box's GPU executors (exchange step). */
+int b200_engine_create(int device, uint64_t pool_bytes, int rank, int world, b200_engine** out);
+void b200_engine_destroy(b200_engine* e);
+const char* b200_last_error(void);
+/* Launch all kernels of this engine on `cuda_stream` (a cudaStream_t); NULL = engine-owned stream. */
+int b200_engine_set_stream(b200_engine* e, void* cuda_stream);
+int b200_engine_synchronize(b200_engine* e);
+/* Number of kernels this engine has launched since creation (bench.py "gpu_launches"). */
+uint64_t b200_engine_kernel_launches(b200_engine* e);
+/* session config (TaskDefinition.props), e.g. "datafusion.execution.batch_size" */
+int b200_engine_set_config(b200_engine* e, const char* key, const char* value);
+
+/* ---- leaf inputs ---------------------------------------------------------------------------- */
+/* DataSourceExec leaf: host RecordBatch (struct array) for `table`, input partition `partition`.
+ * Copies host->device on the engine stream (pinned staging); appends if called repeatedly.
+ * The engine releases `batch` / `schema` when the copy has been issued. */
+int b200_engine_register_batch(b200_engine* e, const char* table, int partition,
+                               struct ArrowArray* batch, struct ArrowSchema* schema);
+int b200_engine_drop_table(b200_engine* e, const char* table);
+/* Synthetic TPC-H-shaped table generated directly in HBM (bench/test input; columns = NULL: all).
+ * Rows [row_begin,row_end) of the table at milli-scale-factor `msf` become partition `partition`. */
+int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, int partition,
+                              int64_t row_begin, int64_t row_end, const char* columns_csv);
+/* Read a registered table partition back to the host (test/diagnostic). */
+int b200_engine_export_table(b200_engine* e, const char* table, int partition,
+                             struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* ---- ExecutionEngine::create_query_stage_exec (execution_engine.rs:50-58) ------------------ */
+/* plan_json: stage plan IR rooted at ShuffleWriterExec / SortShuffleWriterExec (JSON rendering of
+ * the DataFusion physical plan; schema in DESIGN.md).  Errors if the root is not a shuffle
+ * writer, like DefaultExecutionEngine (execution_engine.rs:164-167). */
+int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, const char* plan_json,
+                       uint64_t plan_len, b200_stage** out);
+/* ---- QueryStageExecutor::execute_query_stage (execution_engine.rs:73-77) ------------------- */
+/* Runs input partition `input_partition`; writes up to `cap` entries to `out`, count to *n_out.
+ * `cancel_flag` (may be NULL) is polled between kernels: non-zero => B200_ERR_CANCELLED and all
+ * partial outputs of this task are dropped (Executor::cancel_task, executor.rs:217-237). */
+int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag,
+                       b200_shuffle_write_partition* out, int cap, int* n_out);
+/* ---- QueryStageExecutor::collect_plan_metrics (execution_engine.rs:80) ---------------------- */
+int b200_stage_metrics(b200_stage* s, b200_operator_metrics* out, int cap, int* n_out);
+void b200_stage_release(b200_stage* s);
+
+/* ---- shuffle partitions (ShuffleReaderExec / Flight service side) --------------------------- */
+/* Identity of stored bytes == (job_id, stage_id, out_partition, file_id, is_sort_shuffle), the
+ * tuple create_shuffle_path resolves (ballista/core/src/execution_plans/mod.rs:66-99). */
+/* Host-visible export of ONE output partition (all map tasks' pieces concatenated): what
+ * BallistaFlightService::do_get / fetch_partition_local serve (flight_service.rs:88-184,
+ * shuffle_reader.rs:698-771). */
+int b200_partition_export(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition,
+                          struct ArrowArray* out, struct ArrowSchema* out_schema);
+/* Rows currently stored for (job, stage, out_partition); -1 if absent. */
+int64_t b200_partition_rows(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition);
+/* Device-resident exchange descriptor for peer pulls / NCCL all-to-all: fills device pointers and
+ * byte sizes of the partition's column buffers (see DESIGN.md "Exchange"). */
+typedef struct b200_device_buffer {
+  void* ptr;
+  uint64_t bytes;
+} b200_device_buffer;
+int b200_partition_device_buffers(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition,
+                                  b200_device_buffer* out, int cap, int* n_out, int64_t* n_rows);
+/* Install a partition received from a peer GPU (buffers already in this GPU's HBM, laid out as
+ * b200_partition_device_buffers describes; the engine takes ownership via copy on its stream). */
+int b200_partition_import_device(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition,
+                                 int64_t file_id, const char* schema_json, const b200_device_buffer* bufs,
+                                 int n_bufs, int64_t n_rows);
+/* RemoveJobData RPC (ballista/executor/src/executor_server.rs:921-932). */
+int b200_remove_job_data(b200_engine* e, const char* job_id);
+
+/* ---- pinned host staging (harness side of "RecordBatches are pinned and DMA'd") ------------- */
+void* b200_host_alloc_pinned(uint64_t bytes);
+void b200_host_free_pinned(void* p);
+
+/* Version / build info: "b200exec <ver> sm_100a" */
+const char* b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200EXEC_H */
