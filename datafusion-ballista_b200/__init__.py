@@ -5,6 +5,7 @@ Host-side mirror (Python harness) of the reference plug-in interface
 top of the C-ABI library ``libb200exec.so`` (include/b200exec.h).  All compute happens in the CUDA
 library; this package only marshals Arrow C Data Interface structs and plan JSON.
 """
-from . import plan, tpch, driver  # noqa: F401
+from . import plan, tpch, driver, engine  # noqa: F401
+from .engine import GpuExecutionEngine, QueryStageExecutor, ShuffleWritePartition, B200Error  # noqa: F401
 
-__all__ = ["plan", "tpch", "driver"]
+__all__ = ["plan", "tpch", "driver", "engine", "GpuExecutionEngine", "QueryStageExecutor", "ShuffleWritePartition", "B200Error"]

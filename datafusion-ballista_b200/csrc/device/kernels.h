@@ -1,0 +1,113 @@
+// Host-callable launchers of every CUDA kernel in libb200exec (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace b200 {
+
+// ---- fused pipeline (pipeline.cu) ---------------------------------------------------------------
+cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st);
+
+// ---- aggregate table (kernels.cu) ----------------------------------------------------------------
+struct AccKinds {
+  uint8_t kind[VM_MAX_ACC];
+  int n;
+};
+void launch_agg_table_init(const AggTable& T, const AccKinds& kinds, cudaStream_t st);
+
+enum AggOutKind : uint8_t {
+  AO_KEY = 0,      // a: key index
+  AO_ACC_I128,     // a: acc index, b: count-acc index (valid iff count > 0) or 255
+  AO_ACC_I64,      // low 64 bits of an I128 accumulator (SUM(Int64) wraps) ; b as above
+  AO_ACC_F64,      // f64 sum ; b as above
+  AO_COUNT,        // a: acc index -> Int64/UInt64
+  AO_MINMAX_F64,   // order-key -> double ; b count
+  AO_AVG_DEC,      // a: sum acc, b: count acc, imm: 10^k multiplier exponent
+  AO_AVG_F64       // a: sum acc (f64), b: count acc
+};
+struct AggOut {
+  void* data;
+  uint8_t* valid;
+  uint8_t kind;
+  uint8_t a, b;
+  uint8_t phys;   // output encoding
+  int32_t imm;
+};
+struct AggExtractArgs {
+  AggOut out[VM_MAX_OUT];
+  int n_out;
+  int n_keys;
+  unsigned long long* counter;   // device: rows emitted
+  unsigned int* error;           // device: RunStatus.error
+};
+void launch_agg_extract(const AggTable& T, const AggExtractArgs& A, cudaStream_t st);
+
+// ---- scans, histograms, scatter/gather ------------------------------------------------------------
+// exclusive prefix sum of n uint32 -> uint64 (out[n] = total if out has n+1 slots)
+void launch_scan_u32_to_u64(const uint32_t* in, uint64_t* out, int64_t n, uint64_t* scratch /* >= n/1024+2 */, cudaStream_t st);
+void launch_histogram_u32(const uint32_t* ids, int64_t n, uint32_t n_bins, unsigned long long* counts, cudaStream_t st);
+// dest[i] = cursor[ids[i]]++  (cursor pre-seeded with the exclusive scan of counts)
+void launch_partition_rank(const uint32_t* ids, int64_t n, uint32_t n_bins, unsigned long long* cursor, uint32_t* dest, cudaStream_t st);
+void launch_scatter_fixed(const void* in, void* out, const uint32_t* dest, int64_t n, int width, cudaStream_t st);
+// out[i] = idx[i] >= 0 ? in[idx[i]] : 0 ; valid_out (optional) = idx>=0 && valid_in
+void launch_gather_fixed(const void* in, const uint8_t* valid_in, void* out, uint8_t* valid_out, const int64_t* idx, int64_t n, int width, cudaStream_t st);
+void launch_iota_i64(int64_t* out, int64_t n, cudaStream_t st);
+
+// ---- strings / validity ------------------------------------------------------------------------
+void launch_utf8_to_views(const int32_t* offsets, const uint8_t* chars, unsigned long long* views, int64_t n, cudaStream_t st);
+void launch_view_lengths(const unsigned long long* views, const uint8_t* valid, uint32_t* lens, int64_t n, cudaStream_t st);
+void launch_views_to_utf8(const unsigned long long* views, const uint8_t* valid, const uint64_t* offs64, int32_t* offsets_out, uint8_t* chars_out, int64_t n, cudaStream_t st);
+void launch_bitmap_to_bytes(const uint8_t* bitmap, int64_t bit_offset, uint8_t* bytes, int64_t n, cudaStream_t st);
+void launch_bytes_to_bitmap(const uint8_t* bytes, uint8_t* bitmap, int64_t n, unsigned long long* null_count, cudaStream_t st);
+
+// ---- hash join --------------------------------------------------------------------------------
+struct KeyCol {
+  const void* data;
+  const uint8_t* valid;
+  uint8_t phys;
+  uint8_t width;
+};
+struct JoinKeys {
+  KeyCol build[VM_MAX_KEYS];
+  KeyCol probe[VM_MAX_KEYS];
+  int n_keys;
+  int null_equals_null;
+};
+void launch_join_build(const uint64_t* build_hash, const uint8_t* build_ok, int64_t n_build, int32_t* heads, uint64_t n_buckets, int32_t* next, cudaStream_t st);
+// pass 1: counts per probe row (+ marks); pass 2: write pairs at offsets
+void launch_join_probe_count(const JoinKeys& K, const uint64_t* build_hash, const int32_t* heads, uint64_t n_buckets, const int32_t* next,
+                             const uint64_t* probe_hash, const uint8_t* probe_ok, int64_t n_probe, uint32_t* counts, uint8_t* build_mark, cudaStream_t st);
+void launch_join_probe_write(const JoinKeys& K, const uint64_t* build_hash, const int32_t* heads, uint64_t n_buckets, const int32_t* next,
+                             const uint64_t* probe_hash, const uint8_t* probe_ok, int64_t n_probe, const uint64_t* offsets,
+                             int64_t* out_build_idx, int64_t* out_probe_idx, cudaStream_t st);
+// compaction helpers: indices of rows whose flag byte == want
+void launch_flag_to_u32(const uint8_t* flags, uint8_t want, uint32_t* out, int64_t n, cudaStream_t st);
+void launch_select_indices(const uint32_t* flag01, const uint64_t* offs, int64_t* out_idx, int64_t n, cudaStream_t st);
+void launch_counts_to_flag(const uint32_t* counts, uint8_t* flags, int64_t n, cudaStream_t st);
+void launch_mark_from_idx(const int64_t* idx, int64_t n, uint8_t* marks, cudaStream_t st);
+
+// ---- sort -------------------------------------------------------------------------------------
+struct SortWordArgs {
+  const void* data;
+  const uint8_t* valid;
+  uint8_t phys;
+  uint8_t asc;
+  uint8_t nulls_first;
+  int32_t word;   // which 64-bit word of the normalised key (strings / i128 have several); -1 = null rank word
+};
+void launch_sort_word(const SortWordArgs& A, const uint32_t* perm, uint64_t* out, int64_t n, cudaStream_t st);
+void launch_max_view_len(const unsigned long long* views, const uint8_t* valid, int64_t n, unsigned int* out_max, cudaStream_t st);
+// stable LSD radix sort of (key, val) pairs on 64-bit keys; ping-pong buffers; returns via *result_in_a
+void radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, uint32_t* hist_scratch,
+                          uint64_t* scan_scratch, cudaStream_t st, bool* result_in_a, uint64_t* launches);
+void launch_iota_u32(uint32_t* out, int64_t n, cudaStream_t st);
+void launch_u32_to_i64(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t st);
+
+// ---- synthetic TPC-H input ----------------------------------------------------------------------
+void launch_tpch_fixed(int table, int col, int kind, int64_t msf, int64_t row0, int64_t n, void* out, cudaStream_t st);
+void launch_tpch_str_len(int table, int col, int64_t msf, int64_t row0, int64_t n, uint32_t* lens, cudaStream_t st);
+void launch_tpch_str_fill(int table, int col, int64_t msf, int64_t row0, int64_t n, const uint64_t* offs64, int32_t* offsets, uint8_t* chars, cudaStream_t st);
+
+}  // namespace b200

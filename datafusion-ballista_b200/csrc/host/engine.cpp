@@ -1,0 +1,1834 @@
+// libb200exec host side: the GPU ExecutionEngine / QueryStageExecutor.
+//
+// Mirrors (reference file:line):
+//   DefaultExecutionEngine::create_query_stage_exec     ballista/executor/src/execution_engine.rs:106-169
+//   DefaultQueryStageExec::execute_query_stage          ballista/executor/src/execution_engine.rs:235-254
+//   ShuffleWriterExec::execute_shuffle_write            ballista/core/src/execution_plans/shuffle_writer.rs:203-402
+//   SortShuffleWriterExec::execute_shuffle_write        ballista/core/src/execution_plans/sort_shuffle/writer.rs:199-373
+//   ShuffleReaderExec::execute                          ballista/core/src/execution_plans/shuffle_reader.rs:248-318
+//   collect_plan_metrics                                ballista/core/src/utils.rs:328-339
+// The operator tree below the writer (FilterExec/ProjectionExec/AggregateExec/HashJoinExec/SortExec,
+// DataFusion 53.1 [EXT]) is executed by the CUDA kernels in csrc/device.  There is no CPU path:
+// every operator either runs on the GPU or fails with B200_ERR_UNSUPPORTED.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <set>
+
+#include "../common/arrow_host.hpp"
+#include "../common/tpch_gen.hpp"
+#include "../device/kernels.h"
+#include "lower.hpp"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Piece {
+  int64_t file_id;
+  DevBatchPtr batch;
+  int64_t r0, r1;
+};
+struct ShuffleKey {
+  std::string job;
+  int64_t stage;
+  int64_t part;
+  bool operator<(const ShuffleKey& o) const {
+    if (job != o.job) return job < o.job;
+    if (stage != o.stage) return stage < o.stage;
+    return part < o.part;
+  }
+};
+
+struct OpMetrics {
+  std::string name;
+  uint64_t output_rows = 0, input_rows = 0, elapsed_ns = 0, bytes_read = 0, bytes_written = 0, launches = 0;
+};
+
+}  // namespace
+
+struct b200_engine {
+  int device = 0;
+  int rank = 0, world = 1;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::map<std::string, std::map<int, DevBatchPtr>> tables;
+  std::map<ShuffleKey, std::vector<Piece>> shuffle;
+  uint64_t launches = 0;
+  int64_t batch_size = 8192;
+  std::map<std::string, std::string> config;
+  std::map<std::string, int> agg_hint;       // plan fingerprint -> sink that worked (0 reg, >0 log2 cap)
+  void* pinned_stage = nullptr;              // small pinned buffer for status read-backs
+};
+
+struct b200_stage {
+  b200_engine* eng = nullptr;
+  std::string job_id;
+  int64_t stage_id = 0;
+  PlanPtr plan;
+  std::string fingerprint;
+  std::vector<OpMetrics> metrics;  // pre-order
+  std::map<const PlanNode*, int> metric_index;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Small helpers
+// ------------------------------------------------------------------------------------------------
+struct Exec {
+  b200_engine* e;
+  b200_stage* s;
+  const volatile int32_t* cancel;
+  cudaStream_t st() const { return e->stream; }
+  void check_cancel() const {
+    if (cancel && *cancel) throw EngineError(B200_ERR_CANCELLED, "task cancelled");
+  }
+  void count(uint64_t n = 1) const { e->launches += n; }
+  OpMetrics* m(const PlanNode* n) const {
+    if (!s) return nullptr;
+    auto it = s->metric_index.find(n);
+    return it == s->metric_index.end() ? nullptr : &s->metrics[(size_t)it->second];
+  }
+};
+
+template <class T>
+T d2h_value(const void* dptr, cudaStream_t st) {
+  T v;
+  CUDA_CHECK(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  return v;
+}
+
+uint64_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+DevColumn make_out_column(const std::string& name, const DataType& t, Phys phys, int64_t cap, bool with_valid, cudaStream_t st) {
+  DevColumn c;
+  c.name = name;
+  c.type = t;
+  c.phys = phys;
+  c.n = cap;
+  DevPtr d = dev_alloc((size_t)std::max<int64_t>(cap, 1) * phys_width(phys), st);
+  c.data = (const uint8_t*)d->ptr;
+  c.keep.push_back(d);
+  if (with_valid) {
+    DevPtr v = dev_alloc((size_t)std::max<int64_t>(cap, 1), st);
+    c.valid = (const uint8_t*)v->ptr;
+    c.keep.push_back(v);
+  }
+  c.nullable = with_valid;
+  return c;
+}
+
+// strings as views (needed for gather / scatter / sort / join); zero-copy for non-strings
+DevColumn as_views(const Exec& x, const DevColumn& c) {
+  if (c.phys != PH_UTF8) return c;
+  DevColumn o = c;
+  DevPtr v = dev_alloc((size_t)std::max<int64_t>(c.n, 1) * 16, x.st());
+  launch_utf8_to_views((const int32_t*)c.data, c.chars, (unsigned long long*)v->ptr, c.n, x.st());
+  x.count();
+  o.phys = PH_STRVIEW;
+  o.data = (const uint8_t*)v->ptr;
+  o.chars = nullptr;
+  o.keep.push_back(v);
+  return o;
+}
+
+// views -> Arrow Utf8 (offsets + chars), contiguous
+DevColumn as_utf8(const Exec& x, const DevColumn& c) {
+  if (c.phys != PH_STRVIEW) return c;
+  const int64_t n = c.n;
+  DevPtr lens = dev_alloc((size_t)(n + 1) * 4, x.st());
+  DevPtr offs64 = dev_alloc((size_t)(n + 2) * 8, x.st());
+  DevPtr scratch = dev_alloc((size_t)(n / 1024 + 4) * 8, x.st());
+  launch_view_lengths((const unsigned long long*)c.data, c.valid, (uint32_t*)lens->ptr, n, x.st());
+  launch_scan_u32_to_u64((const uint32_t*)lens->ptr, (uint64_t*)offs64->ptr, n, (uint64_t*)scratch->ptr, x.st());
+  x.count(4);
+  uint64_t total = d2h_value<uint64_t>((const uint64_t*)offs64->ptr + n, x.st());
+  if (total > 0x7FFFFFFFull) throw EngineError(B200_ERR_UNSUPPORTED, "string column exceeds 2 GiB (LargeUtf8 not supported)");
+  DevPtr offsets = dev_alloc((size_t)(n + 1) * 4, x.st());
+  DevPtr chars = dev_alloc((size_t)total + 16, x.st());
+  launch_views_to_utf8((const unsigned long long*)c.data, c.valid, (const uint64_t*)offs64->ptr, (int32_t*)offsets->ptr, (uint8_t*)chars->ptr, n, x.st());
+  x.count();
+  DevColumn o;
+  o.name = c.name;
+  o.type = c.type;
+  o.nullable = c.nullable;
+  o.phys = PH_UTF8;
+  o.n = n;
+  o.data = (const uint8_t*)offsets->ptr;
+  o.chars = (const uint8_t*)chars->ptr;
+  o.chars_bytes = (int64_t)total;
+  o.valid = c.valid;
+  o.keep.push_back(offsets);
+  o.keep.push_back(chars);
+  if (c.valid)
+    for (auto& k : c.keep) o.keep.push_back(k);  // validity lives in the old allocations
+  return o;
+}
+
+DevBatchPtr gather_batch(const Exec& x, const DevBatch& in, const int64_t* idx, int64_t n_out, bool may_be_null) {
+  auto out = std::make_shared<DevBatch>();
+  out->n = n_out;
+  for (auto& c0 : in.cols) {
+    DevColumn c = as_views(x, c0);
+    bool with_valid = c.valid != nullptr || may_be_null;
+    DevColumn o = make_out_column(c.name, c.type, c.phys, n_out, with_valid, x.st());
+    o.n = n_out;
+    launch_gather_fixed(c.data, c.valid, (void*)o.data, (uint8_t*)o.valid, idx, n_out, c.width(), x.st());
+    x.count();
+    for (auto& k : c.keep) o.keep.push_back(k);
+    out->cols.push_back(o);
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arrow import (host -> HBM)
+// ------------------------------------------------------------------------------------------------
+DevBatchPtr import_batch(b200_engine* e, ArrowArray* arr, ArrowSchema* sch) {
+  int64_t n = 0;
+  std::vector<ImportedCol> ics = import_record_batch(arr, sch, &n);
+  auto b = std::make_shared<DevBatch>();
+  b->n = n;
+  cudaStream_t st = e->stream;
+  for (auto& ic : ics) {
+    DevColumn c;
+    c.name = ic.name;
+    c.type = ic.type;
+    c.phys = phys_of(ic.type);
+    c.n = n;
+    c.nullable = ic.null_count > 0;
+    if (ic.type.id == TypeId::Null) throw EngineError(B200_ERR_UNSUPPORTED, "Null-typed columns are not supported");
+    if (ic.null_count > 0 && ic.validity) {
+      int64_t b0 = ic.offset >> 3, b1 = (ic.offset + n + 7) >> 3;
+      DevPtr bm = dev_alloc((size_t)(b1 - b0) + 16, st);
+      CUDA_CHECK(cudaMemcpyAsync(bm->ptr, ic.validity + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+      DevPtr v = dev_alloc((size_t)n + 16, st);
+      launch_bitmap_to_bytes((const uint8_t*)bm->ptr, ic.offset & 7, (uint8_t*)v->ptr, n, st);
+      e->launches++;
+      c.valid = (const uint8_t*)v->ptr;
+      c.keep.push_back(v);
+      c.keep.push_back(bm);
+    }
+    if (ic.type.id == TypeId::Bool) {
+      int64_t b0 = ic.offset >> 3, b1 = (ic.offset + n + 7) >> 3;
+      DevPtr bm = dev_alloc((size_t)(b1 - b0) + 16, st);
+      CUDA_CHECK(cudaMemcpyAsync(bm->ptr, ic.data + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, st));
+      DevPtr v = dev_alloc((size_t)n + 16, st);
+      launch_bitmap_to_bytes((const uint8_t*)bm->ptr, ic.offset & 7, (uint8_t*)v->ptr, n, st);
+      e->launches++;
+      c.data = (const uint8_t*)v->ptr;
+      c.keep.push_back(v);
+      c.keep.push_back(bm);
+    } else if (ic.type.id == TypeId::Utf8) {
+      if (ic.large_offsets) throw EngineError(B200_ERR_UNSUPPORTED, "LargeUtf8/LargeBinary input: cast to Utf8 on the host side");
+      const int32_t* off = (const int32_t*)ic.data + ic.offset;
+      int32_t first = off[0], last = off[n];
+      DevPtr d_off = dev_alloc((size_t)(n + 1) * 4 + 64, st);
+      CUDA_CHECK(cudaMemcpyAsync(d_off->ptr, off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+      DevPtr d_chars = dev_alloc((size_t)(last - first) + 64, st);
+      if (last > first) CUDA_CHECK(cudaMemcpyAsync(d_chars->ptr, ic.extra + first, (size_t)(last - first), cudaMemcpyHostToDevice, st));
+      c.data = (const uint8_t*)d_off->ptr;
+      c.chars = (const uint8_t*)d_chars->ptr - first;
+      c.chars_bytes = last - first;
+      c.keep.push_back(d_off);
+      c.keep.push_back(d_chars);
+    } else {
+      int w = c.width();
+      DevPtr d = dev_alloc((size_t)n * w + 64, st);
+      if (n) CUDA_CHECK(cudaMemcpyAsync(d->ptr, ic.data + ic.offset * w, (size_t)n * w, cudaMemcpyHostToDevice, st));
+      c.data = (const uint8_t*)d->ptr;
+      c.keep.push_back(d);
+    }
+    b->cols.push_back(c);
+  }
+  // the copies above read host memory owned by the Arrow arrays: wait before releasing them
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (arr->release) arr->release(arr);
+  if (sch->release) sch->release(sch);
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arrow export (HBM -> host)
+// ------------------------------------------------------------------------------------------------
+void export_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
+  const int64_t n = r1 - r0;
+  std::vector<HostCol> hcs;
+  cudaStream_t st = x.st();
+  for (auto& c0 : b.cols) {
+    DevColumn c = slice_column(c0, r0, r1);
+    HostCol h;
+    h.name = c.name;
+    h.type = c.type;
+    h.nullable = true;
+    h.n = n;
+    if (c.valid && n) {
+      DevPtr bm = dev_alloc((size_t)(n + 7) / 8 + 16, st);
+      DevPtr cnt = dev_alloc(8, st);
+      CUDA_CHECK(cudaMemsetAsync(cnt->ptr, 0, 8, st));
+      launch_bytes_to_bitmap(c.valid, (uint8_t*)bm->ptr, n, (unsigned long long*)cnt->ptr, st);
+      x.count();
+      h.validity.resize((size_t)(n + 7) / 8);
+      CUDA_CHECK(cudaMemcpyAsync(h.validity.data(), bm->ptr, h.validity.size(), cudaMemcpyDeviceToHost, st));
+      h.null_count = (int64_t)d2h_value<unsigned long long>(cnt->ptr, st);
+      if (h.null_count == 0) h.validity.clear();
+    }
+    if (c.type.id == TypeId::Bool) {
+      h.data.assign((size_t)(n + 7) / 8, 0);
+      if (n) {
+        DevPtr bm = dev_alloc((size_t)(n + 7) / 8 + 16, st);
+        launch_bytes_to_bitmap(c.data, (uint8_t*)bm->ptr, n, nullptr, st);
+        x.count();
+        CUDA_CHECK(cudaMemcpyAsync(h.data.data(), bm->ptr, h.data.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+    } else if (c.type.id == TypeId::Utf8) {
+      DevColumn u = c.phys == PH_STRVIEW ? as_utf8(x, c) : c;
+      h.data.resize((size_t)(n + 1) * 4);
+      CUDA_CHECK(cudaMemcpyAsync(h.data.data(), u.data, h.data.size(), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      int32_t* off = (int32_t*)h.data.data();
+      int32_t first = off[0], last = off[n];
+      h.extra.resize((size_t)(last - first));
+      if (last > first) CUDA_CHECK(cudaMemcpyAsync(h.extra.data(), u.chars + first, h.extra.size(), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      for (int64_t i = 0; i <= n; i++) off[i] -= first;
+    } else {
+      h.data.resize((size_t)n * c.width());
+      if (n) CUDA_CHECK(cudaMemcpyAsync(h.data.data(), c.data, h.data.size(), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    hcs.push_back(std::move(h));
+  }
+  export_record_batch(std::move(hcs), n, out, out_schema);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipeline execution
+// ------------------------------------------------------------------------------------------------
+struct RunOutcome {
+  RunStatus status;
+  float ms = 0;
+};
+
+RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups) {
+  Program& P = pb.prog;
+  DevPtr dstat = dev_alloc(sizeof(RunStatus), x.st());
+  CUDA_CHECK(cudaMemsetAsync(dstat->ptr, 0, sizeof(RunStatus), x.st()));
+  P.status = (RunStatus*)dstat->ptr;
+  const int tile = pb.block * VM_R;
+  int64_t n_tiles = (P.n_rows + tile - 1) / tile;
+  int grid = (int)std::min<int64_t>(std::max<int64_t>(n_tiles, 1), x.e->sm_count);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, x.st()));
+  cudaError_t le = launch_pipeline(P, reg_groups, grid, pb.block, pb.smem_bytes(), x.st());
+  if (le != cudaSuccess) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_CHECK(le);
+  }
+  CUDA_CHECK(cudaEventRecord(e1, x.st()));
+  x.count();
+  RunOutcome o;
+  CUDA_CHECK(cudaMemcpyAsync(&o.status, dstat->ptr, sizeof(RunStatus), cudaMemcpyDeviceToHost, x.st()));
+  cudaError_t se = cudaStreamSynchronize(x.st());
+  if (se == cudaSuccess) cudaEventElapsedTime(&o.ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CUDA_CHECK(se);
+  if (o.status.error == 1) throw EngineError(B200_ERR_EXECUTION, "Arithmetic overflow");
+  if (o.status.error == 2) throw EngineError(B200_ERR_EXECUTION, "Divide by zero");
+  if (o.status.error) throw EngineError(B200_ERR_EXECUTION, "execution error in expression");
+  return o;
+}
+
+uint64_t source_bytes(const PipelineBuilder& pb) {
+  uint64_t b = 0;
+  for (int i = 0; i < pb.prog.n_cols; i++) b += (uint64_t)pb.prog.cols[i].width * (uint64_t)pb.prog.n_rows + (pb.prog.cols[i].valid ? (uint64_t)pb.prog.n_rows : 0);
+  return b;
+}
+
+// materialise `outs` (current builder columns) -> new batch
+DevBatchPtr run_materialize(const Exec& x, PipelineBuilder& pb, const std::vector<ColRef>& outs, const DevBatchPtr& src, OpMetrics* met) {
+  Program& P = pb.prog;
+  if (outs.size() > (size_t)VM_MAX_OUT) throw EngineError(B200_ERR_UNSUPPORTED, "too many output columns in one pipeline");
+  auto out = std::make_shared<DevBatch>();
+  const int64_t cap = src->n;
+  P.sink = SINK_MATERIALIZE;
+  P.n_out = (uint8_t)outs.size();
+  for (size_t j = 0; j < outs.size(); j++) {
+    const ColRef& c = outs[j];
+    Phys ph = c.type.id == TypeId::Utf8 ? PH_STRVIEW : phys_of(c.type);
+    DevColumn oc = make_out_column(c.name, c.type, ph, cap, c.nullable, x.st());
+    for (auto& k : c.keep) oc.keep.push_back(k);
+    OutCol& d = P.out[j];
+    memset(&d, 0, sizeof d);
+    d.src = pb.resolve(c);
+    d.data = (void*)oc.data;
+    d.valid = (uint8_t*)oc.valid;
+    d.phys = ph;
+    out->cols.push_back(oc);
+  }
+  pb.finalize_layout(4096);
+  RunOutcome r = launch_program(x, pb, 1);
+  out->n = (int64_t)r.status.out_rows;
+  uint64_t wbytes = 0;
+  for (auto& c : out->cols) {
+    c.n = out->n;
+    wbytes += (uint64_t)c.width() * (uint64_t)out->n;
+  }
+  // the views may point into the source batch's character buffers
+  for (auto& c : out->cols)
+    if (c.phys == PH_STRVIEW)
+      for (auto& sc : src->cols)
+        if (sc.phys == PH_UTF8 || sc.phys == PH_STRVIEW)
+          for (auto& k : sc.keep) c.keep.push_back(k);
+  for (auto& k : pb.keep)
+    for (auto& c : out->cols)
+      if (c.phys == PH_STRVIEW) c.keep.push_back(k);
+  if (met) {
+    met->elapsed_ns += (uint64_t)(r.ms * 1e6);
+    met->bytes_read += source_bytes(pb);
+    met->bytes_written += wbytes;
+    met->launches += 1;
+  }
+  return out;
+}
+
+// ---- aggregate ------------------------------------------------------------------------------------
+struct AggLowered {
+  std::vector<ColRef> keys;
+  std::vector<AccDesc> accs;
+  std::vector<ColRef> acc_src;
+  struct OutRecipe {
+    uint8_t kind, a, b;
+    Phys phys;
+    int imm;
+    DataType type;
+    std::string name;
+    bool with_valid;
+    int key_idx;
+  };
+  std::vector<OutRecipe> outs;
+};
+
+int add_acc(PipelineBuilder& pb, AggLowered& L, uint8_t kind, const ColRef* src) {
+  Operand so;
+  memset(&so, 0, sizeof so);
+  bool nullable = false;
+  if (src) {
+    so = pb.resolve(*src);
+    nullable = src->nullable;
+  }
+  for (size_t i = 0; i < L.accs.size(); i++) {
+    const AccDesc& a = L.accs[i];
+    if (a.kind == kind && (kind == ACC_COUNT_STAR || (a.src.kind == so.kind && a.src.idx == so.idx && a.src.vk == so.vk))) return (int)i;
+  }
+  if (L.accs.size() >= (size_t)VM_MAX_ACC) throw EngineError(B200_ERR_UNSUPPORTED, "too many aggregates in one AggregateExec");
+  AccDesc a;
+  memset(&a, 0, sizeof a);
+  a.kind = kind;
+  a.src = so;
+  a.nullable = nullable ? 1 : 0;
+  L.accs.push_back(a);
+  if (src) {
+    pb.pin(*src);
+    L.acc_src.push_back(*src);
+  }
+  return (int)L.accs.size() - 1;
+}
+
+void lower_aggregate(PipelineBuilder& pb, const PlanNode& node, AggLowered& L) {
+  const bool from_states = agg_mode_consumes_states(node.agg_mode);
+  const bool emit_states = agg_mode_emits_states(node.agg_mode);
+  const bool scalar = node.group_by.empty();
+  for (size_t g = 0; g < node.group_by.size(); g++) {
+    ColRef k = pb.compile(*node.group_by[g].expr);
+    pb.pin(k);
+    k.name = node.group_by[g].name;
+    L.keys.push_back(k);
+    AggLowered::OutRecipe r{};
+    r.kind = AO_KEY;
+    r.a = (uint8_t)g;
+    r.b = 255;
+    r.type = k.type;
+    r.phys = k.type.id == TypeId::Utf8 ? PH_STRVIEW : phys_of(k.type);
+    r.name = k.name;
+    r.with_valid = k.nullable;
+    r.key_idx = (int)g;
+    L.outs.push_back(r);
+  }
+  const int star = add_acc(pb, L, ACC_COUNT_STAR, nullptr);
+  size_t state_col = node.group_by.size();
+  auto push = [&](uint8_t kind, int a, int b, const DataType& t, const std::string& name, bool with_valid, int imm = 0) {
+    AggLowered::OutRecipe r{};
+    r.kind = kind;
+    r.a = (uint8_t)a;
+    r.b = (uint8_t)b;
+    r.type = t;
+    r.phys = phys_of(t);
+    r.name = name;
+    r.with_valid = with_valid;
+    r.imm = imm;
+    r.key_idx = -1;
+    L.outs.push_back(r);
+  };
+  auto sum_out_kind = [](const DataType& t) -> uint8_t { return t.pk() == PK::F64 ? AO_ACC_F64 : (t.pk() == PK::I128 ? AO_ACC_I128 : AO_ACC_I64); };
+  for (size_t ai = 0; ai < node.aggs.size(); ai++) {
+    const AggExpr& ae = node.aggs[ai];
+    const std::string& nm = ae.name;
+    if (from_states) {
+      ColRef s0 = pb.cols.at(state_col);
+      switch (ae.fn) {
+        case AggFn::Count: {
+          int a = add_acc(pb, L, ACC_SUM_I128, &s0);
+          push(AO_COUNT, a, 255, DataType(TypeId::Int64), nm, false);
+          break;
+        }
+        case AggFn::Sum: {
+          bool f = s0.type.pk() == PK::F64;
+          int a = add_acc(pb, L, f ? ACC_SUM_F64 : ACC_SUM_I128, &s0);
+          int c = s0.nullable ? add_acc(pb, L, ACC_COUNT, &s0) : star;
+          push(sum_out_kind(ae.result_type), a, c, ae.result_type, nm, s0.nullable || scalar);
+          break;
+        }
+        case AggFn::Min:
+        case AggFn::Max: {
+          if (s0.type.pk() == PK::Str) throw EngineError(B200_ERR_UNSUPPORTED, "MIN/MAX over Utf8");
+          bool f = s0.type.pk() == PK::F64, mn = ae.fn == AggFn::Min;
+          int a = add_acc(pb, L, f ? (mn ? ACC_MIN_F64 : ACC_MAX_F64) : (mn ? ACC_MIN_I128 : ACC_MAX_I128), &s0);
+          int c = s0.nullable ? add_acc(pb, L, ACC_COUNT, &s0) : star;
+          push(f ? AO_MINMAX_F64 : sum_out_kind(ae.result_type), a, c, ae.result_type, nm, s0.nullable || scalar);
+          break;
+        }
+        case AggFn::Avg: {
+          ColRef s1 = pb.cols.at(state_col + 1);
+          int c = add_acc(pb, L, ACC_SUM_I128, &s0);
+          bool f = s1.type.pk() == PK::F64;
+          int a = add_acc(pb, L, f ? ACC_SUM_F64 : ACC_SUM_I128, &s1);
+          if (f) push(AO_AVG_F64, a, c, ae.result_type, nm, true);
+          else push(AO_AVG_DEC, a, c, ae.result_type, nm, true, ae.result_type.scale - ae.sum_type.scale);
+          break;
+        }
+      }
+      state_col += (size_t)ae.n_state_cols();
+      continue;
+    }
+    ColRef arg;
+    bool has_arg = ae.arg != nullptr;
+    if (has_arg) arg = pb.compile(*ae.arg);
+    switch (ae.fn) {
+      case AggFn::Count: {
+        int a = (has_arg && arg.nullable) ? add_acc(pb, L, ACC_COUNT, &arg) : star;
+        push(AO_COUNT, a, 255, DataType(TypeId::Int64), emit_states ? nm + "[count]" : nm, false);
+        break;
+      }
+      case AggFn::Sum: {
+        ColRef v = arg;
+        bool f = ae.sum_type.pk() == PK::F64;
+        if (f) v = pb.cast_to(arg, DataType(TypeId::Float64));
+        int a = add_acc(pb, L, f ? ACC_SUM_F64 : ACC_SUM_I128, &v);
+        int c = v.nullable ? add_acc(pb, L, ACC_COUNT, &v) : star;
+        push(sum_out_kind(ae.sum_type), a, c, ae.sum_type, emit_states ? nm + "[sum]" : nm, v.nullable || scalar);
+        break;
+      }
+      case AggFn::Min:
+      case AggFn::Max: {
+        if (arg.type.pk() == PK::Str) throw EngineError(B200_ERR_UNSUPPORTED, "MIN/MAX over Utf8");
+        if (arg.type.id == TypeId::UInt64) throw EngineError(B200_ERR_UNSUPPORTED, "MIN/MAX over UInt64");
+        bool f = arg.type.pk() == PK::F64, mn = ae.fn == AggFn::Min;
+        int a = add_acc(pb, L, f ? (mn ? ACC_MIN_F64 : ACC_MAX_F64) : (mn ? ACC_MIN_I128 : ACC_MAX_I128), &arg);
+        int c = arg.nullable ? add_acc(pb, L, ACC_COUNT, &arg) : star;
+        push(f ? AO_MINMAX_F64 : sum_out_kind(ae.sum_type), a, c, ae.sum_type, emit_states ? nm + (mn ? "[min]" : "[max]") : nm, arg.nullable || scalar);
+        break;
+      }
+      case AggFn::Avg: {
+        ColRef v = arg;
+        bool f = !arg.type.is_decimal();
+        if (f) v = pb.cast_to(arg, DataType(TypeId::Float64));
+        int a = add_acc(pb, L, f ? ACC_SUM_F64 : ACC_SUM_I128, &v);
+        int c = v.nullable ? add_acc(pb, L, ACC_COUNT, &v) : star;
+        if (emit_states) {
+          push(AO_COUNT, c, 255, DataType(TypeId::UInt64), nm + "[count]", false);
+          push(sum_out_kind(ae.sum_type), a, c, ae.sum_type, nm + "[sum]", v.nullable || scalar);
+        } else if (f) {
+          push(AO_AVG_F64, a, c, ae.result_type, nm, true);
+        } else {
+          push(AO_AVG_DEC, a, c, ae.result_type, nm, true, ae.result_type.scale - ae.sum_type.scale);
+        }
+        break;
+      }
+    }
+  }
+}
+
+struct TableMem {
+  AggTable T;
+  std::vector<DevPtr> keep;
+};
+
+TableMem alloc_table(const Exec& x, uint64_t cap, int n_keys, const std::vector<AccDesc>& accs) {
+  TableMem tm;
+  memset(&tm.T, 0, sizeof tm.T);
+  auto A = [&](size_t bytes) {
+    DevPtr p = dev_alloc(bytes, x.st());
+    tm.keep.push_back(p);
+    return p->ptr;
+  };
+  tm.T.cap = cap;
+  tm.T.hash = (unsigned long long*)A(cap * 8);
+  tm.T.state = (unsigned int*)A(cap * 4);
+  tm.T.lock = (unsigned int*)A(cap * 4);
+  tm.T.keys = (unsigned long long*)A(std::max<size_t>(1, (size_t)n_keys) * cap * 16);
+  tm.T.key_valid = (unsigned char*)A(std::max<size_t>(1, (size_t)n_keys) * cap);
+  tm.T.acc = (unsigned long long*)A(std::max<size_t>(1, accs.size()) * cap * 16);
+  tm.T.n_groups = (unsigned int*)A(16);
+  AccKinds k;
+  memset(&k, 0, sizeof k);
+  k.n = (int)accs.size();
+  for (size_t i = 0; i < accs.size(); i++) k.kind[i] = accs[i].kind;
+  launch_agg_table_init(tm.T, k, x.st());
+  x.count();
+  return tm;
+}
+
+DevBatchPtr run_aggregate(const Exec& x, PipelineBuilder& pb, const PlanNode& node, const DevBatchPtr& src, OpMetrics* met) {
+  AggLowered L;
+  lower_aggregate(pb, node, L);
+  Program& P = pb.prog;
+  const int n_keys = (int)L.keys.size();
+  if (n_keys > VM_MAX_KEYS) throw EngineError(B200_ERR_UNSUPPORTED, "too many group-by columns");
+  P.n_keys = (uint8_t)n_keys;
+  P.n_acc = (uint8_t)L.accs.size();
+  for (int k = 0; k < n_keys; k++) P.keys[k] = pb.resolve(L.keys[(size_t)k]);
+  for (size_t a = 0; a < L.accs.size(); a++) P.acc[a] = L.accs[a];
+  memset(&P.key_hash, 0, sizeof P.key_hash);
+  if (n_keys) {
+    ColRef h = pb.hash_of(L.keys);
+    P.key_hash = h.op;
+  }
+  const bool reg_ok = (int)L.accs.size() <= VM_REG_ACC;
+  // strategy ladder: register sink (<= 4 groups) -> global table of growing capacity
+  int node_idx = -1;
+  if (x.s) {
+    auto it = x.s->metric_index.find(&node);
+    if (it != x.s->metric_index.end()) node_idx = it->second;
+  }
+  const std::string hint_key = (x.s ? x.s->fingerprint : std::string("?")) + "#" + std::to_string(node_idx);
+  int start = 0;
+  {
+    std::lock_guard<std::mutex> g(x.e->mu);
+    auto it = x.e->agg_hint.find(hint_key);
+    if (it != x.e->agg_hint.end()) start = it->second;
+  }
+  if (!reg_ok && start == 0) start = 1;
+  TableMem tm;
+  RunOutcome ro;
+  int level = start;
+  for (;; level++) {
+    x.check_cancel();
+    uint64_t cap;
+    int reg_groups = 0;
+    if (level == 0) {
+      P.sink = SINK_AGG_REG;
+      reg_groups = n_keys ? VM_REG_GROUPS : 1;
+      cap = n_keys ? 64 : 2;
+    } else {
+      P.sink = SINK_AGG_GLOBAL;
+      if (!n_keys) cap = 2;
+      else cap = std::min<uint64_t>(next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2), (uint64_t)1 << (12 + 4 * level));
+      if (cap < 16) cap = 16;
+    }
+    tm = alloc_table(x, cap, n_keys, L.accs);
+    P.table = tm.T;
+    pb.finalize_layout((size_t)8 * VM_REG_GROUPS * VM_REG_ACC * 16 + 256);
+    ro = launch_program(x, pb, reg_groups);
+    if (met) {
+      met->elapsed_ns += (uint64_t)(ro.ms * 1e6);
+      met->launches += 2;
+    }
+    if (!ro.status.overflow) break;
+    if (level > 0 && cap >= next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2)) throw EngineError(B200_ERR_EXECUTION, "aggregate hash table overflow");
+  }
+  {
+    std::lock_guard<std::mutex> g(x.e->mu);
+    x.e->agg_hint[hint_key] = level;
+  }
+  unsigned int n_groups = d2h_value<unsigned int>(tm.T.n_groups, x.st());
+  // extraction
+  auto out = std::make_shared<DevBatch>();
+  out->n = n_groups;
+  AggExtractArgs A;
+  memset(&A, 0, sizeof A);
+  if (L.outs.size() > (size_t)VM_MAX_OUT) throw EngineError(B200_ERR_UNSUPPORTED, "too many aggregate output columns");
+  A.n_out = (int)L.outs.size();
+  A.n_keys = n_keys;
+  DevPtr counter = dev_alloc(16, x.st());
+  CUDA_CHECK(cudaMemsetAsync(counter->ptr, 0, 16, x.st()));
+  A.counter = (unsigned long long*)counter->ptr;
+  A.error = (unsigned int*)((uint8_t*)counter->ptr + 8);
+  uint64_t wbytes = 0;
+  for (size_t j = 0; j < L.outs.size(); j++) {
+    const auto& r = L.outs[j];
+    DevColumn oc = make_out_column(r.name, r.type, r.phys, n_groups, r.with_valid, x.st());
+    oc.n = n_groups;
+    if (r.key_idx >= 0) {
+      for (auto& k : L.keys[(size_t)r.key_idx].keep) oc.keep.push_back(k);
+      if (r.phys == PH_STRVIEW) {
+        for (auto& sc : src->cols)
+          for (auto& k : sc.keep) oc.keep.push_back(k);
+        for (auto& k : pb.keep) oc.keep.push_back(k);
+      }
+    }
+    AggOut& o = A.out[j];
+    o.data = (void*)oc.data;
+    o.valid = (uint8_t*)oc.valid;
+    o.kind = r.kind;
+    o.a = r.a;
+    o.b = r.b;
+    o.phys = r.phys;
+    o.imm = r.imm;
+    wbytes += (uint64_t)oc.width() * n_groups;
+    out->cols.push_back(oc);
+  }
+  launch_agg_extract(tm.T, A, x.st());
+  x.count();
+  unsigned int err = d2h_value<unsigned int>(A.error, x.st());
+  if (err) throw EngineError(B200_ERR_EXECUTION, "Arithmetic overflow");
+  for (size_t c = 0; c < out->cols.size() && c < node.schema.size(); c++) out->cols[c].name = node.schema[c].name;
+  if (met) {
+    met->bytes_read += source_bytes(pb);
+    met->bytes_written += wbytes;
+    met->input_rows += (uint64_t)src->n;
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operator tree execution
+// ------------------------------------------------------------------------------------------------
+struct Runner {
+  Exec x;
+  std::string job;
+
+  int n_partitions(const PlanNode& n) {
+    switch (n.op) {
+      case PlanNode::Scan: {
+        std::lock_guard<std::mutex> g(x.e->mu);
+        auto it = x.e->tables.find(n.table);
+        if (it == x.e->tables.end()) throw EngineError(B200_ERR_INVALID, "table not registered: " + n.table);
+        return it->second.empty() ? 0 : it->second.rbegin()->first + 1;
+      }
+      case PlanNode::ShuffleReader: {
+        std::lock_guard<std::mutex> g(x.e->mu);
+        int mx = 0;
+        for (auto& kv : x.e->shuffle)
+          if (kv.first.job == job && kv.first.stage == n.reader_stage_id) mx = std::max(mx, (int)kv.first.part + 1);
+        return mx;
+      }
+      case PlanNode::SortPreservingMerge: return 1;
+      case PlanNode::Passthrough:
+        if (n.op_name == "CoalescePartitionsExec") return 1;
+        return n_partitions(*n.children[0]);
+      case PlanNode::HashJoin: return n_partitions(*n.children[1]);
+      default: return n_partitions(*n.children[0]);
+    }
+  }
+
+  DevBatchPtr concat(const std::vector<DevBatchPtr>& parts, const Schema& schema) {
+    std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>> v;
+    for (auto& p : parts) v.push_back({p, {0, p->n}});
+    return concat_slices(v, schema);
+  }
+
+  DevBatchPtr concat_slices(const std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>>& parts, const Schema& schema) {
+    auto out = std::make_shared<DevBatch>();
+    int64_t total = 0;
+    for (auto& p : parts) total += p.second.second - p.second.first;
+    out->n = total;
+    if (parts.size() == 1) {
+      const DevBatch& b = *parts[0].first;
+      for (auto& c : b.cols) out->cols.push_back(slice_column(c, parts[0].second.first, parts[0].second.second));
+      return out;
+    }
+    for (size_t ci = 0; ci < schema.size(); ci++) {
+      bool any_valid = false;
+      for (auto& p : parts) any_valid |= p.first->cols[ci].valid != nullptr;
+      const DataType& t = schema[ci].type;
+      Phys ph = t.id == TypeId::Utf8 ? PH_STRVIEW : phys_of(t);
+      DevColumn oc = make_out_column(schema[ci].name, t, ph, total, any_valid, x.st());
+      oc.n = total;
+      int64_t pos = 0;
+      for (auto& p : parts) {
+        int64_t r0 = p.second.first, r1 = p.second.second, n = r1 - r0;
+        if (n == 0) continue;
+        DevColumn sc = slice_column(p.first->cols[ci], r0, r1);
+        if (sc.type != t) throw EngineError(B200_ERR_INVALID, "concat: type mismatch in column " + schema[ci].name);
+        DevColumn v = as_views(x, sc);
+        CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.data + pos * oc.width(), v.data, (size_t)n * oc.width(), cudaMemcpyDeviceToDevice, x.st()));
+        if (any_valid) {
+          if (v.valid) CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.valid + pos, v.valid, (size_t)n, cudaMemcpyDeviceToDevice, x.st()));
+          else CUDA_CHECK(cudaMemsetAsync((uint8_t*)oc.valid + pos, 1, (size_t)n, x.st()));
+        }
+        if (ph == PH_STRVIEW)
+          for (auto& k : v.keep) oc.keep.push_back(k);
+        pos += n;
+      }
+      out->cols.push_back(oc);
+    }
+    return out;
+  }
+
+  DevBatchPtr empty_batch(const Schema& s) {
+    auto out = std::make_shared<DevBatch>();
+    for (auto& f : s) {
+      Phys ph = f.type.id == TypeId::Utf8 ? PH_STRVIEW : phys_of(f.type);
+      DevColumn c = make_out_column(f.name, f.type, ph, 0, false, x.st());
+      c.n = 0;
+      out->cols.push_back(c);
+    }
+    return out;
+  }
+
+  DevBatchPtr exec_all(const PlanNode& n) {
+    int np = n_partitions(n);
+    std::vector<DevBatchPtr> parts;
+    for (int p = 0; p < np; p++) parts.push_back(exec(n, p));
+    if (parts.empty()) return empty_batch(n.schema);
+    return concat(parts, n.schema);
+  }
+
+  // Walk down a Filter/Projection chain; returns the base node and the chain (top-down order).
+  const PlanNode* chain_base(const PlanNode& top, std::vector<const PlanNode*>& chain) {
+    const PlanNode* cur = &top;
+    while (cur->op == PlanNode::Filter || cur->op == PlanNode::Projection ||
+           (cur->op == PlanNode::Passthrough && cur->op_name != "CoalescePartitionsExec")) {
+      if (cur->op == PlanNode::Filter && cur->fetch >= 0) break;
+      if (cur->op != PlanNode::Passthrough) chain.push_back(cur);
+      cur = cur->children[0].get();
+    }
+    return cur;
+  }
+
+  void apply_chain(PipelineBuilder& pb, const std::vector<const PlanNode*>& chain) {
+    for (size_t i = chain.size(); i-- > 0;) {
+      const PlanNode* n = chain[i];
+      if (n->op == PlanNode::Filter) {
+        pb.apply_filter(*n->predicate);
+        if (n->has_projection) pb.apply_select(n->projection);
+      } else {
+        pb.apply_projection(n->exprs);
+      }
+    }
+  }
+
+  // Executes `top` (a Filter/Projection chain over some base) fused into one pipeline whose sink is
+  // decided by the caller through `finish`.
+  template <class F>
+  DevBatchPtr with_chain(const PlanNode& top, int part, bool all_parts, F&& finish) {
+    std::vector<const PlanNode*> chain;
+    const PlanNode* base = chain_base(top, chain);
+    DevBatchPtr src = all_parts ? exec_all(*base) : exec(*base, part);
+    PipelineBuilder pb(*src, x.st());
+    apply_chain(pb, chain);
+    for (auto* n : chain)
+      if (OpMetrics* m = x.m(n)) m->input_rows += (uint64_t)src->n;
+    return finish(pb, src);
+  }
+
+  std::vector<ColRef> named_cols(PipelineBuilder& pb, const Schema& schema) {
+    std::vector<ColRef> outs = pb.cols;
+    for (size_t i = 0; i < outs.size() && i < schema.size(); i++) outs[i].name = schema[i].name;
+    return outs;
+  }
+
+  DevBatchPtr exec(const PlanNode& n, int part) {
+    x.check_cancel();
+    OpMetrics* met = x.m(&n);
+    DevBatchPtr out;
+    switch (n.op) {
+      case PlanNode::Scan: {
+        std::lock_guard<std::mutex> g(x.e->mu);
+        auto it = x.e->tables.find(n.table);
+        if (it == x.e->tables.end()) throw EngineError(B200_ERR_INVALID, "table not registered: " + n.table);
+        auto pit = it->second.find(part);
+        if (pit == it->second.end()) {
+          out = empty_batch(n.schema);
+          break;
+        }
+        out = std::make_shared<DevBatch>();
+        out->n = pit->second->n;
+        for (size_t k = 0; k < n.scan_projection.size(); k++) {
+          int idx = n.scan_projection[k];
+          if ((size_t)idx >= pit->second->cols.size()) throw EngineError(B200_ERR_INVALID, "scan projection out of range for " + n.table);
+          DevColumn c = pit->second->cols[(size_t)idx];
+          if (c.type != n.schema[k].type)
+            throw EngineError(B200_ERR_INVALID, "scan: column " + n.schema[k].name + " has type " + c.type.str() + ", plan says " + n.schema[k].type.str());
+          c.name = n.schema[k].name;
+          out->cols.push_back(c);
+        }
+        break;
+      }
+      case PlanNode::ShuffleReader: {
+        std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>> pieces;
+        {
+          std::lock_guard<std::mutex> g(x.e->mu);
+          auto it = x.e->shuffle.find(ShuffleKey{job, n.reader_stage_id, n.broadcast ? 0 : part});
+          if (it != x.e->shuffle.end())
+            for (auto& p : it->second)
+              if (p.r1 > p.r0) pieces.push_back({p.batch, {p.r0, p.r1}});
+        }
+        if (pieces.empty()) out = empty_batch(n.schema);
+        else out = concat_slices(pieces, n.schema);
+        for (size_t c = 0; c < out->cols.size() && c < n.schema.size(); c++) {
+          if (out->cols[c].type != n.schema[c].type)
+            throw EngineError(B200_ERR_INVALID, "shuffle reader: column " + n.schema[c].name + " has type " + out->cols[c].type.str() + ", plan says " + n.schema[c].type.str());
+          out->cols[c].name = n.schema[c].name;
+        }
+        break;
+      }
+      case PlanNode::Filter:
+      case PlanNode::Projection: {
+        if (n.op == PlanNode::Filter && n.fetch >= 0) throw EngineError(B200_ERR_UNSUPPORTED, "FilterExec with fetch");
+        out = with_chain(n, part, false, [&](PipelineBuilder& pb, DevBatchPtr& src) { return run_materialize(x, pb, named_cols(pb, n.schema), src, met); });
+        break;
+      }
+      case PlanNode::Aggregate: {
+        const PlanNode& child = *n.children[0];
+        bool all = (n.agg_mode == AggMode::Final || n.agg_mode == AggMode::Single) && part == 0 && n_partitions(child) > 1;
+        out = with_chain(child, part, all, [&](PipelineBuilder& pb, DevBatchPtr& src) { return run_aggregate(x, pb, n, src, met); });
+        break;
+      }
+      case PlanNode::HashJoin: out = exec_join(n, part, met); break;
+      case PlanNode::Sort: {
+        DevBatchPtr in = exec(*n.children[0], part);
+        out = do_sort(n.sort_keys, n.fetch, in, met);
+        break;
+      }
+      case PlanNode::SortPreservingMerge: {
+        DevBatchPtr in = exec_all(*n.children[0]);
+        out = do_sort(n.sort_keys, n.fetch, in, met);
+        break;
+      }
+      case PlanNode::Passthrough:
+        out = (n.op_name == "CoalescePartitionsExec") ? exec_all(*n.children[0]) : exec(*n.children[0], part);
+        break;
+      case PlanNode::Limit: {
+        DevBatchPtr in = (n.op_name == "GlobalLimitExec") ? exec_all(*n.children[0]) : exec(*n.children[0], part);
+        int64_t r0 = std::min<int64_t>(std::max<int64_t>(0, n.skip), in->n);
+        int64_t r1 = n.fetch >= 0 ? std::min<int64_t>(in->n, r0 + n.fetch) : in->n;
+        out = std::make_shared<DevBatch>();
+        out->n = r1 - r0;
+        for (auto& c : in->cols) out->cols.push_back(slice_column(c, r0, r1));
+        break;
+      }
+      case PlanNode::ShuffleWriter: throw EngineError(B200_ERR_INVALID, "nested ShuffleWriterExec");
+    }
+    if (met) met->output_rows += (uint64_t)out->n;
+    return out;
+  }
+
+  // ---- sort -----------------------------------------------------------------------------------
+  DevBatchPtr do_sort(const std::vector<SortKey>& keys, int64_t fetch, DevBatchPtr in, OpMetrics* met) {
+    const int64_t n = in->n;
+    auto t0 = std::chrono::steady_clock::now();
+    // key columns: plain column references are used in place, anything else is computed first
+    std::vector<DevColumn> kcols;
+    bool need_eval = false;
+    for (auto& k : keys) need_eval |= k.expr->kind != Expr::Col;
+    DevBatchPtr work = in;
+    size_t n_in_cols = in->cols.size();
+    if (need_eval && n > 0) {
+      PipelineBuilder pb(*in, x.st());
+      std::vector<ColRef> outs = pb.cols;
+      for (auto& k : keys) {
+        ColRef c = pb.compile(*k.expr);
+        pb.pin(c);
+        outs.push_back(c);
+      }
+      work = run_materialize(x, pb, outs, in, met);
+      for (size_t k = 0; k < keys.size(); k++) kcols.push_back(work->cols[n_in_cols + k]);
+    } else {
+      for (auto& k : keys) kcols.push_back(in->cols.at((size_t)(k.expr->kind == Expr::Col ? k.expr->col : 0)));
+    }
+    if (n <= 1 || keys.empty()) {
+      auto out = std::make_shared<DevBatch>();
+      int64_t m = fetch >= 0 ? std::min<int64_t>(fetch, n) : n;
+      out->n = m;
+      for (size_t c = 0; c < n_in_cols; c++) out->cols.push_back(slice_column(in->cols[c], 0, m));
+      return out;
+    }
+    if (n >= ((int64_t)1 << 32)) throw EngineError(B200_ERR_UNSUPPORTED, "sort of more than 2^32 rows");
+    const uint32_t n_blocks = (uint32_t)((n + 2047) / 2048);
+    DevPtr ka = dev_alloc((size_t)n * 8, x.st()), kb = dev_alloc((size_t)n * 8, x.st());
+    DevPtr va = dev_alloc((size_t)n * 4, x.st()), vb = dev_alloc((size_t)n * 4, x.st());
+    DevPtr hist = dev_alloc((size_t)256 * n_blocks * 4 + 64, x.st());
+    DevPtr scan = dev_alloc(((size_t)256 * n_blocks + 1 + (size_t)(256 * n_blocks) / 1024 + 8) * 8, x.st());
+    uint32_t* perm = (uint32_t*)va->ptr;
+    uint32_t* perm_alt = (uint32_t*)vb->ptr;
+    launch_iota_u32(perm, n, x.st());
+    x.count();
+    for (size_t ki = keys.size(); ki-- > 0;) {
+      DevColumn kc = as_views(x, kcols[ki]);
+      int n_words = 1;
+      if (kc.phys == PH_DEC128) n_words = 2;
+      if (kc.phys == PH_STRVIEW) {
+        DevPtr mx = dev_alloc(16, x.st());
+        CUDA_CHECK(cudaMemsetAsync(mx->ptr, 0, 16, x.st()));
+        launch_max_view_len((const unsigned long long*)kc.data, kc.valid, n, (unsigned int*)mx->ptr, x.st());
+        x.count();
+        unsigned int maxlen = d2h_value<unsigned int>(mx->ptr, x.st());
+        n_words = (int)(maxlen / 7) + 1;
+      }
+      // least significant word first; the NULL-rank word is the most significant
+      for (int w = n_words - 1; w >= (kc.valid ? -1 : 0); w--) {
+        SortWordArgs A;
+        A.data = kc.data;
+        A.valid = kc.valid;
+        A.phys = kc.phys;
+        A.asc = keys[ki].asc;
+        A.nulls_first = keys[ki].nulls_first;
+        A.word = w;
+        uint64_t* kin = (uint64_t*)ka->ptr;
+        launch_sort_word(A, perm, kin, n, x.st());
+        x.count();
+        bool in_a;
+        uint64_t ln = 0;
+        if (perm == (uint32_t*)va->ptr) {
+          radix_sort_pairs_u64((uint64_t*)ka->ptr, (uint32_t*)va->ptr, (uint64_t*)kb->ptr, (uint32_t*)vb->ptr, n, (uint32_t*)hist->ptr, (uint64_t*)scan->ptr, x.st(), &in_a, &ln);
+          perm = in_a ? (uint32_t*)va->ptr : (uint32_t*)vb->ptr;
+        } else {
+          // current permutation lives in vb: sort with roles swapped (keys were written to ka)
+          radix_sort_pairs_u64((uint64_t*)ka->ptr, (uint32_t*)vb->ptr, (uint64_t*)kb->ptr, (uint32_t*)va->ptr, n, (uint32_t*)hist->ptr, (uint64_t*)scan->ptr, x.st(), &in_a, &ln);
+          perm = in_a ? (uint32_t*)vb->ptr : (uint32_t*)va->ptr;
+        }
+        x.count(ln);
+        (void)perm_alt;
+      }
+    }
+    int64_t m = fetch >= 0 ? std::min<int64_t>(fetch, n) : n;
+    DevPtr idx = dev_alloc((size_t)std::max<int64_t>(m, 1) * 8, x.st());
+    launch_u32_to_i64(perm, (int64_t*)idx->ptr, m, x.st());
+    x.count();
+    DevBatch proj;
+    proj.n = n;
+    for (size_t c = 0; c < n_in_cols; c++) proj.cols.push_back(in->cols[c]);
+    DevBatchPtr out = gather_batch(x, proj, (const int64_t*)idx->ptr, m, false);
+    CUDA_CHECK(cudaStreamSynchronize(x.st()));
+    if (met) {
+      met->elapsed_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+      met->input_rows += (uint64_t)n;
+    }
+    return out;
+  }
+
+  // ---- hash join --------------------------------------------------------------------------------
+  struct JoinSide {
+    DevBatchPtr batch;  // [payload columns..., key columns..., hash, ok]
+    size_t n_payload;
+  };
+  JoinSide prepare_side(const PlanNode& child, int part, bool all, const std::vector<ExprPtr>& key_exprs, bool null_equals_null, OpMetrics* met) {
+    JoinSide js;
+    js.batch = with_chain(child, part, all, [&](PipelineBuilder& pb, DevBatchPtr& src) {
+      std::vector<ColRef> outs = named_cols(pb, child.schema);
+      js.n_payload = outs.size();
+      std::vector<ColRef> keys;
+      for (auto& ke : key_exprs) {
+        ColRef k = pb.compile(*ke);
+        pb.pin(k);
+        keys.push_back(k);
+      }
+      for (auto& k : keys) outs.push_back(k);
+      ColRef h = pb.hash_of(keys);
+      h.name = "__hash";
+      outs.push_back(h);
+      return run_materialize(x, pb, outs, src, met);
+    });
+    (void)null_equals_null;
+    return js;
+  }
+
+  DevBatchPtr exec_join(const PlanNode& n, int part, OpMetrics* met) {
+    const bool collect_left = n.partition_mode == "CollectLeft";
+    std::vector<ExprPtr> lk, rk;
+    for (auto& on : n.on) {
+      lk.push_back(on.first);
+      rk.push_back(on.second);
+    }
+    const size_t nk = lk.size();
+    if (nk > (size_t)VM_MAX_KEYS) throw EngineError(B200_ERR_UNSUPPORTED, "too many join keys");
+    JoinSide L = prepare_side(*n.children[0], part, collect_left, lk, n.null_equals_null, met);
+    JoinSide R = prepare_side(*n.children[1], part, false, rk, n.null_equals_null, met);
+    const int64_t nb = L.batch->n, np = R.batch->n;
+    if (nb >= ((int64_t)1 << 31)) throw EngineError(B200_ERR_UNSUPPORTED, "hash join build side exceeds 2^31 rows");
+    auto t0 = std::chrono::steady_clock::now();
+    JoinKeys K;
+    memset(&K, 0, sizeof K);
+    K.n_keys = (int)nk;
+    K.null_equals_null = n.null_equals_null ? 1 : 0;
+    // rows with a NULL key never match (unless null_equals_null): ok = AND of key validity
+    DevPtr l_ok, r_ok;
+    auto key_col = [&](JoinSide& s, size_t k) -> DevColumn& { return s.batch->cols[s.n_payload + k]; };
+    for (size_t k = 0; k < nk; k++) {
+      DevColumn& b = key_col(L, k);
+      DevColumn& p = key_col(R, k);
+      if (b.phys != p.phys) throw EngineError(B200_ERR_UNSUPPORTED, "join key physical types differ (" + b.type.str() + " vs " + p.type.str() + "): add casts");
+      K.build[k] = KeyCol{b.data, b.valid, (uint8_t)b.phys, (uint8_t)b.width()};
+      K.probe[k] = KeyCol{p.data, p.valid, (uint8_t)p.phys, (uint8_t)p.width()};
+    }
+    const uint64_t* lh = (const uint64_t*)L.batch->cols[L.n_payload + nk].data;
+    const uint64_t* rh = (const uint64_t*)R.batch->cols[R.n_payload + nk].data;
+    uint64_t n_buckets = next_pow2((uint64_t)std::max<int64_t>(nb, 1) * 2);
+    DevPtr heads = dev_alloc((size_t)n_buckets * 4, x.st());
+    CUDA_CHECK(cudaMemsetAsync(heads->ptr, 0xFF, (size_t)n_buckets * 4, x.st()));
+    DevPtr next = dev_alloc((size_t)std::max<int64_t>(nb, 1) * 4, x.st());
+    launch_join_build(lh, nullptr, nb, (int32_t*)heads->ptr, n_buckets, (int32_t*)next->ptr, x.st());
+    x.count();
+    DevPtr counts = dev_alloc((size_t)(np + 1) * 4, x.st());
+    DevPtr offs = dev_alloc((size_t)(np + 2) * 8, x.st());
+    DevPtr scratch = dev_alloc((size_t)(np / 1024 + 4) * 8, x.st());
+    launch_join_probe_count(K, lh, (const int32_t*)heads->ptr, n_buckets, (const int32_t*)next->ptr, rh, nullptr, np, (uint32_t*)counts->ptr, nullptr, x.st());
+    launch_scan_u32_to_u64((const uint32_t*)counts->ptr, (uint64_t*)offs->ptr, np, (uint64_t*)scratch->ptr, x.st());
+    x.count(4);
+    int64_t n_pairs = (int64_t)d2h_value<uint64_t>((const uint64_t*)offs->ptr + np, x.st());
+    DevPtr bi = dev_alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, x.st()), pi = dev_alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, x.st());
+    launch_join_probe_write(K, lh, (const int32_t*)heads->ptr, n_buckets, (const int32_t*)next->ptr, rh, nullptr, np, (const uint64_t*)offs->ptr, (int64_t*)bi->ptr, (int64_t*)pi->ptr, x.st());
+    x.count();
+
+    DevBatch Lp, Rp;  // payload-only views
+    Lp.n = nb;
+    Rp.n = np;
+    for (size_t c = 0; c < L.n_payload; c++) Lp.cols.push_back(L.batch->cols[c]);
+    for (size_t c = 0; c < R.n_payload; c++) Rp.cols.push_back(R.batch->cols[c]);
+
+    const int64_t* bidx = (const int64_t*)bi->ptr;
+    const int64_t* pidx = (const int64_t*)pi->ptr;
+    DevPtr fbi, fpi;  // filtered pair lists
+    if (n.join_filter && n_pairs > 0) {
+      // evaluate the residual filter on the candidate pairs, carrying the pair indices through
+      DevBatchPtr lg = gather_batch(x, Lp, bidx, n_pairs, false), rg = gather_batch(x, Rp, pidx, n_pairs, false);
+      auto cat = std::make_shared<DevBatch>();
+      cat->n = n_pairs;
+      for (auto& c : lg->cols) cat->cols.push_back(c);
+      for (auto& c : rg->cols) cat->cols.push_back(c);
+      DevColumn ib, ip;
+      ib.type = ip.type = DataType(TypeId::Int64);
+      ib.phys = ip.phys = PH_I64;
+      ib.n = ip.n = n_pairs;
+      ib.data = (const uint8_t*)bi->ptr;
+      ip.data = (const uint8_t*)pi->ptr;
+      ib.keep.push_back(bi);
+      ip.keep.push_back(pi);
+      ib.name = "__bi";
+      ip.name = "__pi";
+      cat->cols.push_back(ib);
+      cat->cols.push_back(ip);
+      PipelineBuilder pb(*cat, x.st());
+      pb.apply_filter(*n.join_filter);
+      std::vector<ColRef> outs = {pb.cols[cat->cols.size() - 2], pb.cols[cat->cols.size() - 1]};
+      DevBatchPtr kept = run_materialize(x, pb, outs, cat, met);
+      n_pairs = kept->n;
+      fbi = kept->cols[0].keep[0];
+      fpi = kept->cols[1].keep[0];
+      bidx = (const int64_t*)kept->cols[0].data;
+      pidx = (const int64_t*)kept->cols[1].data;
+    }
+    auto flags_to_indices = [&](const uint8_t* marks, int64_t nrows, bool want, int64_t* n_sel) {
+      DevPtr f = dev_alloc((size_t)(nrows + 1) * 4, x.st());
+      DevPtr o = dev_alloc((size_t)(nrows + 2) * 8, x.st());
+      DevPtr sc = dev_alloc((size_t)(nrows / 1024 + 4) * 8, x.st());
+      launch_flag_to_u32(marks, want ? 1 : 0, (uint32_t*)f->ptr, nrows, x.st());
+      launch_scan_u32_to_u64((const uint32_t*)f->ptr, (uint64_t*)o->ptr, nrows, (uint64_t*)sc->ptr, x.st());
+      x.count(4);
+      *n_sel = (int64_t)d2h_value<uint64_t>((const uint64_t*)o->ptr + nrows, x.st());
+      DevPtr idx = dev_alloc((size_t)std::max<int64_t>(*n_sel, 1) * 8, x.st());
+      launch_select_indices((const uint32_t*)f->ptr, (const uint64_t*)o->ptr, (int64_t*)idx->ptr, nrows, x.st());
+      x.count();
+      return idx;
+    };
+    auto marks_of = [&](const int64_t* idx, int64_t nrows) {
+      DevPtr m = dev_alloc((size_t)std::max<int64_t>(nrows, 1), x.st());
+      CUDA_CHECK(cudaMemsetAsync(m->ptr, 0, (size_t)std::max<int64_t>(nrows, 1), x.st()));
+      if (n_pairs > 0) {
+        launch_mark_from_idx(idx, n_pairs, (uint8_t*)m->ptr, x.st());
+        x.count();
+      }
+      return m;
+    };
+    DevBatchPtr out;
+    switch (n.join_type) {
+      case JoinType::LeftSemi:
+      case JoinType::LeftAnti: {
+        DevPtr m = marks_of(bidx, nb);
+        int64_t ns = 0;
+        DevPtr idx = flags_to_indices((const uint8_t*)m->ptr, nb, n.join_type == JoinType::LeftSemi, &ns);
+        out = gather_batch(x, Lp, (const int64_t*)idx->ptr, ns, false);
+        break;
+      }
+      case JoinType::RightSemi:
+      case JoinType::RightAnti: {
+        DevPtr m = marks_of(pidx, np);
+        int64_t ns = 0;
+        DevPtr idx = flags_to_indices((const uint8_t*)m->ptr, np, n.join_type == JoinType::RightSemi, &ns);
+        out = gather_batch(x, Rp, (const int64_t*)idx->ptr, ns, false);
+        break;
+      }
+      default: {
+        // inner pairs (+ unmatched rows for outer joins, index -1 on the missing side)
+        int64_t extra_l = 0, extra_r = 0;
+        DevPtr ul, ur;
+        const bool left_outer = n.join_type == JoinType::Left || n.join_type == JoinType::Full;
+        const bool right_outer = n.join_type == JoinType::Right || n.join_type == JoinType::Full;
+        if (left_outer) {
+          DevPtr m = marks_of(bidx, nb);
+          ul = flags_to_indices((const uint8_t*)m->ptr, nb, false, &extra_l);
+        }
+        if (right_outer) {
+          DevPtr m = marks_of(pidx, np);
+          ur = flags_to_indices((const uint8_t*)m->ptr, np, false, &extra_r);
+        }
+        const int64_t total = n_pairs + extra_l + extra_r;
+        DevPtr li = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8, x.st()), ri = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8, x.st());
+        if (n_pairs) {
+          CUDA_CHECK(cudaMemcpyAsync(li->ptr, bidx, (size_t)n_pairs * 8, cudaMemcpyDeviceToDevice, x.st()));
+          CUDA_CHECK(cudaMemcpyAsync(ri->ptr, pidx, (size_t)n_pairs * 8, cudaMemcpyDeviceToDevice, x.st()));
+        }
+        if (extra_l) {
+          CUDA_CHECK(cudaMemcpyAsync((int64_t*)li->ptr + n_pairs, ul->ptr, (size_t)extra_l * 8, cudaMemcpyDeviceToDevice, x.st()));
+          CUDA_CHECK(cudaMemsetAsync((int64_t*)ri->ptr + n_pairs, 0xFF, (size_t)extra_l * 8, x.st()));
+        }
+        if (extra_r) {
+          CUDA_CHECK(cudaMemsetAsync((int64_t*)li->ptr + n_pairs + extra_l, 0xFF, (size_t)extra_r * 8, x.st()));
+          CUDA_CHECK(cudaMemcpyAsync((int64_t*)ri->ptr + n_pairs + extra_l, ur->ptr, (size_t)extra_r * 8, cudaMemcpyDeviceToDevice, x.st()));
+        }
+        DevBatchPtr lg = gather_batch(x, Lp, (const int64_t*)li->ptr, total, right_outer);
+        DevBatchPtr rg = gather_batch(x, Rp, (const int64_t*)ri->ptr, total, left_outer);
+        out = std::make_shared<DevBatch>();
+        out->n = total;
+        for (auto& c : lg->cols) out->cols.push_back(c);
+        for (auto& c : rg->cols) out->cols.push_back(c);
+      }
+    }
+    if (n.has_projection) {
+      auto p = std::make_shared<DevBatch>();
+      p->n = out->n;
+      for (int idx : n.projection) p->cols.push_back(out->cols.at((size_t)idx));
+      out = p;
+    }
+    for (size_t c = 0; c < out->cols.size() && c < n.schema.size(); c++) out->cols[c].name = n.schema[c].name;
+    CUDA_CHECK(cudaStreamSynchronize(x.st()));
+    if (met) {
+      met->elapsed_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+      met->input_rows += (uint64_t)(nb + np);
+    }
+    return out;
+  }
+
+  // ---- shuffle writer -----------------------------------------------------------------------------
+  uint64_t slice_bytes(const DevBatch& b, int64_t rows, const std::vector<int64_t>& chars_bytes) {
+    uint64_t t = 0;
+    size_t si = 0;
+    for (auto& c : b.cols) {
+      if (c.type.id == TypeId::Bool) t += (uint64_t)(rows + 7) / 8;
+      else if (c.type.id == TypeId::Utf8) t += 4ull * (uint64_t)(rows + 1) + (uint64_t)chars_bytes[si++];
+      else t += (uint64_t)c.width() * (uint64_t)rows;
+    }
+    return t;
+  }
+
+  std::vector<b200_shuffle_write_partition> execute_stage(const PlanNode& root, int input_partition) {
+    if (root.op != PlanNode::ShuffleWriter) throw EngineError(B200_ERR_INVALID, "stage plan root must be a ShuffleWriterExec");
+    OpMetrics* met = x.m(&root);
+    const PlanNode& child = *root.children[0];
+    const int64_t bs = x.e->batch_size;
+    auto nbatches = [&](uint64_t rows) { return (rows + (uint64_t)bs - 1) / (uint64_t)bs; };
+    std::vector<b200_shuffle_write_partition> res;
+    if (root.n_out_partitions == 0) {
+      DevBatchPtr in = exec(child, input_partition);
+      // canonical Arrow layout for stored partitions (strings contiguous)
+      auto st = std::make_shared<DevBatch>();
+      st->n = in->n;
+      std::vector<int64_t> cb;
+      for (size_t c = 0; c < in->cols.size(); c++) {
+        DevColumn col = in->cols[c];
+        col.name = root.schema[c].name;
+        if (col.type.id == TypeId::Utf8) {
+          if (col.phys == PH_STRVIEW) col = as_utf8(x, col);
+          if (col.chars_bytes < 0) {
+            int32_t o0 = d2h_value<int32_t>(col.data, x.st());
+            int32_t o1 = d2h_value<int32_t>(col.data + 4 * col.n, x.st());
+            col.chars_bytes = o1 - o0;
+          }
+          cb.push_back(col.chars_bytes);
+        }
+        st->cols.push_back(col);
+      }
+      CUDA_CHECK(cudaStreamSynchronize(x.st()));
+      b200_shuffle_write_partition w{};
+      w.partition_id = (uint64_t)input_partition;
+      w.num_rows = (uint64_t)st->n;
+      w.num_batches = nbatches(w.num_rows);
+      w.num_bytes = slice_bytes(*st, st->n, cb);
+      w.file_id = -1;
+      w.is_sort_shuffle = 0;
+      {
+        std::lock_guard<std::mutex> g(x.e->mu);
+        auto& v = x.e->shuffle[ShuffleKey{job, root.stage_id, input_partition}];
+        v.clear();
+        v.push_back(Piece{-1, st, 0, st->n});
+      }
+      if (met) {
+        met->output_rows += w.num_rows;
+        met->input_rows += w.num_rows;
+        met->bytes_written += w.num_bytes;
+      }
+      res.push_back(w);
+      return res;
+    }
+    // hash repartition: pid = hash(keys) % P fused into the child's pipeline, then rank + scatter
+    const uint32_t P = (uint32_t)root.n_out_partitions;
+    size_t n_payload = 0;
+    DevBatchPtr mat = with_chain(child, input_partition, false, [&](PipelineBuilder& pb, DevBatchPtr& src) {
+      std::vector<ColRef> outs = named_cols(pb, root.schema);
+      n_payload = outs.size();
+      std::vector<ColRef> keys;
+      for (auto& e : root.part_exprs) {
+        ColRef k = pb.compile(*e);
+        pb.pin(k);
+        keys.push_back(k);
+      }
+      ColRef h = pb.hash_of(keys);
+      ColRef pid = pb.mod_u64(h, P);
+      pid.name = "__pid";
+      outs.push_back(pid);
+      return run_materialize(x, pb, outs, src, met);
+    });
+    const int64_t n = mat->n;
+    const uint32_t* pid = (const uint32_t*)mat->cols[n_payload].data;
+    DevPtr counts = dev_alloc((size_t)(P + 1) * 8, x.st());
+    CUDA_CHECK(cudaMemsetAsync(counts->ptr, 0, (size_t)(P + 1) * 8, x.st()));
+    launch_histogram_u32(pid, n, P, (unsigned long long*)counts->ptr, x.st());
+    x.count();
+    std::vector<unsigned long long> hc(P);
+    CUDA_CHECK(cudaMemcpyAsync(hc.data(), counts->ptr, (size_t)P * 8, cudaMemcpyDeviceToHost, x.st()));
+    CUDA_CHECK(cudaStreamSynchronize(x.st()));
+    std::vector<int64_t> bounds(P + 1, 0);
+    for (uint32_t p = 0; p < P; p++) bounds[p + 1] = bounds[p] + (int64_t)hc[p];
+    DevPtr cursor = dev_alloc((size_t)(P + 1) * 8, x.st());
+    CUDA_CHECK(cudaMemcpyAsync(cursor->ptr, bounds.data(), (size_t)P * 8, cudaMemcpyHostToDevice, x.st()));
+    DevPtr dest = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st());
+    launch_partition_rank(pid, n, P, (unsigned long long*)cursor->ptr, (uint32_t*)dest->ptr, x.st());
+    x.count();
+    auto st = std::make_shared<DevBatch>();
+    st->n = n;
+    std::vector<std::vector<int64_t>> chars_per_part;  // [string col][p]
+    for (size_t c = 0; c < n_payload; c++) {
+      const DevColumn& sc = mat->cols[c];
+      DevColumn oc = make_out_column(root.schema[c].name, sc.type, sc.phys, n, sc.valid != nullptr, x.st());
+      oc.n = n;
+      launch_scatter_fixed(sc.data, (void*)oc.data, (const uint32_t*)dest->ptr, n, sc.width(), x.st());
+      x.count();
+      if (sc.valid) {
+        launch_scatter_fixed(sc.valid, (void*)oc.valid, (const uint32_t*)dest->ptr, n, 1, x.st());
+        x.count();
+      }
+      for (auto& k : sc.keep) oc.keep.push_back(k);
+      if (oc.phys == PH_STRVIEW) {
+        DevColumn u = as_utf8(x, oc);
+        // chars per partition from the offsets at the partition boundaries
+        std::vector<int32_t> offs(P + 1);
+        DevPtr bidx = dev_alloc((size_t)(P + 1) * 8, x.st());
+        CUDA_CHECK(cudaMemcpyAsync(bidx->ptr, bounds.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, x.st()));
+        DevPtr bo = dev_alloc((size_t)(P + 1) * 4, x.st());
+        launch_gather_fixed(u.data, nullptr, bo->ptr, nullptr, (const int64_t*)bidx->ptr, P + 1, 4, x.st());
+        x.count();
+        CUDA_CHECK(cudaMemcpyAsync(offs.data(), bo->ptr, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, x.st()));
+        CUDA_CHECK(cudaStreamSynchronize(x.st()));
+        std::vector<int64_t> cp(P);
+        for (uint32_t p = 0; p < P; p++) cp[p] = offs[p + 1] - offs[p];
+        chars_per_part.push_back(cp);
+        oc = u;
+      }
+      st->cols.push_back(oc);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(x.st()));
+    uint64_t total_bytes = 0;
+    {
+      std::lock_guard<std::mutex> g(x.e->mu);
+      for (uint32_t p = 0; p < P; p++) {
+        auto& v = x.e->shuffle[ShuffleKey{job, root.stage_id, (int64_t)p}];
+        // a re-run of the same map task replaces its previous output (task retry)
+        v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == input_partition; }), v.end());
+        const int64_t rows = bounds[p + 1] - bounds[p];
+        if (rows == 0) {
+          if (v.empty()) x.e->shuffle.erase(ShuffleKey{job, root.stage_id, (int64_t)p});
+          continue;  // only partitions with rows are reported (sort_shuffle/writer.rs:357-369)
+        }
+        v.push_back(Piece{input_partition, st, bounds[p], bounds[p + 1]});
+        std::vector<int64_t> cb;
+        for (auto& cp : chars_per_part) cb.push_back(cp[p]);
+        b200_shuffle_write_partition w{};
+        w.partition_id = p;
+        w.num_rows = (uint64_t)rows;
+        w.num_batches = nbatches(w.num_rows);
+        w.num_bytes = slice_bytes(*st, rows, cb);
+        w.file_id = input_partition;
+        w.is_sort_shuffle = root.sort_shuffle ? 1 : 0;
+        total_bytes += w.num_bytes;
+        res.push_back(w);
+      }
+    }
+    if (met) {
+      met->output_rows += (uint64_t)n;
+      met->bytes_written += total_bytes;
+      met->bytes_read += total_bytes;
+    }
+    return res;
+  }
+};
+
+void collect_nodes(const PlanNode& n, b200_stage* s) {
+  s->metric_index[&n] = (int)s->metrics.size();
+  OpMetrics m;
+  m.name = n.op_name;
+  s->metrics.push_back(m);
+  for (auto& c : n.children) collect_nodes(*c, s);
+}
+
+int table_id(const std::string& name) {
+  static const char* names[] = {"lineitem", "orders", "customer", "supplier", "part", "partsupp", "nation", "region"};
+  for (int i = 0; i < 8; i++)
+    if (name == names[i]) return i;
+  return -1;
+}
+
+template <class F>
+int guard(F&& f) {
+  try {
+    f();
+    return B200_OK;
+  } catch (const EngineError& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_err = "host out of memory";
+    return B200_ERR_OOM;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return B200_ERR_INVALID;
+  } catch (...) {
+    g_err = "unknown error";
+    return B200_ERR_INVALID;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* b200_version(void) { return "b200exec 0.1 sm_100a"; }
+const char* b200_last_error(void) { return g_err.c_str(); }
+
+int b200_engine_create(int device, uint64_t pool_bytes, int rank, int world, b200_engine** out) {
+  return guard([&] {
+    if (!out) throw EngineError(B200_ERR_INVALID, "null out pointer");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+      throw EngineError(B200_ERR_CUDA, std::string("no CUDA device available: the B200 engine has no CPU path (") + cudaGetErrorString(ce) + ")");
+    if (device < 0 || device >= ndev) throw EngineError(B200_ERR_INVALID, "bad device ordinal");
+    CUDA_CHECK(cudaSetDevice(device));
+    auto* e = new b200_engine();
+    e->device = device;
+    e->rank = rank;
+    e->world = world;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = pool_bytes ? pool_bytes : UINT64_MAX;
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = e;
+  });
+}
+
+void b200_engine_destroy(b200_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->tables.clear();
+  e->shuffle.clear();
+  cudaStreamSynchronize(e->stream);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+int b200_engine_set_stream(b200_engine* e, void* cuda_stream) {
+  return guard([&] {
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  });
+}
+int b200_engine_synchronize(b200_engine* e) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  });
+}
+uint64_t b200_engine_kernel_launches(b200_engine* e) { return e->launches; }
+
+int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
+  return guard([&] {
+    std::lock_guard<std::mutex> g(e->mu);
+    e->config[key] = value;
+    if (std::string(key) == "datafusion.execution.batch_size") e->batch_size = std::max<int64_t>(1, atoll(value));
+  });
+}
+
+int b200_engine_register_batch(b200_engine* e, const char* table, int partition, struct ArrowArray* batch, struct ArrowSchema* schema) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    DevBatchPtr b = import_batch(e, batch, schema);
+    Exec x{e, nullptr, nullptr};
+    DevBatchPtr prev;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      auto& slot = e->tables[table][partition];
+      prev = slot;
+      if (!prev) slot = b;
+    }
+    if (prev) {  // append
+      Runner r{x, ""};
+      Schema s;
+      for (auto& c : prev->cols) s.push_back(Field{c.name, c.type, true});
+      DevBatchPtr cat = r.concat({prev, b}, s);
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      std::lock_guard<std::mutex> g(e->mu);
+      e->tables[table][partition] = cat;
+    }
+  });
+}
+
+int b200_engine_drop_table(b200_engine* e, const char* table) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->mu);
+    e->tables.erase(table);
+  });
+}
+
+int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, int partition, int64_t row_begin, int64_t row_end, const char* columns_csv) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    int t = table_id(table);
+    if (t < 0) throw EngineError(B200_ERR_INVALID, std::string("unknown TPC-H table ") + table);
+    std::vector<int> cols;
+    if (columns_csv && *columns_csv) {
+      std::string s(columns_csv);
+      size_t p = 0;
+      while (p <= s.size()) {
+        size_t q = s.find(',', p);
+        if (q == std::string::npos) q = s.size();
+        std::string nm = s.substr(p, q - p);
+        int found = -1;
+        for (int c = 0; c < tpch::kNumCols[t]; c++)
+          if (nm == tpch::kCols[t][c].name) found = c;
+        if (found < 0) throw EngineError(B200_ERR_INVALID, "unknown column " + nm);
+        cols.push_back(found);
+        p = q + 1;
+      }
+    } else {
+      for (int c = 0; c < tpch::kNumCols[t]; c++) cols.push_back(c);
+    }
+    const int64_t n = row_end - row_begin;
+    if (n < 0) throw EngineError(B200_ERR_INVALID, "bad row range");
+    cudaStream_t st = e->stream;
+    auto b = std::make_shared<DevBatch>();
+    b->n = n;
+    for (int c : cols) {
+      const tpch::ColDef& cd = tpch::kCols[t][c];
+      DevColumn col;
+      col.name = cd.name;
+      col.n = n;
+      col.nullable = false;
+      switch (cd.kind) {
+        case tpch::K_I64: col.type = DataType(TypeId::Int64); break;
+        case tpch::K_I32: col.type = DataType(TypeId::Int32); break;
+        case tpch::K_DEC: col.type = DataType::decimal(15, 2); break;
+        case tpch::K_DATE: col.type = DataType(TypeId::Date32); break;
+        default: col.type = DataType(TypeId::Utf8);
+      }
+      col.phys = phys_of(col.type);
+      if (cd.kind == tpch::K_STR) {
+        DevPtr lens = dev_alloc((size_t)(n + 1) * 4, st);
+        DevPtr offs64 = dev_alloc((size_t)(n + 2) * 8, st);
+        DevPtr scratch = dev_alloc((size_t)(n / 1024 + 4) * 8, st);
+        launch_tpch_str_len(t, c, msf, row_begin, n, (uint32_t*)lens->ptr, st);
+        launch_scan_u32_to_u64((const uint32_t*)lens->ptr, (uint64_t*)offs64->ptr, n, (uint64_t*)scratch->ptr, st);
+        e->launches += 4;
+        uint64_t total = d2h_value<uint64_t>((const uint64_t*)offs64->ptr + n, st);
+        if (total > 0x7FFFFFFFull) throw EngineError(B200_ERR_UNSUPPORTED, "generated string column exceeds 2 GiB; use more partitions");
+        DevPtr offsets = dev_alloc((size_t)(n + 1) * 4 + 64, st);
+        DevPtr chars = dev_alloc((size_t)total + 64, st);
+        launch_tpch_str_fill(t, c, msf, row_begin, n, (const uint64_t*)offs64->ptr, (int32_t*)offsets->ptr, (uint8_t*)chars->ptr, st);
+        e->launches++;
+        col.data = (const uint8_t*)offsets->ptr;
+        col.chars = (const uint8_t*)chars->ptr;
+        col.chars_bytes = (int64_t)total;
+        col.keep.push_back(offsets);
+        col.keep.push_back(chars);
+      } else {
+        DevPtr d = dev_alloc((size_t)std::max<int64_t>(n, 1) * col.width() + 64, st);
+        launch_tpch_fixed(t, c, cd.kind, msf, row_begin, n, d->ptr, st);
+        e->launches++;
+        col.data = (const uint8_t*)d->ptr;
+        col.keep.push_back(d);
+      }
+      b->cols.push_back(col);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> g(e->mu);
+    e->tables[table][partition] = b;
+  });
+}
+
+int b200_engine_export_table(b200_engine* e, const char* table, int partition, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    DevBatchPtr b;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      auto it = e->tables.find(table);
+      if (it == e->tables.end() || !it->second.count(partition)) throw EngineError(B200_ERR_NOT_FOUND, "no such table partition");
+      b = it->second[partition];
+    }
+    Exec x{e, nullptr, nullptr};
+    export_batch(x, *b, 0, b->n, out, out_schema);
+  });
+}
+
+int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, const char* plan_json, uint64_t plan_len, b200_stage** out) {
+  return guard([&] {
+    if (!e || !plan_json || !out) throw EngineError(B200_ERR_INVALID, "null argument");
+    Json j = parse_json(plan_json, plan_len ? (size_t)plan_len : strlen(plan_json));
+    PlanPtr plan = parse_plan(j);
+    if (plan->op != PlanNode::ShuffleWriter)
+      throw EngineError(B200_ERR_INVALID, "Plan passed to new_query_stage_exec is not a ShuffleWriterExec");  // execution_engine.rs:164-167
+    auto* s = new b200_stage();
+    s->eng = e;
+    s->job_id = job_id ? job_id : plan->job_id;
+    s->stage_id = stage_id;
+    plan->stage_id = stage_id;
+    s->fingerprint = s->job_id.substr(0, s->job_id.find('#')) + ":" + std::to_string(stage_id) + ":" + std::to_string(mix64(hash_bytes((const uint8_t*)plan_json, (uint32_t)strlen(plan_json))));
+    collect_nodes(*plan, s);
+    s->plan = std::move(plan);
+    *out = s;
+  });
+}
+
+int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag, b200_shuffle_write_partition* out, int cap, int* n_out) {
+  return guard([&] {
+    if (!s || !n_out) throw EngineError(B200_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(s->eng->device));
+    Exec x{s->eng, s, cancel_flag};
+    Runner r{x, s->job_id};
+    std::vector<b200_shuffle_write_partition> res;
+    try {
+      res = r.execute_stage(*s->plan, input_partition);
+    } catch (...) {
+      cudaStreamSynchronize(s->eng->stream);
+      throw;
+    }
+    if ((int)res.size() > cap) throw EngineError(B200_ERR_INVALID, "output array too small");
+    for (size_t i = 0; i < res.size(); i++) out[i] = res[i];
+    *n_out = (int)res.size();
+  });
+}
+
+int b200_stage_metrics(b200_stage* s, b200_operator_metrics* out, int cap, int* n_out) {
+  return guard([&] {
+    int n = (int)std::min<size_t>(s->metrics.size(), (size_t)cap);
+    for (int i = 0; i < n; i++) {
+      memset(&out[i], 0, sizeof out[i]);
+      snprintf(out[i].name, sizeof out[i].name, "%s", s->metrics[(size_t)i].name.c_str());
+      out[i].output_rows = s->metrics[(size_t)i].output_rows;
+      out[i].input_rows = s->metrics[(size_t)i].input_rows;
+      out[i].elapsed_compute_ns = s->metrics[(size_t)i].elapsed_ns;
+      out[i].bytes_read = s->metrics[(size_t)i].bytes_read;
+      out[i].bytes_written = s->metrics[(size_t)i].bytes_written;
+      out[i].kernel_launches = s->metrics[(size_t)i].launches;
+    }
+    *n_out = n;
+  });
+}
+
+void b200_stage_release(b200_stage* s) { delete s; }
+
+int b200_partition_export(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>> pieces;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      auto it = e->shuffle.find(ShuffleKey{job_id, stage_id, out_partition});
+      if (it == e->shuffle.end()) throw EngineError(B200_ERR_NOT_FOUND, "no such shuffle partition");  // -> FetchFailed
+      for (auto& p : it->second) pieces.push_back({p.batch, {p.r0, p.r1}});
+    }
+    Exec x{e, nullptr, nullptr};
+    if (pieces.size() == 1) {
+      export_batch(x, *pieces[0].first, pieces[0].second.first, pieces[0].second.second, out, out_schema);
+      return;
+    }
+    Runner r{x, job_id};
+    Schema s;
+    for (auto& c : pieces[0].first->cols) s.push_back(Field{c.name, c.type, true});
+    DevBatchPtr cat = r.concat_slices(pieces, s);
+    export_batch(x, *cat, 0, cat->n, out, out_schema);
+  });
+}
+
+int64_t b200_partition_rows(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition) {
+  std::lock_guard<std::mutex> g(e->mu);
+  auto it = e->shuffle.find(ShuffleKey{job_id, stage_id, out_partition});
+  if (it == e->shuffle.end()) return -1;
+  int64_t n = 0;
+  for (auto& p : it->second) n += p.r1 - p.r0;
+  return n;
+}
+
+int b200_partition_device_buffers(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition, b200_device_buffer* out, int cap, int* n_out,
+                                  int64_t* n_rows) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>> pieces;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      auto it = e->shuffle.find(ShuffleKey{job_id, stage_id, out_partition});
+      if (it == e->shuffle.end()) throw EngineError(B200_ERR_NOT_FOUND, "no such shuffle partition");
+      for (auto& p : it->second) pieces.push_back({p.batch, {p.r0, p.r1}});
+    }
+    Exec x{e, nullptr, nullptr};
+    Runner r{x, job_id};
+    Schema s;
+    for (auto& c : pieces[0].first->cols) s.push_back(Field{c.name, c.type, true});
+    DevBatchPtr cat = r.concat_slices(pieces, s);
+    // exchange layout per column: [validity bytes (n) or empty][values | offsets(n+1, rebased)][chars]
+    auto packed = std::make_shared<DevBatch>();
+    packed->n = cat->n;
+    int k = 0;
+    for (auto& c0 : cat->cols) {
+      DevColumn c = c0.phys == PH_STRVIEW ? as_utf8(x, c0) : c0;
+      if (k + 3 > cap) throw EngineError(B200_ERR_INVALID, "buffer array too small");
+      out[k++] = b200_device_buffer{(void*)c.valid, c.valid ? (uint64_t)c.n : 0};
+      if (c.phys == PH_UTF8) {
+        if (c.chars_bytes < 0 || c.n == 0 || d2h_value<int32_t>(c.data, x.st()) != 0) {
+          // rebase through views so that offsets start at 0
+          DevColumn v = as_views(x, c);
+          c = as_utf8(x, v);
+        }
+        out[k++] = b200_device_buffer{(void*)c.data, (uint64_t)(c.n + 1) * 4};
+        out[k++] = b200_device_buffer{(void*)c.chars, (uint64_t)std::max<int64_t>(c.chars_bytes, 0)};
+      } else {
+        out[k++] = b200_device_buffer{(void*)c.data, (uint64_t)c.n * c.width()};
+        out[k++] = b200_device_buffer{nullptr, 0};
+      }
+      packed->cols.push_back(c);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(x.st()));
+    // keep the packed form alive as the partition's single piece
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      auto& v = e->shuffle[ShuffleKey{job_id, stage_id, out_partition}];
+      int64_t fid = v.empty() ? -1 : v[0].file_id;
+      v.clear();
+      v.push_back(Piece{fid, packed, 0, packed->n});
+    }
+    *n_out = k;
+    *n_rows = packed->n;
+  });
+}
+
+int b200_partition_import_device(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition, int64_t file_id, const char* schema_json,
+                                 const b200_device_buffer* bufs, int n_bufs, int64_t n_rows) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    Json j = parse_json(schema_json, strlen(schema_json));
+    Schema s = parse_schema(j);
+    if ((int)s.size() * 3 != n_bufs) throw EngineError(B200_ERR_INVALID, "expected 3 buffers per column");
+    cudaStream_t st = e->stream;
+    auto b = std::make_shared<DevBatch>();
+    b->n = n_rows;
+    for (size_t c = 0; c < s.size(); c++) {
+      const b200_device_buffer& bv = bufs[3 * c];
+      const b200_device_buffer& bd = bufs[3 * c + 1];
+      const b200_device_buffer& bc = bufs[3 * c + 2];
+      DevColumn col;
+      col.name = s[c].name;
+      col.type = s[c].type;
+      col.phys = phys_of(col.type);
+      col.n = n_rows;
+      auto copy_in = [&](const b200_device_buffer& src) -> const uint8_t* {
+        DevPtr d = dev_alloc((size_t)src.bytes + 64, st);
+        if (src.bytes) CUDA_CHECK(cudaMemcpyAsync(d->ptr, src.ptr, (size_t)src.bytes, cudaMemcpyDeviceToDevice, st));
+        col.keep.push_back(d);
+        return (const uint8_t*)d->ptr;
+      };
+      if (bv.bytes) col.valid = copy_in(bv);
+      col.nullable = bv.bytes != 0;
+      col.data = copy_in(bd);
+      if (col.phys == PH_UTF8) {
+        col.chars = copy_in(bc);
+        col.chars_bytes = (int64_t)bc.bytes;
+      }
+      b->cols.push_back(col);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> g(e->mu);
+    auto& v = e->shuffle[ShuffleKey{job_id, stage_id, out_partition}];
+    v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == file_id; }), v.end());
+    v.push_back(Piece{file_id, b, 0, n_rows});
+  });
+}
+
+int b200_remove_job_data(b200_engine* e, const char* job_id) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->mu);
+    for (auto it = e->shuffle.begin(); it != e->shuffle.end();) {
+      if (it->first.job == job_id) it = e->shuffle.erase(it);
+      else ++it;
+    }
+  });
+}
+
+void* b200_host_alloc_pinned(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void b200_host_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+"""ctypes host-side mirror of the reference plug-in interface on top of ``libb200exec.so``.
+
+    reference (Rust)                                           here
+    ---------------------------------------------------------  -------------------------------------
+    trait ExecutionEngine::create_query_stage_exec             GpuExecutionEngine.create_query_stage_exec
+      ballista/executor/src/execution_engine.rs:50-58            -> b200_stage_prepare
+    trait QueryStageExecutor::execute_query_stage              QueryStageExecutor.execute_query_stage
+      ballista/executor/src/execution_engine.rs:73-77            -> b200_stage_execute
+    QueryStageExecutor::collect_plan_metrics  (:80)            QueryStageExecutor.collect_plan_metrics
+    message ShuffleWritePartition (ballista.proto:481-492)     ShuffleWritePartition
+
+The CUDA library is mandatory: importing succeeds without it (so that CPU-only tests can check the
+exported symbols), but constructing an engine raises if the library or a GPU is missing -- there
+is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import pyarrow as pa
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libb200exec.so")
+
+
+class ShuffleWritePartition(C.Structure):
+    _fields_ = [("partition_id", C.c_uint64), ("num_batches", C.c_uint64), ("num_rows", C.c_uint64),
+                ("num_bytes", C.c_uint64), ("file_id", C.c_int64), ("is_sort_shuffle", C.c_int32),
+                ("_pad", C.c_int32)]
+
+    def as_tuple(self):
+        return (self.partition_id, self.num_batches, self.num_rows, self.num_bytes, self.file_id, self.is_sort_shuffle)
+
+
+class OperatorMetrics(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("output_rows", C.c_uint64), ("input_rows", C.c_uint64),
+                ("elapsed_compute_ns", C.c_uint64), ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64),
+                ("kernel_launches", C.c_uint64)]
+
+
+class DeviceBuffer(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+class ArrowSchema(C.Structure):
+    _fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                ("n_children", C.c_int64), ("children", C.c_void_p), ("dictionary", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArray(C.Structure):
+    _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                ("n_children", C.c_int64), ("buffers", C.c_void_p), ("children", C.c_void_p),
+                ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+# every symbol include/b200exec.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "b200_engine_create", "b200_engine_destroy", "b200_last_error", "b200_engine_set_stream",
+    "b200_engine_synchronize", "b200_engine_kernel_launches", "b200_engine_set_config",
+    "b200_engine_register_batch", "b200_engine_drop_table", "b200_engine_tpch_generate",
+    "b200_engine_export_table", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
+    "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
+    "b200_partition_import_device", "b200_remove_job_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
+    "b200_version",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libb200exec.so (no CUDA call is made by loading)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()); "
+                           "the B200 engine has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, cp, i64, u64, ci = C.c_void_p, C.c_char_p, C.c_int64, C.c_uint64, C.c_int
+    L.b200_engine_create.argtypes = [ci, u64, ci, ci, C.POINTER(vp)]
+    L.b200_engine_destroy.argtypes = [vp]
+    L.b200_engine_destroy.restype = None
+    L.b200_last_error.restype = cp
+    L.b200_engine_set_stream.argtypes = [vp, vp]
+    L.b200_engine_synchronize.argtypes = [vp]
+    L.b200_engine_kernel_launches.argtypes = [vp]
+    L.b200_engine_kernel_launches.restype = u64
+    L.b200_engine_set_config.argtypes = [vp, cp, cp]
+    L.b200_engine_register_batch.argtypes = [vp, cp, ci, vp, vp]
+    L.b200_engine_drop_table.argtypes = [vp, cp]
+    L.b200_engine_tpch_generate.argtypes = [vp, cp, i64, ci, i64, i64, cp]
+    L.b200_engine_export_table.argtypes = [vp, cp, ci, vp, vp]
+    L.b200_stage_prepare.argtypes = [vp, cp, i64, cp, u64, C.POINTER(vp)]
+    L.b200_stage_execute.argtypes = [vp, ci, vp, C.POINTER(ShuffleWritePartition), ci, C.POINTER(ci)]
+    L.b200_stage_metrics.argtypes = [vp, C.POINTER(OperatorMetrics), ci, C.POINTER(ci)]
+    L.b200_stage_release.argtypes = [vp]
+    L.b200_stage_release.restype = None
+    L.b200_partition_export.argtypes = [vp, cp, i64, ci, vp, vp]
+    L.b200_partition_rows.argtypes = [vp, cp, i64, ci]
+    L.b200_partition_rows.restype = i64
+    L.b200_partition_device_buffers.argtypes = [vp, cp, i64, ci, C.POINTER(DeviceBuffer), ci, C.POINTER(ci), C.POINTER(i64)]
+    L.b200_partition_import_device.argtypes = [vp, cp, i64, ci, i64, cp, C.POINTER(DeviceBuffer), ci, i64]
+    L.b200_remove_job_data.argtypes = [vp, cp]
+    L.b200_host_alloc_pinned.argtypes = [u64]
+    L.b200_host_alloc_pinned.restype = vp
+    L.b200_host_free_pinned.argtypes = [vp]
+    L.b200_host_free_pinned.restype = None
+    L.b200_version.restype = cp
+    _lib = L
+    return L
+
+
+class B200Error(RuntimeError):
+    """Maps b200_status codes (include/b200exec.h) the way the Rust shim maps them to
+    DataFusionError / BallistaError."""
+    NAMES = {-1: "Plan", -2: "NotImplemented", -3: "Execution", -4: "External(CUDA)", -5: "FetchFailed",
+             -6: "Cancelled", -7: "ResourcesExhausted"}
+
+    def __init__(self, code, msg):
+        super().__init__(f"{self.NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200Error(rc, load_library().b200_last_error().decode(errors="replace"))
+
+
+class QueryStageExecutor:
+    def __init__(self, engine: "GpuExecutionEngine", handle, job_id: str, stage_id: int):
+        self.engine, self.h, self.job_id, self.stage_id = engine, handle, job_id, stage_id
+
+    def execute_query_stage(self, input_partition: int, cancel_flag=None) -> List[ShuffleWritePartition]:
+        cap = 65536
+        out = (ShuffleWritePartition * cap)()
+        n = C.c_int(0)
+        cf = C.addressof(cancel_flag) if cancel_flag is not None else None
+        _check(load_library().b200_stage_execute(self.h, input_partition, cf, out, cap, C.byref(n)))
+        return [out[i] for i in range(n.value)]
+
+    def collect_plan_metrics(self) -> List[dict]:
+        cap = 256
+        out = (OperatorMetrics * cap)()
+        n = C.c_int(0)
+        _check(load_library().b200_stage_metrics(self.h, out, cap, C.byref(n)))
+        return [dict(name=out[i].name.decode(), output_rows=out[i].output_rows, input_rows=out[i].input_rows,
+                     elapsed_compute_ns=out[i].elapsed_compute_ns, bytes_read=out[i].bytes_read,
+                     bytes_written=out[i].bytes_written, kernel_launches=out[i].kernel_launches)
+                for i in range(n.value)]
+
+    def release(self):
+        if self.h:
+            load_library().b200_stage_release(self.h)
+            self.h = None
+
+
+class GpuExecutionEngine:
+    """One per executor process == one per GPU (SURVEY.md 8(b) "Threading")."""
+
+    def __init__(self, device: int = 0, pool_bytes: int = 0, rank: int = 0, world: int = 1):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.b200_engine_create(device, pool_bytes, rank, world, C.byref(h)))
+        self.h = h
+        self.device = device
+        self._parts = {}
+
+    def close(self):
+        if self.h:
+            load_library().b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- config / stream ---------------------------------------------------------------------
+    def set_config(self, key: str, value) -> None:
+        _check(load_library().b200_engine_set_config(self.h, key.encode(), str(value).encode()))
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]) -> None:
+        _check(load_library().b200_engine_set_stream(self.h, cuda_stream_ptr))
+
+    def synchronize(self) -> None:
+        _check(load_library().b200_engine_synchronize(self.h))
+
+    def kernel_launches(self) -> int:
+        return load_library().b200_engine_kernel_launches(self.h)
+
+    # -- leaf inputs ---------------------------------------------------------------------------
+    def register_batch(self, table: str, partition: int, batch: pa.RecordBatch) -> None:
+        arr, sch = ArrowArray(), ArrowSchema()
+        batch._export_to_c(C.addressof(arr), C.addressof(sch))
+        _check(load_library().b200_engine_register_batch(self.h, table.encode(), partition, C.addressof(arr), C.addressof(sch)))
+        self._parts.setdefault(table, set()).add(partition)
+
+    def drop_table(self, table: str) -> None:
+        _check(load_library().b200_engine_drop_table(self.h, table.encode()))
+        self._parts.pop(table, None)
+
+    def tpch_generate(self, table, msf, partition, row_begin, row_end, columns: Optional[List[str]] = None) -> None:
+        csv = ",".join(columns).encode() if columns else None
+        _check(load_library().b200_engine_tpch_generate(self.h, table.encode(), msf, partition, row_begin, row_end, csv))
+        self._parts.setdefault(table, set()).add(partition)
+
+    def export_table(self, table: str, partition: int) -> pa.RecordBatch:
+        arr, sch = ArrowArray(), ArrowSchema()
+        _check(load_library().b200_engine_export_table(self.h, table.encode(), partition, C.addressof(arr), C.addressof(sch)))
+        return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
+    def n_table_partitions(self, table: str) -> int:
+        return max(self._parts[table]) + 1
+
+    # -- ExecutionEngine -------------------------------------------------------------------------
+    def create_query_stage_exec(self, job_id: str, stage_id: int, plan_json: str) -> QueryStageExecutor:
+        h = C.c_void_p()
+        pj = plan_json.encode()
+        _check(load_library().b200_stage_prepare(self.h, job_id.encode(), stage_id, pj, len(pj), C.byref(h)))
+        return QueryStageExecutor(self, h, job_id, stage_id)
+
+    # -- shuffle partitions ----------------------------------------------------------------------
+    def partition_export(self, job_id: str, stage_id: int, out_partition: int) -> pa.RecordBatch:
+        arr, sch = ArrowArray(), ArrowSchema()
+        _check(load_library().b200_partition_export(self.h, job_id.encode(), stage_id, out_partition,
+                                                    C.addressof(arr), C.addressof(sch)))
+        return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
+    def partition_rows(self, job_id: str, stage_id: int, out_partition: int) -> int:
+        return load_library().b200_partition_rows(self.h, job_id.encode(), stage_id, out_partition)
+
+    def partition_device_buffers(self, job_id: str, stage_id: int, out_partition: int):
+        cap = 3 * 64
+        out = (DeviceBuffer * cap)()
+        n = C.c_int(0)
+        rows = C.c_int64(0)
+        _check(load_library().b200_partition_device_buffers(self.h, job_id.encode(), stage_id, out_partition, out, cap,
+                                                            C.byref(n), C.byref(rows)))
+        return [(out[i].ptr or 0, out[i].bytes) for i in range(n.value)], rows.value
+
+    def partition_import_device(self, job_id: str, stage_id: int, out_partition: int, file_id: int, schema_json: str,
+                                bufs, n_rows: int) -> None:
+        arr = (DeviceBuffer * len(bufs))()
+        for i, (p, b) in enumerate(bufs):
+            arr[i].ptr = p
+            arr[i].bytes = b
+        _check(load_library().b200_partition_import_device(self.h, job_id.encode(), stage_id, out_partition, file_id,
+                                                           schema_json.encode(), arr, len(bufs), n_rows))
+
+    def remove_job_data(self, job_id: str) -> None:
+        _check(load_library().b200_remove_job_data(self.h, job_id.encode()))

@@ -1129,10 +1129,7 @@ uint64_t batch_bytes(const OBatch& b) {
       for (size_t r = 0; r < c.n; r++)
         if (c.is_valid(r)) t += c.s[r].size();
     } else t += (uint64_t)c.type.width() * c.n;
-    bool anynull = false;
-    for (auto v : c.valid) anynull |= !v;
-    if (anynull) t += (c.n + 7) / 8;
-  }
+  }  // validity bitmaps are not counted: num_bytes = data buffers (values / offsets / chars)
   return t;
 }
 

@@ -1,0 +1,39 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    import oracle_ffi
+    oracle_ffi.build()
+    return oracle_ffi
+
+
+@pytest.fixture()
+def oracle(oracle_lib):
+    e = oracle_lib.OracleEngine()
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="session")
+def gpu_engine_session():
+    import ballista_b200 as bb
+    e = bb.GpuExecutionEngine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture()
+def gpu(gpu_engine_session):
+    return gpu_engine_session
