@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- TPC-H q1 through the B200 execution engine (BASELINE.json configs[1]).
+
+One "step" = one full pass of the hot path over the resident synthetic lineitem table:
+  stage 1  scan -> FilterExec -> ProjectionExec -> AggregateExec(Partial) -> hash ShuffleWriter
+  stage 2  ShuffleReader -> AggregateExec(FinalPartitioned) -> SortExec -> ShuffleWriter(None)
+  stage 3  ShuffleReader -> SortPreservingMergeExec -> ShuffleWriter(None)
+exactly the stage shapes Ballista's planner emits for q1 (ballista/scheduler/src/planner.rs:655-670).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N>1 is launched by the driver under torchrun (one rank per GPU, NCCL); every rank owns SF10 worth
+of lineitem rows (weak scaling: the global table is SF(10*N)), the partial aggregate states are
+exchanged with an NCCL all-to-all, and `value` is global rows / max-over-ranks device time.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on
+a bounded sample of the same workload: the reference itself (Rust) cannot be built offline.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SF10_MSF = 10000
+ROWS_SF10 = 59_986_052
+BYTES_PER_ROW = 78  # Arrow layout of the 7 referenced columns
+METRIC = "tpch_q1_rows_per_sec"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- clocks ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU arm (oracle) -------------------------------------------------------------------------------
+def cpu_q1(rows: int, threads: int, steps: int, warmup: int):
+    """q1 over `rows` lineitem rows on the CPU oracle: `threads` map tasks in parallel (the reference
+    runs one task per partition on its DedicatedExecutor pool, cpu_bound_executor.rs:94-131)."""
+    import oracle_ffi
+    from concurrent.futures import ThreadPoolExecutor
+    from ballista_b200 import tpch
+    oracle_ffi.build()
+    eng = oracle_ffi.OracleEngine()
+    parts = threads
+    step = (rows + parts - 1) // parts
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(lambda p: eng.tpch_generate("lineitem", SF10_MSF, p, min(rows, p * step), min(rows, (p + 1) * step),
+                                                  tpch.Q1_COLUMNS), range(parts)))
+        stages = tpch.q1(n_partitions=min(16, parts))
+        times = []
+        for it in range(warmup + steps):
+            job = f"cpu{it}"
+            t0 = time.perf_counter()
+            s1 = eng.create_query_stage_exec(job, 1, stages[0].json(job))
+            list(pool.map(lambda p: s1.execute_query_stage(p), range(parts)))
+            s2 = eng.create_query_stage_exec(job, 2, stages[1].json(job))
+            list(pool.map(lambda p: s2.execute_query_stage(p), range(min(16, parts))))
+            s3 = eng.create_query_stage_exec(job, 3, stages[2].json(job))
+            s3.execute_query_stage(0)
+            res = eng.partition_export(job, 3, 0)
+            dt = time.perf_counter() - t0
+            eng.remove_job_data(job)
+            if it >= warmup:
+                times.append(dt)
+            assert res.num_rows == 4
+    eng.close()
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = ROWS_SF10 // 4
+    times = cpu_q1(rows, threads, args.steps, args.warmup)
+    total = sum(times)
+    value = rows * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "decimal128/i128",
+        "data": "synthetic",
+        "config": {"workload": "TPC-H q1 SF10 (BASELINE.json configs[1]); bounded sample", "rows_per_step": rows,
+                   "note": "CPU restatement of the reference path (oracle/liboracle.so); the Rust reference cannot be built offline"},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": f"q1 over {rows} lineitem rows (SF2.5) per step, {threads} map tasks on {threads} threads"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import pyarrow as pa
+    import ballista_b200 as bb
+    from ballista_b200 import tpch, exchange
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched under torchrun (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    eng = bb.GpuExecutionEngine(local_rank, 0, rank, world)
+    stream = torch.cuda.Stream(device=device)
+    eng.set_stream(stream.cuda_stream)
+
+    # this rank's slice of the global SF(10*world) lineitem table, generated directly in HBM
+    msf = SF10_MSF * world
+    r0, r1 = rank * ROWS_SF10, (rank + 1) * ROWS_SF10
+    eng.tpch_generate("lineitem", msf, 0, r0, r1, tpch.Q1_COLUMNS)
+    P = world
+    stages = tpch.q1(n_partitions=P)
+    partial_schema = stages[1].plan["input"]["input"]["input"]["schema"]
+    final_schema = stages[2].plan["input"]["input"]["schema"]
+
+    agg_ns = [0, 0]  # [elapsed ns, launches] of the fused stage-1 kernel inside the timed region
+
+    def step(job, timed=False):
+        s1 = eng.create_query_stage_exec(job, 1, stages[0].json(job))
+        s1.execute_query_stage(0)
+        if timed:
+            for m in s1.collect_plan_metrics():
+                if m["name"] == "AggregateExec":
+                    agg_ns[0] += m["elapsed_compute_ns"]
+                    agg_ns[1] += 1
+        s1.release()
+        if world > 1:
+            with torch.cuda.stream(stream):
+                exchange.exchange_stage(eng, job, 1, P, partial_schema, rank, world, device)
+        s2 = eng.create_query_stage_exec(job, 2, stages[1].json(job))
+        s2.execute_query_stage(rank)
+        s2.release()
+        out = None
+        if world > 1:
+            # final merge on rank 0: gather stage-2 outputs (tiny) as one more exchange to partition 0
+            with torch.cuda.stream(stream):
+                _gather_to_zero(eng, job, 2, world, rank, final_schema, device)
+        if rank == 0:
+            s3 = eng.create_query_stage_exec(job, 3, stages[2].json(job))
+            s3.execute_query_stage(0)
+            s3.release()
+            out = eng.partition_export(job, 3, 0)
+        eng.remove_job_data(job)
+        return out
+
+    def _gather_to_zero(eng_, job, stage_id, world_, rank_, schema, device_):
+        # every rank wrote stage-2 output partition `rank`; rank 0's merge task reads all of them
+        import json as _json
+        rows = eng_.partition_rows(job, stage_id, rank_)
+        bufs, nrows = (eng_.partition_device_buffers(job, stage_id, rank_) if rows >= 0 else ([(0, 0)] * (3 * len(schema)), 0))
+        sizes = torch.tensor([b for _, b in bufs] + [nrows], dtype=torch.int64, device=device_)
+        all_sizes = [torch.empty_like(sizes) for _ in range(world_)]
+        dist.all_gather(all_sizes, sizes)
+        total = int(sizes[:-1].sum())
+        send = torch.empty(total, dtype=torch.uint8, device=device_)
+        pos = 0
+        for ptr, nb in bufs:
+            if nb:
+                send[pos:pos + nb].copy_(exchange._as_tensor(ptr, nb, device_))
+                pos += nb
+        recv_list = [torch.empty(int(s[:-1].sum()), dtype=torch.uint8, device=device_) for s in all_sizes] if rank_ == 0 else None
+        if rank_ == 0:
+            # point-to-point gather (sizes differ per rank)
+            reqs = []
+            for src in range(1, world_):
+                if recv_list[src].numel():
+                    reqs.append(dist.irecv(recv_list[src], src=src))
+            for r in reqs:
+                r.wait()
+            torch.cuda.current_stream(device_).synchronize()
+            for src in range(1, world_):
+                sz = all_sizes[src].cpu().tolist()
+                if sz[-1] == 0:
+                    continue
+                base, pos2, bl = recv_list[src].data_ptr(), 0, []
+                for nb in sz[:-1]:
+                    bl.append((base + pos2 if nb else 0, nb))
+                    pos2 += nb
+                eng_.partition_import_device(job, stage_id, src, -1, _json.dumps(schema), bl, sz[-1])
+        else:
+            if send.numel():
+                dist.send(send, dst=0)
+            torch.cuda.current_stream(device_).synchronize()
+
+    # ---- warm-up (also settles the aggregate strategy hint) ----
+    for w in range(max(args.warmup, 3)):
+        res = step(f"warm#{w}")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        res = step(f"step#{k}", timed=True)
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    launches = eng.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=device)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    total_rows = ROWS_SF10 * world
+    value = total_rows * args.steps / (ms / 1e3)
+
+    # ---- end to end: host (pinned) Arrow buffers -> C-ABI -> result on host, every step (N=1 path) ----
+    e2e = None
+    if world == 1:
+        e2e = measure_e2e(eng, bb, pa, tpch, stream, stages, steps=max(2, min(args.steps, 3)))
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        kern_s = (agg_ns[0] / max(agg_ns[1], 1)) / 1e9
+        alg_bytes = ROWS_SF10 * BYTES_PER_ROW + 4 * (2 * 5 + 13 * 16)
+        achieved = alg_bytes / kern_s / 1e9 if kern_s > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "q1_stage1_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "decimal128/i128", "data": "synthetic",
+            "queries_per_hour": 3600.0 / (ms / 1e3 / args.steps),
+            "config": {"workload": "TPC-H q1 SF10 (BASELINE.json configs[1]): lineitem 59,986,052 rows x 7 columns, "
+                                   "Arrow layout resident in HBM, 1 GPU executor per GPU", "rows_per_gpu": ROWS_SF10,
+                       "target_partitions": P, "l2_policy": "inputs (4.68 GB per GPU) far larger than the 126 MB L2",
+                       "stages": "scan+filter+project+partial-agg+hash-shuffle | final-agg+sort | merge"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "pipeline_kernel<SINK_AGG_REG,4> (stage 1)",
+                         "peak_source": peak_src, "kernel_ms": kern_s * 1e3, "algorithmic_bytes": alg_bytes},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rows = ROWS_SF10 // 4
+            t = cpu_q1(rows, threads, steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": rows * len(t) / sum(t), "unit": "rows/s", "cores": threads, "kind": "port",
+                                    "sample": f"q1 over {rows} lineitem rows (SF2.5), {threads} threads, 2 timed passes"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def measure_e2e(eng, bb, pa, tpch, stream, stages, steps):
+    """Same q1, but every step starts from HOST Arrow buffers (pinned) handed to the C-ABI
+    (b200_engine_register_batch: H2D inside the timed region) and ends with the result on the host."""
+    import numpy as np
+    import torch
+    L = bb.engine.load_library()
+    host = eng.export_table("lineitem", 0)  # device -> pageable host (setup, untimed)
+    n = host.num_rows
+    pinned, arrays, h2d = [], [], 0
+    for col in host.columns:
+        bufs = []
+        for b in col.buffers():
+            if b is None:
+                bufs.append(None)
+                continue
+            p = L.b200_host_alloc_pinned(b.size + 64)
+            if not p:
+                raise RuntimeError("pinned allocation failed")
+            C.memmove(p, b.address, b.size)
+            pinned.append(p)
+            bufs.append(pa.foreign_buffer(p, b.size))
+            h2d += b.size
+        arrays.append(pa.Array.from_buffers(col.type, n, bufs))
+    batch = pa.RecordBatch.from_arrays(arrays, schema=host.schema)
+    del host
+    times = []
+    d2h = 0
+    for k in range(steps + 1):
+        job = f"e2e#{k}"
+        t0 = time.perf_counter()
+        eng.drop_table("lineitem_host")
+        eng.register_batch("lineitem_host", 0, batch)
+        st = [s.json(job).replace('"table":"lineitem"', '"table":"lineitem_host"') for s in stages]
+        for sid, pj, part in ((1, st[0], 0), (2, st[1], 0), (3, st[2], 0)):
+            q = eng.create_query_stage_exec(job, sid, pj)
+            q.execute_query_stage(part)
+            q.release()
+        res = eng.partition_export(job, 3, 0)
+        dt = time.perf_counter() - t0
+        eng.remove_job_data(job)
+        d2h = res.nbytes
+        if k > 0:
+            times.append(dt)
+    eng.drop_table("lineitem_host")
+    for p in pinned:
+        L.b200_host_free_pinned(p)
+    return {"value": n * len(times) / sum(times), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": 1e3 * sum(times) / len(times), "steps": len(times),
+            "note": "host pinned Arrow buffers -> b200_engine_register_batch (H2D) -> 3 stages -> b200_partition_export (D2H)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

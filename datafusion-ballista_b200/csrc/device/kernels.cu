@@ -89,6 +89,17 @@ __global__ void agg_extract_kernel(AggTable T, AggExtractArgs A) {
           if (o.valid) o.valid[pos] = v;
           break;
         }
+        case AO_KEY_PACKED: {
+          unsigned long long w0 = T.keys[((unsigned long long)o.a * T.cap + s) * 2 + 0];
+          unsigned char v = T.key_valid[(unsigned long long)o.a * T.cap + s];
+          unsigned long long len = w0 >> o.imm;
+          unsigned long long bytes = w0 & ((1ull << o.imm) - 1);
+          unsigned long long* dst = (unsigned long long*)o.aux + pos;
+          *dst = bytes;
+          ((ulonglong2*)o.data)[pos] = make_ulonglong2(v ? (unsigned long long)dst : 0ull, v ? len : 0ull);
+          if (o.valid) o.valid[pos] = v;
+          break;
+        }
         default: {
           unsigned long long lo = T.acc[((unsigned long long)o.a * T.cap + s) * 2 + 0];
           unsigned long long hi = T.acc[((unsigned long long)o.a * T.cap + s) * 2 + 1];

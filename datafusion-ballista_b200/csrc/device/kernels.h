@@ -25,11 +25,13 @@ enum AggOutKind : uint8_t {
   AO_COUNT,        // a: acc index -> Int64/UInt64
   AO_MINMAX_F64,   // order-key -> double ; b count
   AO_AVG_DEC,      // a: sum acc, b: count acc, imm: 10^k multiplier exponent
-  AO_AVG_F64       // a: sum acc (f64), b: count acc
+  AO_AVG_F64,      // a: sum acc (f64), b: count acc
+  AO_KEY_PACKED    // a: key index holding a packed short string (OP_STR_PACK8); imm: bit position of the length; aux: 8 B/row chars
 };
 struct AggOut {
   void* data;
   uint8_t* valid;
+  void* aux;
   uint8_t kind;
   uint8_t a, b;
   uint8_t phys;   // output encoding

@@ -12,7 +12,7 @@
 
 namespace b200 {
 
-static const int VM_R = 4;            // rows per thread per tile (register-blocked)
+static const int VM_R = 2;            // rows per thread per tile (register-blocked)
 static const int VM_MAX_COLS = 24;    // source columns of one pipeline
 static const int VM_MAX_REGS = 40;    // VM value registers (shared-memory resident)
 static const int VM_MAX_IMMS = 40;
@@ -68,12 +68,14 @@ enum VOp : uint8_t {
   OP_FILTER,                           // active &= a.value & a.valid
   OP_MOD_U64,                          // dst = (uint64)a % imm64 (partition id); imm = immediate idx
   OP_DEC_MUL_LIT_MINUS,                // fused: dst = a * (imm - b)   [I128 x (I64-range)] checked
-  OP_DEC_MUL_LIT_PLUS                  // fused: dst = a * (imm + b)
+  OP_DEC_MUL_LIT_PLUS,                 // fused: dst = a * (imm + b)
+  OP_STR_PACK8                         // dst(I64) = len<<imm | bytes of a string of <= aux bytes (imm = 56/aux = 7 or imm = 24/aux = 3); longer -> pack_overflow
 };
 
 enum InstrFlags : uint8_t {
   IF_NULLCHK = 1,   // some operand may be NULL: compute validity
-  IF_CHECKED = 2    // overflow / divide-by-zero raise an execution error
+  IF_CHECKED = 2,   // overflow / divide-by-zero raise an execution error
+  IF_FILTER = 4     // comparison fused with FilterExec: active &= result (no destination register)
 };
 
 struct VInstr {
@@ -148,6 +150,8 @@ struct RunStatus {
   unsigned int overflow;    // aggregate table / register-group overflow: retry with a bigger sink
   unsigned long long out_rows;   // materialize sink: rows written
   unsigned long long in_active;  // rows that passed all filters
+  unsigned int pack_overflow;    // OP_STR_PACK8 met a string longer than 7 bytes: re-lower without packing
+  unsigned int _pad;
 };
 
 struct Program {
@@ -173,8 +177,11 @@ struct Program {
   OutCol out[VM_MAX_OUT];       // SINK_MATERIALIZE
   Operand keys[VM_MAX_KEYS];    // aggregate sinks: group keys
   Operand key_hash;             // aggregate sinks: I64 register holding the row hash (OPD_NONE if no keys)
+  uint8_t keys_all_i64;         // every key is an integer-like 64-bit value (ints, dates, bools, packed strings)
+  uint8_t _pad1[3];
   AccDesc acc[VM_MAX_ACC];
   AggTable table;
+  unsigned long long* acc_hi;   // register sink: high 64-bit words [cta][thread][group][acc], pre-zeroed
   RunStatus* status;
   int64_t n_rows;
 };

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <map>
 #include <mutex>
+#include <functional>
 #include <set>
 
 #include "../common/arrow_host.hpp"
@@ -412,7 +413,10 @@ DevBatchPtr run_materialize(const Exec& x, PipelineBuilder& pb, const std::vecto
 
 // ---- aggregate ------------------------------------------------------------------------------------
 struct AggLowered {
-  std::vector<ColRef> keys;
+  std::vector<ColRef> keys;          // what the group table stores (packed strings are Int64 values)
+  std::vector<int> key_pack_shift;   // 0: plain key; 56 / 24: packed short string (bit position of the length)
+  bool fast = false;                 // key_hash is an injective 64-bit image of the whole key
+  ColRef combined;                   // valid when fast
   std::vector<AccDesc> accs;
   std::vector<ColRef> acc_src;
   struct OutRecipe {
@@ -453,28 +457,84 @@ int add_acc(PipelineBuilder& pb, AggLowered& L, uint8_t kind, const ColRef* src)
   return (int)L.accs.size() - 1;
 }
 
-void lower_aggregate(PipelineBuilder& pb, const PlanNode& node, AggLowered& L) {
+static bool narrowable(const DataType& t) {
+  switch (t.id) {
+    case TypeId::Utf8:
+    case TypeId::Bool:
+    case TypeId::Int8:
+    case TypeId::Int16:
+    case TypeId::Int32:
+    case TypeId::UInt8:
+    case TypeId::UInt16:
+    case TypeId::UInt32:
+    case TypeId::Date32: return true;
+    default: return false;
+  }
+}
+
+// pack_mode: 0 = keys as they are; 1 = short strings packed into Int64 (len<<56 | <=7 bytes);
+//            2 = every key squeezed into 32 bits and combined injectively into one 64-bit value
+// The packed forms are optimistic: the kernel raises pack_overflow when a string does not fit and
+// the caller re-lowers with a smaller pack_mode.
+void lower_aggregate(PipelineBuilder& pb, const PlanNode& node, AggLowered& L, int pack_mode) {
   const bool from_states = agg_mode_consumes_states(node.agg_mode);
   const bool emit_states = agg_mode_emits_states(node.agg_mode);
   const bool scalar = node.group_by.empty();
+  std::vector<ColRef> narrow32;  // pack_mode 2: non-negative 32-bit images of the keys
   for (size_t g = 0; g < node.group_by.size(); g++) {
-    ColRef k = pb.compile(*node.group_by[g].expr);
-    pb.pin(k);
+    ColRef k0 = pb.compile(*node.group_by[g].expr);
+    pb.pin(k0);
+    ColRef k = k0;
+    int shift = 0;
+    if (k0.type.id == TypeId::Utf8 && pack_mode > 0) {
+      shift = pack_mode == 2 ? 24 : 56;
+      k = pb.str_pack(k0, pack_mode == 2 ? 3 : 7, shift);
+      pb.pin(k);
+    }
+    if (pack_mode == 2) {
+      ColRef n32 = k;
+      if (k.type.is_signed_int() || k.type.id == TypeId::Date32) {
+        n32 = pb.add_literal_i64(k, 2147483648ll);
+        pb.pin(n32);
+      }
+      narrow32.push_back(n32);
+    }
     k.name = node.group_by[g].name;
     L.keys.push_back(k);
+    L.key_pack_shift.push_back(shift);
     AggLowered::OutRecipe r{};
-    r.kind = AO_KEY;
+    r.kind = shift ? AO_KEY_PACKED : AO_KEY;
     r.a = (uint8_t)g;
     r.b = 255;
-    r.type = k.type;
-    r.phys = k.type.id == TypeId::Utf8 ? PH_STRVIEW : phys_of(k.type);
+    r.type = k0.type;
+    r.phys = k0.type.id == TypeId::Utf8 ? PH_STRVIEW : phys_of(k0.type);
     r.name = k.name;
-    r.with_valid = k.nullable;
+    r.with_valid = k0.nullable;
     r.key_idx = (int)g;
+    r.imm = shift;
     L.outs.push_back(r);
+  }
+  // injective 64-bit key image => the register-cached group directory can be used
+  {
+    bool all_i64 = !L.keys.empty(), any_null = false;
+    for (auto& k : L.keys) {
+      all_i64 &= (k.type.pk() == PK::I64 || k.type.pk() == PK::Bool);
+      any_null |= k.nullable;
+    }
+    if (all_i64 && !any_null) {
+      if (L.keys.size() == 1) {
+        L.fast = true;
+        L.combined = L.keys[0];
+      } else if (pack_mode == 2 && L.keys.size() == 2) {
+        L.fast = true;
+        L.combined = pb.combine32(narrow32[0], narrow32[1]);
+        pb.pin(L.combined);
+      }
+    }
   }
   const int star = add_acc(pb, L, ACC_COUNT_STAR, nullptr);
   size_t state_col = node.group_by.size();
+  (void)emit_states;
   auto push = [&](uint8_t kind, int a, int b, const DataType& t, const std::string& name, bool with_valid, int imm = 0) {
     AggLowered::OutRecipe r{};
     r.kind = kind;
@@ -607,41 +667,65 @@ TableMem alloc_table(const Exec& x, uint64_t cap, int n_keys, const std::vector<
   return tm;
 }
 
-DevBatchPtr run_aggregate(const Exec& x, PipelineBuilder& pb, const PlanNode& node, const DevBatchPtr& src, OpMetrics* met) {
-  AggLowered L;
-  lower_aggregate(pb, node, L);
-  Program& P = pb.prog;
-  const int n_keys = (int)L.keys.size();
+typedef std::function<std::unique_ptr<PipelineBuilder>()> BuilderFactory;
+
+DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const PlanNode& node, const DevBatchPtr& src, OpMetrics* met) {
+  const int n_keys = (int)node.group_by.size();
   if (n_keys > VM_MAX_KEYS) throw EngineError(B200_ERR_UNSUPPORTED, "too many group-by columns");
-  P.n_keys = (uint8_t)n_keys;
-  P.n_acc = (uint8_t)L.accs.size();
-  for (int k = 0; k < n_keys; k++) P.keys[k] = pb.resolve(L.keys[(size_t)k]);
-  for (size_t a = 0; a < L.accs.size(); a++) P.acc[a] = L.accs[a];
-  memset(&P.key_hash, 0, sizeof P.key_hash);
-  if (n_keys) {
-    ColRef h = pb.hash_of(L.keys);
-    P.key_hash = h.op;
+  // initial optimism about the keys
+  int pack_mode = 0;
+  {
+    bool any_str = false, all_narrow = n_keys > 0;
+    for (auto& g : node.group_by) {
+      any_str |= g.expr->type.id == TypeId::Utf8;
+      all_narrow &= narrowable(g.expr->type);
+    }
+    if (n_keys == 2 && all_narrow) pack_mode = 2;
+    else if (any_str) pack_mode = 1;
   }
-  const bool reg_ok = (int)L.accs.size() <= VM_REG_ACC;
-  // strategy ladder: register sink (<= 4 groups) -> global table of growing capacity
   int node_idx = -1;
   if (x.s) {
     auto it = x.s->metric_index.find(&node);
     if (it != x.s->metric_index.end()) node_idx = it->second;
   }
   const std::string hint_key = (x.s ? x.s->fingerprint : std::string("?")) + "#" + std::to_string(node_idx);
-  int start = 0;
+  int level = 0;
   {
     std::lock_guard<std::mutex> g(x.e->mu);
     auto it = x.e->agg_hint.find(hint_key);
-    if (it != x.e->agg_hint.end()) start = it->second;
+    if (it != x.e->agg_hint.end()) {
+      level = it->second / 4;
+      pack_mode = std::min(pack_mode, it->second % 4);
+    }
   }
-  if (!reg_ok && start == 0) start = 1;
+  // strategy ladder: register sink (<= 4 groups) -> global table of growing capacity; packed keys -> plain keys
+  std::unique_ptr<PipelineBuilder> pbp;
+  AggLowered L;
   TableMem tm;
   RunOutcome ro;
-  int level = start;
-  for (;; level++) {
+  for (;;) {
     x.check_cancel();
+    pbp = make_pb();
+    PipelineBuilder& pb = *pbp;
+    L = AggLowered();
+    lower_aggregate(pb, node, L, pack_mode);
+    Program& P = pb.prog;
+    P.n_keys = (uint8_t)n_keys;
+    P.n_acc = (uint8_t)L.accs.size();
+    for (int k = 0; k < n_keys; k++) P.keys[k] = pb.resolve(L.keys[(size_t)k]);
+    for (size_t a = 0; a < L.accs.size(); a++) P.acc[a] = L.accs[a];
+    memset(&P.key_hash, 0, sizeof P.key_hash);
+    P.keys_all_i64 = L.fast ? 1 : 0;
+    if (n_keys) {
+      if (L.fast) {
+        P.key_hash = pb.resolve(L.combined);
+      } else {
+        ColRef h = pb.hash_of(L.keys);
+        P.key_hash = h.op;
+      }
+    }
+    const bool reg_ok = (int)L.accs.size() <= VM_REG_ACC;
+    if (!reg_ok && level == 0) level = 1;
     uint64_t cap;
     int reg_groups = 0;
     if (level == 0) {
@@ -651,24 +735,36 @@ DevBatchPtr run_aggregate(const Exec& x, PipelineBuilder& pb, const PlanNode& no
     } else {
       P.sink = SINK_AGG_GLOBAL;
       if (!n_keys) cap = 2;
-      else cap = std::min<uint64_t>(next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2), (uint64_t)1 << (12 + 4 * level));
+      else cap = std::min<uint64_t>(next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2), (uint64_t)1 << std::min(40, 12 + 4 * level));
       if (cap < 16) cap = 16;
     }
     tm = alloc_table(x, cap, n_keys, L.accs);
     P.table = tm.T;
-    pb.finalize_layout((size_t)8 * VM_REG_GROUPS * VM_REG_ACC * 16 + 256);
+    pb.finalize_layout((size_t)VM_REG_ACC * 512 * 16 + 256);
+    if (level == 0) {
+      const size_t hi_bytes = (size_t)x.e->sm_count * 512 * VM_REG_GROUPS * VM_REG_ACC * 8;
+      DevPtr hi = dev_alloc(hi_bytes, x.st());
+      tm.keep.push_back(hi);
+      P.acc_hi = (unsigned long long*)hi->ptr;
+    }
     ro = launch_program(x, pb, reg_groups);
     if (met) {
       met->elapsed_ns += (uint64_t)(ro.ms * 1e6);
       met->launches += 2;
     }
+    if (ro.status.pack_overflow) {
+      pack_mode = pack_mode == 2 ? 1 : 0;
+      continue;
+    }
     if (!ro.status.overflow) break;
     if (level > 0 && cap >= next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2)) throw EngineError(B200_ERR_EXECUTION, "aggregate hash table overflow");
+    level++;
   }
   {
     std::lock_guard<std::mutex> g(x.e->mu);
-    x.e->agg_hint[hint_key] = level;
+    x.e->agg_hint[hint_key] = level * 4 + pack_mode;
   }
+  PipelineBuilder& pb = *pbp;
   unsigned int n_groups = d2h_value<unsigned int>(tm.T.n_groups, x.st());
   // extraction
   auto out = std::make_shared<DevBatch>();
@@ -698,6 +794,12 @@ DevBatchPtr run_aggregate(const Exec& x, PipelineBuilder& pb, const PlanNode& no
     AggOut& o = A.out[j];
     o.data = (void*)oc.data;
     o.valid = (uint8_t*)oc.valid;
+    o.aux = nullptr;
+    if (r.kind == AO_KEY_PACKED) {
+      DevPtr ch = dev_alloc((size_t)std::max<unsigned int>(n_groups, 1) * 8, x.st());
+      o.aux = ch->ptr;
+      oc.keep.push_back(ch);
+    }
     o.kind = r.kind;
     o.a = r.a;
     o.b = r.b;
@@ -839,16 +941,22 @@ struct Runner {
 
   // Executes `top` (a Filter/Projection chain over some base) fused into one pipeline whose sink is
   // decided by the caller through `finish`.
+  // Executes `top` (a Filter/Projection chain over some base) fused into one pipeline whose sink is
+  // decided by the caller through `finish(make_builder, src)`; make_builder() returns a fresh
+  // builder over `src` with the chain applied (sinks that retry with another lowering call it again).
   template <class F>
   DevBatchPtr with_chain(const PlanNode& top, int part, bool all_parts, F&& finish) {
     std::vector<const PlanNode*> chain;
     const PlanNode* base = chain_base(top, chain);
     DevBatchPtr src = all_parts ? exec_all(*base) : exec(*base, part);
-    PipelineBuilder pb(*src, x.st());
-    apply_chain(pb, chain);
     for (auto* n : chain)
       if (OpMetrics* m = x.m(n)) m->input_rows += (uint64_t)src->n;
-    return finish(pb, src);
+    BuilderFactory make_pb = [&]() {
+      std::unique_ptr<PipelineBuilder> pb(new PipelineBuilder(*src, x.st()));
+      apply_chain(*pb, chain);
+      return pb;
+    };
+    return finish(make_pb, src);
   }
 
   std::vector<ColRef> named_cols(PipelineBuilder& pb, const Schema& schema) {
@@ -905,13 +1013,16 @@ struct Runner {
       case PlanNode::Filter:
       case PlanNode::Projection: {
         if (n.op == PlanNode::Filter && n.fetch >= 0) throw EngineError(B200_ERR_UNSUPPORTED, "FilterExec with fetch");
-        out = with_chain(n, part, false, [&](PipelineBuilder& pb, DevBatchPtr& src) { return run_materialize(x, pb, named_cols(pb, n.schema), src, met); });
+        out = with_chain(n, part, false, [&](const BuilderFactory& mk, DevBatchPtr& src) {
+          auto pb = mk();
+          return run_materialize(x, *pb, named_cols(*pb, n.schema), src, met);
+        });
         break;
       }
       case PlanNode::Aggregate: {
         const PlanNode& child = *n.children[0];
         bool all = (n.agg_mode == AggMode::Final || n.agg_mode == AggMode::Single) && part == 0 && n_partitions(child) > 1;
-        out = with_chain(child, part, all, [&](PipelineBuilder& pb, DevBatchPtr& src) { return run_aggregate(x, pb, n, src, met); });
+        out = with_chain(child, part, all, [&](const BuilderFactory& mk, DevBatchPtr& src) { return run_aggregate(x, mk, n, src, met); });
         break;
       }
       case PlanNode::HashJoin: out = exec_join(n, part, met); break;
@@ -1044,7 +1155,9 @@ struct Runner {
   };
   JoinSide prepare_side(const PlanNode& child, int part, bool all, const std::vector<ExprPtr>& key_exprs, bool null_equals_null, OpMetrics* met) {
     JoinSide js;
-    js.batch = with_chain(child, part, all, [&](PipelineBuilder& pb, DevBatchPtr& src) {
+    js.batch = with_chain(child, part, all, [&](const BuilderFactory& mk, DevBatchPtr& src) {
+      auto pbp = mk();
+      PipelineBuilder& pb = *pbp;
       std::vector<ColRef> outs = named_cols(pb, child.schema);
       js.n_payload = outs.size();
       std::vector<ColRef> keys;
@@ -1303,7 +1416,9 @@ struct Runner {
     // hash repartition: pid = hash(keys) % P fused into the child's pipeline, then rank + scatter
     const uint32_t P = (uint32_t)root.n_out_partitions;
     size_t n_payload = 0;
-    DevBatchPtr mat = with_chain(child, input_partition, false, [&](PipelineBuilder& pb, DevBatchPtr& src) {
+    DevBatchPtr mat = with_chain(child, input_partition, false, [&](const BuilderFactory& mk, DevBatchPtr& src) {
+      auto pbp = mk();
+      PipelineBuilder& pb = *pbp;
       std::vector<ColRef> outs = named_cols(pb, root.schema);
       n_payload = outs.size();
       std::vector<ColRef> keys;
@@ -1817,6 +1932,17 @@ int b200_remove_job_data(b200_engine* e, const char* job_id) {
     std::lock_guard<std::mutex> g(e->mu);
     for (auto it = e->shuffle.begin(); it != e->shuffle.end();) {
       if (it->first.job == job_id) it = e->shuffle.erase(it);
+      else ++it;
+    }
+  });
+}
+
+int b200_remove_stage_data(b200_engine* e, const char* job_id, int64_t stage_id) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->mu);
+    for (auto it = e->shuffle.begin(); it != e->shuffle.end();) {
+      if (it->first.job == job_id && it->first.stage == stage_id) it = e->shuffle.erase(it);
       else ++it;
     }
   });

@@ -33,7 +33,7 @@ class PipelineBuilder {
   Program prog;
   std::vector<ColRef> cols;  // current (virtual) schema
   std::vector<DevPtr> keep;  // literal pools etc.
-  int block = 256;
+  int block = 512;
 
   PipelineBuilder(const DevBatch& src, cudaStream_t st) : src_(src), st_(st) {
     memset(&prog, 0, sizeof prog);
@@ -53,6 +53,25 @@ class PipelineBuilder {
 
   // ---- schema-level steps --------------------------------------------------------------------
   void apply_filter(const Expr& pred) {
+    // FilterExec keeps a row iff the predicate is TRUE; an AND chain therefore decomposes exactly
+    // into successive filters, and a comparison conjunct is fused with the filter itself
+    if (pred.kind == Expr::Bin && pred.op == BinOp::And) {
+      apply_filter(*pred.args[0]);
+      apply_filter(*pred.args[1]);
+      return;
+    }
+    if (pred.kind == Expr::Bin && is_compare(pred.op)) {
+      ColRef a = compile(*pred.args[0]);
+      pin(a);
+      ColRef b = compile(*pred.args[1]);
+      unpin(a);
+      ColRef r = compare(pred.op, a, b);
+      prog.code[prog.n_instr - 1].flags |= IF_FILTER;
+      release(a);
+      release(b);
+      release(r);
+      return;
+    }
     ColRef p = compile(pred);
     VInstr ins = blank(OP_FILTER, VK_BOOL);
     ins.a = resolve(p);
@@ -231,6 +250,43 @@ class PipelineBuilder {
     }
     return h;
   }
+  // OP_STR_PACK8: optimistic packing of a short string into an Int64 (len << shift | bytes)
+  ColRef str_pack(const ColRef& s, int max_len, int shift) {
+    ColRef r = new_reg(DataType(TypeId::Int64), s.nullable);
+    VInstr ins = blank(OP_STR_PACK8, VK_STR);
+    ins.a = resolve(s);
+    ins.dst = r.op;
+    ins.aux = (uint8_t)max_len;
+    ins.imm = shift;
+    if (s.nullable) ins.flags |= IF_NULLCHK;
+    emit(ins);
+    return r;
+  }
+  ColRef add_literal_i64(const ColRef& a, int64_t v) {
+    ColRef r = new_reg(DataType(TypeId::Int64), a.nullable);
+    VInstr ins = blank(OP_ADD, VK_I64);
+    ins.a = resolve(a);
+    ins.b = mk_operand(OPD_IMM, VK_I64, int_imm(v));
+    ins.dst = r.op;
+    if (a.nullable) ins.flags |= IF_NULLCHK;
+    emit(ins);
+    return r;
+  }
+  // lo + hi * 2^32 for two values known to lie in [0, 2^32)
+  ColRef combine32(const ColRef& lo, const ColRef& hi) {
+    ColRef t = new_reg(DataType(TypeId::Int64), false);
+    VInstr m = blank(OP_MUL, VK_I64);
+    m.a = resolve(hi);
+    m.b = mk_operand(OPD_IMM, VK_I64, int_imm(4294967296ll));
+    m.dst = t.op;
+    emit(m);
+    VInstr a = blank(OP_ADD, VK_I64);
+    a.a = resolve(lo);
+    a.b = t.op;
+    a.dst = t.op;
+    emit(a);
+    return t;
+  }
   ColRef mod_u64(const ColRef& h, uint64_t m) {
     ColRef r = new_reg(DataType(TypeId::UInt32), false);
     VInstr ins = blank(OP_MOD_U64, VK_I64);
@@ -260,9 +316,9 @@ class PipelineBuilder {
 
   // ---- layout --------------------------------------------------------------------------------
   // Must be called after all instructions are emitted and the sink is described.
-  void finalize_layout(size_t min_scratch) {
+  void finalize_layout(size_t min_total) {
     static const bool no_tma = getenv("B200_NO_TMA") != nullptr;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 3; attempt++) {
       const int tile = block * VM_R;
       uint32_t off = 0;
       bool aligned = true;
@@ -294,19 +350,21 @@ class PipelineBuilder {
         }
         roff = (roff + 15u) & ~15u;
       }
-      if (roff < min_scratch) roff = (uint32_t)min_scratch;
       prog.regs_bytes = (roff + 127u) & ~127u;
-      const uint32_t budget = 200 * 1024;
+      const uint32_t budget = 216 * 1024;
       int S = prog.stage_bytes ? (int)((budget - prog.regs_bytes) / prog.stage_bytes) : VM_MAX_STAGES;
       if (prog.regs_bytes >= budget) S = 0;
       if (S > VM_MAX_STAGES) S = VM_MAX_STAGES;
       prog.use_tma = (aligned && !no_tma) ? 1 : 0;
       if (S >= 2) {
         prog.n_stages = (uint32_t)S;
+        // the register-sink flush stages its reduction in the (idle) tile buffers
+        const size_t total = (size_t)S * prog.stage_bytes + prog.regs_bytes;
+        if (total < min_total) prog.regs_bytes += (uint32_t)((min_total - total + 127) & ~(size_t)127);
         return;
       }
-      if (block == 256) {
-        block = 128;
+      if (block > 128) {
+        block /= 2;
         continue;
       }
       throw EngineError(B200_ERR_UNSUPPORTED, "pipeline too wide for shared memory (" + std::to_string(prog.stage_bytes) + " B/stage)");

@@ -1,0 +1,97 @@
+"""Exchange step between query stages when there is one executor per GPU.
+
+Reference counterpart: the file-based hash shuffle -- map tasks write
+``work_dir/job/stage/...`` (ballista/core/src/execution_plans/mod.rs:66-99) and reduce tasks pull
+via Arrow Flight (shuffle_reader.rs:522-602, client.rs:143-220).  Semantically an all-to-all(v):
+output partition p of every map task goes to the executor that runs reduce task p.
+
+Here partitions stay in HBM; partition p is owned by rank ``p % world``.  The payload moves with
+NCCL (torch.distributed.all_to_all_single over NVLink/NVSwitch) directly between the device
+buffers the engine exposes (``b200_partition_device_buffers``) -- no host staging, no compression.
+torch is plumbing only (communicator + stream); the engine never sees torch types.
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, List
+
+import torch
+import torch.distributed as dist
+
+
+class _DevView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr: int, nbytes: int, device) -> torch.Tensor:
+    if nbytes == 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevView(ptr, nbytes), device=device)
+
+
+def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, schema: List[dict], rank: int, world: int,
+                   device) -> Dict[str, int]:
+    """All ranks call this after finishing their map tasks of `stage_id`.
+
+    For every output partition p (owner = p % world): each rank sends its local piece of p to the
+    owner; the owner installs the received pieces under file_id = sender rank.  Returns byte counts.
+    """
+    ncols = len(schema)
+    nbuf = 3 * ncols
+    schema_json = json.dumps(schema)
+    # 1. metadata: per (dest rank, partition, buffer) sizes + rows
+    parts_of = {r: [p for p in range(n_out_partitions) if p % world == r] for r in range(world)}
+    max_parts = max(len(v) for v in parts_of.values())
+    meta = torch.zeros((world, max_parts, nbuf + 1), dtype=torch.int64)
+    local: Dict[int, list] = {}
+    for r in range(world):
+        for k, p in enumerate(parts_of[r]):
+            if engine.partition_rows(job_id, stage_id, p) < 0:
+                continue
+            bufs, rows = engine.partition_device_buffers(job_id, stage_id, p)
+            local[p] = bufs
+            for b, (_, nb) in enumerate(bufs):
+                meta[r, k, b] = nb
+            meta[r, k, nbuf] = rows
+    meta_dev = meta.to(device)
+    recv_meta = torch.empty_like(meta_dev)
+    dist.all_to_all_single(recv_meta.view(world, -1), meta_dev.view(world, -1))
+    recv_meta_h = recv_meta.cpu()
+    # 2. payload: one flat byte buffer per destination
+    send_sizes = [int(meta[r, :, :nbuf].sum()) for r in range(world)]
+    recv_sizes = [int(recv_meta_h[r, :, :nbuf].sum()) for r in range(world)]
+    send = torch.empty(sum(send_sizes), dtype=torch.uint8, device=device)
+    pos = 0
+    for r in range(world):
+        for k, p in enumerate(parts_of[r]):
+            if p not in local:
+                continue
+            for (ptr, nb) in local[p]:
+                if nb:
+                    send[pos:pos + nb].copy_(_as_tensor(ptr, nb, device))
+                    pos += nb
+    recv = torch.empty(sum(recv_sizes), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes)
+    torch.cuda.current_stream(device).synchronize()
+    # 3. install what this rank owns (drop its own un-exchanged local pieces first)
+    mine = parts_of[rank]
+    pos = 0
+    base = recv.data_ptr()
+    installs = []
+    for src in range(world):
+        for k, p in enumerate(mine):
+            sizes = [int(recv_meta_h[src, k, b]) for b in range(nbuf)]
+            rows = int(recv_meta_h[src, k, nbuf])
+            bufs = []
+            for nb in sizes:
+                bufs.append((base + pos if nb else 0, nb))
+                pos += nb
+            if rows > 0:
+                installs.append((p, src, bufs, rows))
+    engine.remove_stage_partitions(job_id, stage_id)
+    for p, src, bufs, rows in installs:
+        engine.partition_import_device(job_id, stage_id, p, src, schema_json, bufs, rows)
+    return {"sent_bytes": sum(send_sizes) - send_sizes[rank], "recv_bytes": sum(recv_sizes) - recv_sizes[rank]}

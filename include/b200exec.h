@@ -133,6 +133,9 @@ int b200_partition_import_device(b200_engine* e, const char* job_id, int64_t sta
                                  int n_bufs, int64_t n_rows);
 /* RemoveJobData RPC (ballista/executor/src/executor_server.rs:921-932). */
 int b200_remove_job_data(b200_engine* e, const char* job_id);
+/* Drop every stored partition of one stage (used by the exchange step once the pieces have been
+ * handed to their owning GPUs; the reference deletes map outputs the same way on stage rollback). */
+int b200_remove_stage_data(b200_engine* e, const char* job_id, int64_t stage_id);
 
 /* ---- pinned host staging (harness side of "RecordBatches are pinned and DMA'd") ------------- */
 void* b200_host_alloc_pinned(uint64_t bytes);
