@@ -333,6 +333,10 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups) {
   const int tile = pb.block * VM_R;
   int64_t n_tiles = (P.n_rows + tile - 1) / tile;
   int grid = (int)std::min<int64_t>(std::max<int64_t>(n_tiles, 1), x.e->sm_count);
+  static const bool debug = getenv("B200_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "[b200] pipeline sink=%d rows=%lld cols=%d instr=%d regs=%d block=%d stages=%u stage_bytes=%u regs_bytes=%u tma=%u grid=%d\n", (int)P.sink,
+            (long long)P.n_rows, P.n_cols, P.n_instr, P.n_regs, pb.block, P.n_stages, P.stage_bytes, P.regs_bytes, P.use_tma, grid);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));

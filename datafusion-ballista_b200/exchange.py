@@ -29,7 +29,15 @@ class _DevView:
 def _as_tensor(ptr: int, nbytes: int, device) -> torch.Tensor:
     if nbytes == 0 or not ptr:
         return torch.empty(0, dtype=torch.uint8, device=device)
+    if torch.device(device).type == "cpu":  # host-memory "partitions" (gloo tests of the exchange logic)
+        import ctypes
+        return torch.frombuffer((ctypes.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8)
     return torch.as_tensor(_DevView(ptr, nbytes), device=device)
+
+
+def _sync(device):
+    if torch.device(device).type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
 
 
 def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, schema: List[dict], rank: int, world: int,
@@ -75,7 +83,7 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
                     pos += nb
     recv = torch.empty(sum(recv_sizes), dtype=torch.uint8, device=device)
     dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes)
-    torch.cuda.current_stream(device).synchronize()
+    _sync(device)
     # 3. install what this rank owns (drop its own un-exchanged local pieces first)
     mine = parts_of[rank]
     pos = 0
