@@ -337,6 +337,14 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups) {
   if (debug)
     fprintf(stderr, "[b200] pipeline sink=%d rows=%lld cols=%d instr=%d regs=%d block=%d stages=%u stage_bytes=%u regs_bytes=%u tma=%u grid=%d\n", (int)P.sink,
             (long long)P.n_rows, P.n_cols, P.n_instr, P.n_regs, pb.block, P.n_stages, P.stage_bytes, P.regs_bytes, P.use_tma, grid);
+  if (debug) {
+    for (int i = 0; i < P.n_instr; i++) {
+      const VInstr& v = P.code[i];
+      fprintf(stderr, "[b200]   %2d: op=%d t=%d fl=%d aux=%d dst=(%d,%d,%d) a=(%d,%d,%d) b=(%d,%d,%d) imm=%d\n", i, v.op, v.t, v.flags, v.aux, v.dst.kind, v.dst.vk,
+              v.dst.idx, v.a.kind, v.a.vk, v.a.idx, v.b.kind, v.b.vk, v.b.idx, v.imm);
+    }
+    for (int i = 0; i < P.n_regs; i++) fprintf(stderr, "[b200]   reg %d: vk=%d off=%u valid_off=%u\n", i, P.regs[i].vk, P.regs[i].smem_off, P.regs[i].valid_off);
+  }
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -497,7 +505,7 @@ void lower_aggregate(PipelineBuilder& pb, const PlanNode& node, AggLowered& L, i
     }
     if (pack_mode == 2) {
       ColRef n32 = k;
-      if (k.type.is_signed_int() || k.type.id == TypeId::Date32) {
+      if (shift == 0 && (k0.type.is_signed_int() || k0.type.id == TypeId::Date32)) {
         n32 = pb.add_literal_i64(k, 2147483648ll);
         pb.pin(n32);
       }

@@ -40,6 +40,16 @@ def assert_tables_equal(a, b, sort: bool = True, f64_rtol: float = 0.0, check_na
                     assert math.isnan(x) and math.isnan(y)
                 else:
                     assert abs(x - y) <= f64_rtol * max(abs(x), abs(y), 1e-300), (fa.name, x, y)
+        elif pa.types.is_floating(fa.type):
+            # bit-exact except that any NaN equals any NaN (pyarrow's equals() treats NaN != NaN)
+            la, lb = ca.to_pylist(), cb.to_pylist()
+            for x, y in zip(la, lb):
+                if x is None or y is None:
+                    assert x is None and y is None, (fa.name, x, y)
+                elif math.isnan(x) or math.isnan(y):
+                    assert math.isnan(x) and math.isnan(y), (fa.name, x, y)
+                else:
+                    assert x == y and math.copysign(1.0, x) == math.copysign(1.0, y), (fa.name, x, y)
         else:
             assert ca.equals(cb), f"column {fa.name} differs:\n{ca.to_pylist()[:20]}\nvs\n{cb.to_pylist()[:20]}"
 
