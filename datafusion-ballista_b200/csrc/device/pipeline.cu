@@ -634,6 +634,7 @@ __device__ __noinline__ void cold_op(const Lane L, const uint32_t active, const 
         break;
       }
       case OP_MOD_U64: st1_i64(L, ins.dst, r, (int64_t)((uint64_t)ld1_i64(L, ins.a, r) % PROG.imms[ins.imm].lo)); break;
+      case OP_MADD_I64: st1_i64(L, ins.dst, r, (int64_t)((uint64_t)ld1_i64(L, ins.a, r) + (uint64_t)ld1_i64(L, ins.b, r) * PROG.imms[ins.imm].lo)); break;
       case OP_STR_PACK8: {  // generic operand encodings (the Utf8-column case is a hot op)
         uint64_t w = 0;
         if (lv) {
@@ -788,6 +789,12 @@ __device__ __noinline__ void decode_micro(int pc, MicroOp* m) {
     case OP_CMP_GT:
     case OP_CMP_GE:
       if ((ins.t == VK_I64) && a_ok && b_ok && ins.aux != PH_U64 && (ins.dst.kind == OPD_NONE || m->d_valid_off == 0xFFFFFFFFu)) m->fn = MF_CMP_I64;
+      break;
+    case OP_MADD_I64:
+      if (a_ok && b_ok && m->d_valid_off == 0xFFFFFFFFu) {
+        m->fn = MF_ARITH_I64;
+        m->lit_lo = PROG.imms[ins.imm].lo;
+      }
       break;
     case OP_ADD:
     case OP_SUB:
@@ -1091,8 +1098,8 @@ __device__ __noinline__ void op_hash_i64(const Lane L, const uint32_t active, co
 // ---- micro-op fast paths (non-NULL operands, common encodings) -----------------------------------
 #define SRC_BASE(sel, off) ((sel) == SEL_STAGE ? L.stage + (off) : (const uint8_t*)L.regs + (off))
 
-__device__ __noinline__ uint32_t mf_cmp_i64(const Lane L, uint32_t active, const MicroOp* mp) {
-  const MicroOp m = *mp;
+__device__ __forceinline__ uint32_t mf_cmp_i64(const Lane L, uint32_t active, const MicroOp* mp) {
+  const MicroOp& m = *mp;
   int64_t a[VM_R], b[VM_R];
   if (m.a_sel == SEL_IMM) {
 #pragma unroll
@@ -1121,8 +1128,8 @@ __device__ __noinline__ uint32_t mf_cmp_i64(const Lane L, uint32_t active, const
   ((uint32_t*)(L.regs + m.d_off))[L.tid] = res;
   return active;
 }
-__device__ __noinline__ void mf_arith_i64(const Lane L, const MicroOp* mp) {
-  const MicroOp m = *mp;
+__device__ __forceinline__ void mf_arith_i64(const Lane L, const MicroOp* mp) {
+  const MicroOp& m = *mp;
   int64_t a[VM_R], b[VM_R];
   if (m.a_sel == SEL_IMM) {
 #pragma unroll
@@ -1141,7 +1148,10 @@ __device__ __noinline__ void mf_arith_i64(const Lane L, const MicroOp* mp) {
     FOR_R b[r] = ld_w(pb, m.b_w, r * L.B + L.tid);
   }
   int64_t* d = (int64_t*)(L.regs + m.d_off);
-  if (m.op == OP_ADD) {
+  if (m.op == OP_MADD_I64) {
+#pragma unroll
+    FOR_R d[r * L.B + L.tid] = (int64_t)((uint64_t)a[r] + (uint64_t)b[r] * m.lit_lo);
+  } else if (m.op == OP_ADD) {
 #pragma unroll
     FOR_R d[r * L.B + L.tid] = (int64_t)((uint64_t)a[r] + (uint64_t)b[r]);
   } else if (m.op == OP_SUB) {
@@ -1159,8 +1169,8 @@ __device__ __forceinline__ i128 ld_w128(const uint8_t* base, uint32_t w, int e) 
   }
   return (i128)ld_w(base, w, e);
 }
-__device__ __noinline__ void mf_arith_i128(const Lane L, const uint32_t active, const MicroOp* mp) {
-  const MicroOp m = *mp;
+__device__ __forceinline__ void mf_arith_i128(const Lane L, const uint32_t active, const MicroOp* mp) {
+  const MicroOp& m = *mp;
   i128 a[VM_R], b[VM_R];
   if (m.a_sel == SEL_IMM) {
 #pragma unroll
@@ -1194,8 +1204,8 @@ __device__ __noinline__ void mf_arith_i128(const Lane L, const uint32_t active, 
 #pragma unroll
   FOR_R d[r * L.B + L.tid] = make_ulonglong2(lo64(a[r]), hi64(a[r]));
 }
-__device__ __noinline__ void mf_dec_mul_lit(const Lane L, const uint32_t active, const MicroOp* mp) {
-  const MicroOp m = *mp;
+__device__ __forceinline__ void mf_dec_mul_lit(const Lane L, const uint32_t active, const MicroOp* mp) {
+  const MicroOp& m = *mp;
   const uint8_t* pa = SRC_BASE(m.a_sel, m.a_off);
   const uint8_t* pb = SRC_BASE(m.b_sel, m.b_off);
   const i128 lit = make_i128(m.lit_lo, m.lit_hi);
@@ -1220,8 +1230,8 @@ __device__ __noinline__ void mf_dec_mul_lit(const Lane L, const uint32_t active,
 #pragma unroll
   FOR_R d[r * L.B + L.tid] = make_ulonglong2(lo64(a[r]), hi64(a[r]));
 }
-__device__ __noinline__ void mf_pack8(const Lane L, const uint32_t active, const MicroOp* mp) {
-  const MicroOp m = *mp;
+__device__ __forceinline__ void mf_pack8(const Lane L, const uint32_t active, const MicroOp* mp) {
+  const MicroOp& m = *mp;
   const int32_t* off = (const int32_t*)(L.stage + m.a_off);
   const uint8_t* chars = (const uint8_t*)m.lit_lo;
   int32_t o0[VM_R];
@@ -1705,7 +1715,7 @@ __device__ __forceinline__ void reg_agg_init(RegAggState<G>& S, unsigned long lo
 #pragma unroll
     for (int g = 0; g < G; g++) {
       S.lo[g][a] = id.lo;
-      hi[g * VM_REG_ACC + a] = id.hi;
+      if (hi) hi[g * VM_REG_ACC + a] = id.hi;
     }
   }
 }
@@ -1749,6 +1759,32 @@ __device__ __noinline__ int reg_resolve_row(const Lane L, RegGroupTable* gt, int
   KeyVal kv[VM_MAX_KEYS];
   for (int k = 0; k < n_keys; k++) load_key(L, PROG.keys[k], r, &kv[k]);
   return reg_group_lookup(gt, G, n_keys, (unsigned long long)ld1_i64(L, PROG.key_hash, r), kv);
+}
+
+// rare path of the ADD_ONLY register sink: merge one large addend of group g directly into the
+// global table (same key -> same slot as the end-of-kernel flush)
+__device__ __noinline__ void reg_merge_big(RegGroupTable* gt, int G, int g, int a, i128 v) {
+  const int n_keys = PROG.n_keys;
+  KeyVal kv[VM_MAX_KEYS];
+  unsigned long long h = 0;
+  if (G > 1) {
+    h = gt->hash[g];
+    for (int k = 0; k < n_keys; k++) {
+      kv[k].w0 = gt->key_w0[g][k];
+      kv[k].w1 = gt->key_w1[g][k];
+      kv[k].valid = gt->key_valid[g][k];
+      kv[k].vk = PROG.keys[k].vk;
+    }
+  }
+  const unsigned long long slot = table_upsert(n_keys, h, kv);
+  if (slot == ~0ull) {
+    atomicExch(&PROG.status->overflow, 1u);
+    return;
+  }
+  Acc128 x;
+  x.lo = lo64(v);
+  x.hi = hi64(v);
+  table_merge(ACC_SUM_I128, slot, a, x);
 }
 
 template <int G, bool ADD_ONLY>
@@ -1799,36 +1835,55 @@ __device__ __forceinline__ uint32_t sink_agg_reg(const Lane L, uint32_t active, 
   // accumulate: static register indexing only
   const int n_acc = PROG.n_acc;
   if (ADD_ONLY) {
-    // every accumulator is a COUNT or an integer/decimal SUM: one compact body per accumulator,
-    // sources pre-resolved at CTA start
+    // Every accumulator is a COUNT or an integer/decimal SUM.  Per-thread partial sums are kept as
+    // plain int64: a thread sees < 2^16 rows (host-checked) and every addend is range-checked to
+    // |v| < 2^46, so the partial cannot overflow and is exact; the rare larger addend bypasses the
+    // registers and is merged into the global table directly.
 #pragma unroll
     for (int a = 0; a < VM_REG_ACC; a++) {
       if (a >= n_acc) break;
-      const AccOp ao = accops[a];
-      i128 vi[VM_R];
+      const AccOp& ao = accops[a];
+      int64_t vl[VM_R];
       uint32_t v = active;
       if (ao.sel == SEL_IMM) {
 #pragma unroll
-        FOR_R vi[r] = (i128)(int64_t)ao.imm;
-      } else if (ao.sel == 255) {
-        const AccDesc ad = PROG.acc[a];
-        if (ad.kind != ACC_COUNT_STAR && ad.nullable) v &= fetch_valid(L, ad.src);
-        if (ad.kind == ACC_SUM_I128) {
-          fetch_i128(L, ad.src, vi);
-        } else {
-#pragma unroll
-          FOR_R vi[r] = 1;
-        }
+        FOR_R vl[r] = (int64_t)ao.imm;
       } else {
-        const uint8_t* p = SRC_BASE(ao.sel, ao.off);
+        i128 vi[VM_R];
+        if (ao.sel == 255) {
+          const AccDesc ad = PROG.acc[a];
+          if (ad.kind != ACC_COUNT_STAR && ad.nullable) v &= fetch_valid(L, ad.src);
+          if (ad.kind == ACC_SUM_I128) {
+            fetch_i128(L, ad.src, vi);
+          } else {
 #pragma unroll
-        FOR_R vi[r] = ld_w128(p, ao.w, r * L.B + L.tid);
+            FOR_R vi[r] = 1;
+          }
+        } else {
+          const uint8_t* p = SRC_BASE(ao.sel, ao.off);
+#pragma unroll
+          FOR_R vi[r] = ld_w128(p, ao.w, r * L.B + L.tid);
+        }
+        uint32_t big = 0;
+#pragma unroll
+        FOR_R {
+          vl[r] = (int64_t)lo64(vi[r]);
+          const bool small = fits_i64(vi[r]) && vl[r] < (1ll << 46) && vl[r] > -(1ll << 46);
+          big |= (small ? 0u : 1u) << r;
+        }
+        big &= v;
+        if (big) {  // rare: exact 128-bit merge straight into the global table
+#pragma unroll 1
+          for (int r = 0; r < VM_R; r++)
+            if ((big >> r) & 1) reg_merge_big(gt, G, (int)gid[r], a, vi[r]);
+          v &= ~big;
+        }
       }
 #pragma unroll
       FOR_R {
 #pragma unroll
         for (int g = 0; g < G; g++)
-          if (((v >> r) & 1) && (G == 1 || gid[r] == (uint32_t)g)) acc_lo_add(S.lo[g][a], &hi[g * VM_REG_ACC + a], vi[r]);
+          if (((v >> r) & 1) && (G == 1 || gid[r] == (uint32_t)g)) S.lo[g][a] += (uint64_t)vl[r];
       }
     }
     return active;
@@ -1949,7 +2004,7 @@ __device__ __noinline__ void reg_flush_group(RegGroupTable* gt, Acc128* scratch,
 
 // End of kernel: reduce the per-thread matrices over the CTA (through shared memory, one group at a
 // time) and merge them into the global table with atomics.
-template <int G>
+template <int G, bool ADD_ONLY>
 __device__ __forceinline__ void reg_agg_flush(RegAggState<G>& S, const unsigned long long* hi, RegGroupTable* gt, Acc128* scratch /*[VM_REG_ACC][B]*/, int tid,
                                               int B) {
   const unsigned int ng = (G == 1) ? 1u : gt->n_groups;
@@ -1960,7 +2015,7 @@ __device__ __forceinline__ void reg_agg_flush(RegAggState<G>& S, const unsigned 
     for (int a = 0; a < VM_REG_ACC; a++) {
       Acc128 x;
       x.lo = S.lo[g][a];
-      x.hi = hi[g * VM_REG_ACC + a];
+      x.hi = ADD_ONLY ? (uint64_t)((int64_t)S.lo[g][a] >> 63) : hi[g * VM_REG_ACC + a];
       scratch[a * B + tid] = x;
     }
     reg_flush_group(gt, scratch, g, G, tid, B);
@@ -2009,7 +2064,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
   uint32_t dir_n = 0;
   unsigned long long* acc_hi = nullptr;
   if (SINK == SINK_AGG_REG) {
-    acc_hi = PROG.acc_hi + ((size_t)blockIdx.x * B + tid) * (VM_REG_GROUPS * VM_REG_ACC);
+    if (!ADD_ONLY) acc_hi = PROG.acc_hi + ((size_t)blockIdx.x * B + tid) * (VM_REG_GROUPS * VM_REG_ACC);
     reg_agg_init<G>(S_reg, acc_hi);
 #pragma unroll
     for (int q = 0; q < G; q++) dir[q] = 0xFFFFFFFFFFFFFFFFull;
@@ -2092,7 +2147,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     __syncthreads();
     // scalar aggregates emit their single group even when no CTA saw a row: CTA 0 always flushes
     const bool has_rows = tile_of(0) < n_tiles;
-    if (has_rows || (G == 1 && blockIdx.x == 0)) reg_agg_flush<G>(S_reg, acc_hi, &gtable, (Acc128*)smem, tid, B);
+    if (has_rows || (G == 1 && blockIdx.x == 0)) reg_agg_flush<G, ADD_ONLY>(S_reg, acc_hi, &gtable, (Acc128*)smem, tid, B);
   }
 }
 
@@ -2115,6 +2170,8 @@ cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int bloc
   bool add_only = true;
   for (int a = 0; a < P.n_acc; a++)
     add_only &= (P.acc[a].kind == ACC_SUM_I128 || P.acc[a].kind == ACC_COUNT || P.acc[a].kind == ACC_COUNT_STAR);
+  // exactness bound of the int64 register partials: fewer than 2^16 rows per thread (see sink_agg_reg)
+  add_only &= (P.n_rows / ((int64_t)grid * block) + 2 * VM_R) < 60000;
   switch (P.sink) {
     case SINK_MATERIALIZE: return launch_one<SINK_MATERIALIZE, 1, true>(grid, block, smem, st);
     case SINK_AGG_GLOBAL: return launch_one<SINK_AGG_GLOBAL, 1, true>(grid, block, smem, st);

@@ -69,6 +69,7 @@ enum VOp : uint8_t {
   OP_MOD_U64,                          // dst = (uint64)a % imm64 (partition id); imm = immediate idx
   OP_DEC_MUL_LIT_MINUS,                // fused: dst = a * (imm - b)   [I128 x (I64-range)] checked
   OP_DEC_MUL_LIT_PLUS,                 // fused: dst = a * (imm + b)
+  OP_MADD_I64,                         // dst = a + b * imm64 (imm = immediate index); wrapping
   OP_STR_PACK8                         // dst(I64) = len<<imm | bytes of a string of <= aux bytes (imm = 56/aux = 7 or imm = 24/aux = 3); longer -> pack_overflow
 };
 

@@ -275,16 +275,12 @@ class PipelineBuilder {
   // lo + hi * 2^32 for two values known to lie in [0, 2^32)
   ColRef combine32(const ColRef& lo, const ColRef& hi) {
     ColRef t = new_reg(DataType(TypeId::Int64), false);
-    VInstr m = blank(OP_MUL, VK_I64);
-    m.a = resolve(hi);
-    m.b = mk_operand(OPD_IMM, VK_I64, int_imm(4294967296ll));
+    VInstr m = blank(OP_MADD_I64, VK_I64);
+    m.a = resolve(lo);
+    m.b = resolve(hi);
     m.dst = t.op;
+    m.imm = int_imm(4294967296ll);
     emit(m);
-    VInstr a = blank(OP_ADD, VK_I64);
-    a.a = resolve(lo);
-    a.b = t.op;
-    a.dst = t.op;
-    emit(a);
     return t;
   }
   ColRef mod_u64(const ColRef& h, uint64_t m) {
