@@ -669,9 +669,29 @@ __global__ void radix_skip_check_kernel(const uint32_t* hist, uint32_t n_blocks,
   }
 }
 
+// Small inputs (the tiny ORDER BY stages of TPC-H): one launch, stable rank sort, O(n^2) compares.
+__global__ void rank_sort_kernel(const uint64_t* keys, const uint32_t* vals, uint64_t* keys_out, uint32_t* vals_out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+      const uint64_t kj = keys[j];
+      rank += (kj < k || (kj == k && j < i)) ? 1 : 0;
+    }
+    keys_out[rank] = k;
+    vals_out[rank] = vals[i];
+  }
+}
+
 void radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, uint32_t* hist_scratch,
                           uint64_t* scan_scratch, cudaStream_t st, bool* result_in_a, uint64_t* launches) {
   // hist_scratch: 256*n_blocks u32 ; scan_scratch: 256*n_blocks+1 u64 offsets + scan temp
+  if (n <= 4096) {
+    rank_sort_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(keys_a, vals_a, keys_b, vals_b, (int)n);
+    if (launches) *launches += 1;
+    *result_in_a = false;
+    return;
+  }
   uint32_t n_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
   if (n_blocks < 1) n_blocks = 1;
   uint64_t* offsets = scan_scratch;

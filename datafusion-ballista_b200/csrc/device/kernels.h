@@ -8,7 +8,7 @@
 namespace b200 {
 
 // ---- fused pipeline (pipeline.cu) ---------------------------------------------------------------
-cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st);
+cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st, const FusedSpec* fused = nullptr);
 
 // ---- aggregate table (kernels.cu) ----------------------------------------------------------------
 struct AccKinds {

@@ -31,6 +31,7 @@ typedef __int128 i128;
 typedef unsigned __int128 u128;
 
 __constant__ Program c_prog;  // the running pipeline (one at a time per device; set on the launch stream)
+__constant__ FusedSpec c_fused;  // fused fast-path description (when the program matches the q1/q6 shape)
 #define PROG c_prog
 
 // ------------------------------------------------------------------------------------------------
@@ -2023,9 +2024,190 @@ __device__ __forceinline__ void reg_agg_flush(RegAggState<G>& S, const unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused fast path: filters -> decimal products -> key image -> register aggregate, all in registers.
+// Reference operators fused: FilterExec + ProjectionExec + AggregateExec(Partial) of TPC-H q1/q6
+// (benchmarks/queries/q1.sql, q6.sql); selected by the host when the lowered program matches.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, RegAggState<G>& S, RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n) {
+  const FusedSpec& F = c_fused;
+  // ---- filters
+#pragma unroll
+  for (int i = 0; i < FUSED_MAX_FILTERS; i++) {
+    if (i >= F.n_filters) break;
+    const uint8_t* p = L.stage + F.f[i].off;
+    const uint32_t w = F.f[i].w;
+    const int64_t imm = F.f[i].imm;
+    uint32_t lt = 0, gt_ = 0;
+#pragma unroll
+    FOR_R {
+      const int64_t v = ld_w(p, w, r * L.B + L.tid);
+      lt |= (v < imm ? 1u : 0u) << r;
+      gt_ |= (v > imm ? 1u : 0u) << r;
+    }
+    active &= cmp_mask(F.f[i].op, lt, gt_);
+  }
+  // ---- products (checked decimal arithmetic)
+  i128 p0[VM_R], p1[VM_R];
+#pragma unroll
+  FOR_R p0[r] = p1[r] = 0;
+  uint32_t ovf = 0;
+  if (F.n_prod >= 1) {
+    const FusedProd& q = F.p[0];
+    const uint8_t* pa = L.stage + q.a_off;
+    const uint8_t* pb = L.stage + q.b_off;
+    const i128 lit = make_i128(q.lit_lo, q.lit_hi);
+#pragma unroll
+    FOR_R {
+      const i128 a = ld_w128(pa, q.a_w, r * L.B + L.tid);
+      i128 b = ld_w128(pb, q.b_w, r * L.B + L.tid);
+      if (q.kind == 0) ovf |= (sub_i128_checked(lit, b, &b) ? 1u : 0u) << r;
+      else if (q.kind == 1) ovf |= (add_i128_checked(lit, b, &b) ? 1u : 0u) << r;
+      ovf |= (mul_i128_fast(a, b, &p0[r]) ? 1u : 0u) << r;
+    }
+  }
+  if (F.n_prod >= 2) {
+    const FusedProd& q = F.p[1];
+    const uint8_t* pa = L.stage + q.a_off;
+    const uint8_t* pb = L.stage + q.b_off;
+    const i128 lit = make_i128(q.lit_lo, q.lit_hi);
+#pragma unroll
+    FOR_R {
+      const i128 a = q.a_src ? p0[r] : ld_w128(pa, q.a_w, r * L.B + L.tid);
+      i128 b = ld_w128(pb, q.b_w, r * L.B + L.tid);
+      if (q.kind == 0) ovf |= (sub_i128_checked(lit, b, &b) ? 1u : 0u) << r;
+      else if (q.kind == 1) ovf |= (add_i128_checked(lit, b, &b) ? 1u : 0u) << r;
+      ovf |= (mul_i128_fast(a, b, &p1[r]) ? 1u : 0u) << r;
+    }
+  }
+  if (ovf & active) raise(1);
+  // ---- group resolution
+  uint32_t gid[VM_R];
+#pragma unroll
+  FOR_R gid[r] = 0;
+  if (G > 1) {
+    unsigned long long kv0[VM_R], kv1[VM_R], ck[VM_R];
+#pragma unroll
+    FOR_R kv0[r] = kv1[r] = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (k >= F.n_keys) break;
+      const FusedKey& fk = F.k[k];
+      if (fk.kind == 1) {
+        const int32_t* off = (const int32_t*)(L.stage + fk.off);
+        uint32_t too_long = 0;
+#pragma unroll
+        FOR_R {
+          const int e = r * L.B + L.tid;
+          const int32_t o0 = off[e];
+          const uint32_t len = (uint32_t)(off[e + 1] - o0);
+          const bool lv = (active >> r) & 1;
+          too_long |= (lv && len > fk.max_len) ? 1u : 0u;
+          const unsigned long long v = (lv && len <= fk.max_len) ? pack8(fk.chars + o0, len, fk.shift) : 0ull;
+          if (k == 0) kv0[r] = v;
+          else kv1[r] = v;
+        }
+        if (too_long) atomicExch(&PROG.status->pack_overflow, 1u);
+      } else {
+        const uint8_t* p = L.stage + fk.off;
+#pragma unroll
+        FOR_R {
+          const unsigned long long v = (unsigned long long)ld_w(p, fk.w, r * L.B + L.tid);
+          if (k == 0) kv0[r] = v;
+          else kv1[r] = v;
+        }
+      }
+    }
+#pragma unroll
+    FOR_R ck[r] = F.combine ? ((kv0[r] + (unsigned long long)F.k[0].bias) + (kv1[r] + (unsigned long long)F.k[1].bias) * 4294967296ull) : kv0[r];
+#pragma unroll
+    FOR_R {
+      if ((active >> r) & 1) {
+        int g = -1;
+#pragma unroll
+        for (int q = 0; q < G; q++)
+          if (q < (int)dir_n && dir[q] == ck[r]) g = q;
+        if (g < 0) {
+          KeyVal kv[2];
+          kv[0].w0 = kv0[r];
+          kv[0].w1 = 0;
+          kv[0].valid = 1;
+          kv[0].vk = VK_I64;
+          kv[1].w0 = kv1[r];
+          kv[1].w1 = 0;
+          kv[1].valid = 1;
+          kv[1].vk = VK_I64;
+          g = reg_group_lookup(gt, G, F.n_keys, ck[r], kv);
+          uint32_t pub = 0;
+#pragma unroll
+          for (int q = 0; q < G; q++) {
+            const bool ok = (q == (int)pub) && (*(volatile unsigned int*)&gt->state[q] == 2u);
+            if (ok) {
+              dir[q] = *(volatile unsigned long long*)&gt->hash[q];
+              pub++;
+            }
+          }
+          dir_n = pub;
+        }
+        if (g < 0) {
+          atomicExch(&PROG.status->overflow, 1u);
+          active &= ~(1u << r);
+        } else {
+          gid[r] = (uint32_t)g;
+        }
+      }
+    }
+  }
+  // ---- accumulate (exact int64 partials, see sink_agg_reg)
+#pragma unroll
+  for (int a = 0; a < VM_REG_ACC; a++) {
+    if (a >= F.n_acc) break;
+    const FusedAcc& fa = F.a[a];
+    i128 vi[VM_R];
+    if (fa.src == 3) {
+#pragma unroll
+      FOR_R vi[r] = 1;
+    } else if (fa.src == 1) {
+#pragma unroll
+      FOR_R vi[r] = p0[r];
+    } else if (fa.src == 2) {
+#pragma unroll
+      FOR_R vi[r] = p1[r];
+    } else {
+      const uint8_t* p = L.stage + fa.off;
+#pragma unroll
+      FOR_R vi[r] = ld_w128(p, fa.w, r * L.B + L.tid);
+    }
+    int64_t vl[VM_R];
+    uint32_t big = 0;
+#pragma unroll
+    FOR_R {
+      vl[r] = (int64_t)lo64(vi[r]);
+      const bool small = fits_i64(vi[r]) && vl[r] < (1ll << 46) && vl[r] > -(1ll << 46);
+      big |= (small ? 0u : 1u) << r;
+    }
+    big &= active;
+    uint32_t v = active;
+    if (big) {
+#pragma unroll 1
+      for (int r = 0; r < VM_R; r++)
+        if ((big >> r) & 1) reg_merge_big(gt, G, (int)gid[r], a, vi[r]);
+      v &= ~big;
+    }
+#pragma unroll
+    FOR_R {
+#pragma unroll
+      for (int g = 0; g < G; g++)
+        if (((v >> r) & 1) && (G == 1 || gid[r] == (uint32_t)g)) S.lo[g][a] += (uint64_t)vl[r];
+    }
+  }
+  return active;
+}
+
+// ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int SINK, int G, bool ADD_ONLY>
+template <int SINK, int G, bool ADD_ONLY, bool FUSED>
 __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[VM_MAX_STAGES];
@@ -2050,8 +2232,8 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     mbar_fence_init();
   }
   const int n_instr = PROG.n_instr;
-  if (tid < n_instr) decode_micro(tid, &mops[tid]);
-  if (SINK == SINK_AGG_REG && tid >= 64 && tid < 64 + PROG.n_acc) decode_acc(tid - 64, &accops[tid - 64]);
+  if (!FUSED && tid < n_instr) decode_micro(tid, &mops[tid]);
+  if (!FUSED && SINK == SINK_AGG_REG && tid >= 64 && tid < 64 + PROG.n_acc) decode_acc(tid - 64, &accops[tid - 64]);
   if (SINK == SINK_AGG_REG && tid < VM_REG_GROUPS) {
     gtable.state[tid] = 0;
     gtable.hash[tid] = 0;
@@ -2110,8 +2292,14 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     uint32_t active = 0;
 #pragma unroll
     FOR_R if (r * B + tid < rows) active |= 1u << r;
-    active = run_program(L, active, mops, n_instr);
-    if (SINK == SINK_MATERIALIZE) {
+    if (FUSED) {
+      active = fused_tile<G>(L, active, S_reg, &gtable, dir, dir_n);
+      live_rows += __popc(active);
+    } else {
+      active = run_program(L, active, mops, n_instr);
+    }
+    if (FUSED) {
+    } else if (SINK == SINK_MATERIALIZE) {
       sink_materialize(L, active, warp_tot, &tile_base_sh);
     } else if (SINK == SINK_AGG_GLOBAL) {
       active = sink_agg_global(L, active);
@@ -2154,31 +2342,42 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
 // ------------------------------------------------------------------------------------------------
 // Host launcher
 // ------------------------------------------------------------------------------------------------
-template <int SINK, int G, bool ADD_ONLY>
+template <int SINK, int G, bool ADD_ONLY, bool FUSED>
 static cudaError_t launch_one(int grid, int block, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(pipeline_kernel<SINK, G, ADD_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(pipeline_kernel<SINK, G, ADD_ONLY, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  pipeline_kernel<SINK, G, ADD_ONLY><<<grid, block, smem, st>>>();
+  pipeline_kernel<SINK, G, ADD_ONLY, FUSED><<<grid, block, smem, st>>>();
   return cudaGetLastError();
 }
 
-cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st) {
-  // stream-ordered upload of the program into constant memory (the previous kernel on `st` is done
-  // before this copy executes)
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(Program), 0, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) return e;
+bool pipeline_add_only(const Program& P, int grid, int block) {
   bool add_only = true;
   for (int a = 0; a < P.n_acc; a++)
     add_only &= (P.acc[a].kind == ACC_SUM_I128 || P.acc[a].kind == ACC_COUNT || P.acc[a].kind == ACC_COUNT_STAR);
   // exactness bound of the int64 register partials: fewer than 2^16 rows per thread (see sink_agg_reg)
   add_only &= (P.n_rows / ((int64_t)grid * block) + 2 * VM_R) < 60000;
+  return add_only;
+}
+
+cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st, const FusedSpec* fused) {
+  // stream-ordered upload of the program into constant memory (the previous kernel on `st` is done
+  // before this copy executes)
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(Program), 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  const bool add_only = pipeline_add_only(P, grid, block);
+  if (fused && P.sink == SINK_AGG_REG && add_only) {
+    e = cudaMemcpyToSymbolAsync(c_fused, fused, sizeof(FusedSpec), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    if (reg_groups <= 1) return launch_one<SINK_AGG_REG, 1, true, true>(grid, block, smem, st);
+    return launch_one<SINK_AGG_REG, VM_REG_GROUPS, true, true>(grid, block, smem, st);
+  }
   switch (P.sink) {
-    case SINK_MATERIALIZE: return launch_one<SINK_MATERIALIZE, 1, true>(grid, block, smem, st);
-    case SINK_AGG_GLOBAL: return launch_one<SINK_AGG_GLOBAL, 1, true>(grid, block, smem, st);
+    case SINK_MATERIALIZE: return launch_one<SINK_MATERIALIZE, 1, true, false>(grid, block, smem, st);
+    case SINK_AGG_GLOBAL: return launch_one<SINK_AGG_GLOBAL, 1, true, false>(grid, block, smem, st);
     default:
-      if (reg_groups <= 1) return add_only ? launch_one<SINK_AGG_REG, 1, true>(grid, block, smem, st) : launch_one<SINK_AGG_REG, 1, false>(grid, block, smem, st);
-      return add_only ? launch_one<SINK_AGG_REG, VM_REG_GROUPS, true>(grid, block, smem, st)
-                      : launch_one<SINK_AGG_REG, VM_REG_GROUPS, false>(grid, block, smem, st);
+      if (reg_groups <= 1) return add_only ? launch_one<SINK_AGG_REG, 1, true, false>(grid, block, smem, st) : launch_one<SINK_AGG_REG, 1, false, false>(grid, block, smem, st);
+      return add_only ? launch_one<SINK_AGG_REG, VM_REG_GROUPS, true, false>(grid, block, smem, st)
+                      : launch_one<SINK_AGG_REG, VM_REG_GROUPS, false, false>(grid, block, smem, st);
   }
 }
 

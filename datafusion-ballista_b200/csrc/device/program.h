@@ -187,4 +187,45 @@ struct Program {
   int64_t n_rows;
 };
 
+// ---- fused fast path (scan -> filter -> decimal products -> <=4-group SUM/COUNT aggregate) -----------
+// A pattern-matched specialisation of the lowered program for the TPC-H q1/q6 shape (SURVEY.md 7.1
+// step 3): every value lives in registers, nothing round-trips through the VM register file.
+static const int FUSED_MAX_FILTERS = 6;
+struct FusedFilter {
+  uint32_t off;   // tile column offset inside the stage buffer
+  uint8_t w;      // element width 4 / 8 / 16 (low word)
+  uint8_t op;     // VOp compare
+  uint8_t _pad[2];
+  int64_t imm;
+};
+struct FusedProd {
+  uint32_t a_off, b_off;
+  uint8_t a_src;   // 0: tile column, 1: previous product
+  uint8_t a_w, b_w;
+  uint8_t kind;    // 0: a*(lit-b)  1: a*(lit+b)  2: a*b
+  uint64_t lit_lo, lit_hi;
+};
+struct FusedKey {
+  uint32_t off;
+  uint8_t kind;    // 0: integer column, 1: short Utf8 packed as len<<shift | bytes
+  uint8_t w, max_len, shift;
+  const uint8_t* chars;
+  int64_t bias;    // added to integer keys (non-negative 32-bit image)
+};
+struct FusedAcc {
+  uint32_t off;
+  uint8_t src;     // 0: tile column, 1: product 0, 2: product 1, 3: constant one (COUNT)
+  uint8_t w;
+  uint8_t _pad[2];
+};
+struct FusedSpec {
+  int32_t n_filters, n_prod, n_keys, n_acc;
+  int32_t combine;  // 1: key image = k0 + k1 * 2^32
+  int32_t _pad;
+  FusedFilter f[FUSED_MAX_FILTERS];
+  FusedProd p[2];
+  FusedKey k[2];
+  FusedAcc a[VM_REG_ACC];
+};
+
 }  // namespace b200

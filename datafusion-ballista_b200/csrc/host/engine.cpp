@@ -325,7 +325,7 @@ struct RunOutcome {
   float ms = 0;
 };
 
-RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups) {
+RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedSpec* fused = nullptr) {
   Program& P = pb.prog;
   DevPtr dstat = dev_alloc(sizeof(RunStatus), x.st());
   CUDA_CHECK(cudaMemsetAsync(dstat->ptr, 0, sizeof(RunStatus), x.st()));
@@ -349,7 +349,8 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups) {
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, x.st()));
-  cudaError_t le = launch_pipeline(P, reg_groups, grid, pb.block, pb.smem_bytes(), x.st());
+  if (debug && fused) fprintf(stderr, "[b200]   fused fast path: %d filters, %d products, %d keys, %d accumulators\n", fused->n_filters, fused->n_prod, fused->n_keys, fused->n_acc);
+  cudaError_t le = launch_pipeline(P, reg_groups, grid, pb.block, pb.smem_bytes(), x.st(), fused);
   if (le != cudaSuccess) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -649,6 +650,169 @@ void lower_aggregate(PipelineBuilder& pb, const PlanNode& node, AggLowered& L, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pattern match of a lowered register-aggregate program against the fused fast path
+// (filters on integer-like tile columns -> up to two decimal products -> <= 2 packed/integer keys ->
+// SUM/COUNT accumulators).  Anything outside the pattern keeps the general VM path.
+// ------------------------------------------------------------------------------------------------
+bool match_fused(const Program& P, FusedSpec& F) {
+  memset(&F, 0, sizeof F);
+  if (P.sink != SINK_AGG_REG) return false;
+  if (getenv("B200_NO_FUSED")) return false;
+  auto int_col = [&](const Operand& o, uint32_t* off, uint8_t* w, bool want_i128) -> bool {
+    if (o.kind != OPD_COL) return false;
+    const ColDesc& cd = P.cols[o.idx];
+    if (cd.valid) return false;
+    if (!(cd.phys == PH_I32 || cd.phys == PH_I64 || cd.phys == PH_DEC128)) return false;
+    if (want_i128 && o.vk == VK_I128 && cd.phys != PH_DEC128) return false;
+    if (o.vk != VK_I128 && cd.phys == PH_DEC128) {
+      // narrow view of a decimal: low word only
+    }
+    *off = cd.smem_off;
+    *w = (o.vk == VK_I128) ? 16 : cd.width;
+    return true;
+  };
+  int prod_reg[2] = {-1, -1};
+  struct PackInfo { int reg; FusedKey k; };
+  std::vector<PackInfo> packs;      // packed-string / biased-int key images by register
+  int combined_reg = -1, comb_a = -1, comb_b = -1;
+  for (int i = 0; i < P.n_instr; i++) {
+    const VInstr& v = P.code[i];
+    if (v.flags & IF_NULLCHK) return false;
+    switch (v.op) {
+      case OP_CMP_EQ: case OP_CMP_NE: case OP_CMP_LT: case OP_CMP_LE: case OP_CMP_GT: case OP_CMP_GE: {
+        if (!(v.flags & IF_FILTER) || v.t != VK_I64 || v.aux == PH_U64) return false;
+        if (F.n_filters >= FUSED_MAX_FILTERS) return false;
+        FusedFilter& f = F.f[F.n_filters];
+        Operand col = v.a, imm = v.b;
+        uint8_t op = v.op;
+        if (v.a.kind == OPD_IMM && v.b.kind == OPD_COL) {
+          col = v.b;
+          imm = v.a;
+          op = v.op == OP_CMP_LT ? OP_CMP_GT : v.op == OP_CMP_LE ? OP_CMP_GE : v.op == OP_CMP_GT ? OP_CMP_LT : v.op == OP_CMP_GE ? OP_CMP_LE : v.op;
+        }
+        if (imm.kind != OPD_IMM || P.imms[imm.idx].is_null) return false;
+        Operand c64 = col;
+        c64.vk = VK_I64;
+        if (!int_col(c64, &f.off, &f.w, false)) return false;
+        if (P.cols[col.idx].phys == PH_DEC128) f.w = 16;
+        f.op = op;
+        f.imm = (int64_t)P.imms[imm.idx].lo;
+        F.n_filters++;
+        break;
+      }
+      case OP_DEC_MUL_LIT_MINUS: case OP_DEC_MUL_LIT_PLUS: case OP_MUL: {
+        if (v.op == OP_MUL && v.t != VK_I128) return false;
+        if (F.n_prod >= 2 || v.dst.kind != OPD_REG) return false;
+        FusedProd& q = F.p[F.n_prod];
+        q.kind = v.op == OP_DEC_MUL_LIT_MINUS ? 0 : v.op == OP_DEC_MUL_LIT_PLUS ? 1 : 2;
+        if (v.a.kind == OPD_REG && F.n_prod == 1 && (int)v.a.idx == prod_reg[0]) {
+          q.a_src = 1;
+        } else if (!int_col(v.a, &q.a_off, &q.a_w, true)) {
+          return false;
+        }
+        if (!int_col(v.b, &q.b_off, &q.b_w, true)) return false;
+        if (q.kind != 2) {
+          q.lit_lo = P.imms[v.imm].lo;
+          q.lit_hi = P.imms[v.imm].hi;
+        }
+        prod_reg[F.n_prod++] = v.dst.idx;
+        break;
+      }
+      case OP_STR_PACK8: {
+        if (v.a.kind != OPD_COL || P.cols[v.a.idx].phys != PH_UTF8 || P.cols[v.a.idx].valid || v.dst.kind != OPD_REG) return false;
+        PackInfo pi;
+        pi.reg = v.dst.idx;
+        memset(&pi.k, 0, sizeof pi.k);
+        pi.k.kind = 1;
+        pi.k.off = P.cols[v.a.idx].smem_off;
+        pi.k.chars = P.cols[v.a.idx].chars;
+        pi.k.max_len = v.aux;
+        pi.k.shift = (uint8_t)v.imm;
+        packs.push_back(pi);
+        break;
+      }
+      case OP_MADD_I64: {
+        if (v.a.kind != OPD_REG || v.b.kind != OPD_REG || v.dst.kind != OPD_REG || P.imms[v.imm].lo != 4294967296ull) return false;
+        combined_reg = v.dst.idx;
+        comb_a = v.a.idx;
+        comb_b = v.b.idx;
+        break;
+      }
+      default: return false;
+    }
+  }
+  // keys
+  F.n_keys = P.n_keys;
+  if (P.n_keys > 2) return false;
+  if (P.n_keys > 0 && !P.keys_all_i64) return false;
+  auto key_from = [&](const Operand& o, FusedKey& k) -> bool {
+    if (o.kind == OPD_REG) {
+      for (auto& pi : packs)
+        if (pi.reg == (int)o.idx) {
+          k = pi.k;
+          return true;
+        }
+      return false;
+    }
+    if (o.kind == OPD_COL) {
+      memset(&k, 0, sizeof k);
+      uint32_t off;
+      uint8_t w;
+      Operand c64 = o;
+      c64.vk = VK_I64;
+      if (!int_col(c64, &off, &w, false) || P.cols[o.idx].phys == PH_DEC128) return false;
+      k.kind = 0;
+      k.off = off;
+      k.w = w;
+      return true;
+    }
+    return false;
+  };
+  for (int k = 0; k < P.n_keys; k++)
+    if (!key_from(P.keys[k], F.k[k])) return false;
+  if (P.n_keys == 1) {
+    if (!(P.key_hash.kind == P.keys[0].kind && P.key_hash.idx == P.keys[0].idx)) return false;
+    F.combine = 0;
+  } else if (P.n_keys == 2) {
+    // only the all-packed-string form: the 32-bit images are the pack registers themselves
+    if (P.key_hash.kind != OPD_REG || (int)P.key_hash.idx != combined_reg) return false;
+    if (!(P.keys[0].kind == OPD_REG && P.keys[1].kind == OPD_REG && comb_a == (int)P.keys[0].idx && comb_b == (int)P.keys[1].idx)) return false;
+    F.combine = 1;
+  }
+  if (combined_reg >= 0 && P.n_keys != 2) return false;
+  // accumulators
+  if (P.n_acc > VM_REG_ACC) return false;
+  F.n_acc = P.n_acc;
+  for (int a = 0; a < P.n_acc; a++) {
+    const AccDesc& ad = P.acc[a];
+    FusedAcc& fa = F.a[a];
+    if (ad.kind == ACC_COUNT_STAR || (ad.kind == ACC_COUNT && !ad.nullable)) {
+      fa.src = 3;
+      continue;
+    }
+    if (ad.kind != ACC_SUM_I128 || ad.nullable) return false;
+    if (ad.src.kind == OPD_REG) {
+      if ((int)ad.src.idx == prod_reg[0]) fa.src = 1;
+      else if ((int)ad.src.idx == prod_reg[1]) fa.src = 2;
+      else return false;
+    } else if (ad.src.kind == OPD_COL) {
+      if (!int_col(ad.src, &fa.off, &fa.w, true)) return false;
+      if (ad.src.vk != VK_I128 && P.cols[ad.src.idx].phys == PH_DEC128) return false;
+      fa.src = 0;
+    } else {
+      return false;
+    }
+  }
+  // every packed register must be a key (no stray uses)
+  for (auto& pi : packs) {
+    bool used = false;
+    for (int k = 0; k < P.n_keys; k++) used |= P.keys[k].kind == OPD_REG && (int)P.keys[k].idx == pi.reg;
+    if (!used) return false;
+  }
+  return true;
+}
+
 struct TableMem {
   AggTable T;
   std::vector<DevPtr> keep;
@@ -759,7 +923,9 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       tm.keep.push_back(hi);
       P.acc_hi = (unsigned long long*)hi->ptr;
     }
-    ro = launch_program(x, pb, reg_groups);
+    FusedSpec fspec;
+    const bool use_fused = level == 0 && match_fused(P, fspec);
+    ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr);
     if (met) {
       met->elapsed_ns += (uint64_t)(ro.ms * 1e6);
       met->launches += 2;

@@ -1135,7 +1135,7 @@ uint64_t batch_bytes(const OBatch& b) {
 
 struct Oracle {
   std::mutex mu;
-  std::map<std::string, std::map<int, OBatch>> tables;
+  std::map<std::string, std::map<int, std::shared_ptr<OBatch>>> tables;
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
   int64_t batch_size = 8192;
   std::string err;
@@ -1174,16 +1174,20 @@ struct Oracle {
   OBatch exec(const PlanNode& n, int part, const std::string& job) {
     switch (n.op) {
       case PlanNode::Scan: {
-        std::lock_guard<std::mutex> g(mu);
-        auto it = tables.find(n.table);
-        if (it == tables.end()) exec_fail("table not registered: " + n.table);
-        auto pit = it->second.find(part);
+        std::shared_ptr<OBatch> src;
+        {
+          std::lock_guard<std::mutex> g(mu);
+          auto it = tables.find(n.table);
+          if (it == tables.end()) exec_fail("table not registered: " + n.table);
+          auto pit = it->second.find(part);
+          if (pit != it->second.end()) src = pit->second;
+        }
         OBatch out;
-        if (pit == it->second.end()) return empty_batch(n.schema);
-        out.n = pit->second.n;
+        if (!src) return empty_batch(n.schema);
+        out.n = src->n;
         for (int idx : n.scan_projection) {
-          if ((size_t)idx >= pit->second.cols.size()) exec_fail("scan projection out of range for " + n.table);
-          out.cols.push_back(pit->second.cols[(size_t)idx]);
+          if ((size_t)idx >= src->cols.size()) exec_fail("scan projection out of range for " + n.table);
+          out.cols.push_back(src->cols[(size_t)idx]);
         }
         for (size_t c = 0; c < out.cols.size(); c++)
           if (out.cols[c].type != n.schema[c].type)
@@ -1388,8 +1392,13 @@ int oracle_register_batch(void* o_, const char* table, int partition, ArrowArray
     OBatch b = import_batch(arr, sch);
     std::lock_guard<std::mutex> g(o->mu);
     auto& slot = o->tables[table][partition];
-    if (slot.cols.empty()) slot = std::move(b);
-    else append(slot, b);
+    if (!slot || slot->cols.empty()) {
+      slot = std::make_shared<OBatch>(std::move(b));
+    } else {
+      auto merged = std::make_shared<OBatch>(*slot);
+      append(*merged, b);
+      slot = merged;
+    }
   });
 }
 
@@ -1438,7 +1447,7 @@ int oracle_tpch_generate(void* o_, const char* table, int64_t msf, int partition
     }
     OBatch b = tpch_generate(t, msf, row_begin, row_end, cols);
     std::lock_guard<std::mutex> g(o->mu);
-    o->tables[table][partition] = std::move(b);
+    o->tables[table][partition] = std::make_shared<OBatch>(std::move(b));
   });
 }
 
@@ -1448,7 +1457,7 @@ int oracle_export_table(void* o_, const char* table, int partition, ArrowArray* 
     std::lock_guard<std::mutex> g(o->mu);
     auto it = o->tables.find(table);
     if (it == o->tables.end() || !it->second.count(partition)) throw ExecError(B200_ERR_NOT_FOUND, "no such table partition");
-    export_batch(it->second[partition], nullptr, out, out_schema);
+    export_batch(*it->second[partition], nullptr, out, out_schema);
   });
 }
 
