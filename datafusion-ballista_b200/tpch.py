@@ -135,3 +135,93 @@ def q6(n_partitions: int = 16) -> List[Stage]:
                      P.coalesce_partitions(P.shuffle_reader(1, partial_schema)))
     st2 = Stage(2, P.shuffle_writer(s2, 2), n_tasks=1)
     return [st1, st2]
+
+
+def _sch(table, cols):
+    return [f for name in cols for f in SCHEMAS[table] if f["name"] == name]
+
+
+Q5_TABLES = {"region": ["r_regionkey", "r_name"], "nation": ["n_nationkey", "n_name", "n_regionkey"],
+             "customer": ["c_custkey", "c_nationkey"], "orders": ["o_orderkey", "o_custkey", "o_orderdate"],
+             "lineitem": ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], "supplier": ["s_suppkey", "s_nationkey"]}
+
+
+def q5(n_partitions: int = 4) -> List[Stage]:
+    """benchmarks/queries/q5.sql -- 6-way join (HashJoinExec, Partitioned + CollectLeft) with hash shuffles on
+    the join keys, then a low-cardinality aggregate and ORDER BY revenue DESC (BASELINE.json configs[2])."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    # S1: nation |x| region(r_name = 'ASIA')  (both tiny: CollectLeft inside one task)
+    reg = P.filter_(P.binop("=", c("r_name"), P.lit_utf8("ASIA")), table_scan("region", Q5_TABLES["region"]), projection=[0])
+    s1 = P.hash_join(reg, table_scan("nation", Q5_TABLES["nation"]), [[c(0), c("n_regionkey")]], "Inner", "CollectLeft", projection=[1, 2])
+    st1 = Stage(1, P.shuffle_writer(s1, 1), n_tasks=1)
+    nat = [P.field("n_nationkey", i64, True), P.field("n_name", "utf8", True)]
+    # S2: customer |x| nation (broadcast build side)
+    s2 = P.hash_join(P.shuffle_reader(1, nat, broadcast=True), table_scan("customer", Q5_TABLES["customer"]),
+                     [[c(0), c("c_nationkey")]], "Inner", "CollectLeft", projection=[2, 3, 1])
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(0)], Pn))
+    cust = [P.field("c_custkey", i64, True), P.field("c_nationkey", i64, True), P.field("n_name", "utf8", True)]
+    # S3: orders filtered by date
+    s3 = P.filter_(P.and_(P.binop(">=", c("o_orderdate"), P.lit_date("1994-01-01")), P.binop("<", c("o_orderdate"), P.lit_date("1995-01-01"))),
+                   table_scan("orders", Q5_TABLES["orders"]), projection=[0, 1])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(1)], Pn))
+    ords = [P.field("o_orderkey", i64, True), P.field("o_custkey", i64, True)]
+    # S4: customer' |x| orders' on custkey
+    s4 = P.hash_join(P.shuffle_reader(2, cust), P.shuffle_reader(3, ords), [[c(0), c(1)]], "Inner", "Partitioned", projection=[3, 1, 2])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    co = [P.field("o_orderkey", i64, True), P.field("c_nationkey", i64, True), P.field("n_name", "utf8", True)]
+    # S5: lineitem by orderkey
+    st5 = Stage(5, P.shuffle_writer(table_scan("lineitem", Q5_TABLES["lineitem"]), 5, [c(0)], Pn))
+    li = _sch("lineitem", Q5_TABLES["lineitem"])
+    li = [dict(f, nullable=True) for f in li]
+    # S6: (customer, orders) |x| lineitem on orderkey
+    s6 = P.hash_join(P.shuffle_reader(4, co), P.shuffle_reader(5, li), [[c(0), c(0)]], "Inner", "Partitioned", projection=[4, 1, 2, 5, 6])
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(0)], Pn))
+    col6 = [P.field("l_suppkey", i64, True), P.field("c_nationkey", i64, True), P.field("n_name", "utf8", True),
+            P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    # S7: supplier by suppkey
+    st7 = Stage(7, P.shuffle_writer(table_scan("supplier", Q5_TABLES["supplier"]), 7, [c(0)], Pn))
+    sup = [P.field("s_suppkey", i64, True), P.field("s_nationkey", i64, True)]
+    # S8: supplier |x| ... on (suppkey, nationkey) -> partial aggregate by n_name
+    s8 = P.hash_join(P.shuffle_reader(7, sup), P.shuffle_reader(6, col6), [[c(0), c(0)], [c(1), c(1)]], "Inner", "Partitioned", projection=[4, 5, 6])
+    s8 = P.project([(c(0), "n_name"), (P.binop("*", c(1), one_minus(c(2))), "rev")], s8)
+    s8 = P.aggregate("Partial", [(c(0), "n_name")], [P.agg("sum", c(1), "revenue")], s8)
+    st8 = Stage(8, P.shuffle_writer(s8, 8, [c(0)], Pn))
+    part = [P.field("n_name", "utf8", True), P.field("revenue[sum]", P.dec(38, 4), True)]
+    s9 = P.aggregate("FinalPartitioned", [(c(0), "n_name")], [P.agg("sum", None, "revenue")], P.shuffle_reader(8, part))
+    keys = [P.sort_key(c(1), asc=False)]
+    s9 = P.sort(keys, s9, preserve_partitioning=True)
+    st9 = Stage(9, P.shuffle_writer(s9, 9))
+    fin = [P.field("n_name", "utf8", True), P.field("revenue", P.dec(38, 4), True)]
+    st10 = Stage(10, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(9, fin)), 10), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8, st9, st10]
+
+
+Q17_TABLES = {"lineitem": ["l_partkey", "l_quantity", "l_extendedprice"], "part": ["p_partkey", "p_brand", "p_container"]}
+
+
+def q17(n_partitions: int = 4, brand: str = "Brand#23", container: str = "MED BOX") -> List[Stage]:
+    """benchmarks/queries/q17.sql after decorrelation: high-cardinality AVG per l_partkey joined back to the
+    filtered parts and lineitems (`l_quantity < 0.2 * avg`, fp64), final `sum(l_extendedprice) / 7.0` (configs[3])."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    li = table_scan("lineitem", Q17_TABLES["lineitem"])
+    s1 = P.aggregate("Partial", [(c("l_partkey"), "l_partkey")], [P.agg("avg", c("l_quantity"), "avg_qty")], li)
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st_avg = [P.field("l_partkey", i64, True), P.field("avg_qty[count]", "u64", True), P.field("avg_qty[sum]", P.dec(25, 2), True)]
+    prt = P.filter_(P.and_(P.binop("=", c("p_brand"), P.lit_utf8(brand)), P.binop("=", c("p_container"), P.lit_utf8(container))),
+                    table_scan("part", Q17_TABLES["part"]), projection=[0])
+    st2 = Stage(2, P.shuffle_writer(prt, 2, [c(0)], Pn))
+    st3 = Stage(3, P.shuffle_writer(table_scan("lineitem", Q17_TABLES["lineitem"]), 3, [c(0)], Pn))
+    lis = [dict(f, nullable=True) for f in _sch("lineitem", Q17_TABLES["lineitem"])]
+    avg = P.aggregate("FinalPartitioned", [(c(0), "l_partkey")], [P.agg("avg", None, "avg_qty", D152)], P.shuffle_reader(1, st_avg))
+    thr = P.project([(c(0), "pk"), (P.binop("*", P.lit_f64(0.2), P.cast(c(1), "f64")), "thr")], avg)
+    pl = P.hash_join(P.shuffle_reader(2, [P.field("p_partkey", i64, True)]), P.shuffle_reader(3, lis), [[c(0), c(0)]], "Inner", "Partitioned",
+                     projection=[1, 2, 3])
+    # residual filter over concat(thr(pk, thr), pl(l_partkey, l_quantity, l_extendedprice))
+    j = P.hash_join(thr, pl, [[c(0), c(0)]], "Inner", "Partitioned", filter=P.binop("<", P.cast(c(3), "f64"), c(1)), projection=[4])
+    s4 = P.aggregate("Partial", [], [P.agg("sum", c(0), "s")], j)
+    st4 = Stage(4, P.shuffle_writer(s4, 4))
+    s5 = P.aggregate("Final", [], [P.agg("sum", None, "s")], P.coalesce_partitions(P.shuffle_reader(4, [P.field("s[sum]", P.dec(25, 2), True)])))
+    s5 = P.project([(P.binop("/", P.cast(c(0), "f64"), P.lit_f64(7.0)), "avg_yearly")], s5)
+    return [st1, st2, st3, st4 if False else Stage(4, P.shuffle_writer(s4, 4)), Stage(5, P.shuffle_writer(s5, 5), n_tasks=1)]

@@ -1,0 +1,98 @@
+"""q5 (6-way hash join + shuffles) and q17 (high-cardinality aggregate, join with residual filter, fp64):
+BASELINE.json configs[2] and configs[3] as parity cases at small scale.
+  * not gpu: the oracle against an independent pandas/python-int computation;
+  * gpu: the CUDA engine against the oracle (decimals bit-exact, the fp64 result within 1e-12)."""
+import decimal
+
+import pyarrow as pa
+import pytest
+
+from ballista_b200 import driver, tpch
+from util import assert_tables_equal
+
+D = decimal.Decimal
+
+
+def load_tables(engine, oracle_lib, msf, tables, parts):
+    for t, cols in tables.items():
+        n = oracle_lib.lib().oracle_tpch_table_rows(t.encode(), msf)
+        np_ = 1 if n < 100 else parts
+        step = (n + np_ - 1) // np_
+        engine.drop_table(t)
+        for p in range(np_):
+            engine.tpch_generate(t, msf, p, min(n, p * step), min(n, (p + 1) * step), cols)
+
+
+def table_df(engine, t, n_parts):
+    batches = [engine.export_table(t, p) for p in range(n_parts)]
+    return pa.Table.from_batches(batches).to_pandas()
+
+
+def test_q5_oracle_against_pandas(oracle, oracle_lib):
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q5_TABLES, parts)
+    got = driver.run_stages(oracle, tpch.q5(3), "q5o")
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q5_TABLES}
+    import datetime as dt
+    o = df["orders"]
+    o = o[(o.o_orderdate >= dt.date(1994, 1, 1)) & (o.o_orderdate < dt.date(1995, 1, 1))]
+    r = df["region"][df["region"].r_name == "ASIA"]
+    m = df["nation"].merge(r, left_on="n_regionkey", right_on="r_regionkey")
+    m = df["customer"].merge(m, left_on="c_nationkey", right_on="n_nationkey").merge(o, left_on="c_custkey", right_on="o_custkey")
+    m = m.merge(df["lineitem"], left_on="o_orderkey", right_on="l_orderkey")
+    m = m.merge(df["supplier"], left_on=["l_suppkey", "c_nationkey"], right_on=["s_suppkey", "s_nationkey"])
+    want = {}
+    for name, ext, disc in zip(m.n_name, m.l_extendedprice, m.l_discount):
+        want[name] = want.get(name, 0) + int(ext.scaleb(2)) * (100 - int(disc.scaleb(2)))
+    assert got is not None and got.num_rows == len(want) and len(want) > 0
+    gd = dict(zip(got.column("n_name").to_pylist(), got.column("revenue").to_pylist()))
+    assert gd == {k: D(v).scaleb(-4) for k, v in want.items()}
+    revs = got.column("revenue").to_pylist()
+    assert revs == sorted(revs, reverse=True)  # ORDER BY revenue DESC
+
+
+def test_q17_oracle_against_python(oracle, oracle_lib):
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q17_TABLES, parts)
+    df_p = table_df(oracle, "part", oracle.n_table_partitions("part"))
+    brand, cont = df_p.p_brand.iloc[0], df_p.p_container.iloc[0]   # a combination that exists at this tiny scale
+    got = driver.run_stages(oracle, tpch.q17(3, brand, cont), "q17o")
+    li = table_df(oracle, "lineitem", oracle.n_table_partitions("lineitem"))
+    keys = set(df_p[(df_p.p_brand == brand) & (df_p.p_container == cont)].p_partkey)
+    assert keys
+    sums, cnts = {}, {}
+    for pk, q in zip(li.l_partkey, li.l_quantity):
+        sums[pk] = sums.get(pk, 0) + int(q.scaleb(2))
+        cnts[pk] = cnts.get(pk, 0) + 1
+    total = 0
+    for pk, q, e in zip(li.l_partkey, li.l_quantity, li.l_extendedprice):
+        if pk in keys:
+            avg6 = (sums[pk] * 10**4) // cnts[pk]           # Decimal128(19,6), truncated
+            if float(q) < 0.2 * float(D(avg6).scaleb(-6)):
+                total += int(e.scaleb(2))
+    want = float(D(total).scaleb(-2)) / 7.0 if total else None
+    val = got.column(0)[0].as_py()
+    assert (val is None and want is None) or abs(val - want) <= 1e-12 * abs(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("msf,parts,P", [(20, 2, 3), (100, 3, 8)])
+def test_q5_gpu(gpu, oracle, oracle_lib, msf, parts, P):
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, msf, tpch.Q5_TABLES, parts)
+    got = driver.run_stages(gpu, tpch.q5(P), f"q5-{msf}")
+    want = driver.run_stages(oracle, tpch.q5(P), f"q5-{msf}")
+    assert want.num_rows > 0
+    assert_tables_equal(got, want, sort=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("msf,parts,P", [(20, 2, 3), (100, 3, 8)])
+def test_q17_gpu(gpu, oracle, oracle_lib, msf, parts, P):
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, msf, tpch.Q17_TABLES, parts)
+    first = pa.Table.from_batches([oracle.export_table("part", 0)]).slice(0, 1).to_pylist()[0]
+    st = tpch.q17(P, first["p_brand"], first["p_container"])
+    got = driver.run_stages(gpu, st, f"q17-{msf}")
+    want = driver.run_stages(oracle, st, f"q17-{msf}")
+    assert_tables_equal(got, want, sort=False, f64_rtol=1e-12)
