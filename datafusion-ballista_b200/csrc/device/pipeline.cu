@@ -2031,6 +2031,40 @@ __device__ __forceinline__ void reg_agg_flush(RegAggState<G>& S, const unsigned 
 template <int G>
 __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, RegAggState<G>& S, RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n) {
   const FusedSpec& F = c_fused;
+  // ---- key images first: the dependent global loads of short-string keys are issued before the
+  // ---- filters / products so that their latency overlaps with that arithmetic
+  unsigned long long kv0[VM_R], kv1[VM_R];
+  uint32_t key_too_long = 0;
+#pragma unroll
+  FOR_R kv0[r] = kv1[r] = 0;
+  if (G > 1) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (k >= F.n_keys) break;
+      const FusedKey& fk = F.k[k];
+      if (fk.kind == 1) {
+        const int32_t* off = (const int32_t*)(L.stage + fk.off);
+#pragma unroll
+        FOR_R {
+          const int e = r * L.B + L.tid;
+          const int32_t o0 = off[e];
+          const uint32_t len = (uint32_t)(off[e + 1] - o0);
+          key_too_long |= (len > fk.max_len ? 1u : 0u) << r;
+          const unsigned long long v = pack8(fk.chars + o0, len > fk.max_len ? 0u : len, fk.shift);
+          if (k == 0) kv0[r] = v;
+          else kv1[r] = v;
+        }
+      } else {
+        const uint8_t* p = L.stage + fk.off;
+#pragma unroll
+        FOR_R {
+          const unsigned long long v = (unsigned long long)ld_w(p, fk.w, r * L.B + L.tid);
+          if (k == 0) kv0[r] = v;
+          else kv1[r] = v;
+        }
+      }
+    }
+  }
   // ---- filters
 #pragma unroll
   for (int i = 0; i < FUSED_MAX_FILTERS; i++) {
@@ -2086,38 +2120,8 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
 #pragma unroll
   FOR_R gid[r] = 0;
   if (G > 1) {
-    unsigned long long kv0[VM_R], kv1[VM_R], ck[VM_R];
-#pragma unroll
-    FOR_R kv0[r] = kv1[r] = 0;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      if (k >= F.n_keys) break;
-      const FusedKey& fk = F.k[k];
-      if (fk.kind == 1) {
-        const int32_t* off = (const int32_t*)(L.stage + fk.off);
-        uint32_t too_long = 0;
-#pragma unroll
-        FOR_R {
-          const int e = r * L.B + L.tid;
-          const int32_t o0 = off[e];
-          const uint32_t len = (uint32_t)(off[e + 1] - o0);
-          const bool lv = (active >> r) & 1;
-          too_long |= (lv && len > fk.max_len) ? 1u : 0u;
-          const unsigned long long v = (lv && len <= fk.max_len) ? pack8(fk.chars + o0, len, fk.shift) : 0ull;
-          if (k == 0) kv0[r] = v;
-          else kv1[r] = v;
-        }
-        if (too_long) atomicExch(&PROG.status->pack_overflow, 1u);
-      } else {
-        const uint8_t* p = L.stage + fk.off;
-#pragma unroll
-        FOR_R {
-          const unsigned long long v = (unsigned long long)ld_w(p, fk.w, r * L.B + L.tid);
-          if (k == 0) kv0[r] = v;
-          else kv1[r] = v;
-        }
-      }
-    }
+    if (key_too_long & active) atomicExch(&PROG.status->pack_overflow, 1u);
+    unsigned long long ck[VM_R];
 #pragma unroll
     FOR_R ck[r] = F.combine ? ((kv0[r] + (unsigned long long)F.k[0].bias) + (kv1[r] + (unsigned long long)F.k[1].bias) * 4294967296ull) : kv0[r];
 #pragma unroll
@@ -2289,6 +2293,9 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
       __syncthreads();
     }
     L.stage = stage;
+    // the sink-overflow flag is sampled by one thread before the tile's arithmetic (its latency hides
+    // behind the compute) and published CTA-uniformly by the end-of-tile barrier
+    const unsigned int stop_early = (SINK != SINK_MATERIALIZE && tid == 0) ? *(volatile unsigned int*)&PROG.status->overflow : 0u;
     uint32_t active = 0;
 #pragma unroll
     FOR_R if (r * B + tid < rows) active |= 1u << r;
@@ -2310,7 +2317,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     }
     // everyone is done with this stage buffer (and the VM registers); the sink-overflow flag is
     // sampled CTA-uniformly so that all threads leave the loop together
-    if (__syncthreads_or(SINK != SINK_MATERIALIZE && *(volatile unsigned int*)&PROG.status->overflow != 0)) {
+    if (__syncthreads_or(stop_early != 0)) {
       // drain bulk copies that are still in flight before the CTA may exit
       for (int64_t kk = k + 1; kk < k + S; kk++) {
         const int64_t tt = tile_of(kk);
