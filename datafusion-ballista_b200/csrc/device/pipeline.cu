@@ -2023,6 +2023,75 @@ __device__ __forceinline__ void reg_agg_flush(RegAggState<G>& S, const unsigned 
   }
 }
 
+__device__ __noinline__ int fused_resolve_slow(RegGroupTable* gt, int G, int n_keys, unsigned long long ck, unsigned long long k0, unsigned long long k1) {
+  KeyVal kv[2];
+  kv[0].w0 = k0;
+  kv[0].w1 = 0;
+  kv[0].valid = 1;
+  kv[0].vk = VK_I64;
+  kv[1].w0 = k1;
+  kv[1].w1 = 0;
+  kv[1].valid = 1;
+  kv[1].vk = VK_I64;
+  return reg_group_lookup(gt, G, n_keys, ck, kv);
+}
+
+// Checked decimal product entirely in registers.  Fast path: both operands fit 64 bits (always the
+// case for TPC-H prices/discounts); non-negative operands use the unsigned multiply-high.
+struct Prod128 {
+  uint64_t lo, hi;
+  uint32_t ovf;
+};
+__device__ __noinline__ Prod128 mul128_slow_val(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
+  i128 out = 0;
+  Prod128 r;
+  r.ovf = mul_i128_slow(make_i128(alo, ahi), make_i128(blo, bhi), &out) ? 1u : 0u;
+  r.lo = lo64(out);
+  r.hi = hi64(out);
+  return r;
+}
+__device__ __forceinline__ Prod128 mul128_fast_val(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
+  Prod128 r;
+  r.ovf = 0;
+  const bool a64 = ahi == (uint64_t)((int64_t)alo >> 63), b64 = bhi == (uint64_t)((int64_t)blo >> 63);
+  if (a64 && b64) {
+    r.lo = alo * blo;
+    if ((int64_t)(alo | blo) >= 0) r.hi = __umul64hi(alo, blo);
+    else r.hi = (uint64_t)__mul64hi((int64_t)alo, (int64_t)blo);
+    return r;
+  }
+  return mul128_slow_val(alo, ahi, blo, bhi);
+}
+// raw (lo, hi) of a tile operand of width 4 / 8 / 16
+__device__ __forceinline__ void ld_raw128(const uint8_t* base, uint32_t w, int e, uint64_t& lo, uint64_t& hi) {
+  if (w == 16) {
+    const ulonglong2 x = ((const ulonglong2*)base)[e];
+    lo = x.x;
+    hi = x.y;
+  } else {
+    const int64_t v = (w == 8) ? ((const int64_t*)base)[e] : (int64_t)((const int32_t*)base)[e];
+    lo = (uint64_t)v;
+    hi = (uint64_t)(v >> 63);
+  }
+}
+__device__ __forceinline__ uint32_t addsub128(bool minus, uint64_t llo, uint64_t lhi, uint64_t& blo, uint64_t& bhi) {
+  // b := lit -/+ b with signed-overflow detection
+  const uint64_t xlo = blo, xhi = bhi;
+  uint64_t rlo, rhi;
+  if (minus) {
+    rlo = llo - xlo;
+    rhi = lhi - xhi - (llo < xlo ? 1ull : 0ull);
+    blo = rlo;
+    bhi = rhi;
+    return (((int64_t)lhi < 0) != ((int64_t)xhi < 0)) && (((int64_t)rhi < 0) != ((int64_t)lhi < 0)) ? 1u : 0u;
+  }
+  rlo = llo + xlo;
+  rhi = lhi + xhi + (rlo < llo ? 1ull : 0ull);
+  blo = rlo;
+  bhi = rhi;
+  return (((int64_t)lhi < 0) == ((int64_t)xhi < 0)) && (((int64_t)rhi < 0) != ((int64_t)lhi < 0)) ? 1u : 0u;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fused fast path: filters -> decimal products -> key image -> register aggregate, all in registers.
 // Reference operators fused: FilterExec + ProjectionExec + AggregateExec(Partial) of TPC-H q1/q6
@@ -2031,12 +2100,22 @@ __device__ __forceinline__ void reg_agg_flush(RegAggState<G>& S, const unsigned 
 template <int G>
 __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, RegAggState<G>& S, RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n) {
   const FusedSpec& F = c_fused;
-  // ---- key images first: the dependent global loads of short-string keys are issued before the
-  // ---- filters / products so that their latency overlaps with that arithmetic
-  unsigned long long kv0[VM_R], kv1[VM_R];
+  const int e0 = L.tid;  // element index of row r is e0 + r * B
+  // ---- key images, phase 1: offsets from the tile, then ALL dependent chars loads issued back to
+  // ---- back (two aligned 8-byte words per string; allocations carry slack) so that their DRAM/L2
+  // ---- latency overlaps with the filters and products below
+  uint32_t klen[2][VM_R], ksh[2][VM_R];
+  uint64_t kw0[2][VM_R], kw1[2][VM_R];
   uint32_t key_too_long = 0;
 #pragma unroll
-  FOR_R kv0[r] = kv1[r] = 0;
+  for (int k = 0; k < 2; k++) {
+#pragma unroll
+    FOR_R {
+      klen[k][r] = 0;
+      ksh[k][r] = 0;
+      kw0[k][r] = kw1[k][r] = 0;
+    }
+  }
   if (G > 1) {
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -2044,24 +2123,26 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
       const FusedKey& fk = F.k[k];
       if (fk.kind == 1) {
         const int32_t* off = (const int32_t*)(L.stage + fk.off);
+        const uint8_t* chars = fk.chars;
+        const uint32_t max_len = fk.max_len;
 #pragma unroll
         FOR_R {
-          const int e = r * L.B + L.tid;
+          const int e = e0 + r * L.B;
           const int32_t o0 = off[e];
           const uint32_t len = (uint32_t)(off[e + 1] - o0);
-          key_too_long |= (len > fk.max_len ? 1u : 0u) << r;
-          const unsigned long long v = pack8(fk.chars + o0, len > fk.max_len ? 0u : len, fk.shift);
-          if (k == 0) kv0[r] = v;
-          else kv1[r] = v;
+          key_too_long |= (len > max_len ? 1u : 0u) << r;
+          const uint8_t* p = chars + o0;
+          const uint64_t* base = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
+          klen[k][r] = len > max_len ? 0u : len;
+          ksh[k][r] = (uint32_t)((uintptr_t)p & 7) * 8;
+          kw0[k][r] = base[0];
+          kw1[k][r] = base[1];
         }
       } else {
         const uint8_t* p = L.stage + fk.off;
+        const uint32_t w = fk.w;
 #pragma unroll
-        FOR_R {
-          const unsigned long long v = (unsigned long long)ld_w(p, fk.w, r * L.B + L.tid);
-          if (k == 0) kv0[r] = v;
-          else kv1[r] = v;
-        }
+        FOR_R kw0[k][r] = (uint64_t)ld_w(p, w, e0 + r * L.B);
       }
     }
   }
@@ -2075,43 +2156,51 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
     uint32_t lt = 0, gt_ = 0;
 #pragma unroll
     FOR_R {
-      const int64_t v = ld_w(p, w, r * L.B + L.tid);
+      const int64_t v = ld_w(p, w, e0 + r * L.B);
       lt |= (v < imm ? 1u : 0u) << r;
       gt_ |= (v > imm ? 1u : 0u) << r;
     }
     active &= cmp_mask(F.f[i].op, lt, gt_);
   }
-  // ---- products (checked decimal arithmetic)
-  i128 p0[VM_R], p1[VM_R];
+  // ---- products (checked decimal arithmetic, in registers)
+  uint64_t p0lo[VM_R], p0hi[VM_R], p1lo[VM_R], p1hi[VM_R];
 #pragma unroll
-  FOR_R p0[r] = p1[r] = 0;
+  FOR_R p0lo[r] = p0hi[r] = p1lo[r] = p1hi[r] = 0;
   uint32_t ovf = 0;
   if (F.n_prod >= 1) {
     const FusedProd& q = F.p[0];
     const uint8_t* pa = L.stage + q.a_off;
     const uint8_t* pb = L.stage + q.b_off;
-    const i128 lit = make_i128(q.lit_lo, q.lit_hi);
+    const uint32_t aw = q.a_w, bw = q.b_w, kind = q.kind;
+    const uint64_t llo = q.lit_lo, lhi = q.lit_hi;
 #pragma unroll
     FOR_R {
-      const i128 a = ld_w128(pa, q.a_w, r * L.B + L.tid);
-      i128 b = ld_w128(pb, q.b_w, r * L.B + L.tid);
-      if (q.kind == 0) ovf |= (sub_i128_checked(lit, b, &b) ? 1u : 0u) << r;
-      else if (q.kind == 1) ovf |= (add_i128_checked(lit, b, &b) ? 1u : 0u) << r;
-      ovf |= (mul_i128_fast(a, b, &p0[r]) ? 1u : 0u) << r;
+      uint64_t alo, ahi, blo, bhi;
+      ld_raw128(pa, aw, e0 + r * L.B, alo, ahi);
+      ld_raw128(pb, bw, e0 + r * L.B, blo, bhi);
+      if (kind != 2) ovf |= addsub128(kind == 0, llo, lhi, blo, bhi) << r;
+      const Prod128 pr = mul128_fast_val(alo, ahi, blo, bhi);
+      p0lo[r] = pr.lo;
+      p0hi[r] = pr.hi;
+      ovf |= pr.ovf << r;
     }
   }
   if (F.n_prod >= 2) {
     const FusedProd& q = F.p[1];
     const uint8_t* pa = L.stage + q.a_off;
     const uint8_t* pb = L.stage + q.b_off;
-    const i128 lit = make_i128(q.lit_lo, q.lit_hi);
+    const uint32_t aw = q.a_w, bw = q.b_w, kind = q.kind, a_src = q.a_src;
+    const uint64_t llo = q.lit_lo, lhi = q.lit_hi;
 #pragma unroll
     FOR_R {
-      const i128 a = q.a_src ? p0[r] : ld_w128(pa, q.a_w, r * L.B + L.tid);
-      i128 b = ld_w128(pb, q.b_w, r * L.B + L.tid);
-      if (q.kind == 0) ovf |= (sub_i128_checked(lit, b, &b) ? 1u : 0u) << r;
-      else if (q.kind == 1) ovf |= (add_i128_checked(lit, b, &b) ? 1u : 0u) << r;
-      ovf |= (mul_i128_fast(a, b, &p1[r]) ? 1u : 0u) << r;
+      uint64_t alo = p0lo[r], ahi = p0hi[r], blo, bhi;
+      if (!a_src) ld_raw128(pa, aw, e0 + r * L.B, alo, ahi);
+      ld_raw128(pb, bw, e0 + r * L.B, blo, bhi);
+      if (kind != 2) ovf |= addsub128(kind == 0, llo, lhi, blo, bhi) << r;
+      const Prod128 pr = mul128_fast_val(alo, ahi, blo, bhi);
+      p1lo[r] = pr.lo;
+      p1hi[r] = pr.hi;
+      ovf |= pr.ovf << r;
     }
   }
   if (ovf & active) raise(1);
@@ -2121,9 +2210,30 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
   FOR_R gid[r] = 0;
   if (G > 1) {
     if (key_too_long & active) atomicExch(&PROG.status->pack_overflow, 1u);
-    unsigned long long ck[VM_R];
+    unsigned long long kv0[VM_R], kv1[VM_R], ck[VM_R];
+    // key images, phase 2: finish the packing now that the chars words have arrived
 #pragma unroll
-    FOR_R ck[r] = F.combine ? ((kv0[r] + (unsigned long long)F.k[0].bias) + (kv1[r] + (unsigned long long)F.k[1].bias) * 4294967296ull) : kv0[r];
+    for (int k = 0; k < 2; k++) {
+      const bool packed = k < F.n_keys && F.k[k].kind == 1;
+      const int shift = F.k[k].shift;
+#pragma unroll
+      FOR_R {
+        unsigned long long v = kw0[k][r];
+        if (packed) {
+          const uint32_t len = klen[k][r], sh = ksh[k][r];
+          unsigned long long w = kw0[k][r] >> sh;
+          if (sh) w |= kw1[k][r] << (64 - sh);
+          w &= (len >= 8) ? ~0ull : ((1ull << (len * 8)) - 1);
+          v = len ? (w | ((unsigned long long)len << shift)) : 0ull;
+        }
+        if (k == 0) kv0[r] = v;
+        else kv1[r] = v;
+      }
+    }
+    const unsigned long long bias0 = (unsigned long long)F.k[0].bias, bias1 = (unsigned long long)F.k[1].bias;
+    const bool combine = F.combine != 0;
+#pragma unroll
+    FOR_R ck[r] = combine ? ((kv0[r] + bias0) + (kv1[r] + bias1) * 4294967296ull) : kv0[r];
 #pragma unroll
     FOR_R {
       if ((active >> r) & 1) {
@@ -2132,16 +2242,7 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
         for (int q = 0; q < G; q++)
           if (q < (int)dir_n && dir[q] == ck[r]) g = q;
         if (g < 0) {
-          KeyVal kv[2];
-          kv[0].w0 = kv0[r];
-          kv[0].w1 = 0;
-          kv[0].valid = 1;
-          kv[0].vk = VK_I64;
-          kv[1].w0 = kv1[r];
-          kv[1].w1 = 0;
-          kv[1].valid = 1;
-          kv[1].vk = VK_I64;
-          g = reg_group_lookup(gt, G, F.n_keys, ck[r], kv);
+          g = fused_resolve_slow(gt, G, F.n_keys, ck[r], kv0[r], kv1[r]);
           uint32_t pub = 0;
 #pragma unroll
           for (int q = 0; q < G; q++) {
@@ -2163,31 +2264,41 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
     }
   }
   // ---- accumulate (exact int64 partials, see sink_agg_reg)
+  const int n_acc = F.n_acc;
 #pragma unroll
   for (int a = 0; a < VM_REG_ACC; a++) {
-    if (a >= F.n_acc) break;
-    const FusedAcc& fa = F.a[a];
-    i128 vi[VM_R];
-    if (fa.src == 3) {
+    if (a >= n_acc) break;
+    const uint32_t src = F.a[a].src;
+    uint64_t vlo[VM_R], vhi[VM_R];
+    if (src == 3) {
 #pragma unroll
-      FOR_R vi[r] = 1;
-    } else if (fa.src == 1) {
+      FOR_R {
+        vlo[r] = 1;
+        vhi[r] = 0;
+      }
+    } else if (src == 1) {
 #pragma unroll
-      FOR_R vi[r] = p0[r];
-    } else if (fa.src == 2) {
+      FOR_R {
+        vlo[r] = p0lo[r];
+        vhi[r] = p0hi[r];
+      }
+    } else if (src == 2) {
 #pragma unroll
-      FOR_R vi[r] = p1[r];
+      FOR_R {
+        vlo[r] = p1lo[r];
+        vhi[r] = p1hi[r];
+      }
     } else {
-      const uint8_t* p = L.stage + fa.off;
+      const uint8_t* p = L.stage + F.a[a].off;
+      const uint32_t w = F.a[a].w;
 #pragma unroll
-      FOR_R vi[r] = ld_w128(p, fa.w, r * L.B + L.tid);
+      FOR_R ld_raw128(p, w, e0 + r * L.B, vlo[r], vhi[r]);
     }
-    int64_t vl[VM_R];
     uint32_t big = 0;
 #pragma unroll
     FOR_R {
-      vl[r] = (int64_t)lo64(vi[r]);
-      const bool small = fits_i64(vi[r]) && vl[r] < (1ll << 46) && vl[r] > -(1ll << 46);
+      // |v| < 2^46  <=>  hi is the sign extension of lo and (lo + 2^46) < 2^47 (unsigned)
+      const bool small = vhi[r] == (uint64_t)((int64_t)vlo[r] >> 63) && (vlo[r] + (1ull << 46)) < (1ull << 47);
       big |= (small ? 0u : 1u) << r;
     }
     big &= active;
@@ -2195,14 +2306,14 @@ __device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, Re
     if (big) {
 #pragma unroll 1
       for (int r = 0; r < VM_R; r++)
-        if ((big >> r) & 1) reg_merge_big(gt, G, (int)gid[r], a, vi[r]);
+        if ((big >> r) & 1) reg_merge_big(gt, G, (int)gid[r], a, make_i128(vlo[r], vhi[r]));
       v &= ~big;
     }
 #pragma unroll
     FOR_R {
+      const uint64_t add = ((v >> r) & 1) ? vlo[r] : 0ull;
 #pragma unroll
-      for (int g = 0; g < G; g++)
-        if (((v >> r) & 1) && (G == 1 || gid[r] == (uint32_t)g)) S.lo[g][a] += (uint64_t)vl[r];
+      for (int g = 0; g < G; g++) S.lo[g][a] += (G == 1 || gid[r] == (uint32_t)g) ? add : 0ull;
     }
   }
   return active;
@@ -2273,15 +2384,16 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     }
   }
   uint32_t phase_bits = 0;
-  for (int64_t k = 0;; k++) {
+  int s = 0;  // k % S, maintained incrementally
+  for (int64_t k = 0;; k++, s = (s + 1 == S) ? 0 : s + 1) {
     const int64_t t = tile_of(k);
     if (t >= n_tiles) break;
-    const int s = (int)(k % S);
     uint8_t* stage = stage0 + (size_t)s * stage_bytes;
     // prefetch tile k+S-1 into the buffer released at the end of iteration k-1
     if (tid == 0) {
       const int64_t kn = k + S - 1, tn = tile_of(kn);
-      if (tn < n_tiles && tile_is_tma(tn)) issue_tile_tma(stage0 + (size_t)(kn % S) * stage_bytes, &full_bar[kn % S], tn * TILE, TILE);
+      const int sn = (s == 0) ? S - 1 : s - 1;  // (k + S - 1) % S
+      if (tn < n_tiles && tile_is_tma(tn)) issue_tile_tma(stage0 + (size_t)sn * stage_bytes, &full_bar[sn], tn * TILE, TILE);
     }
     const int64_t row0 = t * TILE;
     const int rows = (int)((n_rows - row0) < TILE ? (n_rows - row0) : TILE);
