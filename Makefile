@@ -6,7 +6,7 @@ SRC       := $(PKG)/csrc
 OUT       := $(PKG)/lib
 NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-function
 OBJS      := $(OUT)/pipeline.o $(OUT)/kernels.o $(OUT)/engine.o
-COMMON    := $(wildcard $(SRC)/common/*.hpp) $(wildcard $(SRC)/device/*.h) $(wildcard $(SRC)/host/*.hpp) include/b200exec.h include/b200_arrow_abi.h
+COMMON    := $(wildcard $(SRC)/common/*.hpp) $(wildcard $(SRC)/device/*.h) $(wildcard $(SRC)/device/*.cuh) $(wildcard $(SRC)/host/*.hpp) include/b200exec.h include/b200_arrow_abi.h
 
 all: $(OUT)/libb200exec.so oracle
 

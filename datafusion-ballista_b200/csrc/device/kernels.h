@@ -8,7 +8,12 @@
 namespace b200 {
 
 // ---- fused pipeline (pipeline.cu) ---------------------------------------------------------------
-cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st, const FusedSpec* fused = nullptr);
+cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st);
+// fused scan->filter->project->aggregate kernel (fused.cuh); *is_static: 1 when an ahead-of-time shape ran
+cudaError_t launch_fused_pipeline(const Program& P, const FusedSpec& F, FusedShape shape, int reg_groups, int grid, int block, size_t smem, cudaStream_t st,
+                                  int* is_static);
+bool fused_rows_ok(const Program& P, int grid, int block, int rows_per_thread);
+bool pipeline_add_only(const Program& P, int grid, int block);
 
 // ---- aggregate table (kernels.cu) ----------------------------------------------------------------
 struct AccKinds {

@@ -2093,236 +2093,9 @@ __device__ __forceinline__ uint32_t addsub128(bool minus, uint64_t llo, uint64_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused fast path: filters -> decimal products -> key image -> register aggregate, all in registers.
-// Reference operators fused: FilterExec + ProjectionExec + AggregateExec(Partial) of TPC-H q1/q6
-// (benchmarks/queries/q1.sql, q6.sql); selected by the host when the lowered program matches.
-// ------------------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ uint32_t fused_tile(const Lane L, uint32_t active, RegAggState<G>& S, RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n) {
-  const FusedSpec& F = c_fused;
-  const int e0 = L.tid;  // element index of row r is e0 + r * B
-  // ---- key images, phase 1: offsets from the tile, then ALL dependent chars loads issued back to
-  // ---- back (two aligned 8-byte words per string; allocations carry slack) so that their DRAM/L2
-  // ---- latency overlaps with the filters and products below
-  uint32_t klen[2][VM_R], ksh[2][VM_R];
-  uint64_t kw0[2][VM_R], kw1[2][VM_R];
-  uint32_t key_too_long = 0;
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-#pragma unroll
-    FOR_R {
-      klen[k][r] = 0;
-      ksh[k][r] = 0;
-      kw0[k][r] = kw1[k][r] = 0;
-    }
-  }
-  if (G > 1) {
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      if (k >= F.n_keys) break;
-      const FusedKey& fk = F.k[k];
-      if (fk.kind == 1) {
-        const int32_t* off = (const int32_t*)(L.stage + fk.off);
-        const uint8_t* chars = fk.chars;
-        const uint32_t max_len = fk.max_len;
-#pragma unroll
-        FOR_R {
-          const int e = e0 + r * L.B;
-          const int32_t o0 = off[e];
-          const uint32_t len = (uint32_t)(off[e + 1] - o0);
-          key_too_long |= (len > max_len ? 1u : 0u) << r;
-          const uint8_t* p = chars + o0;
-          const uint64_t* base = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
-          klen[k][r] = len > max_len ? 0u : len;
-          ksh[k][r] = (uint32_t)((uintptr_t)p & 7) * 8;
-          kw0[k][r] = base[0];
-          kw1[k][r] = base[1];
-        }
-      } else {
-        const uint8_t* p = L.stage + fk.off;
-        const uint32_t w = fk.w;
-#pragma unroll
-        FOR_R kw0[k][r] = (uint64_t)ld_w(p, w, e0 + r * L.B);
-      }
-    }
-  }
-  // ---- filters
-#pragma unroll
-  for (int i = 0; i < FUSED_MAX_FILTERS; i++) {
-    if (i >= F.n_filters) break;
-    const uint8_t* p = L.stage + F.f[i].off;
-    const uint32_t w = F.f[i].w;
-    const int64_t imm = F.f[i].imm;
-    uint32_t lt = 0, gt_ = 0;
-#pragma unroll
-    FOR_R {
-      const int64_t v = ld_w(p, w, e0 + r * L.B);
-      lt |= (v < imm ? 1u : 0u) << r;
-      gt_ |= (v > imm ? 1u : 0u) << r;
-    }
-    active &= cmp_mask(F.f[i].op, lt, gt_);
-  }
-  // ---- products (checked decimal arithmetic, in registers)
-  uint64_t p0lo[VM_R], p0hi[VM_R], p1lo[VM_R], p1hi[VM_R];
-#pragma unroll
-  FOR_R p0lo[r] = p0hi[r] = p1lo[r] = p1hi[r] = 0;
-  uint32_t ovf = 0;
-  if (F.n_prod >= 1) {
-    const FusedProd& q = F.p[0];
-    const uint8_t* pa = L.stage + q.a_off;
-    const uint8_t* pb = L.stage + q.b_off;
-    const uint32_t aw = q.a_w, bw = q.b_w, kind = q.kind;
-    const uint64_t llo = q.lit_lo, lhi = q.lit_hi;
-#pragma unroll
-    FOR_R {
-      uint64_t alo, ahi, blo, bhi;
-      ld_raw128(pa, aw, e0 + r * L.B, alo, ahi);
-      ld_raw128(pb, bw, e0 + r * L.B, blo, bhi);
-      if (kind != 2) ovf |= addsub128(kind == 0, llo, lhi, blo, bhi) << r;
-      const Prod128 pr = mul128_fast_val(alo, ahi, blo, bhi);
-      p0lo[r] = pr.lo;
-      p0hi[r] = pr.hi;
-      ovf |= pr.ovf << r;
-    }
-  }
-  if (F.n_prod >= 2) {
-    const FusedProd& q = F.p[1];
-    const uint8_t* pa = L.stage + q.a_off;
-    const uint8_t* pb = L.stage + q.b_off;
-    const uint32_t aw = q.a_w, bw = q.b_w, kind = q.kind, a_src = q.a_src;
-    const uint64_t llo = q.lit_lo, lhi = q.lit_hi;
-#pragma unroll
-    FOR_R {
-      uint64_t alo = p0lo[r], ahi = p0hi[r], blo, bhi;
-      if (!a_src) ld_raw128(pa, aw, e0 + r * L.B, alo, ahi);
-      ld_raw128(pb, bw, e0 + r * L.B, blo, bhi);
-      if (kind != 2) ovf |= addsub128(kind == 0, llo, lhi, blo, bhi) << r;
-      const Prod128 pr = mul128_fast_val(alo, ahi, blo, bhi);
-      p1lo[r] = pr.lo;
-      p1hi[r] = pr.hi;
-      ovf |= pr.ovf << r;
-    }
-  }
-  if (ovf & active) raise(1);
-  // ---- group resolution
-  uint32_t gid[VM_R];
-#pragma unroll
-  FOR_R gid[r] = 0;
-  if (G > 1) {
-    if (key_too_long & active) atomicExch(&PROG.status->pack_overflow, 1u);
-    unsigned long long kv0[VM_R], kv1[VM_R], ck[VM_R];
-    // key images, phase 2: finish the packing now that the chars words have arrived
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const bool packed = k < F.n_keys && F.k[k].kind == 1;
-      const int shift = F.k[k].shift;
-#pragma unroll
-      FOR_R {
-        unsigned long long v = kw0[k][r];
-        if (packed) {
-          const uint32_t len = klen[k][r], sh = ksh[k][r];
-          unsigned long long w = kw0[k][r] >> sh;
-          if (sh) w |= kw1[k][r] << (64 - sh);
-          w &= (len >= 8) ? ~0ull : ((1ull << (len * 8)) - 1);
-          v = len ? (w | ((unsigned long long)len << shift)) : 0ull;
-        }
-        if (k == 0) kv0[r] = v;
-        else kv1[r] = v;
-      }
-    }
-    const unsigned long long bias0 = (unsigned long long)F.k[0].bias, bias1 = (unsigned long long)F.k[1].bias;
-    const bool combine = F.combine != 0;
-#pragma unroll
-    FOR_R ck[r] = combine ? ((kv0[r] + bias0) + (kv1[r] + bias1) * 4294967296ull) : kv0[r];
-#pragma unroll
-    FOR_R {
-      if ((active >> r) & 1) {
-        int g = -1;
-#pragma unroll
-        for (int q = 0; q < G; q++)
-          if (q < (int)dir_n && dir[q] == ck[r]) g = q;
-        if (g < 0) {
-          g = fused_resolve_slow(gt, G, F.n_keys, ck[r], kv0[r], kv1[r]);
-          uint32_t pub = 0;
-#pragma unroll
-          for (int q = 0; q < G; q++) {
-            const bool ok = (q == (int)pub) && (*(volatile unsigned int*)&gt->state[q] == 2u);
-            if (ok) {
-              dir[q] = *(volatile unsigned long long*)&gt->hash[q];
-              pub++;
-            }
-          }
-          dir_n = pub;
-        }
-        if (g < 0) {
-          atomicExch(&PROG.status->overflow, 1u);
-          active &= ~(1u << r);
-        } else {
-          gid[r] = (uint32_t)g;
-        }
-      }
-    }
-  }
-  // ---- accumulate (exact int64 partials, see sink_agg_reg)
-  const int n_acc = F.n_acc;
-#pragma unroll
-  for (int a = 0; a < VM_REG_ACC; a++) {
-    if (a >= n_acc) break;
-    const uint32_t src = F.a[a].src;
-    uint64_t vlo[VM_R], vhi[VM_R];
-    if (src == 3) {
-#pragma unroll
-      FOR_R {
-        vlo[r] = 1;
-        vhi[r] = 0;
-      }
-    } else if (src == 1) {
-#pragma unroll
-      FOR_R {
-        vlo[r] = p0lo[r];
-        vhi[r] = p0hi[r];
-      }
-    } else if (src == 2) {
-#pragma unroll
-      FOR_R {
-        vlo[r] = p1lo[r];
-        vhi[r] = p1hi[r];
-      }
-    } else {
-      const uint8_t* p = L.stage + F.a[a].off;
-      const uint32_t w = F.a[a].w;
-#pragma unroll
-      FOR_R ld_raw128(p, w, e0 + r * L.B, vlo[r], vhi[r]);
-    }
-    uint32_t big = 0;
-#pragma unroll
-    FOR_R {
-      // |v| < 2^46  <=>  hi is the sign extension of lo and (lo + 2^46) < 2^47 (unsigned)
-      const bool small = vhi[r] == (uint64_t)((int64_t)vlo[r] >> 63) && (vlo[r] + (1ull << 46)) < (1ull << 47);
-      big |= (small ? 0u : 1u) << r;
-    }
-    big &= active;
-    uint32_t v = active;
-    if (big) {
-#pragma unroll 1
-      for (int r = 0; r < VM_R; r++)
-        if ((big >> r) & 1) reg_merge_big(gt, G, (int)gid[r], a, make_i128(vlo[r], vhi[r]));
-      v &= ~big;
-    }
-#pragma unroll
-    FOR_R {
-      const uint64_t add = ((v >> r) & 1) ? vlo[r] : 0ull;
-#pragma unroll
-      for (int g = 0; g < G; g++) S.lo[g][a] += (G == 1 || gid[r] == (uint32_t)g) ? add : 0ull;
-    }
-  }
-  return active;
-}
-
-// ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int SINK, int G, bool ADD_ONLY, bool FUSED>
+template <int SINK, int G, bool ADD_ONLY>
 __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[VM_MAX_STAGES];
@@ -2347,8 +2120,8 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     mbar_fence_init();
   }
   const int n_instr = PROG.n_instr;
-  if (!FUSED && tid < n_instr) decode_micro(tid, &mops[tid]);
-  if (!FUSED && SINK == SINK_AGG_REG && tid >= 64 && tid < 64 + PROG.n_acc) decode_acc(tid - 64, &accops[tid - 64]);
+  if (tid < n_instr) decode_micro(tid, &mops[tid]);
+  if (SINK == SINK_AGG_REG && tid >= 64 && tid < 64 + PROG.n_acc) decode_acc(tid - 64, &accops[tid - 64]);
   if (SINK == SINK_AGG_REG && tid < VM_REG_GROUPS) {
     gtable.state[tid] = 0;
     gtable.hash[tid] = 0;
@@ -2411,14 +2184,10 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     uint32_t active = 0;
 #pragma unroll
     FOR_R if (r * B + tid < rows) active |= 1u << r;
-    if (FUSED) {
-      active = fused_tile<G>(L, active, S_reg, &gtable, dir, dir_n);
-      live_rows += __popc(active);
-    } else {
+    {
       active = run_program(L, active, mops, n_instr);
     }
-    if (FUSED) {
-    } else if (SINK == SINK_MATERIALIZE) {
+    if (SINK == SINK_MATERIALIZE) {
       sink_materialize(L, active, warp_tot, &tile_base_sh);
     } else if (SINK == SINK_AGG_GLOBAL) {
       active = sink_agg_global(L, active);
@@ -2458,14 +2227,18 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
   }
 }
 
+}  // namespace b200
+#include "fused.cuh"
+namespace b200 {
+
 // ------------------------------------------------------------------------------------------------
 // Host launcher
 // ------------------------------------------------------------------------------------------------
-template <int SINK, int G, bool ADD_ONLY, bool FUSED>
+template <int SINK, int G, bool ADD_ONLY>
 static cudaError_t launch_one(int grid, int block, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(pipeline_kernel<SINK, G, ADD_ONLY, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(pipeline_kernel<SINK, G, ADD_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  pipeline_kernel<SINK, G, ADD_ONLY, FUSED><<<grid, block, smem, st>>>();
+  pipeline_kernel<SINK, G, ADD_ONLY><<<grid, block, smem, st>>>();
   return cudaGetLastError();
 }
 
@@ -2478,26 +2251,33 @@ bool pipeline_add_only(const Program& P, int grid, int block) {
   return add_only;
 }
 
-cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st, const FusedSpec* fused) {
+cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st) {
   // stream-ordered upload of the program into constant memory (the previous kernel on `st` is done
   // before this copy executes)
   cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(Program), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   const bool add_only = pipeline_add_only(P, grid, block);
-  if (fused && P.sink == SINK_AGG_REG && add_only) {
-    e = cudaMemcpyToSymbolAsync(c_fused, fused, sizeof(FusedSpec), 0, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    if (reg_groups <= 1) return launch_one<SINK_AGG_REG, 1, true, true>(grid, block, smem, st);
-    return launch_one<SINK_AGG_REG, VM_REG_GROUPS, true, true>(grid, block, smem, st);
-  }
   switch (P.sink) {
-    case SINK_MATERIALIZE: return launch_one<SINK_MATERIALIZE, 1, true, false>(grid, block, smem, st);
-    case SINK_AGG_GLOBAL: return launch_one<SINK_AGG_GLOBAL, 1, true, false>(grid, block, smem, st);
+    case SINK_MATERIALIZE: return launch_one<SINK_MATERIALIZE, 1, true>(grid, block, smem, st);
+    case SINK_AGG_GLOBAL: return launch_one<SINK_AGG_GLOBAL, 1, true>(grid, block, smem, st);
     default:
-      if (reg_groups <= 1) return add_only ? launch_one<SINK_AGG_REG, 1, true, false>(grid, block, smem, st) : launch_one<SINK_AGG_REG, 1, false, false>(grid, block, smem, st);
-      return add_only ? launch_one<SINK_AGG_REG, VM_REG_GROUPS, true, false>(grid, block, smem, st)
-                      : launch_one<SINK_AGG_REG, VM_REG_GROUPS, false, false>(grid, block, smem, st);
+      if (reg_groups <= 1) return add_only ? launch_one<SINK_AGG_REG, 1, true>(grid, block, smem, st) : launch_one<SINK_AGG_REG, 1, false>(grid, block, smem, st);
+      return add_only ? launch_one<SINK_AGG_REG, VM_REG_GROUPS, true>(grid, block, smem, st) : launch_one<SINK_AGG_REG, VM_REG_GROUPS, false>(grid, block, smem, st);
   }
+}
+
+// exactness bound of the fused kernel's int64 partials: |addend| < 2^46 and < 60000 rows per thread
+bool fused_rows_ok(const Program& P, int grid, int block, int rows_per_thread) {
+  return (P.n_rows / ((int64_t)grid * block) + 2 * rows_per_thread) < 60000;
+}
+
+cudaError_t launch_fused_pipeline(const Program& P, const FusedSpec& F, FusedShape shape, int reg_groups, int grid, int block, size_t smem, cudaStream_t st,
+                                  int* is_static) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(Program), 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbolAsync(c_fused, &F, sizeof(FusedSpec), 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return e;
+  return launch_fused(F, shape, reg_groups, grid, block, smem, st, is_static);
 }
 
 }  // namespace b200

@@ -189,8 +189,22 @@ struct Program {
 
 // ---- fused fast path (scan -> filter -> decimal products -> <=4-group SUM/COUNT aggregate) -----------
 // A pattern-matched specialisation of the lowered program for the TPC-H q1/q6 shape (SURVEY.md 7.1
-// step 3): every value lives in registers, nothing round-trips through the VM register file.
+// step 3): FilterExec + ProjectionExec + AggregateExec(Partial) run in one kernel whose every value
+// lives in registers.  Each WARP owns a private ring of TMA-filled stage buffers (no CTA barrier on
+// the data path).  The kernel is compiled once per "shape" (widths, compare ops, product kinds,
+// accumulator sources -- see FusedShape) for the shapes listed in pipeline.cu, plus one variant that
+// reads the same description from constant memory at run time for everything else.
 static const int FUSED_MAX_FILTERS = 6;
+static const int FUSED_MAX_COLS = 12;
+static const int FUSED_MAX_STAGES = 8;
+static const int FUSED_MAX_WARPS = 16;
+struct FusedCol {
+  const void* data;     // column values (Utf8: the int32 offsets)
+  uint32_t width;       // bytes per row
+  uint32_t off;         // offset inside a warp's stage buffer (16-byte aligned)
+  uint32_t tile_bytes;  // bytes one warp tile copies (Utf8: one extra offset, padded to 16)
+  uint32_t utf8;
+};
 struct FusedFilter {
   uint32_t off;   // tile column offset inside the stage buffer
   uint8_t w;      // element width 4 / 8 / 16 (low word)
@@ -221,11 +235,57 @@ struct FusedAcc {
 struct FusedSpec {
   int32_t n_filters, n_prod, n_keys, n_acc;
   int32_t combine;  // 1: key image = k0 + k1 * 2^32
-  int32_t _pad;
+  int32_t n_cols;
+  int32_t rows_per_thread;  // R: a warp tile is 32 * R rows
+  int32_t n_stages;         // per-warp ring depth
+  uint32_t stage_bytes;     // one warp stage
+  uint32_t tile_tx;         // bytes one tile's bulk copies deliver
+  uint32_t use_tma;
+  uint32_t _pad;
+  FusedCol cols[FUSED_MAX_COLS];
   FusedFilter f[FUSED_MAX_FILTERS];
   FusedProd p[2];
   FusedKey k[2];
   FusedAcc a[VM_REG_ACC];
 };
+
+// Compile-time image of everything in a FusedSpec that changes the generated code (not offsets,
+// pointers or literals).  (0, 0) means "not static: read the spec at run time".
+struct FusedShape {
+  uint64_t a, b;
+};
+#if defined(__CUDACC__)
+#define B200_CX __host__ __device__
+#else
+#define B200_CX
+#endif
+B200_CX constexpr uint64_t fused_wcode(uint32_t w) { return w == 16 ? 2u : (w == 8 ? 1u : 0u); }
+B200_CX constexpr uint32_t fused_wbytes(uint64_t c) { return c == 2 ? 16u : (c == 1 ? 8u : 4u); }
+// layout of FusedShape::a : [0..2] n_filters | 6 x {w:2, op:3} from bit 3 | [33..34] n_keys | 2 x {kind:1, w:2} from
+// bit 35 | [41] combine | [42..43] n_prod | 2 x {kind:2, a_src:1, a_w:2, b_w:2} from bit 44 | [63] static marker
+// layout of FusedShape::b : [0..2] n_acc | 6 x {src:2, w:2} from bit 3
+struct FusedShapeDesc {
+  int nf;
+  uint8_t fw[FUSED_MAX_FILTERS], fop[FUSED_MAX_FILTERS];  // fop: 0 EQ 1 NE 2 LT 3 LE 4 GT 5 GE
+  int nk;
+  uint8_t kkind[2], kw[2];
+  int combine;
+  int np;
+  uint8_t pkind[2], pasrc[2], paw[2], pbw[2];
+  int na;
+  uint8_t asrc[VM_REG_ACC], aw[VM_REG_ACC];
+};
+B200_CX constexpr FusedShape fused_shape_encode(const FusedShapeDesc& d) {
+  uint64_t a = (uint64_t)d.nf | (1ull << 63), b = (uint64_t)d.na;
+  for (int i = 0; i < d.nf; i++) a |= (fused_wcode(d.fw[i]) | ((uint64_t)d.fop[i] << 2)) << (3 + 5 * i);
+  a |= (uint64_t)d.nk << 33;
+  for (int k = 0; k < d.nk; k++) a |= ((uint64_t)d.kkind[k] | ((d.kkind[k] ? 0ull : fused_wcode(d.kw[k])) << 1)) << (35 + 3 * k);
+  a |= (uint64_t)(d.combine ? 1 : 0) << 41;
+  a |= (uint64_t)d.np << 42;
+  for (int j = 0; j < d.np; j++)
+    a |= ((uint64_t)d.pkind[j] | ((uint64_t)d.pasrc[j] << 2) | ((d.pasrc[j] ? 0ull : fused_wcode(d.paw[j])) << 3) | (fused_wcode(d.pbw[j]) << 5)) << (44 + 7 * j);
+  for (int i = 0; i < d.na; i++) b |= ((uint64_t)d.asrc[i] | ((d.asrc[i] == 0 ? fused_wcode(d.aw[i]) : 0ull) << 2)) << (3 + 4 * i);
+  return FusedShape{a, b};
+}
 
 }  // namespace b200

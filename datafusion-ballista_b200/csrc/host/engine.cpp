@@ -325,14 +325,31 @@ struct RunOutcome {
   float ms = 0;
 };
 
-RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedSpec* fused = nullptr) {
+// the fused kernel's description of a program it can run instead of the tile VM (match_fused)
+struct FusedPlan {
+  FusedSpec spec;
+  FusedShape shape;
+  int block = 0;
+  size_t smem = 0;
+};
+
+RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedPlan* fused = nullptr) {
   Program& P = pb.prog;
   DevPtr dstat = dev_alloc(sizeof(RunStatus), x.st());
   CUDA_CHECK(cudaMemsetAsync(dstat->ptr, 0, sizeof(RunStatus), x.st()));
   P.status = (RunStatus*)dstat->ptr;
-  const int tile = pb.block * VM_R;
-  int64_t n_tiles = (P.n_rows + tile - 1) / tile;
-  int grid = (int)std::min<int64_t>(std::max<int64_t>(n_tiles, 1), x.e->sm_count);
+  int grid;
+  if (fused) {
+    const int64_t warp_tile = 32 * fused->spec.rows_per_thread, nw = fused->block / 32;
+    const int64_t n_wt = (P.n_rows + warp_tile - 1) / warp_tile;
+    grid = (int)std::min<int64_t>(std::max<int64_t>((n_wt + nw - 1) / nw, 1), x.e->sm_count);
+    if (!fused_rows_ok(P, grid, fused->block, fused->spec.rows_per_thread)) fused = nullptr;
+  }
+  if (!fused) {
+    const int tile = pb.block * VM_R;
+    int64_t n_tiles = (P.n_rows + tile - 1) / tile;
+    grid = (int)std::min<int64_t>(std::max<int64_t>(n_tiles, 1), x.e->sm_count);
+  }
   static const bool debug = getenv("B200_DEBUG") != nullptr;
   if (debug)
     fprintf(stderr, "[b200] pipeline sink=%d rows=%lld cols=%d instr=%d regs=%d block=%d stages=%u stage_bytes=%u regs_bytes=%u tma=%u grid=%d\n", (int)P.sink,
@@ -349,8 +366,24 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, x.st()));
-  if (debug && fused) fprintf(stderr, "[b200]   fused fast path: %d filters, %d products, %d keys, %d accumulators\n", fused->n_filters, fused->n_prod, fused->n_keys, fused->n_acc);
-  cudaError_t le = launch_pipeline(P, reg_groups, grid, pb.block, pb.smem_bytes(), x.st(), fused);
+  cudaError_t le;
+  if (fused) {
+    int is_static = 0;
+    le = launch_fused_pipeline(P, fused->spec, fused->shape, reg_groups, grid, fused->block, fused->smem, x.st(), &is_static);
+    if (debug) {
+      const FusedSpec& F = fused->spec;
+      fprintf(stderr, "[b200]   fused kernel: static=%d shape=(%#llx,%#llx) block=%d R=%d stages=%d stage_bytes=%u smem=%zu grid=%d tma=%u\n", is_static,
+              (unsigned long long)fused->shape.a, (unsigned long long)fused->shape.b, fused->block, F.rows_per_thread, F.n_stages, F.stage_bytes, fused->smem, grid,
+              F.use_tma);
+      for (int i = 0; i < F.n_filters; i++) fprintf(stderr, "[b200]     filter %d: w=%d op=%d\n", i, F.f[i].w, F.f[i].op - OP_CMP_EQ);
+      for (int k = 0; k < F.n_keys; k++) fprintf(stderr, "[b200]     key %d: kind=%d w=%d max_len=%d shift=%d\n", k, F.k[k].kind, F.k[k].w, F.k[k].max_len, F.k[k].shift);
+      for (int j = 0; j < F.n_prod; j++) fprintf(stderr, "[b200]     prod %d: kind=%d a_src=%d a_w=%d b_w=%d\n", j, F.p[j].kind, F.p[j].a_src, F.p[j].a_w, F.p[j].b_w);
+      for (int a = 0; a < F.n_acc; a++) fprintf(stderr, "[b200]     acc %d: src=%d w=%d\n", a, F.a[a].src, F.a[a].w);
+      fprintf(stderr, "[b200]     combine=%d\n", F.combine);
+    }
+  } else {
+    le = launch_pipeline(P, reg_groups, grid, pb.block, pb.smem_bytes(), x.st());
+  }
   if (le != cudaSuccess) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -655,10 +688,68 @@ void lower_aggregate(PipelineBuilder& pb, const PlanNode& node, AggLowered& L, i
 // (filters on integer-like tile columns -> up to two decimal products -> <= 2 packed/integer keys ->
 // SUM/COUNT accumulators).  Anything outside the pattern keeps the general VM path.
 // ------------------------------------------------------------------------------------------------
-bool match_fused(const Program& P, FusedSpec& F) {
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// Recognise the scan -> filter -> decimal products -> small SUM/COUNT aggregate shape in a lowered
+// program and lay out the per-warp stage buffers of the fused kernel (fused.cuh).
+bool match_fused(const Program& P, FusedPlan& FP) {
+  FusedSpec& F = FP.spec;
   memset(&F, 0, sizeof F);
   if (P.sink != SINK_AGG_REG) return false;
   if (getenv("B200_NO_FUSED")) return false;
+  for (int a = 0; a < P.n_acc; a++)
+    if (!(P.acc[a].kind == ACC_SUM_I128 || P.acc[a].kind == ACC_COUNT || P.acc[a].kind == ACC_COUNT_STAR)) return false;
+  // stage layout: every column of the program, one warp tile of 32*R rows each
+  // measured on B200 (profiles/r01_summary.md): grouped shapes are issue-bound and want 16 warps,
+  // scalar shapes are bandwidth-bound and want more rows in flight per thread
+  const int R = env_int("B200_FUSED_R", P.n_keys ? 2 : 4);
+  if (!(R == 2 || R == 4)) return false;
+  int block = env_int("B200_FUSED_B", R == 4 ? 384 : 512);
+  if (block > (R == 4 ? 384 : 512) || block < 32 || (block & 31)) return false;
+  const uint32_t TR = 32u * (uint32_t)R;
+  if (P.n_cols > FUSED_MAX_COLS || P.n_cols == 0) return false;
+  uint32_t fused_off[VM_MAX_COLS];
+  uint32_t cur = 0, tx = 0;
+  bool aligned = true;
+  for (int c = 0; c < P.n_cols; c++) {
+    const ColDesc& cd = P.cols[c];
+    if (cd.valid) return false;
+    FusedCol& fc = F.cols[c];
+    fc.data = cd.data;
+    fc.width = cd.width;
+    fc.utf8 = cd.phys == PH_UTF8 ? 1u : 0u;
+    fc.tile_bytes = TR * cd.width + (fc.utf8 ? 16u : 0u);
+    if (fc.tile_bytes & 15u) return false;
+    fc.off = cur;
+    fused_off[c] = cur;
+    cur += fc.tile_bytes;
+    tx += fc.tile_bytes;
+    if (((uintptr_t)cd.data & 15) != 0) aligned = false;
+  }
+  F.n_cols = P.n_cols;
+  F.rows_per_thread = R;
+  F.stage_bytes = (cur + 127u) & ~127u;
+  F.tile_tx = tx;
+  F.use_tma = (aligned && !getenv("B200_NO_TMA")) ? 1u : 0u;
+  {
+    const size_t budget = 216 * 1024;
+    int S = 0;
+    for (;; block -= 32) {
+      if (block < 64) return false;
+      S = (int)(budget / ((size_t)(block / 32) * F.stage_bytes));
+      if (S >= 2) break;
+    }
+    S = std::min(S, env_int("B200_FUSED_S", FUSED_MAX_STAGES));
+    S = std::min(S, (int)FUSED_MAX_STAGES);
+    if (S < 2) return false;
+    F.n_stages = S;
+    FP.block = block;
+    // the end-of-kernel reduction stages [VM_REG_ACC][block] 16-byte partials in the idle rings
+    FP.smem = std::max((size_t)(block / 32) * S * F.stage_bytes, (size_t)VM_REG_ACC * block * 16);
+  }
   auto int_col = [&](const Operand& o, uint32_t* off, uint8_t* w, bool want_i128) -> bool {
     if (o.kind != OPD_COL) return false;
     const ColDesc& cd = P.cols[o.idx];
@@ -668,7 +759,7 @@ bool match_fused(const Program& P, FusedSpec& F) {
     if (o.vk != VK_I128 && cd.phys == PH_DEC128) {
       // narrow view of a decimal: low word only
     }
-    *off = cd.smem_off;
+    *off = fused_off[o.idx];
     *w = (o.vk == VK_I128) ? 16 : cd.width;
     return true;
   };
@@ -725,7 +816,7 @@ bool match_fused(const Program& P, FusedSpec& F) {
         pi.reg = v.dst.idx;
         memset(&pi.k, 0, sizeof pi.k);
         pi.k.kind = 1;
-        pi.k.off = P.cols[v.a.idx].smem_off;
+        pi.k.off = fused_off[v.a.idx];
         pi.k.chars = P.cols[v.a.idx].chars;
         pi.k.max_len = v.aux;
         pi.k.shift = (uint8_t)v.imm;
@@ -810,6 +901,33 @@ bool match_fused(const Program& P, FusedSpec& F) {
     for (int k = 0; k < P.n_keys; k++) used |= P.keys[k].kind == OPD_REG && (int)P.keys[k].idx == pi.reg;
     if (!used) return false;
   }
+  // the code-shaping part of the spec (program.h FusedShape)
+  FusedShapeDesc d;
+  memset(&d, 0, sizeof d);
+  d.nf = F.n_filters;
+  for (int i = 0; i < F.n_filters; i++) {
+    d.fw[i] = F.f[i].w;
+    d.fop[i] = (uint8_t)(F.f[i].op - OP_CMP_EQ);
+  }
+  d.nk = F.n_keys;
+  for (int k = 0; k < F.n_keys; k++) {
+    d.kkind[k] = F.k[k].kind;
+    d.kw[k] = F.k[k].w;
+  }
+  d.combine = F.combine;
+  d.np = F.n_prod;
+  for (int j = 0; j < F.n_prod; j++) {
+    d.pkind[j] = F.p[j].kind;
+    d.pasrc[j] = F.p[j].a_src;
+    d.paw[j] = F.p[j].a_w;
+    d.pbw[j] = F.p[j].b_w;
+  }
+  d.na = F.n_acc;
+  for (int a = 0; a < F.n_acc; a++) {
+    d.asrc[a] = F.a[a].src;
+    d.aw[a] = F.a[a].w;
+  }
+  FP.shape = fused_shape_encode(d);
   return true;
 }
 
@@ -923,7 +1041,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       tm.keep.push_back(hi);
       P.acc_hi = (unsigned long long*)hi->ptr;
     }
-    FusedSpec fspec;
+    FusedPlan fspec;
     const bool use_fused = level == 0 && match_fused(P, fspec);
     ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr);
     if (met) {
