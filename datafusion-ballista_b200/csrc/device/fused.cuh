@@ -11,7 +11,7 @@
 //     mbarriers.  There is no CTA-wide barrier on the data path: a warp only ever waits for its
 //     own bytes.
 //   * all arithmetic is in registers; aggregate partials are exact int64 per (group, accumulator)
-//     per thread (|addend| < 2^46 checked per tile, rare large addends go straight to the global
+//     per thread (|addend| < 2^40 checked per row, rare large addends go straight to the global
 //     table), reduced over the CTA and merged into the global table once at the end.
 //   * the code is compiled per FusedShape (program.h): widths, compare operators, product kinds and
 //     accumulator sources are template constants for the listed shapes; shape (0,0) reads them from
@@ -40,13 +40,14 @@ struct FusedX {
   static __device__ __forceinline__ uint32_t aw(int i) { return ST ? fused_wbytes((SB >> (5 + 4 * i)) & 3) : (uint32_t)c_fused.a[i].w; }
 };
 
-// one tile's bulk copies (issued by lane 0 of the owning warp)
-__device__ __noinline__ void fused_issue(uint8_t* stage, uint64_t* bar, int64_t row0) {
+// one tile's bulk copies: lane c issues column c (the whole warp takes part so that the address
+// arithmetic is not a single-lane detour of ~25 instructions per column)
+__device__ __forceinline__ void fused_issue(uint8_t* stage, uint64_t* bar, int64_t row0, int lane) {
   const FusedSpec& F = c_fused;
-  mbar_expect_tx(bar, F.tile_tx);
-  const int n = F.n_cols;
-  for (int c = 0; c < n; c++) {
-    const FusedCol& fc = F.cols[c];
+  if (lane == 0) mbar_expect_tx(bar, F.tile_tx);
+  __syncwarp();
+  if (lane < F.n_cols) {
+    const FusedCol& fc = F.cols[lane];
     bulk_g2s(stage + fc.off, (const uint8_t*)fc.data + row0 * fc.width, fc.tile_bytes, bar);
   }
 }
@@ -87,21 +88,104 @@ __device__ __forceinline__ bool fused_cmp(int fop, int64_t v, int64_t imm) {
   }
 }
 
-// |v| < 2^46 test, accumulated: returns bits that are non-zero iff (lo, hi) is NOT a small value
+// |v| < 2^40 test: returns bits that are non-zero iff (lo, hi) is NOT a small value.  A thread adds
+// at most 2^22 small addends into an int64 partial (fused_rows_ok), so the partials are exact.
 __device__ __forceinline__ uint64_t fused_range_bits(uint64_t lo, uint64_t hi) {
   const uint64_t s = (uint64_t)((int64_t)hi >> 63);
-  return (hi ^ s) | ((lo ^ s) >> 46);
+  return (hi ^ s) | ((lo ^ s) >> 40);
 }
 
-template <int G, int R, class X>
-__device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage, const int lane, uint32_t active, RegAggState<G>& S, RegGroupTable* gt,
-                                               unsigned long long (&dir)[G], uint32_t& dir_n) {
+// ------------------------------------------------------------------------------------------------
+// One row, every exceptional case, out of line and shape-agnostic (reads the spec at run time):
+// operands wider than 64 bits, literal +- operand overflow, keys longer than the packed image,
+// a group this thread has not cached yet, addends >= 2^40.  Returns 1 when the row takes part in
+// the aggregate; then *gid_out is its group and out_add[] its int64 addends (0 for addends that
+// were merged straight into the global table).
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t fused_row_slow(const uint8_t* stage, int e, int G, RegGroupTable* gt, uint64_t* out_add, uint32_t* gid_out) {
   const FusedSpec& F = c_fused;
+  for (int i = 0; i < F.n_filters; i++) {
+    const int64_t v = ld_w(stage + F.f[i].off, F.f[i].w, e);
+    if (!fused_cmp((int)F.f[i].op - (int)OP_CMP_EQ, v, F.f[i].imm)) return 0;
+  }
+  i128 prod[2] = {0, 0};
+  for (int j = 0; j < F.n_prod; j++) {
+    const FusedProd& q = F.p[j];
+    i128 a = (j == 1 && q.a_src) ? prod[0] : ld_w128(stage + q.a_off, q.a_w, e);
+    i128 b = ld_w128(stage + q.b_off, q.b_w, e);
+    const i128 lit = make_i128(q.lit_lo, q.lit_hi);
+    bool ovf = false;
+    if (q.kind == 0) ovf = sub_i128_checked(lit, b, &b);
+    else if (q.kind == 1) ovf = add_i128_checked(lit, b, &b);
+    i128 out = 0;
+    ovf |= mul_i128_slow(a, b, &out);
+    if (ovf) raise(1);
+    prod[j] = out;
+  }
+  uint32_t g = 0;
+  if (G > 1) {
+    unsigned long long kv[2] = {0, 0};
+    for (int k = 0; k < F.n_keys; k++) {
+      const FusedKey& fk = F.k[k];
+      if (fk.kind == 1) {
+        const int32_t* off = (const int32_t*)(stage + fk.off);
+        const int32_t o0 = off[e];
+        uint32_t len = (uint32_t)(off[e + 1] - o0);
+        if (len > fk.max_len) {
+          atomicExch(&PROG.status->pack_overflow, 1u);  // the host re-runs with a wider key image
+          len = 0;
+        }
+        unsigned long long v = 0;
+        for (uint32_t c = 0; c < len; c++) v |= (unsigned long long)fk.chars[o0 + c] << (8 * c);
+        kv[k] = len ? (v | ((unsigned long long)len << fk.shift)) : 0ull;
+      } else {
+        kv[k] = (unsigned long long)ld_w(stage + fk.off, fk.w, e);
+      }
+    }
+    const unsigned long long ck = F.combine ? ((kv[0] + (unsigned long long)F.k[0].bias) + (kv[1] + (unsigned long long)F.k[1].bias) * 4294967296ull) : kv[0];
+    const int gg = fused_resolve_slow(gt, G, F.n_keys, ck, kv[0], kv[1]);
+    if (gg < 0) {
+      atomicExch(&PROG.status->overflow, 1u);
+      return 0;
+    }
+    g = (uint32_t)gg;
+  }
+  *gid_out = g;
+  for (int a = 0; a < F.n_acc; a++) {
+    const FusedAcc& fa = F.a[a];
+    i128 v = fa.src == 3 ? (i128)1 : fa.src == 1 ? prod[0] : fa.src == 2 ? prod[1] : ld_w128(stage + fa.off, fa.w, e);
+    if (fused_range_bits(lo64(v), hi64(v))) {
+      reg_merge_big(gt, G, (int)g, a, v);
+      v = 0;
+    }
+    out_add[a] = lo64(v);
+  }
+  return 1;
+}
+
+// 64x64 -> 128 signed product without branches (operands already known to fit 64 bits)
+__device__ __forceinline__ void fused_mul64(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
+  lo = a * b;
+  hi = __umul64hi(a, b) - (((int64_t)a < 0) ? b : 0ull) - (((int64_t)b < 0) ? a : 0ull);
+}
+__device__ __forceinline__ uint32_t fused_wide(uint64_t lo, uint64_t hi) {  // non-zero iff (lo, hi) does not fit int64
+  const uint64_t d = hi ^ (uint64_t)((int64_t)lo >> 63);
+  return (uint32_t)d | (uint32_t)(d >> 32);
+}
+
+// Hot path: straight-line code for the tile's R rows per thread.  Anything unusual about a row only
+// sets its bit in `slow`; those rows are redone by fused_row_slow afterwards.
+template <int G, int R, class X>
+__device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage, const int lane, uint32_t active, RegAggState<G>& S, uint64_t* accs, const int B,
+                                               RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n) {
+  const FusedSpec& F = c_fused;
+  uint32_t slow = 0;
   // ---- key images, phase 1: offsets from the tile, then the dependent chars loads issued back to
-  // ---- back (aligned 8-byte words; allocations carry slack) so their latency overlaps the rest
+  // ---- back (aligned words; allocations carry slack) so their latency overlaps the rest.
+  // Packed keys come in two widths: kw == 4: len<<24 | <=3 bytes (32-bit arithmetic, funnel shift),
+  // kw == 8: len<<shift | <=7 bytes.
   uint32_t klen[2][R], ksh[2][R];
   uint64_t kw0[2][R], kw1[2][R];
-  uint32_t key_too_long = 0;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
 #pragma unroll
@@ -120,20 +204,26 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
         const int32_t* off = (const int32_t*)(stage + fk.off);
         const uint8_t* chars = fk.chars;
         const uint32_t max_len = fk.max_len;
+        const bool short4 = X::kw(k) == 4;
 #pragma unroll
         for (int r = 0; r < R; r++) {
           const int e = lane + 32 * r;
           const int32_t o0 = off[e];
           const uint32_t len = (uint32_t)(off[e + 1] - o0);
-          key_too_long |= (len > max_len ? 1u : 0u) << r;
+          slow |= (len > max_len ? 1u : 0u) << r;
           const uint8_t* p = chars + o0;
-          const uint64_t* base = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
-          const uint32_t l = len > max_len ? 0u : len;
-          const uint32_t sh = (uint32_t)((uintptr_t)p & 7) * 8;
-          klen[k][r] = l;
-          ksh[k][r] = sh;
-          kw0[k][r] = l ? base[0] : 0ull;
-          kw1[k][r] = (sh + l * 8 > 64) ? base[1] : 0ull;
+          klen[k][r] = len;
+          if (short4) {
+            const uint32_t* base = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+            ksh[k][r] = (uint32_t)((uintptr_t)p & 3) * 8;
+            kw0[k][r] = base[0];
+            kw1[k][r] = base[1];
+          } else {
+            const uint64_t* base = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
+            ksh[k][r] = (uint32_t)((uintptr_t)p & 7) * 8;
+            kw0[k][r] = base[0];
+            kw1[k][r] = base[1];
+          }
         }
       } else {
         const uint8_t* p = stage + fk.off;
@@ -156,11 +246,10 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
     for (int r = 0; r < R; r++) pass |= (fused_cmp(fop, ld_w(p, w, lane + 32 * r), imm) ? 1u : 0u) << r;
     active &= pass;
   }
-  // ---- products (checked decimal arithmetic, in registers)
+  // ---- products: operands that fit 64 bits multiply inline; wider ones mark the row slow
   uint64_t p0lo[R], p0hi[R], p1lo[R], p1hi[R];
 #pragma unroll
   for (int r = 0; r < R; r++) p0lo[r] = p0hi[r] = p1lo[r] = p1hi[r] = 0;
-  uint32_t ovf = 0;
   if (X::np() >= 1) {
     const FusedProd& q = F.p[0];
     const uint8_t* pa = stage + q.a_off;
@@ -173,11 +262,12 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
       uint64_t alo, ahi, blo, bhi;
       ld_raw128(pa, aw, lane + 32 * r, alo, ahi);
       ld_raw128(pb, bw, lane + 32 * r, blo, bhi);
-      if (kind != 2) ovf |= addsub128(kind == 0, llo, lhi, blo, bhi) << r;
-      const Prod128 pr = mul128_fast_val(alo, ahi, blo, bhi);
-      p0lo[r] = pr.lo;
-      p0hi[r] = pr.hi;
-      ovf |= pr.ovf << r;
+      uint32_t odd = 0;
+      if (kind != 2) odd = addsub128(kind == 0, llo, lhi, blo, bhi);
+      if (aw == 16) odd |= fused_wide(alo, ahi);
+      if (bw == 16 || kind != 2) odd |= fused_wide(blo, bhi);
+      slow |= (odd ? 1u : 0u) << r;
+      fused_mul64(alo, blo, p0lo[r], p0hi[r]);
     }
   }
   if (X::np() >= 2) {
@@ -192,35 +282,40 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
       uint64_t alo = p0lo[r], ahi = p0hi[r], blo, bhi;
       if (!a_src) ld_raw128(pa, aw, lane + 32 * r, alo, ahi);
       ld_raw128(pb, bw, lane + 32 * r, blo, bhi);
-      if (kind != 2) ovf |= addsub128(kind == 0, llo, lhi, blo, bhi) << r;
-      const Prod128 pr = mul128_fast_val(alo, ahi, blo, bhi);
-      p1lo[r] = pr.lo;
-      p1hi[r] = pr.hi;
-      ovf |= pr.ovf << r;
+      uint32_t odd = 0;
+      if (kind != 2) odd = addsub128(kind == 0, llo, lhi, blo, bhi);
+      if (a_src || aw == 16) odd |= fused_wide(alo, ahi);
+      if (bw == 16 || kind != 2) odd |= fused_wide(blo, bhi);
+      slow |= (odd ? 1u : 0u) << r;
+      fused_mul64(alo, blo, p1lo[r], p1hi[r]);
     }
   }
-  if (ovf & active) raise(1);
-  // ---- group resolution: one-hot membership oh[r][g] (0/1) against the register-cached directory
-  uint32_t oh[R][G];
-  if (G == 1) {
+  // ---- group resolution against the register-cached directory.  (The always-true test on dir_n
+  // ---- keeps ptxas from hoisting the consumers of the chars loads above the products: their
+  // ---- latency is meant to hide behind that arithmetic.)
+  uint32_t gid[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) oh[r][0] = (active >> r) & 1;
-  } else {
-    if (key_too_long & active) atomicExch(&PROG.status->pack_overflow, 1u);
-    unsigned long long kv0[R], kv1[R], ck[R];
+  for (int r = 0; r < R; r++) gid[r] = 0;
+  if (G > 1 && dir_n <= (uint32_t)G) {
     // key images, phase 2: finish the packing now that the chars words have arrived
+    unsigned long long kv0[R], kv1[R];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       const bool packed = k < X::nk() && X::kkind(k) == 1;
+      const bool short4 = packed && X::kw(k) == 4;
       const int shift = F.k[k].shift;
 #pragma unroll
       for (int r = 0; r < R; r++) {
         unsigned long long v = kw0[k][r];
-        if (packed) {
+        if (short4) {
+          const uint32_t len = klen[k][r];
+          const uint32_t x = __funnelshift_r((uint32_t)kw0[k][r], (uint32_t)kw1[k][r], ksh[k][r]);
+          v = (unsigned long long)((x & ((1u << ((len * 8) & 31)) - 1u)) | (len << 24));
+        } else if (packed) {
           const uint32_t len = klen[k][r], sh = ksh[k][r];
           unsigned long long w = kw0[k][r] >> sh;
           if (sh) w |= kw1[k][r] << ((64 - sh) & 63);
-          w &= (len >= 8) ? ~0ull : ((1ull << (len * 8)) - 1);
+          w &= (1ull << ((len * 8) & 63)) - 1;
           v = len ? (w | ((unsigned long long)len << shift)) : 0ull;
         }
         if (k == 0) kv0[r] = v;
@@ -230,95 +325,104 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
     const unsigned long long bias0 = (unsigned long long)F.k[0].bias, bias1 = (unsigned long long)F.k[1].bias;
     const bool combine = X::combine();
 #pragma unroll
-    for (int r = 0; r < R; r++) ck[r] = combine ? ((kv0[r] + bias0) + (kv1[r] + bias1) * 4294967296ull) : kv0[r];
-#pragma unroll
     for (int r = 0; r < R; r++) {
-      const bool on = (active >> r) & 1;
-      uint32_t hit = 0;
+      const unsigned long long ck = combine ? ((kv0[r] + bias0) + (kv1[r] + bias1) * 4294967296ull) : kv0[r];
+      uint32_t g = 0, hit = 0;
 #pragma unroll
       for (int q = 0; q < G; q++) {
-        const uint32_t m = (on && q < (int)dir_n && dir[q] == ck[r]) ? 1u : 0u;
-        oh[r][q] = m;
-        hit |= m;
+        const bool m = q < (int)dir_n && dir[q] == ck;
+        g = m ? (uint32_t)q : g;
+        hit |= m ? 1u : 0u;
       }
-      if (on && !hit) {  // rare: a key this thread has not seen yet
-        const int g = fused_resolve_slow(gt, G, X::nk(), ck[r], kv0[r], kv1[r]);
-        uint32_t pub = 0;
-#pragma unroll
-        for (int q = 0; q < G; q++) {
-          const bool ok = (q == (int)pub) && (*(volatile unsigned int*)&gt->state[q] == 2u);
-          if (ok) {
-            dir[q] = *(volatile unsigned long long*)&gt->hash[q];
-            pub++;
-          }
-        }
-        dir_n = pub;
-        if (g < 0) {
-          atomicExch(&PROG.status->overflow, 1u);
-          active &= ~(1u << r);
-        } else {
-#pragma unroll
-          for (int q = 0; q < G; q++) oh[r][q] = (q == g) ? 1u : 0u;
-        }
-      }
+      gid[r] = g;
+      slow |= (hit ^ 1u) << r;
     }
   }
-  // ---- accumulate (exact int64 partials)
+  // ---- addends (exact int64 partials); anything >= 2^40 in magnitude marks the row slow
+  uint64_t add[VM_REG_ACC][R];
 #pragma unroll
   for (int a = 0; a < VM_REG_ACC; a++) {
-    if (a >= X::na()) break;
+#pragma unroll
+    for (int r = 0; r < R; r++) add[a][r] = 0;
+    if (a >= X::na()) continue;
     const int src = X::asrc(a);
     if (src == 3) {  // COUNT
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-#pragma unroll
-        for (int g = 0; g < G; g++) S.lo[g][a] += (uint64_t)oh[r][g];
-      }
+      for (int r = 0; r < R; r++) add[a][r] = 1;
       continue;
     }
-    uint64_t vlo[R], vhi[R];
+    uint64_t vhi[R];
     const uint32_t w = (src == 0) ? X::aw(a) : 16u;
     if (src == 1) {
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        vlo[r] = p0lo[r];
+        add[a][r] = p0lo[r];
         vhi[r] = p0hi[r];
       }
     } else if (src == 2) {
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        vlo[r] = p1lo[r];
+        add[a][r] = p1lo[r];
         vhi[r] = p1hi[r];
       }
     } else {
       const uint8_t* p = stage + F.a[a].off;
 #pragma unroll
-      for (int r = 0; r < R; r++) ld_raw128(p, w, lane + 32 * r, vlo[r], vhi[r]);
+      for (int r = 0; r < R; r++) ld_raw128(p, w, lane + 32 * r, add[a][r], vhi[r]);
     }
-    uint64_t big = 0;
     if (w != 4) {
 #pragma unroll
-      for (int r = 0; r < R; r++) big |= fused_range_bits(vlo[r], vhi[r]);
+      for (int r = 0; r < R; r++) slow |= (fused_range_bits(add[a][r], vhi[r]) ? 1u : 0u) << r;
     }
-    if (big) {  // rare: some addend of this thread is >= 2^46 in magnitude -> straight to the global table
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        uint32_t any = 0, gsel = 0;
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          any |= oh[r][g];
-          if (oh[r][g]) gsel = (uint32_t)g;
-        }
-        if (any && fused_range_bits(vlo[r], vhi[r])) {
-          reg_merge_big(gt, G, (int)gsel, a, make_i128(vlo[r], vhi[r]));
-          vlo[r] = 0;
-        }
-      }
-    }
+  }
+  // ---- the unusual rows (none in steady state), one at a time
+  slow &= active;
+  if (slow) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
+      if ((slow >> r) & 1) {
+        uint64_t out[VM_REG_ACC];
+        uint32_t g = 0;
+        const uint32_t on = fused_row_slow(stage, lane + 32 * r, G, gt, out, &g);
+        if (!on) active &= ~(1u << r);
+        gid[r] = g;
 #pragma unroll
-      for (int g = 0; g < G; g++) S.lo[g][a] += vlo[r] * (uint64_t)oh[r][g];
+        for (int a = 0; a < VM_REG_ACC; a++) add[a][r] = out[a];
+      }
+    }
+    if (G > 1) {  // pick up the groups published so far
+      uint32_t pub = 0;
+#pragma unroll
+      for (int q = 0; q < G; q++) {
+        const bool ok = (q == (int)pub) && (*(volatile unsigned int*)&gt->state[q] == 2u);
+        if (ok) {
+          dir[q] = *(volatile unsigned long long*)&gt->hash[q];
+          pub++;
+        }
+      }
+      dir_n = pub;
+    }
+  }
+  if (G == 1) {
+    // scalar aggregate: the partials live in registers
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint64_t m = ((active >> r) & 1) ? ~0ull : 0ull;
+#pragma unroll
+      for (int a = 0; a < VM_REG_ACC; a++)
+        if (a < X::na()) S.lo[0][a] += add[a][r] & m;
+    }
+  } else {
+    // grouped aggregate: per-thread partials in shared memory, [group][acc][thread] (conflict-free),
+    // indexed by the row's group -- no G-fold work and no accumulator registers
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if ((active >> r) & 1) {
+        uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
+#pragma unroll
+        for (int a = 0; a < VM_REG_ACC; a++)
+          if (a < X::na()) pa[a * B] += add[a][r];
+      }
     }
   }
   return active;
@@ -329,21 +433,25 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
   typedef FusedX<SA, SB> X;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[FUSED_MAX_WARPS * FUSED_MAX_STAGES];
+  __shared__ uint32_t stage_tile[FUSED_MAX_WARPS * FUSED_MAX_STAGES];  // tile held by each (warp, stage)
+  __shared__ unsigned int next_claim;                                   // CTA-wide tile dispenser
   __shared__ RegGroupTable gtable;
   const FusedSpec& F = c_fused;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = blockDim.x, NW = B >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = blockDim.x;
   constexpr int TR = 32 * R;
   const int64_t n_rows = PROG.n_rows;
-  const int64_t n_tiles = (n_rows + TR - 1) / TR;
+  const uint32_t n_tiles = (uint32_t)((n_rows + TR - 1) / TR);      // host guarantees < 2^31
+  const uint32_t n_full = F.use_tma ? (uint32_t)(n_rows / TR) : 0u;  // tiles below n_full arrive by TMA
   const int S = F.n_stages;
   const uint32_t stage_bytes = F.stage_bytes;
-  const bool use_tma = F.use_tma != 0;
   uint8_t* ring = smem + (size_t)warp * S * stage_bytes;
   uint64_t* bar = bars + warp * FUSED_MAX_STAGES;
+  uint32_t* my_tile = stage_tile + warp * FUSED_MAX_STAGES;
   if (lane == 0) {
     for (int s = 0; s < S; s++) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
+  if (tid == 0) next_claim = 0;
   if (tid < VM_REG_GROUPS) {
     gtable.state[tid] = 0;
     gtable.hash[tid] = 0;
@@ -357,36 +465,49 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
 #pragma unroll
     for (int a = 0; a < VM_REG_ACC; a++) S_reg.lo[g][a] = 0;
   }
+  // grouped shapes keep the per-thread partials in shared memory behind the rings
+  uint64_t* accs = (uint64_t*)(smem + F.acc_off) + tid;
+  if (G > 1) {
+    for (int i = 0; i < G * VM_REG_ACC; i++) accs[i * B] = 0;
+  }
   unsigned long long dir[G];
   uint32_t dir_n = 0;
 #pragma unroll
   for (int q = 0; q < G; q++) dir[q] = 0xFFFFFFFFFFFFFFFFull;
   uint32_t live_rows = 0;
 
-  // warp tiles are dealt round-robin over all warps of the grid: adjacent warps read adjacent rows
-  const int64_t gw = (int64_t)blockIdx.x * NW + warp, stride = (int64_t)gridDim.x * NW;
-  auto tile_is_tma = [&](int64_t t) { return use_tma && (t + 1) * (int64_t)TR <= n_rows; };
-  if (lane == 0) {
-    for (int k = 0; k < S - 1; k++) {
-      const int64_t t = gw + k * stride;
-      if (t < n_tiles && tile_is_tma(t)) fused_issue(ring + (size_t)k * stage_bytes, &bar[k], t * TR);
-    }
-  }
+  // Warp tiles are claimed dynamically from a CTA-wide counter (warps of one CTA do not run at the
+  // same speed; a static deal leaves the fast ones idle at the end): the c-th claim of CTA b is
+  // tile c * gridDim.x + b, so the grid sweeps the table front to back.
+  auto claim_into = [&](int st) {
+    unsigned int c = 0;
+    if (lane == 0) c = atomicAdd(&next_claim, 1u);
+    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+    const unsigned long long t64 = (unsigned long long)c * gridDim.x + blockIdx.x;
+    const uint32_t t = t64 < n_tiles ? (uint32_t)t64 : 0xFFFFFFFFu;
+    if (lane == 0) my_tile[st] = t;
+    if (t < n_full) fused_issue(ring + (size_t)st * stage_bytes, &bar[st], (int64_t)t * TR, lane);
+  };
+  for (int k = 0; k < S - 1; k++) claim_into(k);
   uint32_t phase_bits = 0;
   int s = 0;
-  for (int64_t t = gw; t < n_tiles; t += stride, s = (s + 1 == S) ? 0 : s + 1) {
+  uint32_t it = 0;
+  for (;; s = (s + 1 == S) ? 0 : s + 1, it++) {
     uint8_t* stage = ring + (size_t)s * stage_bytes;
+    // every lane is done with the buffer consumed in the previous iteration: refill it
+    __syncwarp();
+    claim_into((s == 0) ? S - 1 : s - 1);
+    __syncwarp();
+    const uint32_t t = my_tile[s];
+    if (t == 0xFFFFFFFFu) break;  // claims are monotonic: nothing of this warp is in flight any more
+    // the sink-overflow flag (another CTA met a 5th group, ...) is polled every 8th tile; all lanes
+    // read the same word, the value is consumed at the end of the tile
     unsigned int stop = 0;
-    if (lane == 0) {
-      // refill the buffer this warp released at the end of the previous iteration
-      const int64_t tn = t + (int64_t)(S - 1) * stride;
-      const int sn = (s == 0) ? S - 1 : s - 1;
-      if (tn < n_tiles && tile_is_tma(tn)) fused_issue(ring + (size_t)sn * stage_bytes, &bar[sn], tn * TR);
-      stop = *(volatile unsigned int*)&PROG.status->overflow;  // sampled early, consumed at the end of the tile
-    }
-    const int64_t row0 = t * TR;
+    const bool poll = (it & 7u) == 7u;
+    if (poll) stop = *(volatile unsigned int*)&PROG.status->overflow;
+    const int64_t row0 = (int64_t)t * TR;
     const int rows = (int)((n_rows - row0) < TR ? (n_rows - row0) : TR);
-    if (tile_is_tma(t)) {
+    if (t < n_full) {
       mbar_wait(&bar[s], (phase_bits >> s) & 1);
       phase_bits ^= 1u << s;
     } else {
@@ -397,23 +518,30 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
 #pragma unroll
     for (int r = 0; r < R; r++)
       if (lane + 32 * r < rows) active |= 1u << r;
-    active = fused_rows<G, R, X>(stage, lane, active, S_reg, &gtable, dir, dir_n);
+    active = fused_rows<G, R, X>(stage, lane, active, S_reg, accs, B, &gtable, dir, dir_n);
     live_rows += __popc(active);
-    // warp-uniform exit test; also the point after which lane 0 may overwrite this stage
-    if (__any_sync(0xFFFFFFFFu, stop != 0)) {
+    if (poll && stop) {
+      __syncwarp();
+      int sj = s;
       for (int j = 1; j < S; j++) {  // drain bulk copies still in flight before the CTA may exit
-        const int64_t tt = t + j * stride;
-        const int sj = (s + j) % S;
-        if (tt < n_tiles && tile_is_tma(tt)) mbar_wait(&bar[sj], (phase_bits >> sj) & 1);
+        sj = (sj + 1 == S) ? 0 : sj + 1;
+        if (my_tile[sj] < n_full) mbar_wait(&bar[sj], (phase_bits >> sj) & 1);
       }
       break;
     }
   }
   live_rows = __reduce_add_sync(0xFFFFFFFFu, live_rows);
   if (lane == 0 && live_rows) atomicAdd(&PROG.status->in_active, (unsigned long long)live_rows);
+  if (G > 1) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#pragma unroll
+      for (int a = 0; a < VM_REG_ACC; a++) S_reg.lo[g][a] = accs[(g * VM_REG_ACC + a) * B];
+    }
+  }
   __syncthreads();
   // scalar aggregates emit their single group even when no CTA saw a row: CTA 0 always flushes
-  const bool has_rows = (int64_t)blockIdx.x * NW < n_tiles;
+  const bool has_rows = blockIdx.x < n_tiles;
   if (has_rows || (G == 1 && blockIdx.x == 0)) reg_agg_flush<G, true>(S_reg, nullptr, &gtable, (Acc128*)smem, tid, B);
 }
 
@@ -429,7 +557,7 @@ static cudaError_t launch_fused_one(int grid, int block, size_t smem, cudaStream
 // ---- shapes compiled ahead of time -----------------------------------------------------------------
 // TPC-H q1 (benchmarks/queries/q1.sql): 1 date filter, 2 packed single-character keys,
 // disc_price = price*(1-disc), charge = disc_price*(1+tax); count + 4 decimal sums + sum(disc)
-constexpr FusedShapeDesc kShapeQ1 = {1, {4}, {3 /*LE*/}, 2, {1, 1}, {0, 0}, 1, 2, {0, 1}, {0, 1}, {16, 0}, {16, 16}, 6,
+constexpr FusedShapeDesc kShapeQ1 = {1, {4}, {3 /*LE*/}, 2, {1, 1}, {4, 4}, 1, 2, {0, 1}, {0, 1}, {16, 0}, {16, 16}, 6,
                                      {3, 0, 0, 1, 2, 0}, {0, 16, 16, 0, 0, 16}};
 // TPC-H q6 (benchmarks/queries/q6.sql): date range, discount BETWEEN, quantity <; count + sum(price*disc)
 constexpr FusedShapeDesc kShapeQ6 = {5, {4, 4, 16, 16, 16}, {5 /*GE*/, 2 /*LT*/, 5, 3 /*LE*/, 2}, 0, {0, 0}, {0, 0}, 0, 1, {2, 0}, {0, 0}, {16, 0}, {16, 0}, 2,
@@ -443,6 +571,7 @@ static cudaError_t launch_fused_variant(int R, int grid, int block, size_t smem,
   if (R == 2) {
     if (block <= 256) return launch_fused_one<G, 2, 256, SA, SB>(grid, block, smem, st);
     if (block <= 384) return launch_fused_one<G, 2, 384, SA, SB>(grid, block, smem, st);
+    if (block <= 416) return launch_fused_one<G, 2, 416, SA, SB>(grid, block, smem, st);
     return launch_fused_one<G, 2, 512, SA, SB>(grid, block, smem, st);
   }
   if (R == 4) {

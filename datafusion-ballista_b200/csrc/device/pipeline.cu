@@ -1976,10 +1976,12 @@ __device__ __noinline__ Acc128 acc_combine(int kind, Acc128 x, Acc128 y) {
 __device__ __noinline__ void reg_flush_group(RegGroupTable* gt, Acc128* scratch, int g, int G, int tid, int B) {
   const int n_acc = PROG.n_acc, n_keys = PROG.n_keys;
   __syncthreads();
-  for (int stride = B >> 1; stride > 0; stride >>= 1) {
+  for (int n = B; n > 1;) {  // B need not be a power of two
+    const int half = (n + 1) >> 1;
     for (int a = 0; a < n_acc; a++)
-      if (tid < stride) scratch[a * B + tid] = acc_combine(PROG.acc[a].kind, scratch[a * B + tid], scratch[a * B + tid + stride]);
+      if (tid < n - half) scratch[a * B + tid] = acc_combine(PROG.acc[a].kind, scratch[a * B + tid], scratch[a * B + tid + half]);
     __syncthreads();
+    n = half;
   }
   if (tid == 0) {
     KeyVal kv[VM_MAX_KEYS];
@@ -2266,9 +2268,11 @@ cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int bloc
   }
 }
 
-// exactness bound of the fused kernel's int64 partials: |addend| < 2^46 and < 60000 rows per thread
+// exactness bound of the fused kernel's int64 partials: |addend| < 2^40 and (tiles are claimed
+// dynamically, so in the worst case one warp handles every tile of its CTA) < 2^22 rows per thread
 bool fused_rows_ok(const Program& P, int grid, int block, int rows_per_thread) {
-  return (P.n_rows / ((int64_t)grid * block) + 2 * rows_per_thread) < 60000;
+  (void)block;
+  return (P.n_rows / ((int64_t)grid * 32) + 2 * rows_per_thread) < (1ll << 22) && P.n_rows < (1ll << 36);
 }
 
 cudaError_t launch_fused_pipeline(const Program& P, const FusedSpec& F, FusedShape shape, int reg_groups, int grid, int block, size_t smem, cudaStream_t st,

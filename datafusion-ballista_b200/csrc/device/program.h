@@ -222,7 +222,8 @@ struct FusedProd {
 struct FusedKey {
   uint32_t off;
   uint8_t kind;    // 0: integer column, 1: short Utf8 packed as len<<shift | bytes
-  uint8_t w, max_len, shift;
+  uint8_t w;       // integer column: element width; packed: 4 = 32-bit image (shift 24, <= 3 bytes), 8 = 64-bit image
+  uint8_t max_len, shift;
   const uint8_t* chars;
   int64_t bias;    // added to integer keys (non-negative 32-bit image)
 };
@@ -241,7 +242,7 @@ struct FusedSpec {
   uint32_t stage_bytes;     // one warp stage
   uint32_t tile_tx;         // bytes one tile's bulk copies deliver
   uint32_t use_tma;
-  uint32_t _pad;
+  uint32_t acc_off;         // grouped shapes: byte offset of the [group][acc][thread] int64 partials
   FusedCol cols[FUSED_MAX_COLS];
   FusedFilter f[FUSED_MAX_FILTERS];
   FusedProd p[2];
@@ -279,7 +280,7 @@ B200_CX constexpr FusedShape fused_shape_encode(const FusedShapeDesc& d) {
   uint64_t a = (uint64_t)d.nf | (1ull << 63), b = (uint64_t)d.na;
   for (int i = 0; i < d.nf; i++) a |= (fused_wcode(d.fw[i]) | ((uint64_t)d.fop[i] << 2)) << (3 + 5 * i);
   a |= (uint64_t)d.nk << 33;
-  for (int k = 0; k < d.nk; k++) a |= ((uint64_t)d.kkind[k] | ((d.kkind[k] ? 0ull : fused_wcode(d.kw[k])) << 1)) << (35 + 3 * k);
+  for (int k = 0; k < d.nk; k++) a |= ((uint64_t)d.kkind[k] | (fused_wcode(d.kw[k]) << 1)) << (35 + 3 * k);
   a |= (uint64_t)(d.combine ? 1 : 0) << 41;
   a |= (uint64_t)d.np << 42;
   for (int j = 0; j < d.np; j++)

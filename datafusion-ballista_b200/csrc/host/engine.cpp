@@ -735,20 +735,27 @@ bool match_fused(const Program& P, FusedPlan& FP) {
   F.tile_tx = tx;
   F.use_tma = (aligned && !getenv("B200_NO_TMA")) ? 1u : 0u;
   {
+    // shared memory: per-warp rings, then (grouped shapes) 8 bytes per (group, accumulator, thread)
     const size_t budget = 216 * 1024;
+    const size_t acc_per_thread = P.n_keys ? (size_t)VM_REG_GROUPS * VM_REG_ACC * 8 : 0;
+    const int want_S = std::min(env_int("B200_FUSED_S", FUSED_MAX_STAGES), (int)FUSED_MAX_STAGES);
     int S = 0;
     for (;; block -= 32) {
       if (block < 64) return false;
-      S = (int)(budget / ((size_t)(block / 32) * F.stage_bytes));
+      const size_t acc = acc_per_thread * block;
+      if (acc >= budget) continue;
+      S = (int)((budget - acc) / ((size_t)(block / 32) * F.stage_bytes));
       if (S >= 2) break;
     }
-    S = std::min(S, env_int("B200_FUSED_S", FUSED_MAX_STAGES));
-    S = std::min(S, (int)FUSED_MAX_STAGES);
+    S = std::min(S, want_S);
     if (S < 2) return false;
     F.n_stages = S;
     FP.block = block;
     // the end-of-kernel reduction stages [VM_REG_ACC][block] 16-byte partials in the idle rings
-    FP.smem = std::max((size_t)(block / 32) * S * F.stage_bytes, (size_t)VM_REG_ACC * block * 16);
+    size_t ring = std::max((size_t)(block / 32) * S * F.stage_bytes, (size_t)VM_REG_ACC * block * 16);
+    ring = (ring + 127) & ~(size_t)127;
+    F.acc_off = (uint32_t)ring;
+    FP.smem = ring + acc_per_thread * block;
   }
   auto int_col = [&](const Operand& o, uint32_t* off, uint8_t* w, bool want_i128) -> bool {
     if (o.kind != OPD_COL) return false;
@@ -820,6 +827,7 @@ bool match_fused(const Program& P, FusedPlan& FP) {
         pi.k.chars = P.cols[v.a.idx].chars;
         pi.k.max_len = v.aux;
         pi.k.shift = (uint8_t)v.imm;
+        pi.k.w = (pi.k.shift == 24 && pi.k.max_len <= 3) ? 4 : 8;
         packs.push_back(pi);
         break;
       }
