@@ -18,6 +18,10 @@
 //     constant memory so that any matching program still runs.
 #pragma once
 
+#ifndef FUSED_PRELOAD
+#define FUSED_PRELOAD 1  // load the group partials before the tile's arithmetic (see fused_try_narrow)
+#endif
+
 namespace b200 {
 
 template <uint64_t SA, uint64_t SB>
@@ -40,39 +44,37 @@ struct FusedX {
   static __device__ __forceinline__ uint32_t aw(int i) { return ST ? fused_wbytes((SB >> (5 + 4 * i)) & 3) : (uint32_t)c_fused.a[i].w; }
 };
 
-// one tile's bulk copies: lane c issues column c (the whole warp takes part so that the address
-// arithmetic is not a single-lane detour of ~25 instructions per column)
-__device__ __forceinline__ void fused_issue(uint8_t* stage, uint64_t* bar, int64_t row0, int lane) {
+// One batch of bulk copies: the fixed-width columns of tile `row0` and -- software pipelining of the
+// string keys -- the Utf8 offset slices of the warp's NEXT tile `row0n` (< 0: none).  Lane c issues
+// column c (the whole warp takes part so that the address arithmetic is not a single-lane detour).
+__device__ __forceinline__ void fused_issue(uint8_t* stage, uint64_t* bar, int64_t row0, int64_t row0n, int lane) {
   const FusedSpec& F = c_fused;
-  if (lane == 0) mbar_expect_tx(bar, F.tile_tx);
+  if (lane == 0) mbar_expect_tx(bar, F.tile_tx + (row0n >= 0 ? F.tile_tx_utf8 : 0u));
   __syncwarp();
   if (lane < F.n_cols) {
     const FusedCol& fc = F.cols[lane];
-    bulk_g2s(stage + fc.off, (const uint8_t*)fc.data + row0 * fc.width, fc.tile_bytes, bar);
+    const int64_t r0 = fc.utf8 ? row0n : row0;
+    if (r0 >= 0) bulk_g2s(stage + fc.off, (const uint8_t*)fc.data + r0 * fc.width, fc.tile_bytes, bar);
   }
 }
 
-// ragged last tile / unaligned slices: the warp loads its tile itself, zero (or empty-string) fill
+// ragged last tile / unaligned slices: the warp loads the fixed-width columns of its tile itself,
+// zero fill past the end (string offsets are then read from global memory by fused_key_loads)
 __device__ __noinline__ void fused_load_coop(uint8_t* stage, int64_t row0, int rows, int tile_rows, int lane) {
   const FusedSpec& F = c_fused;
   const int n = F.n_cols;
   for (int c = 0; c < n; c++) {
     const FusedCol& fc = F.cols[c];
+    if (fc.utf8) continue;
     uint8_t* dst = stage + fc.off;
-    if (fc.utf8) {
-      const int32_t* src = (const int32_t*)fc.data + row0;
-      int32_t* d = (int32_t*)dst;
-      for (int k = lane; k <= tile_rows; k += 32) d[k] = src[k <= rows ? k : rows];
+    const uint8_t* src = (const uint8_t*)fc.data + row0 * fc.width;
+    const uint32_t nb = (uint32_t)rows * fc.width, tb = (uint32_t)tile_rows * fc.width;
+    if ((fc.width & 3) == 0 && (((uintptr_t)src) & 3) == 0) {
+      const uint32_t* s4 = (const uint32_t*)src;
+      uint32_t* d4 = (uint32_t*)dst;
+      for (uint32_t k = lane; k < tb / 4; k += 32) d4[k] = (k * 4 < nb) ? s4[k] : 0u;
     } else {
-      const uint8_t* src = (const uint8_t*)fc.data + row0 * fc.width;
-      const uint32_t nb = (uint32_t)rows * fc.width, tb = (uint32_t)tile_rows * fc.width;
-      if ((fc.width & 3) == 0 && (((uintptr_t)src) & 3) == 0) {
-        const uint32_t* s4 = (const uint32_t*)src;
-        uint32_t* d4 = (uint32_t*)dst;
-        for (uint32_t k = lane; k < tb / 4; k += 32) d4[k] = (k * 4 < nb) ? s4[k] : 0u;
-      } else {
-        for (uint32_t k = lane; k < tb; k += 32) dst[k] = (k < nb) ? src[k] : 0;
-      }
+      for (uint32_t k = lane; k < tb; k += 32) dst[k] = (k < nb) ? src[k] : 0;
     }
   }
 }
@@ -102,7 +104,7 @@ __device__ __forceinline__ uint64_t fused_range_bits(uint64_t lo, uint64_t hi) {
 // the aggregate; then *gid_out is its group and out_add[] its int64 addends (0 for addends that
 // were merged straight into the global table).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t fused_row_slow(const uint8_t* stage, int e, int G, RegGroupTable* gt, uint64_t* out_add, uint32_t* gid_out) {
+__device__ __noinline__ uint32_t fused_row_slow(const uint8_t* stage, int e, int64_t row0, int G, RegGroupTable* gt, uint64_t* out_add, uint32_t* gid_out) {
   const FusedSpec& F = c_fused;
   for (int i = 0; i < F.n_filters; i++) {
     const int64_t v = ld_w(stage + F.f[i].off, F.f[i].w, e);
@@ -128,7 +130,7 @@ __device__ __noinline__ uint32_t fused_row_slow(const uint8_t* stage, int e, int
     for (int k = 0; k < F.n_keys; k++) {
       const FusedKey& fk = F.k[k];
       if (fk.kind == 1) {
-        const int32_t* off = (const int32_t*)(stage + fk.off);
+        const int32_t* off = fk.offsets + row0;  // the stage holds the NEXT tile's offsets
         const int32_t o0 = off[e];
         uint32_t len = (uint32_t)(off[e + 1] - o0);
         if (len > fk.max_len) {
@@ -173,19 +175,16 @@ __device__ __forceinline__ uint32_t fused_wide(uint64_t lo, uint64_t hi) {  // n
   return (uint32_t)d | (uint32_t)(d >> 32);
 }
 
-// Hot path: straight-line code for the tile's R rows per thread.  Anything unusual about a row only
-// sets its bit in `slow`; those rows are redone by fused_row_slow afterwards.
-template <int G, int R, class X>
-__device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage, const int lane, uint32_t active, RegAggState<G>& S, uint64_t* accs, const int B,
-                                               RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n) {
+// ---- string keys, software-pipelined one tile ahead -------------------------------------------------
+// fused_key_loads (start of the iteration that processes the PREVIOUS tile): offsets of the rows,
+// then the dependent chars loads (aligned words; allocations carry slack).  fused_key_finish (end of
+// that iteration, a whole tile's arithmetic later): the packed images.  Two widths: kw == 4:
+// len<<24 | <=3 bytes (32-bit arithmetic, funnel shift), kw == 8: len<<shift | <=7 bytes.
+template <int R, class X>
+__device__ __forceinline__ void fused_key_loads(const uint8_t* stage /* null: offsets from global */, int64_t row0, int lim, int lane, uint32_t (&klen)[2][R],
+                                                uint32_t (&ksh)[2][R], uint64_t (&kw0)[2][R], uint64_t (&kw1)[2][R], uint32_t& kslow) {
   const FusedSpec& F = c_fused;
-  uint32_t slow = 0;
-  // ---- key images, phase 1: offsets from the tile, then the dependent chars loads issued back to
-  // ---- back (aligned words; allocations carry slack) so their latency overlaps the rest.
-  // Packed keys come in two widths: kw == 4: len<<24 | <=3 bytes (32-bit arithmetic, funnel shift),
-  // kw == 8: len<<shift | <=7 bytes.
-  uint32_t klen[2][R], ksh[2][R];
-  uint64_t kw0[2][R], kw1[2][R];
+  kslow = 0;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
 #pragma unroll
@@ -194,45 +193,274 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
       ksh[k][r] = 0;
       kw0[k][r] = kw1[k][r] = 0;
     }
-  }
-  if (G > 1) {
+    if (k >= X::nk() || X::kkind(k) != 1) continue;
+    const FusedKey& fk = F.k[k];
+    const int32_t* off = stage ? (const int32_t*)(stage + fk.off) : fk.offsets + row0;
+    const uint8_t* chars = fk.chars;
+    const uint32_t max_len = fk.max_len;
+    const bool short4 = X::kw(k) == 4;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      if (k >= X::nk()) break;
-      const FusedKey& fk = F.k[k];
-      if (X::kkind(k) == 1) {
-        const int32_t* off = (const int32_t*)(stage + fk.off);
-        const uint8_t* chars = fk.chars;
-        const uint32_t max_len = fk.max_len;
-        const bool short4 = X::kw(k) == 4;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const int e = lane + 32 * r;
-          const int32_t o0 = off[e];
-          const uint32_t len = (uint32_t)(off[e + 1] - o0);
-          slow |= (len > max_len ? 1u : 0u) << r;
-          const uint8_t* p = chars + o0;
-          klen[k][r] = len;
-          if (short4) {
-            const uint32_t* base = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
-            ksh[k][r] = (uint32_t)((uintptr_t)p & 3) * 8;
-            kw0[k][r] = base[0];
-            kw1[k][r] = base[1];
-          } else {
-            const uint64_t* base = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
-            ksh[k][r] = (uint32_t)((uintptr_t)p & 7) * 8;
-            kw0[k][r] = base[0];
-            kw1[k][r] = base[1];
-          }
-        }
+    for (int r = 0; r < R; r++) {
+      const int e = lane + 32 * r;
+      const int32_t o0 = off[min(e, lim)];
+      const uint32_t len = (uint32_t)(off[min(e + 1, lim)] - o0);
+      kslow |= (len > max_len ? 1u : 0u) << r;
+      const uint8_t* p = chars + o0;
+      klen[k][r] = len;
+      if (short4) {
+        const uint32_t* base = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+        ksh[k][r] = (uint32_t)((uintptr_t)p & 3) * 8;
+        kw0[k][r] = base[0];
+        kw1[k][r] = base[1];
       } else {
-        const uint8_t* p = stage + fk.off;
-        const uint32_t w = X::kw(k);
-#pragma unroll
-        for (int r = 0; r < R; r++) kw0[k][r] = (uint64_t)ld_w(p, w, lane + 32 * r);
+        const uint64_t* base = (const uint64_t*)((uintptr_t)p & ~(uintptr_t)7);
+        ksh[k][r] = (uint32_t)((uintptr_t)p & 7) * 8;
+        kw0[k][r] = base[0];
+        kw1[k][r] = base[1];
       }
     }
   }
+}
+template <int R, class X>
+__device__ __forceinline__ void fused_key_finish(const uint32_t (&klen)[2][R], const uint32_t (&ksh)[2][R], const uint64_t (&kw0)[2][R], const uint64_t (&kw1)[2][R],
+                                                 uint64_t (&kv)[2][R]) {
+  const FusedSpec& F = c_fused;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const bool packed = k < X::nk() && X::kkind(k) == 1;
+    const bool short4 = packed && X::kw(k) == 4;
+    const int shift = F.k[k].shift;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      uint64_t v = 0;
+      if (short4) {
+        const uint32_t len = klen[k][r];
+        const uint32_t x = __funnelshift_r((uint32_t)kw0[k][r], (uint32_t)kw1[k][r], ksh[k][r]);
+        v = (uint64_t)((x & ((1u << ((len * 8) & 31)) - 1u)) | (len << 24));
+      } else if (packed) {
+        const uint32_t len = klen[k][r], sh = ksh[k][r];
+        uint64_t w = kw0[k][r] >> sh;
+        if (sh) w |= kw1[k][r] << ((64 - sh) & 63);
+        w &= (1ull << ((len * 8) & 63)) - 1;
+        v = len ? (w | ((uint64_t)len << shift)) : 0ull;
+      }
+      kv[k][r] = v;
+    }
+  }
+}
+
+// add the tile's addends to the per-thread partials
+template <int G, int R, class X>
+__device__ __forceinline__ void fused_accumulate(const uint32_t active, const uint32_t (&gid)[R], const uint64_t (&add)[VM_REG_ACC][R], RegAggState<G>& S, uint64_t* accs,
+                                                 const int B) {
+  if (G == 1) {
+    // scalar aggregate: the partials live in registers
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint64_t m = ((active >> r) & 1) ? ~0ull : 0ull;
+#pragma unroll
+      for (int a = 0; a < VM_REG_ACC; a++)
+        if (a < X::na()) S.lo[0][a] += add[a][r] & m;
+    }
+  } else {
+    // grouped aggregate: per-thread partials in shared memory, [group][acc][thread] (conflict-free),
+    // indexed by the row's group -- no G-fold work and no accumulator registers
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if ((active >> r) & 1) {
+        uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
+#pragma unroll
+        for (int a = 0; a < VM_REG_ACC; a++)
+          if (a < X::na()) pa[a * B] += add[a][r];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Speculative narrow path.  Money columns are Decimal128 in Arrow but their values almost always fit
+// 31 bits; then a*(lit-b) is one 32x32->64 multiply instead of checked 128-bit arithmetic.  The
+// function computes the whole tile in 32/64-bit arithmetic WITHOUT side effects and reports whether
+// every active row of this thread stayed inside the assumptions (operands in [0, 2^31), literal
+// differences non-negative, products and addends < 2^40, key cached, key short enough).  If any lane
+// of the warp says no, the warp redoes the tile with fused_rows (general, exact for everything).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fused_ld_narrow(const uint8_t* base, uint32_t w, int e, uint32_t& bad) {
+  if (w == 16) {
+    const uint4 v = ((const uint4*)base)[e];
+    bad |= v.y | v.z | v.w | (v.x & 0x80000000u);
+    return v.x;
+  }
+  if (w == 8) {
+    const uint2 v = ((const uint2*)base)[e];
+    bad |= v.y | (v.x & 0x80000000u);
+    return v.x;
+  }
+  const uint32_t v = ((const uint32_t*)base)[e];
+  bad |= v & 0x80000000u;
+  return v;
+}
+
+// grouped accumulate with the old partials already in registers: new = old + addend, stored back.
+// A row whose group equals that of an earlier active row of the same thread holds a stale `old`
+// and falls back to a read-modify-write behind that row's store.
+template <int G, int R, class X>
+__device__ __forceinline__ void fused_accumulate_preloaded(const uint32_t active, const uint32_t (&gid)[R], const uint64_t (&add)[VM_REG_ACC][R],
+                                                           const uint64_t (&old)[VM_REG_ACC][R], uint64_t* accs, const int B) {
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if ((active >> r) & 1) {
+      bool stale = false;
+#pragma unroll
+      for (int q = 0; q < r; q++) stale |= ((active >> q) & 1) && gid[q] == gid[r];
+      uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
+      if (stale) {
+#pragma unroll
+        for (int a = 0; a < VM_REG_ACC; a++)
+          if (a < X::na()) pa[a * B] += add[a][r];
+      } else {
+#pragma unroll
+        for (int a = 0; a < VM_REG_ACC; a++)
+          if (a < X::na()) pa[a * B] = old[a][r] + add[a][r];
+      }
+    }
+  }
+}
+
+template <int G, int R, class X>
+__device__ __forceinline__ bool fused_try_narrow(const uint8_t* __restrict__ stage, const int lane, uint32_t& active_io, uint32_t (&gid)[R],
+                                                 uint64_t (&add)[VM_REG_ACC][R], uint64_t (&old)[VM_REG_ACC][R], const uint64_t* accs, const int B,
+                                                 const unsigned long long (&dir)[G], const uint32_t dir_n, const uint64_t (&kvs)[2][R], const uint32_t kslow) {
+  const FusedSpec& F = c_fused;
+  uint32_t active = active_io;
+  uint32_t bad[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) bad[r] = (kslow >> r) & 1;
+  // ---- group resolution against the register-cached directory
+#pragma unroll
+  for (int r = 0; r < R; r++) gid[r] = 0;
+  if (G > 1) {
+    unsigned long long kv0[R], kv1[R];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const bool intkey = k < X::nk() && X::kkind(k) == 0;
+      const uint8_t* p = stage + F.k[k].off;
+      const uint32_t w = X::kw(k);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const unsigned long long v = intkey ? (unsigned long long)ld_w(p, w, lane + 32 * r) : kvs[k][r];
+        if (k == 0) kv0[r] = v;
+        else kv1[r] = v;
+      }
+    }
+    const unsigned long long bias0 = (unsigned long long)F.k[0].bias, bias1 = (unsigned long long)F.k[1].bias;
+    const bool combine = X::combine();
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const unsigned long long ck = combine ? ((kv0[r] + bias0) + (kv1[r] + bias1) * 4294967296ull) : kv0[r];
+      uint32_t g = 0, hit = 0;
+#pragma unroll
+      for (int q = 0; q < G; q++) {
+        const bool m = q < (int)dir_n && dir[q] == ck;
+        g = m ? (uint32_t)q : g;
+        hit |= m ? 1u : 0u;
+      }
+      gid[r] = g;
+      bad[r] |= hit ^ 1u;
+    }
+  }
+  // the partials these rows will update: loaded now, a whole tile's arithmetic before they are
+  // needed, so the shared-memory round trip is off the critical path (see fused_accumulate_preloaded)
+  if (G > 1 && FUSED_PRELOAD) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
+#pragma unroll
+      for (int a = 0; a < VM_REG_ACC; a++) old[a][r] = a < X::na() ? pa[a * B] : 0ull;
+    }
+  }
+  // ---- filters
+#pragma unroll
+  for (int i = 0; i < FUSED_MAX_FILTERS; i++) {
+    if (i >= X::nf()) break;
+    const uint8_t* p = stage + F.f[i].off;
+    const uint32_t w = X::fw(i);
+    const int fop = X::fop(i);
+    const int64_t imm = F.f[i].imm;
+    uint32_t pass = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) pass |= (fused_cmp(fop, ld_w(p, w, lane + 32 * r), imm) ? 1u : 0u) << r;
+    active &= pass;
+  }
+  // ---- products in 32x32->64 / 64x32->96 bit arithmetic
+  uint64_t prod0[R], prod1[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) prod0[r] = prod1[r] = 0;
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    if (j >= X::np()) break;
+    const FusedProd& q = F.p[j];
+    const uint8_t* pa = stage + q.a_off;
+    const uint8_t* pb = stage + q.b_off;
+    const uint32_t aw = X::paw(j), bw = X::pbw(j);
+    const int kind = X::pkind(j);
+    const bool a_prev = j == 1 && X::pasrc(j) != 0;
+    const uint32_t lit = (uint32_t)q.lit_lo;
+    const uint32_t lit_bad = (kind != 2 && (q.lit_hi != 0 || q.lit_lo >= 0x80000000ull)) ? 1u : 0u;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int e = lane + 32 * r;
+      const uint32_t b = fused_ld_narrow(pb, bw, e, bad[r]);
+      const uint32_t m = kind == 0 ? lit - b : kind == 1 ? lit + b : b;
+      if (kind == 0) bad[r] |= m & 0x80000000u;
+      bad[r] |= lit_bad;
+      uint64_t pr;
+      if (a_prev) {
+        // prod0 < 2^40 on rows that are still good: 64 x 32 -> bits 0..95, must stay below 2^40
+        const uint64_t lo = (uint64_t)(uint32_t)prod0[r] * m;
+        const uint64_t hi = (uint64_t)(uint32_t)(prod0[r] >> 32) * m + (lo >> 32);
+        bad[r] |= (uint32_t)(hi >> 8) | (uint32_t)(hi >> 32);
+        pr = (hi << 32) | (uint32_t)lo;
+      } else {
+        const uint32_t a = fused_ld_narrow(pa, aw, e, bad[r]);
+        pr = (uint64_t)a * m;
+        bad[r] |= (uint32_t)(pr >> 40);
+      }
+      if (j == 0) prod0[r] = pr;
+      else prod1[r] = pr;
+    }
+  }
+  // ---- addends
+#pragma unroll
+  for (int a = 0; a < VM_REG_ACC; a++) {
+#pragma unroll
+    for (int r = 0; r < R; r++) add[a][r] = 0;
+    if (a >= X::na()) continue;
+    const int src = X::asrc(a);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (src == 3) add[a][r] = 1;
+      else if (src == 1) add[a][r] = prod0[r];
+      else if (src == 2) add[a][r] = prod1[r];
+      else add[a][r] = (uint64_t)fused_ld_narrow(stage + F.a[a].off, X::aw(a), lane + 32 * r, bad[r]);
+    }
+  }
+  uint32_t any_bad = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) any_bad |= ((active >> r) & 1) ? bad[r] : 0u;
+  active_io = active;
+  return any_bad == 0;
+}
+
+// Hot path: straight-line code for the tile's R rows per thread.  Anything unusual about a row only
+// sets its bit in `slow`; those rows are redone by fused_row_slow afterwards.  kvs/kslow: the packed
+// string-key images of this tile, prepared during the previous iteration.
+template <int G, int R, class X>
+__device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage, const int64_t row0, const int lane, uint32_t active, RegAggState<G>& S,
+                                               uint64_t* accs, const int B, RegGroupTable* gt, unsigned long long (&dir)[G], uint32_t& dir_n,
+                                               const uint64_t (&kvs)[2][R], const uint32_t kslow) {
+  const FusedSpec& F = c_fused;
+  uint32_t slow = kslow;
   // ---- filters
 #pragma unroll
   for (int i = 0; i < FUSED_MAX_FILTERS; i++) {
@@ -290,34 +518,20 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
       fused_mul64(alo, blo, p1lo[r], p1hi[r]);
     }
   }
-  // ---- group resolution against the register-cached directory.  (The always-true test on dir_n
-  // ---- keeps ptxas from hoisting the consumers of the chars loads above the products: their
-  // ---- latency is meant to hide behind that arithmetic.)
+  // ---- group resolution against the register-cached directory
   uint32_t gid[R];
 #pragma unroll
   for (int r = 0; r < R; r++) gid[r] = 0;
-  if (G > 1 && dir_n <= (uint32_t)G) {
-    // key images, phase 2: finish the packing now that the chars words have arrived
+  if (G > 1) {
     unsigned long long kv0[R], kv1[R];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-      const bool packed = k < X::nk() && X::kkind(k) == 1;
-      const bool short4 = packed && X::kw(k) == 4;
-      const int shift = F.k[k].shift;
+      const bool intkey = k < X::nk() && X::kkind(k) == 0;
+      const uint8_t* p = stage + F.k[k].off;
+      const uint32_t w = X::kw(k);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        unsigned long long v = kw0[k][r];
-        if (short4) {
-          const uint32_t len = klen[k][r];
-          const uint32_t x = __funnelshift_r((uint32_t)kw0[k][r], (uint32_t)kw1[k][r], ksh[k][r]);
-          v = (unsigned long long)((x & ((1u << ((len * 8) & 31)) - 1u)) | (len << 24));
-        } else if (packed) {
-          const uint32_t len = klen[k][r], sh = ksh[k][r];
-          unsigned long long w = kw0[k][r] >> sh;
-          if (sh) w |= kw1[k][r] << ((64 - sh) & 63);
-          w &= (1ull << ((len * 8) & 63)) - 1;
-          v = len ? (w | ((unsigned long long)len << shift)) : 0ull;
-        }
+        const unsigned long long v = intkey ? (unsigned long long)ld_w(p, w, lane + 32 * r) : kvs[k][r];
         if (k == 0) kv0[r] = v;
         else kv1[r] = v;
       }
@@ -383,7 +597,7 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
       if ((slow >> r) & 1) {
         uint64_t out[VM_REG_ACC];
         uint32_t g = 0;
-        const uint32_t on = fused_row_slow(stage, lane + 32 * r, G, gt, out, &g);
+        const uint32_t on = fused_row_slow(stage, lane + 32 * r, row0, G, gt, out, &g);
         if (!on) active &= ~(1u << r);
         gid[r] = g;
 #pragma unroll
@@ -403,29 +617,25 @@ __device__ __forceinline__ uint32_t fused_rows(const uint8_t* __restrict__ stage
       dir_n = pub;
     }
   }
-  if (G == 1) {
-    // scalar aggregate: the partials live in registers
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const uint64_t m = ((active >> r) & 1) ? ~0ull : 0ull;
-#pragma unroll
-      for (int a = 0; a < VM_REG_ACC; a++)
-        if (a < X::na()) S.lo[0][a] += add[a][r] & m;
-    }
-  } else {
-    // grouped aggregate: per-thread partials in shared memory, [group][acc][thread] (conflict-free),
-    // indexed by the row's group -- no G-fold work and no accumulator registers
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      if ((active >> r) & 1) {
-        uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
-#pragma unroll
-        for (int a = 0; a < VM_REG_ACC; a++)
-          if (a < X::na()) pa[a * B] += add[a][r];
-      }
-    }
-  }
+  fused_accumulate<G, R, X>(active, gid, add, S, accs, B);
   return active;
+}
+
+// The general path as a real call for grouped shapes, so that its register appetite (checked 128-bit
+// arithmetic for R rows) does not dictate the allocation of the speculative path around it.  The
+// caller's register-resident directory travels by value.
+template <int G, int R>
+struct FusedGeneralIO {
+  uint32_t active, dir_n, kslow, _pad;
+  unsigned long long dir[G];
+  uint64_t kvs[2][R];
+};
+template <int G, int R, class X>
+__device__ __noinline__ FusedGeneralIO<G, R> fused_rows_call(const uint8_t* stage, const int64_t row0, const int lane, uint64_t* accs, const int B, RegGroupTable* gt,
+                                                              FusedGeneralIO<G, R> io) {
+  RegAggState<G> unused;  // grouped partials live in shared memory
+  io.active = fused_rows<G, R, X>(stage, row0, lane, io.active, unused, accs, B, gt, io.dir, io.dir_n, io.kvs, io.kslow);
+  return io;
 }
 
 template <int G, int R, int BT, uint64_t SA, uint64_t SB>
@@ -434,6 +644,7 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[FUSED_MAX_WARPS * FUSED_MAX_STAGES];
   __shared__ uint32_t stage_tile[FUSED_MAX_WARPS * FUSED_MAX_STAGES];  // tile held by each (warp, stage)
+  __shared__ uint32_t stage_next[FUSED_MAX_WARPS * FUSED_MAX_STAGES];  // ... and the warp's following tile
   __shared__ unsigned int next_claim;                                   // CTA-wide tile dispenser
   __shared__ RegGroupTable gtable;
   const FusedSpec& F = c_fused;
@@ -478,17 +689,39 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
 
   // Warp tiles are claimed dynamically from a CTA-wide counter (warps of one CTA do not run at the
   // same speed; a static deal leaves the fast ones idle at the end): the c-th claim of CTA b is
-  // tile c * gridDim.x + b, so the grid sweeps the table front to back.
-  auto claim_into = [&](int st) {
+  // tile c * gridDim.x + b, so the grid sweeps the table front to back.  Every batch also carries
+  // the string offsets of the warp's following tile, so claims run one tile ahead of the issues.
+  uint32_t* my_next = stage_next + warp * FUSED_MAX_STAGES;
+  auto claim = [&]() -> uint32_t {
     unsigned int c = 0;
     if (lane == 0) c = atomicAdd(&next_claim, 1u);
     c = __shfl_sync(0xFFFFFFFFu, c, 0);
     const unsigned long long t64 = (unsigned long long)c * gridDim.x + blockIdx.x;
-    const uint32_t t = t64 < n_tiles ? (uint32_t)t64 : 0xFFFFFFFFu;
-    if (lane == 0) my_tile[st] = t;
-    if (t < n_full) fused_issue(ring + (size_t)st * stage_bytes, &bar[st], (int64_t)t * TR, lane);
+    return t64 < n_tiles ? (uint32_t)t64 : 0xFFFFFFFFu;
   };
-  for (int k = 0; k < S - 1; k++) claim_into(k);
+  uint32_t ahead = claim();
+  const uint32_t first = ahead;
+  auto issue_into = [&](int st) {
+    const uint32_t cur = ahead;
+    if (cur != 0xFFFFFFFFu) ahead = claim();
+    if (lane == 0) {
+      my_tile[st] = cur;
+      my_next[st] = ahead;
+    }
+    if (cur < n_full) fused_issue(ring + (size_t)st * stage_bytes, &bar[st], (int64_t)cur * TR, ahead < n_full ? (int64_t)ahead * TR : -1, lane);
+  };
+  for (int k = 0; k < S - 1; k++) issue_into(k);
+  // string keys of the first tile: straight from global memory (the only exposed latency)
+  uint64_t kv_cur[2][R];
+  uint32_t kslow_cur = 0;
+  {
+    uint32_t klen[2][R], ksh[2][R];
+    uint64_t kw0[2][R], kw1[2][R];
+    const int64_t r0 = first != 0xFFFFFFFFu ? (int64_t)first * TR : 0;
+    const int lim = first != 0xFFFFFFFFu ? (int)((n_rows - r0) < TR ? (n_rows - r0) : TR) : 0;
+    if (G > 1) fused_key_loads<R, X>(nullptr, r0, lim, lane, klen, ksh, kw0, kw1, kslow_cur);
+    fused_key_finish<R, X>(klen, ksh, kw0, kw1, kv_cur);
+  }
   uint32_t phase_bits = 0;
   int s = 0;
   uint32_t it = 0;
@@ -496,9 +729,9 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
     uint8_t* stage = ring + (size_t)s * stage_bytes;
     // every lane is done with the buffer consumed in the previous iteration: refill it
     __syncwarp();
-    claim_into((s == 0) ? S - 1 : s - 1);
+    issue_into((s == 0) ? S - 1 : s - 1);
     __syncwarp();
-    const uint32_t t = my_tile[s];
+    const uint32_t t = my_tile[s], tn = my_next[s];
     if (t == 0xFFFFFFFFu) break;  // claims are monotonic: nothing of this warp is in flight any more
     // the sink-overflow flag (another CTA met a 5th group, ...) is polled every 8th tile; all lanes
     // read the same word, the value is consumed at the end of the tile
@@ -514,12 +747,55 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
       fused_load_coop(stage, row0, rows, TR, lane);
       __syncwarp();
     }
+    // string keys of the NEXT tile: issue the loads now, finish them after this tile's arithmetic
+    uint32_t klen[2][R], ksh[2][R];
+    uint64_t kw0[2][R], kw1[2][R];
+    uint32_t kslow_next = 0;
+    if (G > 1) {
+      const bool in_stage = t < n_full && tn < n_full;  // the batch carried the next tile's offsets
+      const int64_t rn = tn != 0xFFFFFFFFu ? (int64_t)tn * TR : 0;
+      const int limn = tn != 0xFFFFFFFFu ? (int)((n_rows - rn) < TR ? (n_rows - rn) : TR) : 0;
+      fused_key_loads<R, X>(in_stage ? stage : nullptr, rn, limn, lane, klen, ksh, kw0, kw1, kslow_next);
+    }
     uint32_t active = 0;
 #pragma unroll
     for (int r = 0; r < R; r++)
       if (lane + 32 * r < rows) active |= 1u << r;
-    active = fused_rows<G, R, X>(stage, lane, active, S_reg, accs, B, &gtable, dir, dir_n);
+    {
+      uint32_t gid[R];
+      uint64_t add[VM_REG_ACC][R], old[VM_REG_ACC][R];
+      uint32_t act = active;
+      const bool ok = fused_try_narrow<G, R, X>(stage, lane, act, gid, add, old, accs, B, dir, dir_n, kv_cur, kslow_cur);
+      if (__all_sync(0xFFFFFFFFu, ok)) {
+        active = act;
+        if (G == 1 || !FUSED_PRELOAD) fused_accumulate<G, R, X>(active, gid, add, S_reg, accs, B);
+        else fused_accumulate_preloaded<G, R, X>(active, gid, add, old, accs, B);
+      } else if (G == 1) {
+        active = fused_rows<G, R, X>(stage, row0, lane, active, S_reg, accs, B, &gtable, dir, dir_n, kv_cur, kslow_cur);
+      } else {
+        FusedGeneralIO<G, R> io;
+        io.active = active;
+        io.dir_n = dir_n;
+        io.kslow = kslow_cur;
+#pragma unroll
+        for (int q = 0; q < G; q++) io.dir[q] = dir[q];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+#pragma unroll
+          for (int r = 0; r < R; r++) io.kvs[k][r] = kv_cur[k][r];
+        }
+        io = fused_rows_call<G, R, X>(stage, row0, lane, accs, B, &gtable, io);
+        active = io.active;
+        dir_n = io.dir_n;
+#pragma unroll
+        for (int q = 0; q < G; q++) dir[q] = io.dir[q];
+      }
+    }
     live_rows += __popc(active);
+    if (G > 1) {
+      fused_key_finish<R, X>(klen, ksh, kw0, kw1, kv_cur);
+      kslow_cur = kslow_next;
+    }
     if (poll && stop) {
       __syncwarp();
       int sj = s;

@@ -225,6 +225,7 @@ struct FusedKey {
   uint8_t w;       // integer column: element width; packed: 4 = 32-bit image (shift 24, <= 3 bytes), 8 = 64-bit image
   uint8_t max_len, shift;
   const uint8_t* chars;
+  const int32_t* offsets;  // packed keys: the column's Arrow offsets in global memory
   int64_t bias;    // added to integer keys (non-negative 32-bit image)
 };
 struct FusedAcc {
@@ -240,7 +241,8 @@ struct FusedSpec {
   int32_t rows_per_thread;  // R: a warp tile is 32 * R rows
   int32_t n_stages;         // per-warp ring depth
   uint32_t stage_bytes;     // one warp stage
-  uint32_t tile_tx;         // bytes one tile's bulk copies deliver
+  uint32_t tile_tx;         // bytes one tile's bulk copies deliver (fixed-width columns)
+  uint32_t tile_tx_utf8;    // ... plus the Utf8 offset slices, which belong to the warp's NEXT tile
   uint32_t use_tma;
   uint32_t acc_off;         // grouped shapes: byte offset of the [group][acc][thread] int64 partials
   FusedCol cols[FUSED_MAX_COLS];

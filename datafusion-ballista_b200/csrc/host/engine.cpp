@@ -707,12 +707,12 @@ bool match_fused(const Program& P, FusedPlan& FP) {
   // scalar shapes are bandwidth-bound and want more rows in flight per thread
   const int R = env_int("B200_FUSED_R", P.n_keys ? 2 : 4);
   if (!(R == 2 || R == 4)) return false;
-  int block = env_int("B200_FUSED_B", R == 4 ? 384 : 512);
+  int block = env_int("B200_FUSED_B", 384);
   if (block > (R == 4 ? 384 : 512) || block < 32 || (block & 31)) return false;
   const uint32_t TR = 32u * (uint32_t)R;
   if (P.n_cols > FUSED_MAX_COLS || P.n_cols == 0) return false;
   uint32_t fused_off[VM_MAX_COLS];
-  uint32_t cur = 0, tx = 0;
+  uint32_t cur = 0, tx = 0, tx_utf8 = 0;
   bool aligned = true;
   for (int c = 0; c < P.n_cols; c++) {
     const ColDesc& cd = P.cols[c];
@@ -726,13 +726,15 @@ bool match_fused(const Program& P, FusedPlan& FP) {
     fc.off = cur;
     fused_off[c] = cur;
     cur += fc.tile_bytes;
-    tx += fc.tile_bytes;
+    if (fc.utf8) tx_utf8 += fc.tile_bytes;
+    else tx += fc.tile_bytes;
     if (((uintptr_t)cd.data & 15) != 0) aligned = false;
   }
   F.n_cols = P.n_cols;
   F.rows_per_thread = R;
   F.stage_bytes = (cur + 127u) & ~127u;
   F.tile_tx = tx;
+  F.tile_tx_utf8 = tx_utf8;
   F.use_tma = (aligned && !getenv("B200_NO_TMA")) ? 1u : 0u;
   {
     // shared memory: per-warp rings, then (grouped shapes) 8 bytes per (group, accumulator, thread)
@@ -825,6 +827,7 @@ bool match_fused(const Program& P, FusedPlan& FP) {
         pi.k.kind = 1;
         pi.k.off = fused_off[v.a.idx];
         pi.k.chars = P.cols[v.a.idx].chars;
+        pi.k.offsets = (const int32_t*)P.cols[v.a.idx].data;
         pi.k.max_len = v.aux;
         pi.k.shift = (uint8_t)v.imm;
         pi.k.w = (pi.k.shift == 24 && pi.k.max_len <= 3) ? 4 : 8;

@@ -22,7 +22,7 @@ from typing import List, Optional
 import pyarrow as pa
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libb200exec.so")
+LIB_PATH = os.environ.get("B200EXEC_LIB") or os.path.join(_PKG, "lib", "libb200exec.so")
 
 
 class ShuffleWritePartition(C.Structure):
