@@ -191,7 +191,17 @@ def run_b200(args):
 
     agg_ns = [0, 0]  # [elapsed ns, launches] of the fused stage-1 kernel inside the timed region
 
+    trace = os.environ.get("B200_BENCH_TRACE")
+    tr = {}
+
+    def _mark(name, t0):
+        if trace:
+            torch.cuda.synchronize(device)
+            tr[name] = tr.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     def step(job, timed=False):
+        t0 = time.perf_counter()
         s1 = eng.create_query_stage_exec(job, 1, stages[0].json(job))
         s1.execute_query_stage(0)
         if timed:
@@ -200,63 +210,34 @@ def run_b200(args):
                     agg_ns[0] += m["elapsed_compute_ns"]
                     agg_ns[1] += 1
         s1.release()
+        t0 = _mark("stage1", t0)
         if world > 1:
             with torch.cuda.stream(stream):
                 exchange.exchange_stage(eng, job, 1, P, partial_schema, rank, world, device)
+            t0 = _mark("exchange1", t0)
         s2 = eng.create_query_stage_exec(job, 2, stages[1].json(job))
         s2.execute_query_stage(rank)
         s2.release()
+        t0 = _mark("stage2", t0)
         out = None
         if world > 1:
             # final merge on rank 0: gather stage-2 outputs (tiny) as one more exchange to partition 0
             with torch.cuda.stream(stream):
                 _gather_to_zero(eng, job, 2, world, rank, final_schema, device)
+            t0 = _mark("gather", t0)
         if rank == 0:
             s3 = eng.create_query_stage_exec(job, 3, stages[2].json(job))
             s3.execute_query_stage(0)
             s3.release()
             out = eng.partition_export(job, 3, 0)
         eng.remove_job_data(job)
+        _mark("stage3", t0)
         return out
 
     def _gather_to_zero(eng_, job, stage_id, world_, rank_, schema, device_):
-        # every rank wrote stage-2 output partition `rank`; rank 0's merge task reads all of them
-        import json as _json
-        rows = eng_.partition_rows(job, stage_id, rank_)
-        bufs, nrows = (eng_.partition_device_buffers(job, stage_id, rank_) if rows >= 0 else ([(0, 0)] * (3 * len(schema)), 0))
-        sizes = torch.tensor([b for _, b in bufs] + [nrows], dtype=torch.int64, device=device_)
-        all_sizes = [torch.empty_like(sizes) for _ in range(world_)]
-        dist.all_gather(all_sizes, sizes)
-        total = int(sizes[:-1].sum())
-        send = torch.empty(total, dtype=torch.uint8, device=device_)
-        pos = 0
-        for ptr, nb in bufs:
-            if nb:
-                send[pos:pos + nb].copy_(exchange._as_tensor(ptr, nb, device_))
-                pos += nb
-        recv_list = [torch.empty(int(s[:-1].sum()), dtype=torch.uint8, device=device_) for s in all_sizes] if rank_ == 0 else None
-        if rank_ == 0:
-            # point-to-point gather (sizes differ per rank)
-            reqs = []
-            for src in range(1, world_):
-                if recv_list[src].numel():
-                    reqs.append(dist.irecv(recv_list[src], src=src))
-            for r in reqs:
-                r.wait()
-            torch.cuda.current_stream(device_).synchronize()
-            for src in range(1, world_):
-                sz = all_sizes[src].cpu().tolist()
-                if sz[-1] == 0:
-                    continue
-                base, pos2, bl = recv_list[src].data_ptr(), 0, []
-                for nb in sz[:-1]:
-                    bl.append((base + pos2 if nb else 0, nb))
-                    pos2 += nb
-                eng_.partition_import_device(job, stage_id, src, -1, _json.dumps(schema), bl, sz[-1])
-        else:
-            if send.numel():
-                dist.send(send, dst=0)
-            torch.cuda.current_stream(device_).synchronize()
+        # every rank wrote stage-2 output partition `rank`; rank 0's merge task reads all of them:
+        # the same exchange with every partition owned by rank 0
+        exchange.exchange_stage(eng_, job, stage_id, world_, schema, rank_, world_, device_, owner=lambda p: 0)
 
     # ---- warm-up (also settles the aggregate strategy hint) ----
     for w in range(max(args.warmup, 3)):
@@ -265,6 +246,7 @@ def run_b200(args):
         dist.barrier()
     torch.cuda.synchronize(device)
 
+    tr.clear()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -290,6 +272,9 @@ def run_b200(args):
 
     total_rows = ROWS_SF10 * world
     value = total_rows * args.steps / (ms / 1e3)
+
+    if trace:
+        print(f"[trace rank {rank}] per-step ms: " + ", ".join(f"{k}={v / args.steps:.3f}" for k, v in tr.items()), file=sys.stderr)
 
     # ---- end to end: host (pinned) Arrow buffers -> C-ABI -> result on host, every step (N=1 path) ----
     e2e = None

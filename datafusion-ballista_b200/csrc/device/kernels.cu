@@ -327,6 +327,36 @@ void launch_gather_fixed(const void* in, const uint8_t* valid_in, void* out, uin
     default: gather_kernel<ulonglong2><<<g, 256, 0, st>>>((const ulonglong2*)in, valid_in, (ulonglong2*)out, valid_out, idx, n); break;
   }
 }
+// every column of a batch in one launch (blockIdx.y = column): the tail of a query handles a few rows
+// in a dozen columns and is bound by launch count, not bytes
+template <typename T>
+__device__ __forceinline__ void gather_one(const GatherCol& c, const int64_t* idx, int64_t i) {
+  const int64_t j = idx[i];
+  T z;
+  memset(&z, 0, sizeof(T));
+  ((T*)c.out)[i] = j >= 0 ? ((const T*)c.in)[j] : z;
+}
+__global__ void gather_multi_kernel(const GatherCols cols, const int64_t* idx, int64_t n) {
+  const GatherCol& c = cols.c[blockIdx.y];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    switch (c.width) {
+      case 1: gather_one<uint8_t>(c, idx, i); break;
+      case 2: gather_one<uint16_t>(c, idx, i); break;
+      case 4: gather_one<uint32_t>(c, idx, i); break;
+      case 8: gather_one<uint64_t>(c, idx, i); break;
+      default: gather_one<ulonglong2>(c, idx, i); break;
+    }
+    if (c.valid_out) {
+      const int64_t j = idx[i];
+      c.valid_out[i] = j >= 0 ? (c.valid_in ? c.valid_in[j] : 1) : 0;
+    }
+  }
+}
+void launch_gather_multi(const GatherCols& cols, const int64_t* idx, int64_t n, cudaStream_t st) {
+  if (cols.n <= 0) return;
+  dim3 grid((unsigned)grid_for(n, 256, 4), (unsigned)cols.n);
+  gather_multi_kernel<<<grid, 256, 0, st>>>(cols, idx, n);
+}
 __global__ void iota_i64_kernel(int64_t* out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = i;
 }

@@ -60,6 +60,21 @@ void launch_partition_rank(const uint32_t* ids, int64_t n, uint32_t n_bins, unsi
 void launch_scatter_fixed(const void* in, void* out, const uint32_t* dest, int64_t n, int width, cudaStream_t st);
 // out[i] = idx[i] >= 0 ? in[idx[i]] : 0 ; valid_out (optional) = idx>=0 && valid_in
 void launch_gather_fixed(const void* in, const uint8_t* valid_in, void* out, uint8_t* valid_out, const int64_t* idx, int64_t n, int width, cudaStream_t st);
+// the same for up to GATHER_MAX_COLS columns in one launch
+static const int GATHER_MAX_COLS = 32;
+struct GatherCol {
+  const void* in;
+  const uint8_t* valid_in;
+  void* out;
+  uint8_t* valid_out;
+  int width;
+  int _pad;
+};
+struct GatherCols {
+  GatherCol c[GATHER_MAX_COLS];
+  int n;
+};
+void launch_gather_multi(const GatherCols& cols, const int64_t* idx, int64_t n, cudaStream_t st);
 void launch_iota_i64(int64_t* out, int64_t n, cudaStream_t st);
 
 // ---- strings / validity ------------------------------------------------------------------------

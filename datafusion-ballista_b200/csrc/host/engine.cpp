@@ -182,16 +182,31 @@ DevColumn as_utf8(const Exec& x, const DevColumn& c) {
 DevBatchPtr gather_batch(const Exec& x, const DevBatch& in, const int64_t* idx, int64_t n_out, bool may_be_null) {
   auto out = std::make_shared<DevBatch>();
   out->n = n_out;
+  GatherCols gc;
+  gc.n = 0;
+  auto flush = [&]() {
+    if (gc.n) {
+      launch_gather_multi(gc, idx, n_out, x.st());
+      x.count();
+      gc.n = 0;
+    }
+  };
   for (auto& c0 : in.cols) {
     DevColumn c = as_views(x, c0);
     bool with_valid = c.valid != nullptr || may_be_null;
     DevColumn o = make_out_column(c.name, c.type, c.phys, n_out, with_valid, x.st());
     o.n = n_out;
-    launch_gather_fixed(c.data, c.valid, (void*)o.data, (uint8_t*)o.valid, idx, n_out, c.width(), x.st());
-    x.count();
+    GatherCol& g = gc.c[gc.n++];
+    g.in = c.data;
+    g.valid_in = c.valid;
+    g.out = (void*)o.data;
+    g.valid_out = (uint8_t*)o.valid;
+    g.width = c.width();
+    if (gc.n == GATHER_MAX_COLS) flush();
     for (auto& k : c.keep) o.keep.push_back(k);
     out->cols.push_back(o);
   }
+  flush();
   return out;
 }
 
@@ -1272,7 +1287,20 @@ struct Runner {
     return outs;
   }
 
+  // B200_TIMING=1: inclusive host wall time per operator (launch + synchronisation overheads)
   DevBatchPtr exec(const PlanNode& n, int part) {
+    static const bool timing = getenv("B200_TIMING") != nullptr;
+    if (!timing) return exec_impl(n, part);
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint64_t l0 = x.e->launches;
+    DevBatchPtr out = exec_impl(n, part);
+    cudaStreamSynchronize(x.st());
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[b200-time] op=%d part=%d rows_out=%lld host_ms=%.3f launches=%llu\n", (int)n.op, part, (long long)(out ? out->n : -1), ms,
+            (unsigned long long)(x.e->launches - l0));
+    return out;
+  }
+  DevBatchPtr exec_impl(const PlanNode& n, int part) {
     x.check_cancel();
     OpMetrics* met = x.m(&n);
     DevBatchPtr out;
@@ -1678,7 +1706,10 @@ struct Runner {
     const int64_t bs = x.e->batch_size;
     auto nbatches = [&](uint64_t rows) { return (rows + (uint64_t)bs - 1) / (uint64_t)bs; };
     std::vector<b200_shuffle_write_partition> res;
-    if (root.n_out_partitions == 0) {
+    // no repartitioning; also hash partitioning into ONE partition (hash % 1 == 0 for every row), which
+    // keeps the rows of this task together as output partition 0
+    const bool single = root.n_out_partitions == 1;
+    if (root.n_out_partitions == 0 || single) {
       DevBatchPtr in = exec(child, input_partition);
       // canonical Arrow layout for stored partitions (strings contiguous)
       auto st = std::make_shared<DevBatch>();
@@ -1700,24 +1731,31 @@ struct Runner {
       }
       CUDA_CHECK(cudaStreamSynchronize(x.st()));
       b200_shuffle_write_partition w{};
-      w.partition_id = (uint64_t)input_partition;
+      w.partition_id = single ? 0u : (uint64_t)input_partition;
       w.num_rows = (uint64_t)st->n;
       w.num_batches = nbatches(w.num_rows);
       w.num_bytes = slice_bytes(*st, st->n, cb);
-      w.file_id = -1;
-      w.is_sort_shuffle = 0;
+      w.file_id = single ? (int64_t)input_partition : -1;
+      w.is_sort_shuffle = (single && root.sort_shuffle) ? 1 : 0;
       {
         std::lock_guard<std::mutex> g(x.e->mu);
-        auto& v = x.e->shuffle[ShuffleKey{job, root.stage_id, input_partition}];
-        v.clear();
-        v.push_back(Piece{-1, st, 0, st->n});
+        auto& v = x.e->shuffle[ShuffleKey{job, root.stage_id, single ? 0 : input_partition}];
+        if (single) {
+          const int64_t fid = (int64_t)input_partition;
+          v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == fid; }), v.end());
+          if (st->n > 0) v.push_back(Piece{fid, st, 0, st->n});
+          else if (v.empty()) x.e->shuffle.erase(ShuffleKey{job, root.stage_id, 0});
+        } else {
+          v.clear();
+          v.push_back(Piece{-1, st, 0, st->n});
+        }
       }
       if (met) {
         met->output_rows += w.num_rows;
         met->input_rows += w.num_rows;
         met->bytes_written += w.num_bytes;
       }
-      res.push_back(w);
+      if (!(single && st->n == 0)) res.push_back(w);  // only partitions with rows are reported
       return res;
     }
     // hash repartition: pid = hash(keys) % P fused into the child's pipeline, then rank + scatter
@@ -2240,6 +2278,19 @@ int b200_remove_job_data(b200_engine* e, const char* job_id) {
     for (auto it = e->shuffle.begin(); it != e->shuffle.end();) {
       if (it->first.job == job_id) it = e->shuffle.erase(it);
       else ++it;
+    }
+  });
+}
+
+int b200_device_gather(b200_engine* e, const b200_device_buffer* bufs, int n, void* dst, uint64_t dst_bytes) {
+  return guard([&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    uint64_t pos = 0;
+    for (int i = 0; i < n; i++) {
+      if (!bufs[i].bytes) continue;
+      if (pos + bufs[i].bytes > dst_bytes) throw EngineError(B200_ERR_INVALID, "b200_device_gather: destination too small");
+      CUDA_CHECK(cudaMemcpyAsync((uint8_t*)dst + pos, bufs[i].ptr, (size_t)bufs[i].bytes, cudaMemcpyDeviceToDevice, e->stream));
+      pos += bufs[i].bytes;
     }
   });
 }

@@ -63,7 +63,7 @@ EXPORTED_SYMBOLS = [
     "b200_engine_register_batch", "b200_engine_drop_table", "b200_engine_tpch_generate",
     "b200_engine_export_table", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
-    "b200_partition_import_device", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
+    "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
     "b200_version",
 ]
 
@@ -105,6 +105,7 @@ def load_library():
     L.b200_partition_import_device.argtypes = [vp, cp, i64, ci, i64, cp, C.POINTER(DeviceBuffer), ci, i64]
     L.b200_remove_job_data.argtypes = [vp, cp]
     L.b200_remove_stage_data.argtypes = [vp, cp, i64]
+    L.b200_device_gather.argtypes = [vp, C.POINTER(DeviceBuffer), ci, vp, u64]
     L.b200_host_alloc_pinned.argtypes = [u64]
     L.b200_host_alloc_pinned.restype = vp
     L.b200_host_free_pinned.argtypes = [vp]
@@ -251,6 +252,14 @@ class GpuExecutionEngine:
             arr[i].bytes = b
         _check(load_library().b200_partition_import_device(self.h, job_id.encode(), stage_id, out_partition, file_id,
                                                            schema_json.encode(), arr, len(bufs), n_rows))
+
+    def device_gather(self, bufs, dst_ptr: int, dst_bytes: int) -> None:
+        """Pack device buffers [(ptr, bytes), ...] back to back into dst (b200_device_gather)."""
+        arr = (DeviceBuffer * max(len(bufs), 1))()
+        for i, (p, b) in enumerate(bufs):
+            arr[i].ptr = p
+            arr[i].bytes = b
+        _check(load_library().b200_device_gather(self.h, arr, len(bufs), dst_ptr, dst_bytes))
 
     def remove_job_data(self, job_id: str) -> None:
         _check(load_library().b200_remove_job_data(self.h, job_id.encode()))

@@ -41,58 +41,65 @@ def _sync(device):
 
 
 def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, schema: List[dict], rank: int, world: int,
-                   device) -> Dict[str, int]:
+                   device, owner=None) -> Dict[str, int]:
     """All ranks call this after finishing their map tasks of `stage_id`.
 
-    For every output partition p (owner = p % world): each rank sends its local piece of p to the
-    owner; the owner installs the received pieces under file_id = sender rank.  Returns byte counts.
+    For every output partition p (owner = owner(p), default p % world): each rank sends its local
+    piece of p to the owner; the owner installs the received pieces under file_id = sender rank.
+    Two collectives: the sizes (one small all-to-all) and the payload (one all-to-all-v of a single
+    contiguous message per peer, packed by the engine with b200_device_gather).  Returns byte counts.
     """
+    owner = owner or (lambda p: p % world)
     ncols = len(schema)
     nbuf = 3 * ncols
     schema_json = json.dumps(schema)
+    is_cuda = torch.device(device).type == "cuda"
     # 1. metadata: per (dest rank, partition, buffer) sizes + rows
-    parts_of = {r: [p for p in range(n_out_partitions) if p % world == r] for r in range(world)}
-    max_parts = max(len(v) for v in parts_of.values())
+    parts_of = {r: [p for p in range(n_out_partitions) if owner(p) == r] for r in range(world)}
+    max_parts = max(1, max(len(v) for v in parts_of.values()))
     meta = torch.zeros((world, max_parts, nbuf + 1), dtype=torch.int64)
-    local: Dict[int, list] = {}
+    order = []  # buffers in send order
     for r in range(world):
         for k, p in enumerate(parts_of[r]):
             if engine.partition_rows(job_id, stage_id, p) < 0:
                 continue
             bufs, rows = engine.partition_device_buffers(job_id, stage_id, p)
-            local[p] = bufs
             for b, (_, nb) in enumerate(bufs):
                 meta[r, k, b] = nb
             meta[r, k, nbuf] = rows
+            order.extend(bufs)
     meta_dev = meta.to(device)
     recv_meta = torch.empty_like(meta_dev)
     dist.all_to_all_single(recv_meta.view(world, -1), meta_dev.view(world, -1))
     recv_meta_h = recv_meta.cpu()
     # 2. payload: one flat byte buffer per destination
-    send_sizes = [int(meta[r, :, :nbuf].sum()) for r in range(world)]
-    recv_sizes = [int(recv_meta_h[r, :, :nbuf].sum()) for r in range(world)]
-    send = torch.empty(sum(send_sizes), dtype=torch.uint8, device=device)
-    pos = 0
-    for r in range(world):
-        for k, p in enumerate(parts_of[r]):
-            if p not in local:
-                continue
-            for (ptr, nb) in local[p]:
-                if nb:
-                    send[pos:pos + nb].copy_(_as_tensor(ptr, nb, device))
-                    pos += nb
-    recv = torch.empty(sum(recv_sizes), dtype=torch.uint8, device=device)
-    dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes)
+    send_sizes = meta[:, :, :nbuf].sum(dim=(1, 2)).tolist()
+    recv_sizes = recv_meta_h[:, :, :nbuf].sum(dim=(1, 2)).tolist()
+    total_send = int(sum(send_sizes))
+    send = torch.empty(max(total_send, 1), dtype=torch.uint8, device=device)
+    if is_cuda:
+        engine.device_gather(order, send.data_ptr(), total_send)  # enqueued on the engine's stream (== torch's current stream)
+    else:
+        pos = 0
+        for (ptr, nb) in order:
+            if nb:
+                send[pos:pos + nb].copy_(_as_tensor(ptr, nb, device))
+                pos += nb
+    total_recv = int(sum(recv_sizes))
+    recv = torch.empty(max(total_recv, 1), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv[:total_recv], send[:total_send], output_split_sizes=[int(x) for x in recv_sizes],
+                           input_split_sizes=[int(x) for x in send_sizes])
     _sync(device)
     # 3. install what this rank owns (drop its own un-exchanged local pieces first)
     mine = parts_of[rank]
     pos = 0
     base = recv.data_ptr()
     installs = []
+    rm = recv_meta_h.tolist()
     for src in range(world):
         for k, p in enumerate(mine):
-            sizes = [int(recv_meta_h[src, k, b]) for b in range(nbuf)]
-            rows = int(recv_meta_h[src, k, nbuf])
+            sizes = rm[src][k][:nbuf]
+            rows = rm[src][k][nbuf]
             bufs = []
             for nb in sizes:
                 bufs.append((base + pos if nb else 0, nb))
@@ -102,4 +109,4 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
     engine.remove_stage_partitions(job_id, stage_id)
     for p, src, bufs, rows in installs:
         engine.partition_import_device(job_id, stage_id, p, src, schema_json, bufs, rows)
-    return {"sent_bytes": sum(send_sizes) - send_sizes[rank], "recv_bytes": sum(recv_sizes) - recv_sizes[rank]}
+    return {"sent_bytes": int(total_send - send_sizes[rank]), "recv_bytes": int(total_recv - recv_sizes[rank])}

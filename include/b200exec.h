@@ -131,6 +131,12 @@ int b200_partition_device_buffers(b200_engine* e, const char* job_id, int64_t st
 int b200_partition_import_device(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition,
                                  int64_t file_id, const char* schema_json, const b200_device_buffer* bufs,
                                  int n_bufs, int64_t n_rows);
+/* Pack `n` device buffers back to back into `dst` (device memory of this GPU, >= the sum of their
+ * sizes) on the engine's stream: the send side of the exchange builds one contiguous message per
+ * peer this way (the reference's counterpart is the IPC writer appending batches to one shuffle file,
+ * ballista/core/src/execution_plans/shuffle_writer.rs:262-330).  Returns after the copies are
+ * enqueued; call b200_engine_synchronize (or use the same stream) before reading `dst`. */
+int b200_device_gather(b200_engine* e, const b200_device_buffer* bufs, int n, void* dst, uint64_t dst_bytes);
 /* RemoveJobData RPC (ballista/executor/src/executor_server.rs:921-932). */
 int b200_remove_job_data(b200_engine* e, const char* job_id);
 /* Drop every stored partition of one stage (used by the exchange step once the pieces have been
