@@ -63,6 +63,7 @@ struct b200_engine {
   std::map<std::string, std::map<int, DevBatchPtr>> tables;
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
   uint64_t launches = 0;
+  uint64_t n_fused = 0, n_fused_static = 0, n_vm = 0;  // pipelines per kernel family (b200_engine_counter)
   int64_t batch_size = 8192;
   std::map<std::string, std::string> config;
   std::map<std::string, int> agg_hint;       // plan fingerprint -> sink that worked (0 reg, >0 log2 cap)
@@ -385,6 +386,8 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
   if (fused) {
     int is_static = 0;
     le = launch_fused_pipeline(P, fused->spec, fused->shape, reg_groups, grid, fused->block, fused->smem, x.st(), &is_static);
+    x.e->n_fused++;
+    if (is_static) x.e->n_fused_static++;
     if (debug) {
       const FusedSpec& F = fused->spec;
       fprintf(stderr, "[b200]   fused kernel: static=%d shape=(%#llx,%#llx) block=%d R=%d stages=%d stage_bytes=%u smem=%zu grid=%d tma=%u\n", is_static,
@@ -398,6 +401,7 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
     }
   } else {
     le = launch_pipeline(P, reg_groups, grid, pb.block, pb.smem_bytes(), x.st());
+    x.e->n_vm++;
   }
   if (le != cudaSuccess) {
     cudaEventDestroy(e0);
@@ -1957,6 +1961,13 @@ int b200_engine_synchronize(b200_engine* e) {
   });
 }
 uint64_t b200_engine_kernel_launches(b200_engine* e) { return e->launches; }
+uint64_t b200_engine_counter(b200_engine* e, const char* name) {
+  const std::string n = name ? name : "";
+  if (n == "fused") return e->n_fused;
+  if (n == "fused_static") return e->n_fused_static;
+  if (n == "vm") return e->n_vm;
+  return 0;
+}
 
 int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
   return guard([&] {

@@ -59,7 +59,7 @@ class ArrowArray(C.Structure):
 # every symbol include/b200exec.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
     "b200_engine_create", "b200_engine_destroy", "b200_last_error", "b200_engine_set_stream",
-    "b200_engine_synchronize", "b200_engine_kernel_launches", "b200_engine_set_config",
+    "b200_engine_synchronize", "b200_engine_kernel_launches", "b200_engine_counter", "b200_engine_set_config",
     "b200_engine_register_batch", "b200_engine_drop_table", "b200_engine_tpch_generate",
     "b200_engine_export_table", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
@@ -88,6 +88,8 @@ def load_library():
     L.b200_engine_synchronize.argtypes = [vp]
     L.b200_engine_kernel_launches.argtypes = [vp]
     L.b200_engine_kernel_launches.restype = u64
+    L.b200_engine_counter.argtypes = [vp, cp]
+    L.b200_engine_counter.restype = u64
     L.b200_engine_set_config.argtypes = [vp, cp, cp]
     L.b200_engine_register_batch.argtypes = [vp, cp, ci, vp, vp]
     L.b200_engine_drop_table.argtypes = [vp, cp]
@@ -193,6 +195,10 @@ class GpuExecutionEngine:
 
     def kernel_launches(self) -> int:
         return load_library().b200_engine_kernel_launches(self.h)
+
+    def counter(self, name: str) -> int:
+        """Pipelines run per kernel family: 'fused', 'fused_static', 'vm' (b200_engine_counter)."""
+        return load_library().b200_engine_counter(self.h, name.encode())
 
     # -- leaf inputs ---------------------------------------------------------------------------
     def register_batch(self, table: str, partition: int, batch: pa.RecordBatch) -> None:

@@ -32,7 +32,9 @@ def test_q1(gpu, oracle, oracle_lib, msf, parts, P):
         e.drop_table("lineitem")
         _load(e, oracle_lib, "lineitem", msf, tpch.Q1_COLUMNS, parts)
     job = f"q1-{msf}-{parts}-{P}"
+    s0 = gpu.counter("fused_static")
     got = driver.run_stages(gpu, tpch.q1(P), job)
+    assert gpu.counter("fused_static") >= s0 + parts  # stage 1 ran on the shape-specialised fused kernel
     want = driver.run_stages(oracle, tpch.q1(P), job)
     assert got.num_rows == 4
     assert_tables_equal(got, want, sort=False)  # ORDER BY l_returnflag, l_linestatus
@@ -44,6 +46,8 @@ def test_q6(gpu, oracle, oracle_lib, msf, parts):
         e.drop_table("lineitem")
         _load(e, oracle_lib, "lineitem", msf, tpch.Q6_COLUMNS, parts)
     job = f"q6-{msf}-{parts}"
+    s0 = gpu.counter("fused_static")
     got = driver.run_stages(gpu, tpch.q6(4), job)
+    assert gpu.counter("fused_static") >= s0 + parts
     want = driver.run_stages(oracle, tpch.q6(4), job)
     assert_tables_equal(got, want)
