@@ -722,11 +722,12 @@ bool match_fused(const Program& P, FusedPlan& FP) {
   for (int a = 0; a < P.n_acc; a++)
     if (!(P.acc[a].kind == ACC_SUM_I128 || P.acc[a].kind == ACC_COUNT || P.acc[a].kind == ACC_COUNT_STAR)) return false;
   // stage layout: every column of the program, one warp tile of 32*R rows each
-  // measured on B200 (profiles/r01_summary.md): grouped shapes are issue-bound and want 16 warps,
-  // scalar shapes are bandwidth-bound and want more rows in flight per thread
-  const int R = env_int("B200_FUSED_R", P.n_keys ? 2 : 4);
+  // measured on B200 (profiles/r01_summary.md): 4 rows per thread amortise the per-tile work (claim, TMA
+  // issue, barrier wait) best; grouped shapes then fit 8 warps of up to 255 registers next to their
+  // shared-memory partials, scalar shapes 12 warps
+  const int R = env_int("B200_FUSED_R", 4);
   if (!(R == 2 || R == 4)) return false;
-  int block = env_int("B200_FUSED_B", 384);
+  int block = env_int("B200_FUSED_B", (R == 4 && P.n_keys) ? 256 : 384);
   if (block > (R == 4 ? 384 : 512) || block < 32 || (block & 31)) return false;
   const uint32_t TR = 32u * (uint32_t)R;
   if (P.n_cols > FUSED_MAX_COLS || P.n_cols == 0) return false;

@@ -225,3 +225,83 @@ def q17(n_partitions: int = 4, brand: str = "Brand#23", container: str = "MED BO
     s5 = P.aggregate("Final", [], [P.agg("sum", None, "s")], P.coalesce_partitions(P.shuffle_reader(4, [P.field("s[sum]", P.dec(25, 2), True)])))
     s5 = P.project([(P.binop("/", P.cast(c(0), "f64"), P.lit_f64(7.0)), "avg_yearly")], s5)
     return [st1, st2, st3, st4 if False else Stage(4, P.shuffle_writer(s4, 4)), Stage(5, P.shuffle_writer(s5, 5), n_tasks=1)]
+
+
+Q3_TABLES = {"customer": ["c_custkey", "c_mktsegment"], "orders": ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"],
+             "lineitem": ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]}
+
+
+def q3(n_partitions: int = 4, segment: str = "BUILDING", date: str = "1995-03-15") -> List[Stage]:
+    """benchmarks/queries/q3.sql -- customer |x| orders |x| lineitem (Partitioned hash joins on hash-shuffled
+    inputs), aggregate on (l_orderkey, o_orderdate, o_shippriority), top-10 by revenue (SortExec fetch +
+    SortPreservingMergeExec fetch, the cut the planner makes at `planner.rs:214-230`)."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.binop("=", c("c_mktsegment"), P.lit_utf8(segment)), table_scan("customer", Q3_TABLES["customer"]), projection=[0])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    s2 = P.filter_(P.binop("<", c("o_orderdate"), P.lit_date(date)), table_scan("orders", Q3_TABLES["orders"]))
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(1)], Pn))
+    ords = [dict(f, nullable=True) for f in _sch("orders", Q3_TABLES["orders"])]
+    # S3: customer' |x| orders' on custkey -> (o_orderkey, o_orderdate, o_shippriority), re-shuffled on orderkey
+    s3 = P.hash_join(P.shuffle_reader(1, [P.field("c_custkey", i64, True)]), P.shuffle_reader(2, ords), [[c(0), c(1)]], "Inner", "Partitioned",
+                     projection=[1, 3, 4])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    co = [P.field("o_orderkey", i64, True), P.field("o_orderdate", "date32", True), P.field("o_shippriority", "i32", True)]
+    s4 = P.filter_(P.binop(">", c("l_shipdate"), P.lit_date(date)), table_scan("lineitem", Q3_TABLES["lineitem"]), projection=[0, 1, 2])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    li = [P.field("l_orderkey", i64, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    # S5: (customer, orders) |x| lineitem' on orderkey -> partial aggregate
+    s5 = P.hash_join(P.shuffle_reader(3, co), P.shuffle_reader(4, li), [[c(0), c(0)]], "Inner", "Partitioned", projection=[3, 1, 2, 4, 5])
+    s5 = P.project([(c(0), "l_orderkey"), (c(1), "o_orderdate"), (c(2), "o_shippriority"),
+                    (P.binop("*", c(3), one_minus(c(4))), "rev")], s5)
+    gb = [(c(0), "l_orderkey"), (c(1), "o_orderdate"), (c(2), "o_shippriority")]
+    s5 = P.aggregate("Partial", gb, [P.agg("sum", c(3), "revenue")], s5)
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(0), c(1), c(2)], Pn))
+    part = [P.field("l_orderkey", i64, True), P.field("o_orderdate", "date32", True), P.field("o_shippriority", "i32", True),
+            P.field("revenue[sum]", P.dec(38, 4), True)]
+    s6 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "revenue")], P.shuffle_reader(5, part))
+    s6 = P.project([(c(0), "l_orderkey"), (c(3), "revenue"), (c(1), "o_orderdate"), (c(2), "o_shippriority")], s6)
+    keys = [P.sort_key(c(1), asc=False), P.sort_key(c(2))]
+    s6 = P.sort(keys, s6, fetch=10, preserve_partitioning=True)
+    st6 = Stage(6, P.shuffle_writer(s6, 6))
+    fin = [P.field("l_orderkey", i64, True), P.field("revenue", P.dec(38, 4), True), P.field("o_orderdate", "date32", True),
+           P.field("o_shippriority", "i32", True)]
+    st7 = Stage(7, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(6, fin), fetch=10), 7), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7]
+
+
+Q12_TABLES = {"lineitem": ["l_orderkey", "l_shipdate", "l_commitdate", "l_receiptdate", "l_shipmode"],
+              "orders": ["o_orderkey", "o_orderpriority"]}
+
+
+def q12(n_partitions: int = 4, modes=("MAIL", "SHIP"), year: int = 1994) -> List[Stage]:
+    """benchmarks/queries/q12.sql -- IN list, column-vs-column date compares, join, SUM(CASE WHEN ... THEN 1 ELSE 0 END)
+    (Int64 sums), GROUP BY l_shipmode ORDER BY l_shipmode."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    pred = P.and_(P.in_list(c("l_shipmode"), [P.lit_utf8(m) for m in modes]),
+                  P.binop("<", c("l_commitdate"), c("l_receiptdate")),
+                  P.binop("<", c("l_shipdate"), c("l_commitdate")),
+                  P.binop(">=", c("l_receiptdate"), P.lit_date(f"{year}-01-01")),
+                  P.binop("<", c("l_receiptdate"), P.lit_date(f"{year + 1}-01-01")))
+    s1 = P.filter_(pred, table_scan("lineitem", Q12_TABLES["lineitem"]), projection=[0, 4])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st2 = Stage(2, P.shuffle_writer(table_scan("orders", Q12_TABLES["orders"]), 2, [c(0)], Pn))
+    li = [P.field("l_orderkey", i64, True), P.field("l_shipmode", "utf8", True)]
+    od = [P.field("o_orderkey", i64, True), P.field("o_orderpriority", "utf8", True)]
+    j = P.hash_join(P.shuffle_reader(1, li), P.shuffle_reader(2, od), [[c(0), c(0)]], "Inner", "Partitioned", projection=[1, 3])
+    urgent = P.or_(P.binop("=", c(1), P.lit_utf8("1-URGENT")), P.binop("=", c(1), P.lit_utf8("2-HIGH")))
+    other = P.and_(P.binop("<>", c(1), P.lit_utf8("1-URGENT")), P.binop("<>", c(1), P.lit_utf8("2-HIGH")))
+    one, zero = P.lit_i64(1), P.lit_i64(0)
+    s3 = P.project([(c(0), "l_shipmode"), (P.case([[urgent, one]], zero), "hi"), (P.case([[other, one]], zero), "lo")], j)
+    s3 = P.aggregate("Partial", [(c(0), "l_shipmode")], [P.agg("sum", c(1), "high_line_count"), P.agg("sum", c(2), "low_line_count")], s3)
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    part = [P.field("l_shipmode", "utf8", True), P.field("high_line_count[sum]", i64, True), P.field("low_line_count[sum]", i64, True)]
+    s4 = P.aggregate("FinalPartitioned", [(c(0), "l_shipmode")], [P.agg("sum", None, "high_line_count"), P.agg("sum", None, "low_line_count")],
+                     P.shuffle_reader(3, part))
+    keys = [P.sort_key(c(0))]
+    s4 = P.sort(keys, s4, preserve_partitioning=True)
+    st4 = Stage(4, P.shuffle_writer(s4, 4))
+    fin = [P.field("l_shipmode", "utf8", True), P.field("high_line_count", i64, True), P.field("low_line_count", i64, True)]
+    st5 = Stage(5, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(4, fin)), 5), n_tasks=1)
+    return [st1, st2, st3, st4, st5]

@@ -96,3 +96,78 @@ def test_q17_gpu(gpu, oracle, oracle_lib, msf, parts, P):
     got = driver.run_stages(gpu, st, f"q17-{msf}")
     want = driver.run_stages(oracle, st, f"q17-{msf}")
     assert_tables_equal(got, want, sort=False, f64_rtol=1e-12)
+
+
+# ---- q3: 3-way join + aggregate + top-10; q12: IN list, date-vs-date compares, SUM(CASE ...) -------------
+def test_q3_oracle_against_pandas(oracle, oracle_lib):
+    import datetime as dt
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q3_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q3_TABLES}
+    seg = df["customer"].c_mktsegment.iloc[0]
+    day = dt.date(1995, 3, 15)
+    got = driver.run_stages(oracle, tpch.q3(3, seg), "q3o")
+    cu = df["customer"][df["customer"].c_mktsegment == seg]
+    o = df["orders"][df["orders"].o_orderdate < day]
+    li = df["lineitem"][df["lineitem"].l_shipdate > day]
+    m = cu.merge(o, left_on="c_custkey", right_on="o_custkey").merge(li, left_on="o_orderkey", right_on="l_orderkey")
+    want = {}
+    for ok, od, sp, ext, disc in zip(m.l_orderkey, m.o_orderdate, m.o_shippriority, m.l_extendedprice, m.l_discount):
+        k = (ok, od, sp)
+        want[k] = want.get(k, 0) + int(ext.scaleb(2)) * (100 - int(disc.scaleb(2)))
+    assert len(want) > 10
+    top = sorted(want.items(), key=lambda kv: (-kv[1], kv[0][1]))[:10]
+    rows = got.to_pylist()
+    assert len(rows) == 10
+    # revenue DESC, o_orderdate ASC; ties beyond the sort keys may come in any order
+    assert [(r["revenue"], r["o_orderdate"]) for r in rows] == [(D(v).scaleb(-4), k[1]) for k, v in top]
+    for r in rows:
+        assert want[(r["l_orderkey"], r["o_orderdate"], r["o_shippriority"])] == int(r["revenue"].scaleb(4))
+
+
+def test_q12_oracle_against_pandas(oracle, oracle_lib):
+    import datetime as dt
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q12_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q12_TABLES}
+    got = driver.run_stages(oracle, tpch.q12(3), "q12o")
+    li = df["lineitem"]
+    li = li[li.l_shipmode.isin(["MAIL", "SHIP"]) & (li.l_commitdate < li.l_receiptdate) & (li.l_shipdate < li.l_commitdate)
+            & (li.l_receiptdate >= dt.date(1994, 1, 1)) & (li.l_receiptdate < dt.date(1995, 1, 1))]
+    m = li.merge(df["orders"], left_on="l_orderkey", right_on="o_orderkey")
+    want = {}
+    for mode, pr in zip(m.l_shipmode, m.o_orderpriority):
+        hi = 1 if pr in ("1-URGENT", "2-HIGH") else 0
+        w = want.setdefault(mode, [0, 0])
+        w[0] += hi
+        w[1] += 1 - hi
+    assert want
+    rows = got.to_pylist()
+    assert [r["l_shipmode"] for r in rows] == sorted(want)
+    assert {r["l_shipmode"]: [r["high_line_count"], r["low_line_count"]] for r in rows} == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("msf,parts,P", [(20, 2, 3), (100, 3, 8)])
+def test_q3_gpu(gpu, oracle, oracle_lib, msf, parts, P):
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, msf, tpch.Q3_TABLES, parts)
+    seg = pa.Table.from_batches([oracle.export_table("customer", 0)]).slice(0, 1).to_pylist()[0]["c_mktsegment"]
+    got = driver.run_stages(gpu, tpch.q3(P, seg), f"q3-{msf}")
+    want = driver.run_stages(oracle, tpch.q3(P, seg), f"q3-{msf}")
+    assert want.num_rows == 10
+    # ORDER BY revenue DESC, o_orderdate: compare the ordered sort keys, then the rows as a set
+    assert got.column("revenue").to_pylist() == want.column("revenue").to_pylist()
+    assert got.column("o_orderdate").to_pylist() == want.column("o_orderdate").to_pylist()
+    assert_tables_equal(got, want, sort=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("msf,parts,P", [(20, 2, 3), (100, 3, 8)])
+def test_q12_gpu(gpu, oracle, oracle_lib, msf, parts, P):
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, msf, tpch.Q12_TABLES, parts)
+    got = driver.run_stages(gpu, tpch.q12(P), f"q12-{msf}")
+    want = driver.run_stages(oracle, tpch.q12(P), f"q12-{msf}")
+    assert want.num_rows > 0
+    assert_tables_equal(got, want, sort=False)
