@@ -275,6 +275,8 @@ def run_b200(args):
 
     if trace:
         print(f"[trace rank {rank}] per-step ms: " + ", ".join(f"{k}={v / args.steps:.3f}" for k, v in tr.items()), file=sys.stderr)
+        if world > 1:
+            print(f"[trace rank {rank}] exchange phases (whole run, ms): " + ", ".join(f"{k}={v:.2f}" for k, v in exchange._TRACE.items()), file=sys.stderr)
 
     # ---- end to end: host (pinned) Arrow buffers -> C-ABI -> result on host, every step (N=1 path) ----
     e2e = None

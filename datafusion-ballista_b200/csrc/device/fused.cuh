@@ -47,15 +47,28 @@ struct FusedX {
 // One batch of bulk copies: the fixed-width columns of tile `row0` and -- software pipelining of the
 // string keys -- the Utf8 offset slices of the warp's NEXT tile `row0n` (< 0: none).  Lane c issues
 // column c (the whole warp takes part so that the address arithmetic is not a single-lane detour).
-__device__ __forceinline__ void fused_issue(uint8_t* stage, uint64_t* bar, int64_t row0, int64_t row0n, int lane) {
+struct FusedLaneCol {  // lane c's column, read from constant memory once per kernel
+  const uint8_t* data;
+  uint32_t width, off, bytes, utf8;
+};
+__device__ __forceinline__ FusedLaneCol fused_lane_col(int lane) {
+  const FusedSpec& F = c_fused;
+  FusedLaneCol lc;
+  const bool on = lane < F.n_cols;
+  const FusedCol& fc = F.cols[on ? lane : 0];
+  lc.data = (const uint8_t*)fc.data;
+  lc.width = fc.width;
+  lc.off = fc.off;
+  lc.bytes = on ? fc.tile_bytes : 0u;
+  lc.utf8 = fc.utf8;
+  return lc;
+}
+__device__ __forceinline__ void fused_issue(uint8_t* stage, uint64_t* bar, int64_t row0, int64_t row0n, int lane, const FusedLaneCol& lc) {
   const FusedSpec& F = c_fused;
   if (lane == 0) mbar_expect_tx(bar, F.tile_tx + (row0n >= 0 ? F.tile_tx_utf8 : 0u));
   __syncwarp();
-  if (lane < F.n_cols) {
-    const FusedCol& fc = F.cols[lane];
-    const int64_t r0 = fc.utf8 ? row0n : row0;
-    if (r0 >= 0) bulk_g2s(stage + fc.off, (const uint8_t*)fc.data + r0 * fc.width, fc.tile_bytes, bar);
-  }
+  const int64_t r0 = lc.utf8 ? row0n : row0;
+  if (lc.bytes && r0 >= 0) bulk_g2s(stage + lc.off, lc.data + r0 * lc.width, lc.bytes, bar);
 }
 
 // ragged last tile / unaligned slices: the warp loads the fixed-width columns of its tile itself,
@@ -699,6 +712,7 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
     const unsigned long long t64 = (unsigned long long)c * gridDim.x + blockIdx.x;
     return t64 < n_tiles ? (uint32_t)t64 : 0xFFFFFFFFu;
   };
+  const FusedLaneCol lane_col = fused_lane_col(lane);
   uint32_t ahead = claim();
   const uint32_t first = ahead;
   auto issue_into = [&](int st) {
@@ -708,7 +722,7 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
       my_tile[st] = cur;
       my_next[st] = ahead;
     }
-    if (cur < n_full) fused_issue(ring + (size_t)st * stage_bytes, &bar[st], (int64_t)cur * TR, ahead < n_full ? (int64_t)ahead * TR : -1, lane);
+    if (cur < n_full) fused_issue(ring + (size_t)st * stage_bytes, &bar[st], (int64_t)cur * TR, ahead < n_full ? (int64_t)ahead * TR : -1, lane, lane_col);
   };
   for (int k = 0; k < S - 1; k++) issue_into(k);
   // string keys of the first tile: straight from global memory (the only exposed latency)

@@ -327,6 +327,20 @@ void launch_gather_fixed(const void* in, const uint8_t* valid_in, void* out, uin
     default: gather_kernel<ulonglong2><<<g, 256, 0, st>>>((const ulonglong2*)in, valid_in, (ulonglong2*)out, valid_out, idx, n); break;
   }
 }
+// Arrow offsets of a row slice -> offsets starting at 0; also reports the slice's first/last offset
+// (the chars range) without a host round trip per column
+__global__ void rebase_offsets_kernel(const int32_t* in, int64_t n_plus_1, int32_t* out, int32_t* first_last) {
+  const int32_t base = in[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_plus_1; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] - base;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    first_last[0] = base;
+    first_last[1] = in[n_plus_1 - 1];
+  }
+}
+void launch_rebase_offsets(const int32_t* in, int64_t n_plus_1, int32_t* out, int32_t* first_last, cudaStream_t st) {
+  rebase_offsets_kernel<<<grid_for(n_plus_1, 256, 4), 256, 0, st>>>(in, n_plus_1, out, first_last);
+}
+
 // every column of a batch in one launch (blockIdx.y = column): the tail of a query handles a few rows
 // in a dozen columns and is bound by launch count, not bytes
 template <typename T>

@@ -2209,15 +2209,26 @@ int b200_partition_device_buffers(b200_engine* e, const char* job_id, int64_t st
     auto packed = std::make_shared<DevBatch>();
     packed->n = cat->n;
     int k = 0;
+    // Utf8 columns that are row slices of a larger column: rebase the offsets on the device and learn
+    // the chars range of every such column with ONE read-back (not a view round trip per column)
+    struct Pending { size_t col; int out_chars; };
+    std::vector<Pending> pending;
+    DevPtr fl = dev_alloc(8 * (cat->cols.size() + 1), x.st());
     for (auto& c0 : cat->cols) {
       DevColumn c = c0.phys == PH_STRVIEW ? as_utf8(x, c0) : c0;
       if (k + 3 > cap) throw EngineError(B200_ERR_INVALID, "buffer array too small");
       out[k++] = b200_device_buffer{(void*)c.valid, c.valid ? (uint64_t)c.n : 0};
       if (c.phys == PH_UTF8) {
-        if (c.chars_bytes < 0 || c.n == 0 || d2h_value<int32_t>(c.data, x.st()) != 0) {
-          // rebase through views so that offsets start at 0
+        if (c.n == 0) {
           DevColumn v = as_views(x, c);
           c = as_utf8(x, v);
+        } else if (c0.phys != PH_STRVIEW) {  // as_utf8 output already starts at 0 and knows its length
+          DevPtr ro = dev_alloc((size_t)(c.n + 1) * 4 + 64, x.st());
+          launch_rebase_offsets((const int32_t*)c.data, c.n + 1, (int32_t*)ro->ptr, (int32_t*)fl->ptr + 2 * pending.size(), x.st());
+          x.count();
+          c.data = (const uint8_t*)ro->ptr;
+          c.keep.push_back(ro);
+          pending.push_back(Pending{packed->cols.size(), k + 1});
         }
         out[k++] = b200_device_buffer{(void*)c.data, (uint64_t)(c.n + 1) * 4};
         out[k++] = b200_device_buffer{(void*)c.chars, (uint64_t)std::max<int64_t>(c.chars_bytes, 0)};
@@ -2226,6 +2237,17 @@ int b200_partition_device_buffers(b200_engine* e, const char* job_id, int64_t st
         out[k++] = b200_device_buffer{nullptr, 0};
       }
       packed->cols.push_back(c);
+    }
+    if (!pending.empty()) {
+      std::vector<int32_t> h(2 * pending.size());
+      CUDA_CHECK(cudaMemcpyAsync(h.data(), fl->ptr, h.size() * 4, cudaMemcpyDeviceToHost, x.st()));
+      CUDA_CHECK(cudaStreamSynchronize(x.st()));
+      for (size_t i = 0; i < pending.size(); i++) {
+        DevColumn& c = packed->cols[pending[i].col];
+        c.chars = c.chars + h[2 * i];
+        c.chars_bytes = (int64_t)h[2 * i + 1] - (int64_t)h[2 * i];
+        out[pending[i].out_chars] = b200_device_buffer{(void*)c.chars, (uint64_t)c.chars_bytes};
+      }
     }
     CUDA_CHECK(cudaStreamSynchronize(x.st()));
     // keep the packed form alive as the partition's single piece

@@ -13,10 +13,15 @@ torch is plumbing only (communicator + stream); the engine never sees torch type
 from __future__ import annotations
 
 import json
+import os
+import time
 from typing import Dict, List
 
 import torch
 import torch.distributed as dist
+
+
+_TRACE: Dict[str, float] = {}  # B200_BENCH_TRACE=1: accumulated ms per exchange phase (diagnostic)
 
 
 class _DevView:
@@ -50,6 +55,17 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
     contiguous message per peer, packed by the engine with b200_device_gather).  Returns byte counts.
     """
     owner = owner or (lambda p: p % world)
+    trace = _TRACE if os.environ.get("B200_BENCH_TRACE") else None
+    t0 = time.perf_counter()
+
+    def mark(name):
+        nonlocal t0
+        if trace is not None:
+            _sync(device)
+            t1 = time.perf_counter()
+            trace[name] = trace.get(name, 0.0) + (t1 - t0) * 1e3
+            t0 = t1
+
     ncols = len(schema)
     nbuf = 3 * ncols
     schema_json = json.dumps(schema)
@@ -68,10 +84,12 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
                 meta[r, k, b] = nb
             meta[r, k, nbuf] = rows
             order.extend(bufs)
+    mark("buffers")
     meta_dev = meta.to(device)
     recv_meta = torch.empty_like(meta_dev)
     dist.all_to_all_single(recv_meta.view(world, -1), meta_dev.view(world, -1))
     recv_meta_h = recv_meta.cpu()
+    mark("meta")
     # 2. payload: one flat byte buffer per destination
     send_sizes = meta[:, :, :nbuf].sum(dim=(1, 2)).tolist()
     recv_sizes = recv_meta_h[:, :, :nbuf].sum(dim=(1, 2)).tolist()
@@ -90,6 +108,7 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
     dist.all_to_all_single(recv[:total_recv], send[:total_send], output_split_sizes=[int(x) for x in recv_sizes],
                            input_split_sizes=[int(x) for x in send_sizes])
     _sync(device)
+    mark("payload")
     # 3. install what this rank owns (drop its own un-exchanged local pieces first)
     mine = parts_of[rank]
     pos = 0
@@ -109,4 +128,5 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
     engine.remove_stage_partitions(job_id, stage_id)
     for p, src, bufs, rows in installs:
         engine.partition_import_device(job_id, stage_id, p, src, schema_json, bufs, rows)
+    mark("install")
     return {"sent_bytes": int(total_send - send_sizes[rank]), "recv_bytes": int(total_recv - recv_sizes[rank])}
