@@ -589,6 +589,15 @@ struct PlanNode {
   bool sort_shuffle = true;
 };
 
+// deep copy of an expression with every column reference moved by `delta` positions
+inline ExprPtr shift_cols(const ExprPtr& e, int delta) {
+  if (!e || delta == 0) return e;
+  auto c = std::make_shared<Expr>(*e);
+  if (c->kind == Expr::Col) c->col += delta;
+  for (auto& a : c->args) a = shift_cols(a, delta);
+  return c;
+}
+
 inline std::vector<SortKey> parse_sort_keys(const Json& j, const Schema& in) {
   std::vector<SortKey> ks;
   for (size_t i = 0; i < j.size(); i++) {
@@ -754,12 +763,16 @@ inline PlanPtr parse_plan(const Json& j) {
         n->schema.push_back(Field{ae.name, ae.result_type, ae.fn != AggFn::Count});
       }
     }
-  } else if (op == "HashJoinExec") {
+  } else if (op == "HashJoinExec" || op == "SortMergeJoinExec") {
+    // SortMergeJoinExec (datafusion.proto:1433, Ballista's default join, extension.rs:683): same matching
+    // semantics as the hash join over co-partitioned inputs; its contract adds an output ordered by the
+    // join keys (sort_options), which both engines establish by sorting the join result.
+    const bool smj = op == "SortMergeJoinExec";
     n->op = PlanNode::HashJoin;
     PlanNode* l = parse_child("left");
     PlanNode* r = parse_child("right");
     n->join_type = parse_join_type(j.get_str("join_type", "Inner"));
-    n->partition_mode = j.get_str("mode", "CollectLeft");
+    n->partition_mode = smj ? std::string("Partitioned") : j.get_str("mode", "CollectLeft");
     n->null_equals_null = j.get_bool("null_equals_null", false);
     const Json& on = j.at("on");
     for (size_t i = 0; i < on.size(); i++) {
@@ -800,6 +813,21 @@ inline PlanPtr parse_plan(const Json& j) {
       }
     } else {
       n->schema = both;
+    }
+    if (smj) {
+      if (n->has_projection) throw std::runtime_error("SortMergeJoinExec has no projection");
+      const bool right_side = n->join_type == JoinType::Right || n->join_type == JoinType::RightSemi || n->join_type == JoinType::RightAnti;
+      const int shift = n->join_type == JoinType::Right ? (int)l->schema.size() : 0;
+      for (size_t i = 0; i < n->on.size(); i++) {
+        SortKey k;
+        k.expr = right_side ? shift_cols(n->on[i].second, shift) : n->on[i].first;
+        if (j.has("sort_options") && i < j.at("sort_options").size()) {
+          const Json& so = j.at("sort_options").at(i);
+          k.asc = so.get_bool("asc", true);
+          k.nulls_first = so.get_bool("nulls_first", !k.asc);
+        }
+        n->sort_keys.push_back(k);
+      }
     }
   } else if (op == "SortExec" || op == "SortPreservingMergeExec") {
     n->op = op == "SortExec" ? PlanNode::Sort : PlanNode::SortPreservingMerge;

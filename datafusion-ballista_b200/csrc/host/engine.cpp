@@ -1365,7 +1365,10 @@ struct Runner {
         out = with_chain(child, part, all, [&](const BuilderFactory& mk, DevBatchPtr& src) { return run_aggregate(x, mk, n, src, met); });
         break;
       }
-      case PlanNode::HashJoin: out = exec_join(n, part, met); break;
+      case PlanNode::HashJoin:
+        out = exec_join(n, part, met);
+        if (!n.sort_keys.empty()) out = do_sort(n.sort_keys, -1, out, met);  // SortMergeJoinExec: ordered by the join keys
+        break;
       case PlanNode::Sort: {
         DevBatchPtr in = exec(*n.children[0], part);
         out = do_sort(n.sort_keys, n.fetch, in, met);

@@ -169,6 +169,18 @@ def hash_join(left: Json, right: Json, on: Sequence[Sequence[Json]], join_type: 
     return n
 
 
+def sort_merge_join(left: Json, right: Json, on: Sequence[Sequence[Json]], join_type: str = "Inner",
+                    filter: Optional[Json] = None, sort_options: Optional[Sequence[Json]] = None) -> Json:
+    """SortMergeJoinExecNode (datafusion.proto:1433): Ballista's default join strategy (extension.rs:683).
+    Inputs are co-partitioned on the keys; the output is ordered by them."""
+    n: Json = {"op": "SortMergeJoinExec", "left": left, "right": right, "on": [list(p) for p in on], "join_type": join_type}
+    if filter is not None:
+        n["filter"] = filter
+    if sort_options is not None:
+        n["sort_options"] = list(sort_options)
+    return n
+
+
 def sort_key(expr: Json, asc: bool = True, nulls_first: Optional[bool] = None) -> Json:
     return {"expr": expr, "asc": asc, "nulls_first": (not asc) if nulls_first is None else nulls_first}
 

@@ -1239,7 +1239,9 @@ struct Oracle {
       case PlanNode::HashJoin: {
         OBatch L = n.partition_mode == "CollectLeft" ? exec_all(*n.children[0], job) : exec(*n.children[0], part, job);
         OBatch R = exec(*n.children[1], part, job);
-        return do_hash_join(n, L, R);
+        OBatch J = do_hash_join(n, L, R);
+        if (!n.sort_keys.empty()) return do_sort(n.sort_keys, -1, J);  // SortMergeJoinExec output order (plan.hpp)
+        return J;
       }
       case PlanNode::Sort: {
         OBatch in = exec(*n.children[0], part, job);

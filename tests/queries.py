@@ -53,7 +53,7 @@ def q_order_limit(table, schema, key, asc, fetch):
     return [st1, Stage(2, P.shuffle_writer(s2, 2), n_tasks=1)]
 
 
-def q_self_join(table, schema, key="id", gt=2, n_parts=2, join_type="Inner"):
+def q_self_join(table, schema, key="id", gt=2, n_parts=2, join_type="Inner", smj=False):
     """select t1.id from t t1 join t t2 on t1.id = t2.id where t1.id > 2 order by id desc
     (context_checks.rs:1015-1066, prefer_hash_join=true, PartitionMode::Partitioned)"""
     ki = [f["name"] for f in schema].index(key)
@@ -63,7 +63,11 @@ def q_self_join(table, schema, key="id", gt=2, n_parts=2, join_type="Inner"):
     s2 = P.project([(c(key), key)], P.scan(table, schema))
     st2 = Stage(2, P.shuffle_writer(s2, 2, [c(0)], n_parts))
     side = [P.field(key, kt, True)]
-    j = P.hash_join(P.shuffle_reader(1, side), P.shuffle_reader(2, side), [[c(0), c(0)]], join_type, "Partitioned")
+    if smj:  # the default plan (prefer_hash_join=false, extension.rs:683): SortMergeJoinExec over sorted, co-partitioned inputs
+        srt = lambda x: P.sort([P.sort_key(c(0))], x, preserve_partitioning=True)
+        j = P.sort_merge_join(srt(P.shuffle_reader(1, side)), srt(P.shuffle_reader(2, side)), [[c(0), c(0)]], join_type)
+    else:
+        j = P.hash_join(P.shuffle_reader(1, side), P.shuffle_reader(2, side), [[c(0), c(0)]], join_type, "Partitioned")
     out_cols = 1 if join_type in ("LeftSemi", "LeftAnti", "RightSemi", "RightAnti") else 2
     s3 = P.sort([P.sort_key(c(0), asc=False)], P.project([(c(0), "id")], j), preserve_partitioning=True)
     st3 = Stage(3, P.shuffle_writer(s3, 3))

@@ -91,6 +91,30 @@ def test_join_against_pyarrow(oracle):
         assert gl == wl, jt
 
 
+def test_sort_merge_join_ordering(oracle):
+    """SortMergeJoinExec: the same rows as the hash join, delivered ordered by the join keys (per task)"""
+    rng = np.random.default_rng(12)
+    l = pa.table({"id": pa.array(rng.integers(0, 40, 300), type=pa.int64()), "a": pa.array(rng.integers(0, 9, 300), type=pa.int64())})
+    r = pa.table({"id": pa.array(rng.integers(0, 40, 200), type=pa.int64()), "b": pa.array([f"s{i}" for i in range(200)])})
+    G.register(oracle, "l", l, 3)
+    G.register(oracle, "r", r, 2)
+    c = P.col
+    ls, rs = [P.field("id", "i64"), P.field("a", "i64")], [P.field("id", "i64"), P.field("b", "utf8")]
+    rows = lambda tb: sorted(tuple(str(v) for v in rw) for rw in zip(*[col.to_pylist() for col in tb.columns]))
+    for jt in ("Inner", "Left", "Right", "LeftSemi", "LeftAnti", "RightSemi"):
+        st1 = Q.Stage(1, P.shuffle_writer(P.scan("l", ls), 1, [c(0)], 1))
+        st2 = Q.Stage(2, P.shuffle_writer(P.scan("r", rs), 2, [c(0)], 1))
+        hj = P.hash_join(P.shuffle_reader(1, ls), P.shuffle_reader(2, rs), [[c(0), c(0)]], jt, "Partitioned")
+        sm = P.sort_merge_join(P.shuffle_reader(1, ls), P.shuffle_reader(2, rs), [[c(0), c(0)]], jt,
+                               sort_options=[{"asc": False, "nulls_first": True}])
+        a = driver.run_stages(oracle, [st1, st2, Q.Stage(3, P.shuffle_writer(hj, 3))], "smj-h" + jt)
+        b = driver.run_stages(oracle, [st1, st2, Q.Stage(3, P.shuffle_writer(sm, 3))], "smj-s" + jt)
+        assert rows(a) == rows(b), jt
+        key_col = 2 if jt == "Right" else 0
+        keys = b.column(key_col).to_pylist()
+        assert keys == sorted(keys, key=lambda v: (v is not None, -(v if v is not None else 0))), jt  # DESC NULLS FIRST
+
+
 def test_sort_against_pyarrow(oracle):
     t = _rand_table(500, seed=5)
     G.register(oracle, "t", t, 1)

@@ -99,6 +99,14 @@ def test_hash_join_when_opted_in(engine):
     assert out.column(0).to_pylist() == REF["hash_join_ids_desc"]
 
 
+def test_default_sort_merge_join(engine):
+    """same query with Ballista's default join strategy (SortMergeJoinExec): same golden result"""
+    t, sch = alltypes()
+    G.register(engine, "test", t, 2)
+    out = driver.run_stages(engine, Q.q_self_join("test", sch, smj=True), "g7s")
+    assert out.column(0).to_pylist() == REF["hash_join_ids_desc"]
+
+
 @pytest.mark.parametrize("jt,want", [("LeftSemi", [7, 6, 5, 4, 3]), ("LeftAnti", []), ("RightSemi", [7, 6, 5, 4, 3]),
                                      ("RightAnti", [2, 1, 0]), ("Left", [7, 6, 5, 4, 3]), ("Right", [7, 6, 5, 4, 3, None, None, None]),
                                      ("Full", [7, 6, 5, 4, 3, None, None, None])])
