@@ -5,7 +5,8 @@ PKG       := datafusion-ballista_b200
 SRC       := $(PKG)/csrc
 OUT       := $(PKG)/lib
 NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-function
-OBJS      := $(OUT)/pipeline.o $(OUT)/kernels.o $(OUT)/engine.o
+OBJS      := $(OUT)/pipeline.o $(OUT)/kernels.o $(OUT)/engine.o $(OUT)/host_narrow.o
+CXX       ?= g++
 COMMON    := $(wildcard $(SRC)/common/*.hpp) $(wildcard $(SRC)/device/*.h) $(wildcard $(SRC)/device/*.cuh) $(wildcard $(SRC)/host/*.hpp) include/b200exec.h include/b200_arrow_abi.h
 
 all: $(OUT)/libb200exec.so oracle
@@ -19,6 +20,9 @@ $(OUT)/kernels.o: $(SRC)/device/kernels.cu $(COMMON)
 $(OUT)/engine.o: $(SRC)/host/engine.cpp $(COMMON)
 	@mkdir -p $(OUT)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+$(OUT)/host_narrow.o: $(SRC)/host/host_narrow.cpp
+	@mkdir -p $(OUT)
+	$(CXX) -O3 -std=c++17 -fPIC -c $< -o $@
 $(OUT)/libb200exec.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
 

@@ -327,6 +327,20 @@ void launch_gather_fixed(const void* in, const uint8_t* valid_in, void* out, uin
     default: gather_kernel<ulonglong2><<<g, 256, 0, st>>>((const ulonglong2*)in, valid_in, (ulonglong2*)out, valid_out, idx, n); break;
   }
 }
+// ingest: sign-extend host-narrowed Decimal128 values (int32 / int64) back to 16 bytes
+template <typename T>
+__global__ void widen_to_i128_kernel(const T* in, ulonglong2* out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long v = (long long)in[i];
+    out[i] = make_ulonglong2((unsigned long long)v, (unsigned long long)(v >> 63));
+  }
+}
+void launch_widen_to_i128(const void* in, int width, void* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  if (width == 4) widen_to_i128_kernel<int32_t><<<grid_for(n, 256, 4), 256, 0, st>>>((const int32_t*)in, (ulonglong2*)out, n);
+  else widen_to_i128_kernel<int64_t><<<grid_for(n, 256, 4), 256, 0, st>>>((const int64_t*)in, (ulonglong2*)out, n);
+}
+
 // Arrow offsets of a row slice -> offsets starting at 0; also reports the slice's first/last offset
 // (the chars range) without a host round trip per column
 __global__ void rebase_offsets_kernel(const int32_t* in, int64_t n_plus_1, int32_t* out, int32_t* first_last) {

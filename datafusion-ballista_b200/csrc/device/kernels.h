@@ -75,6 +75,8 @@ struct GatherCols {
   int n;
 };
 void launch_gather_multi(const GatherCols& cols, const int64_t* idx, int64_t n, cudaStream_t st);
+// ingest: int32 / int64 (width 4 / 8) -> sign-extended 16-byte Decimal128 values
+void launch_widen_to_i128(const void* in, int width, void* out, int64_t n, cudaStream_t st);
 // out[i] = in[i] - in[0] for i < n_plus_1; first_last[0..1] = in[0], in[n_plus_1 - 1] (device memory)
 void launch_rebase_offsets(const int32_t* in, int64_t n_plus_1, int32_t* out, int32_t* first_last, cudaStream_t st);
 void launch_iota_i64(int64_t* out, int64_t n, cudaStream_t st);

@@ -76,7 +76,8 @@ int b200_engine_synchronize(b200_engine* e);
 uint64_t b200_engine_kernel_launches(b200_engine* e);
 /* Introspection for tests and bench.py: how many pipelines ran on which kernel family so far.
  * name: "fused" (fused.cuh kernel, any variant), "fused_static" (an ahead-of-time shape),
- * "vm" (tile VM pipeline_kernel).  Unknown names return 0. */
+ * "vm" (tile VM pipeline_kernel); "ingest_bytes_saved": host->device bytes NOT sent because
+ * Decimal128 values were narrowed on the host and widened on the device.  Unknown names return 0. */
 uint64_t b200_engine_counter(b200_engine* e, const char* name);
 /* session config (TaskDefinition.props), e.g. "datafusion.execution.batch_size" */
 int b200_engine_set_config(b200_engine* e, const char* key, const char* value);
