@@ -99,6 +99,23 @@ def measured_hbm_peak():
 
 
 # ---- CPU arm (oracle) -------------------------------------------------------------------------------
+def usable_cpus() -> int:
+    """CPUs this process may actually use: the cgroup quota when there is one (the B200 boxes expose 128
+    hardware threads under a 16-CPU quota; oversubscribing it only adds throttling), else os.cpu_count()."""
+    n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(quota) // int(period)))
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_q1(rows: int, threads: int, steps: int, warmup: int):
     """q1 over `rows` lineitem rows on the CPU oracle: `threads` map tasks in parallel (the reference
     runs one task per partition on its DedicatedExecutor pool, cpu_bound_executor.rs:94-131)."""
@@ -137,7 +154,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     rows = ROWS_SF10 // 4
     times = cpu_q1(rows, threads, args.steps, args.warmup)
     total = sum(times)
@@ -314,7 +331,7 @@ def run_b200(args):
             line["e2e"] = e2e
         # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = usable_cpus()
             rows = ROWS_SF10 // 4
             t = cpu_q1(rows, threads, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": rows * len(t) / sum(t), "unit": "rows/s", "cores": threads, "kind": "port",
