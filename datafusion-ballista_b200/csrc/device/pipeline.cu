@@ -2038,32 +2038,6 @@ __device__ __noinline__ int fused_resolve_slow(RegGroupTable* gt, int G, int n_k
   return reg_group_lookup(gt, G, n_keys, ck, kv);
 }
 
-// Checked decimal product entirely in registers.  Fast path: both operands fit 64 bits (always the
-// case for TPC-H prices/discounts); non-negative operands use the unsigned multiply-high.
-struct Prod128 {
-  uint64_t lo, hi;
-  uint32_t ovf;
-};
-__device__ __noinline__ Prod128 mul128_slow_val(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
-  i128 out = 0;
-  Prod128 r;
-  r.ovf = mul_i128_slow(make_i128(alo, ahi), make_i128(blo, bhi), &out) ? 1u : 0u;
-  r.lo = lo64(out);
-  r.hi = hi64(out);
-  return r;
-}
-__device__ __forceinline__ Prod128 mul128_fast_val(uint64_t alo, uint64_t ahi, uint64_t blo, uint64_t bhi) {
-  Prod128 r;
-  r.ovf = 0;
-  const bool a64 = ahi == (uint64_t)((int64_t)alo >> 63), b64 = bhi == (uint64_t)((int64_t)blo >> 63);
-  if (a64 && b64) {
-    r.lo = alo * blo;
-    if ((int64_t)(alo | blo) >= 0) r.hi = __umul64hi(alo, blo);
-    else r.hi = (uint64_t)__mul64hi((int64_t)alo, (int64_t)blo);
-    return r;
-  }
-  return mul128_slow_val(alo, ahi, blo, bhi);
-}
 // raw (lo, hi) of a tile operand of width 4 / 8 / 16
 __device__ __forceinline__ void ld_raw128(const uint8_t* base, uint32_t w, int e, uint64_t& lo, uint64_t& hi) {
   if (w == 16) {

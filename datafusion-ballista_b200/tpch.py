@@ -305,3 +305,61 @@ def q12(n_partitions: int = 4, modes=("MAIL", "SHIP"), year: int = 1994) -> List
     fin = [P.field("l_shipmode", "utf8", True), P.field("high_line_count", i64, True), P.field("low_line_count", i64, True)]
     st5 = Stage(5, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(4, fin)), 5), n_tasks=1)
     return [st1, st2, st3, st4, st5]
+
+
+Q4_TABLES = {"orders": ["o_orderkey", "o_orderdate", "o_orderpriority"], "lineitem": ["l_orderkey", "l_commitdate", "l_receiptdate"]}
+
+
+def q4(n_partitions: int = 4, date_from: str = "1993-07-01", date_to: str = "1993-10-01") -> List[Stage]:
+    """benchmarks/queries/q4.sql -- EXISTS subquery decorrelated into a semi join (orders LEFT SEMI lineitem on
+    orderkey), COUNT(*) GROUP BY o_orderpriority ORDER BY o_orderpriority."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.and_(P.binop(">=", c("o_orderdate"), P.lit_date(date_from)), P.binop("<", c("o_orderdate"), P.lit_date(date_to))),
+                   table_scan("orders", Q4_TABLES["orders"]), projection=[0, 2])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    s2 = P.filter_(P.binop("<", c("l_commitdate"), c("l_receiptdate")), table_scan("lineitem", Q4_TABLES["lineitem"]), projection=[0])
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(0)], Pn))
+    od = [P.field("o_orderkey", i64, True), P.field("o_orderpriority", "utf8", True)]
+    # build = lineitem keys, probe = orders: RightSemi keeps every probe-side order that has a match
+    j = P.hash_join(P.shuffle_reader(2, [P.field("l_orderkey", i64, True)]), P.shuffle_reader(1, od), [[c(0), c(0)]], "RightSemi", "Partitioned")
+    s3 = P.aggregate("Partial", [(c(1), "o_orderpriority")], [P.agg("count", None, "order_count")], j)
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    part = [P.field("o_orderpriority", "utf8", True), P.field("order_count[count]", i64)]
+    s4 = P.aggregate("FinalPartitioned", [(c(0), "o_orderpriority")], [P.agg("count", None, "order_count")], P.shuffle_reader(3, part))
+    keys = [P.sort_key(c(0))]
+    s4 = P.sort(keys, s4, preserve_partitioning=True)
+    st4 = Stage(4, P.shuffle_writer(s4, 4))
+    fin = [P.field("o_orderpriority", "utf8", True), P.field("order_count", i64)]
+    st5 = Stage(5, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(4, fin)), 5), n_tasks=1)
+    return [st1, st2, st3, st4, st5]
+
+
+Q13_TABLES = {"customer": ["c_custkey"], "orders": ["o_orderkey", "o_custkey", "o_comment"]}
+
+
+def q13(n_partitions: int = 4, pattern: str = "%special%requests%") -> List[Stage]:
+    """benchmarks/queries/q13.sql -- customer LEFT OUTER JOIN orders (NOT LIKE filter pushed below the join),
+    COUNT(o_orderkey) per customer (SinglePartitioned: the join output is already partitioned on c_custkey), then the
+    distribution of that count: GROUP BY c_count ORDER BY custdist DESC, c_count DESC."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    st1 = Stage(1, P.shuffle_writer(table_scan("customer", Q13_TABLES["customer"]), 1, [c(0)], Pn))
+    s2 = P.filter_(P.like(c("o_comment"), pattern, negated=True), table_scan("orders", Q13_TABLES["orders"]), projection=[0, 1])
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(1)], Pn))
+    od = [P.field("o_orderkey", i64, True), P.field("o_custkey", i64, True)]
+    # build = orders, probe = customer: Right join keeps every probe-side customer, NULL orders where none match
+    j = P.hash_join(P.shuffle_reader(2, od), P.shuffle_reader(1, [P.field("c_custkey", i64, True)]), [[c(1), c(0)]], "Right", "Partitioned",
+                    projection=[2, 0])
+    s3 = P.aggregate("SinglePartitioned", [(c(0), "c_custkey")], [P.agg("count", c(1), "c_count")], j)
+    s3 = P.project([(c(1), "c_count")], s3)
+    s3 = P.aggregate("Partial", [(c(0), "c_count")], [P.agg("count", None, "custdist")], s3)
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    part = [P.field("c_count", i64, True), P.field("custdist[count]", i64)]
+    s4 = P.aggregate("FinalPartitioned", [(c(0), "c_count")], [P.agg("count", None, "custdist")], P.shuffle_reader(3, part))
+    keys = [P.sort_key(c(1), asc=False), P.sort_key(c(0), asc=False)]
+    s4 = P.sort(keys, s4, preserve_partitioning=True)
+    st4 = Stage(4, P.shuffle_writer(s4, 4))
+    fin = [P.field("c_count", i64, True), P.field("custdist", i64)]
+    st5 = Stage(5, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(4, fin)), 5), n_tasks=1)
+    return [st1, st2, st3, st4, st5]

@@ -171,3 +171,69 @@ def test_q12_gpu(gpu, oracle, oracle_lib, msf, parts, P):
     want = driver.run_stages(oracle, tpch.q12(P), f"q12-{msf}")
     assert want.num_rows > 0
     assert_tables_equal(got, want, sort=False)
+
+
+# ---- q4: semi join (EXISTS); q13: left outer join + NOT LIKE + two-level aggregation ----------------------
+def test_q4_oracle_against_pandas(oracle, oracle_lib):
+    import datetime as dt
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q4_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q4_TABLES}
+    o = df["orders"]
+    lo, hi = o.o_orderdate.min(), o.o_orderdate.max()
+    mid = lo + (hi - lo) / 3
+    d0, d1 = mid, mid + dt.timedelta(days=400)
+    got = driver.run_stages(oracle, tpch.q4(3, d0.isoformat(), d1.isoformat()), "q4o")
+    li = df["lineitem"]
+    keys = set(li[li.l_commitdate < li.l_receiptdate].l_orderkey)
+    o = o[(o.o_orderdate >= d0) & (o.o_orderdate < d1) & o.o_orderkey.isin(keys)]
+    want = o.groupby("o_orderpriority").size().to_dict()
+    assert want
+    rows = got.to_pylist()
+    assert [r["o_orderpriority"] for r in rows] == sorted(want)
+    assert {r["o_orderpriority"]: r["order_count"] for r in rows} == want
+
+
+def test_q13_oracle_against_pandas(oracle, oracle_lib):
+    import re
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q13_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q13_TABLES}
+    pattern = "%q%z%"
+    got = driver.run_stages(oracle, tpch.q13(3, pattern), "q13o")
+    rx = re.compile("^.*q.*z.*$", re.S)
+    o = df["orders"]
+    o = o[~o.o_comment.map(lambda s: bool(rx.match(s)))]
+    assert 0 < len(o) < len(df["orders"])       # the pattern is selective on this generator's comments
+    cnt = o.groupby("o_custkey").size().to_dict()
+    dist = {}
+    for ck in df["customer"].c_custkey:
+        k = cnt.get(ck, 0)
+        dist[k] = dist.get(k, 0) + 1
+    rows = got.to_pylist()
+    assert {r["c_count"]: r["custdist"] for r in rows} == dist
+    assert [(r["custdist"], r["c_count"]) for r in rows] == sorted(((v, k) for k, v in dist.items()), reverse=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("msf,parts,P", [(20, 2, 3), (100, 3, 8)])
+def test_q4_gpu(gpu, oracle, oracle_lib, msf, parts, P):
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, msf, tpch.Q4_TABLES, parts)
+    st = tpch.q4(P, "1993-01-01", "1996-01-01")
+    got = driver.run_stages(gpu, st, f"q4-{msf}")
+    want = driver.run_stages(oracle, st, f"q4-{msf}")
+    assert want.num_rows > 0
+    assert_tables_equal(got, want, sort=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("msf,parts,P", [(20, 2, 3), (100, 3, 8)])
+def test_q13_gpu(gpu, oracle, oracle_lib, msf, parts, P):
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, msf, tpch.Q13_TABLES, parts)
+    st = tpch.q13(P, "%q%z%")
+    got = driver.run_stages(gpu, st, f"q13-{msf}")
+    want = driver.run_stages(oracle, st, f"q13-{msf}")
+    assert want.num_rows > 1
+    assert_tables_equal(got, want, sort=False)
