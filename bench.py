@@ -43,6 +43,9 @@ def log(*a):
 
 # ---- clocks ---------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML (nvidia_ml_py) is polled in-process every
+    2 ms -- the timed region of this benchmark is tens of milliseconds, shorter than one `nvidia-smi -lms` tick;
+    nvidia-smi is only the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -50,8 +53,52 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.handle = None
+        self.sm, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.t = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _nvml_loop(self):
+        while not self.stop_flag:
+            try:
+                self._nvml_sample()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.gpu_index
+            if vis:
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                if self.gpu_index < len(ids) and ids[self.gpu_index].strip().isdigit():
+                    phys = int(ids[self.gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._nvml_sample()  # at least one sample at the start of the timed region
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception as e:
+            self.nvml = None
+            log("NVML clock sampling unavailable (", e, "); falling back to nvidia-smi")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
@@ -65,6 +112,16 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            try:
+                self._nvml_sample()  # ... and one at its end
+            except Exception:
+                pass
+            self.stop_flag = True
+            if self.t:
+                self.t.join(timeout=1)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.proc.terminate()
@@ -86,7 +143,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_hbm_peak():
