@@ -113,9 +113,16 @@ struct Exec {
 
 template <class T>
 T d2h_value(const void* dptr, cudaStream_t st) {
+  // small read-backs (row counts, string lengths, status words) land in a per-thread pinned slot: a
+  // pageable destination would make the "async" copy a staged, slower one
+  static thread_local void* slot = nullptr;
+  static_assert(sizeof(T) <= 64, "d2h_value is for scalars");
+  if (!slot && cudaHostAlloc(&slot, 64, cudaHostAllocDefault) != cudaSuccess) slot = nullptr;
   T v;
-  CUDA_CHECK(cudaMemcpyAsync(&v, dptr, sizeof(T), cudaMemcpyDeviceToHost, st));
+  void* dst = slot ? slot : (void*)&v;
+  CUDA_CHECK(cudaMemcpyAsync(dst, dptr, sizeof(T), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (slot) memcpy(&v, slot, sizeof(T));
   return v;
 }
 
@@ -371,8 +378,116 @@ DevBatchPtr import_batch(b200_engine* e, ArrowArray* arr, ArrowSchema* sch) {
 // ------------------------------------------------------------------------------------------------
 // Arrow export (HBM -> host)
 // ------------------------------------------------------------------------------------------------
+// Small results (the tail of most queries is a handful of rows): every buffer is copied asynchronously
+// into one pinned arena and the stream is synchronised twice in total (fixed-size parts, then string
+// bytes) instead of once per buffer.
+static const int64_t SMALL_EXPORT_ROWS = 4096;
+static const size_t SMALL_EXPORT_ARENA = (size_t)4 << 20;
+
+bool export_batch_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
+  const int64_t n = r1 - r0;
+  static thread_local uint8_t* arena = nullptr;
+  if (!arena && cudaHostAlloc((void**)&arena, SMALL_EXPORT_ARENA, cudaHostAllocDefault) != cudaSuccess) {
+    arena = nullptr;
+    return false;
+  }
+  cudaStream_t st = x.st();
+  struct Slot { size_t validity = 0, count = 0, data = 0, chars = 0; DevColumn u; bool has_valid = false; };
+  std::vector<Slot> slots(b.cols.size());
+  std::vector<HostCol> hcs(b.cols.size());
+  size_t pos = 0;
+  auto take = [&](size_t bytes) {
+    size_t p = pos;
+    pos += (bytes + 63) & ~(size_t)63;
+    return p;
+  };
+  // phase 1: validity bitmaps, null counts, fixed-width data / offsets
+  for (size_t ci = 0; ci < b.cols.size(); ci++) {
+    DevColumn c = slice_column(b.cols[ci], r0, r1);
+    HostCol& h = hcs[ci];
+    Slot& sl = slots[ci];
+    h.name = c.name;
+    h.type = c.type;
+    h.nullable = true;
+    h.n = n;
+    size_t need = (size_t)(n + 7) / 8 + 64 + (size_t)(n + 1) * 16 + 128;
+    if (pos + need > SMALL_EXPORT_ARENA / 2) return false;  // leave room for the string bytes
+    if (c.valid && n) {
+      sl.has_valid = true;
+      DevPtr bm = dev_alloc((size_t)(n + 7) / 8 + 16, st);
+      DevPtr cnt = dev_alloc(8, st);
+      CUDA_CHECK(cudaMemsetAsync(cnt->ptr, 0, 8, st));
+      launch_bytes_to_bitmap(c.valid, (uint8_t*)bm->ptr, n, (unsigned long long*)cnt->ptr, st);
+      x.count();
+      sl.validity = take((size_t)(n + 7) / 8);
+      sl.count = take(8);
+      CUDA_CHECK(cudaMemcpyAsync(arena + sl.validity, bm->ptr, (size_t)(n + 7) / 8, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(arena + sl.count, cnt->ptr, 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (c.type.id == TypeId::Bool) {
+      h.data.assign((size_t)(n + 7) / 8, 0);
+      if (n) {
+        DevPtr bm = dev_alloc((size_t)(n + 7) / 8 + 16, st);
+        launch_bytes_to_bitmap(c.data, (uint8_t*)bm->ptr, n, nullptr, st);
+        x.count();
+        sl.data = take(h.data.size());
+        CUDA_CHECK(cudaMemcpyAsync(arena + sl.data, bm->ptr, h.data.size(), cudaMemcpyDeviceToHost, st));
+      }
+    } else if (c.type.id == TypeId::Utf8) {
+      sl.u = c.phys == PH_STRVIEW ? as_utf8(x, c) : c;
+      h.data.resize((size_t)(n + 1) * 4);
+      sl.data = take(h.data.size());
+      CUDA_CHECK(cudaMemcpyAsync(arena + sl.data, sl.u.data, h.data.size(), cudaMemcpyDeviceToHost, st));
+    } else {
+      h.data.resize((size_t)n * c.width());
+      sl.data = take(h.data.size());
+      if (n) CUDA_CHECK(cudaMemcpyAsync(arena + sl.data, c.data, h.data.size(), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  // phase 2: string bytes (their range is known only now)
+  bool any_chars = false;
+  for (size_t ci = 0; ci < b.cols.size(); ci++) {
+    HostCol& h = hcs[ci];
+    Slot& sl = slots[ci];
+    if (sl.has_valid) {
+      unsigned long long nulls = 0;
+      memcpy(&nulls, arena + sl.count, 8);
+      h.null_count = (int64_t)nulls;
+      if (nulls) h.validity.assign(arena + sl.validity, arena + sl.validity + (size_t)(n + 7) / 8);
+    }
+    if (!h.data.empty()) memcpy(h.data.data(), arena + sl.data, h.data.size());
+    if (h.type.id == TypeId::Utf8) {
+      int32_t* off = (int32_t*)h.data.data();
+      const int32_t first = off[0], last = off[n];
+      h.extra.resize((size_t)(last - first));
+      if (last > first) {
+        if (pos + h.extra.size() > SMALL_EXPORT_ARENA) {  // long strings: straight into the vector
+          CUDA_CHECK(cudaMemcpyAsync(h.extra.data(), sl.u.chars + first, h.extra.size(), cudaMemcpyDeviceToHost, st));
+          CUDA_CHECK(cudaStreamSynchronize(st));
+          sl.chars = (size_t)-1;
+        } else {
+          sl.chars = take(h.extra.size());
+          CUDA_CHECK(cudaMemcpyAsync(arena + sl.chars, sl.u.chars + first, h.extra.size(), cudaMemcpyDeviceToHost, st));
+          any_chars = true;
+        }
+      }
+      for (int64_t i = 0; i <= n; i++) off[i] -= first;
+    }
+  }
+  if (any_chars) {
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t ci = 0; ci < b.cols.size(); ci++)
+      if (hcs[ci].type.id == TypeId::Utf8 && !hcs[ci].extra.empty() && slots[ci].chars != (size_t)-1)
+        memcpy(hcs[ci].extra.data(), arena + slots[ci].chars, hcs[ci].extra.size());
+  }
+  export_record_batch(std::move(hcs), n, out, out_schema);
+  return true;
+}
+
 void export_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
   const int64_t n = r1 - r0;
+  if (n <= SMALL_EXPORT_ROWS && export_batch_small(x, b, r0, r1, out, out_schema)) return;
   std::vector<HostCol> hcs;
   cudaStream_t st = x.st();
   for (auto& c0 : b.cols) {
