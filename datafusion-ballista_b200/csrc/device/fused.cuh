@@ -18,10 +18,6 @@
 //     constant memory so that any matching program still runs.
 #pragma once
 
-#ifndef FUSED_PRELOAD
-#define FUSED_PRELOAD 1  // load the group partials before the tile's arithmetic (see fused_try_narrow)
-#endif
-
 namespace b200 {
 
 template <uint64_t SA, uint64_t SB>
@@ -314,36 +310,10 @@ __device__ __forceinline__ uint32_t fused_ld_narrow(const uint8_t* base, uint32_
   return v;
 }
 
-// grouped accumulate with the old partials already in registers: new = old + addend, stored back.
-// A row whose group equals that of an earlier active row of the same thread holds a stale `old`
-// and falls back to a read-modify-write behind that row's store.
-template <int G, int R, class X>
-__device__ __forceinline__ void fused_accumulate_preloaded(const uint32_t active, const uint32_t (&gid)[R], const uint64_t (&add)[VM_REG_ACC][R],
-                                                           const uint64_t (&old)[VM_REG_ACC][R], uint64_t* accs, const int B) {
-#pragma unroll
-  for (int r = 0; r < R; r++) {
-    if ((active >> r) & 1) {
-      bool stale = false;
-#pragma unroll
-      for (int q = 0; q < r; q++) stale |= ((active >> q) & 1) && gid[q] == gid[r];
-      uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
-      if (stale) {
-#pragma unroll
-        for (int a = 0; a < VM_REG_ACC; a++)
-          if (a < X::na()) pa[a * B] += add[a][r];
-      } else {
-#pragma unroll
-        for (int a = 0; a < VM_REG_ACC; a++)
-          if (a < X::na()) pa[a * B] = old[a][r] + add[a][r];
-      }
-    }
-  }
-}
-
 template <int G, int R, class X>
 __device__ __forceinline__ bool fused_try_narrow(const uint8_t* __restrict__ stage, const int lane, uint32_t& active_io, uint32_t (&gid)[R],
-                                                 uint64_t (&add)[VM_REG_ACC][R], uint64_t (&old)[VM_REG_ACC][R], const uint64_t* accs, const int B,
-                                                 const unsigned long long (&dir)[G], const uint32_t dir_n, const uint64_t (&kvs)[2][R], const uint32_t kslow) {
+                                                 uint64_t (&add)[VM_REG_ACC][R], const unsigned long long (&dir)[G], const uint32_t dir_n,
+                                                 const uint64_t (&kvs)[2][R], const uint32_t kslow) {
   const FusedSpec& F = c_fused;
   uint32_t active = active_io;
   uint32_t bad[R];
@@ -380,16 +350,6 @@ __device__ __forceinline__ bool fused_try_narrow(const uint8_t* __restrict__ sta
       }
       gid[r] = g;
       bad[r] |= hit ^ 1u;
-    }
-  }
-  // the partials these rows will update: loaded now, a whole tile's arithmetic before they are
-  // needed, so the shared-memory round trip is off the critical path (see fused_accumulate_preloaded)
-  if (G > 1 && FUSED_PRELOAD) {
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const uint64_t* pa = accs + (size_t)gid[r] * (VM_REG_ACC * B);
-#pragma unroll
-      for (int a = 0; a < VM_REG_ACC; a++) old[a][r] = a < X::na() ? pa[a * B] : 0ull;
     }
   }
   // ---- filters
@@ -777,13 +737,12 @@ __global__ void __launch_bounds__(BT, 1) fused_kernel() {
       if (lane + 32 * r < rows) active |= 1u << r;
     {
       uint32_t gid[R];
-      uint64_t add[VM_REG_ACC][R], old[VM_REG_ACC][R];
+      uint64_t add[VM_REG_ACC][R];
       uint32_t act = active;
-      const bool ok = fused_try_narrow<G, R, X>(stage, lane, act, gid, add, old, accs, B, dir, dir_n, kv_cur, kslow_cur);
+      const bool ok = fused_try_narrow<G, R, X>(stage, lane, act, gid, add, dir, dir_n, kv_cur, kslow_cur);
       if (__all_sync(0xFFFFFFFFu, ok)) {
         active = act;
-        if (G == 1 || !FUSED_PRELOAD) fused_accumulate<G, R, X>(active, gid, add, S_reg, accs, B);
-        else fused_accumulate_preloaded<G, R, X>(active, gid, add, old, accs, B);
+        fused_accumulate<G, R, X>(active, gid, add, S_reg, accs, B);
       } else if (G == 1) {
         active = fused_rows<G, R, X>(stage, row0, lane, active, S_reg, accs, B, &gtable, dir, dir_n, kv_cur, kslow_cur);
       } else {
