@@ -380,7 +380,7 @@ def run_b200(args):
                        "target_partitions": P, "l2_policy": "inputs (4.68 GB per GPU) far larger than the 126 MB L2",
                        "stages": "scan+filter+project+partial-agg+hash-shuffle | final-agg+sort | merge"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fused_kernel<G=4,R=2,shape=q1> (stage 1: scan+filter+project+partial aggregate)",
+                         "traffic": traffic, "kernel": "fused_kernel<G=4,R=4,BT=256,shape=q1> (stage 1: scan+filter+project+partial aggregate)",
                          "peak_source": peak_src, "kernel_ms": kern_s * 1e3, "algorithmic_bytes": alg_bytes},
             "gpu_launches": launches, "clocks": clocks,
         }
