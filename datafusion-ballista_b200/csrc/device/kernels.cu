@@ -615,8 +615,11 @@ __global__ void sort_word_kernel(SortWordArgs A, const uint32_t* perm, uint64_t*
         case PH_U64: w = ((const uint64_t*)A.data)[i]; break;
         case PH_F32:
         case PH_F64: {
-          double d = A.phys == PH_F32 ? (double)((const float*)A.data)[i] : ((const double*)A.data)[i];
-          long long x = __double_as_longlong(d);
+          // raw bits as an INTEGER: if the compiler sees a double here it turns `bits ^ signbit` into an
+          // FP negate, and neg.f64 of a NaN does not return the sign-flipped bit pattern (NaN keys were
+          // ordered below -0.0); found by tests/test_gpu_sort.py
+          long long x = A.phys == PH_F32 ? __double_as_longlong((double)((const float*)A.data)[i]) : ((const long long*)A.data)[i];
+          asm volatile("" : "+l"(x));
           x ^= (long long)((unsigned long long)(x >> 63) >> 1);  // IEEE total order
           w = (uint64_t)x ^ 0x8000000000000000ull;
           break;
@@ -649,6 +652,74 @@ __global__ void sort_word_kernel(SortWordArgs A, const uint32_t* perm, uint64_t*
 void launch_sort_word(const SortWordArgs& A, const uint32_t* perm, uint64_t* out, int64_t n, cudaStream_t st) {
   sort_word_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(A, perm, out, n);
 }
+// ---- small-n comparison sort ---------------------------------------------------------------------
+// three-way compare of rows i and j under one key; mirrors the word encoding of sort_word_kernel
+__device__ __forceinline__ int small_sort_cmp(const SortWordArgs& A, int64_t i, int64_t j) {
+  const bool vi = !A.valid || A.valid[i], vj = !A.valid || A.valid[j];
+  if (vi != vj) {  // the null-rank word is not affected by asc/desc
+    const int ri = vi ? (A.nulls_first ? 1 : 0) : (A.nulls_first ? 0 : 1);
+    const int rj = vj ? (A.nulls_first ? 1 : 0) : (A.nulls_first ? 0 : 1);
+    return ri < rj ? -1 : 1;
+  }
+  if (!vi) return 0;
+  int c = 0;
+  switch (A.phys) {
+    case PH_I8: { const int8_t a = ((const int8_t*)A.data)[i], b = ((const int8_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_I16: { const int16_t a = ((const int16_t*)A.data)[i], b = ((const int16_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_I32: { const int32_t a = ((const int32_t*)A.data)[i], b = ((const int32_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_I64: { const int64_t a = ((const int64_t*)A.data)[i], b = ((const int64_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_U8:
+    case PH_BOOL8: { const uint8_t a = ((const uint8_t*)A.data)[i], b = ((const uint8_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_U16: { const uint16_t a = ((const uint16_t*)A.data)[i], b = ((const uint16_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_U32: { const uint32_t a = ((const uint32_t*)A.data)[i], b = ((const uint32_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_U64: { const uint64_t a = ((const uint64_t*)A.data)[i], b = ((const uint64_t*)A.data)[j]; c = a < b ? -1 : a > b; break; }
+    case PH_F32:
+    case PH_F64: {
+      long long a = A.phys == PH_F32 ? __double_as_longlong((double)((const float*)A.data)[i]) : ((const long long*)A.data)[i];
+      long long b = A.phys == PH_F32 ? __double_as_longlong((double)((const float*)A.data)[j]) : ((const long long*)A.data)[j];
+      asm volatile("" : "+l"(a), "+l"(b));  // keep the bit patterns integers (see sort_word_kernel)
+      a ^= (long long)((unsigned long long)(a >> 63) >> 1);  // IEEE total order
+      b ^= (long long)((unsigned long long)(b >> 63) >> 1);
+      c = a < b ? -1 : a > b;
+      break;
+    }
+    case PH_DEC128: {
+      const uint64_t* pa = (const uint64_t*)A.data + 2 * i;
+      const uint64_t* pb = (const uint64_t*)A.data + 2 * j;
+      const int64_t ha = (int64_t)pa[1], hb = (int64_t)pb[1];
+      c = ha != hb ? (ha < hb ? -1 : 1) : (pa[0] < pb[0] ? -1 : pa[0] > pb[0]);
+      break;
+    }
+    case PH_STRVIEW: {
+      const unsigned long long* va = (const unsigned long long*)A.data + 2 * i;
+      const unsigned long long* vb = (const unsigned long long*)A.data + 2 * j;
+      const uint8_t* sa = (const uint8_t*)va[0];
+      const uint8_t* sb = (const uint8_t*)vb[0];
+      const uint32_t la = (uint32_t)va[1], lb = (uint32_t)vb[1], m = la < lb ? la : lb;
+      for (uint32_t p = 0; p < m && c == 0; p++) c = sa[p] < sb[p] ? -1 : sa[p] > sb[p];
+      if (c == 0) c = la < lb ? -1 : la > lb;
+      break;
+    }
+    default: break;
+  }
+  return A.asc ? c : -c;
+}
+__global__ void small_sort_kernel(const SmallSortKeys K, int64_t* perm_out, int64_t n) {
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    int64_t rank = 0;
+    for (int64_t j = 0; j < n; j++) {
+      int c = 0;
+      for (int k = 0; k < K.n_keys && c == 0; k++) c = small_sort_cmp(K.k[k], j, i);
+      rank += (c < 0 || (c == 0 && j < i)) ? 1 : 0;  // stable
+    }
+    perm_out[rank] = i;
+  }
+}
+void launch_small_sort(const SmallSortKeys& K, int64_t* perm_out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  small_sort_kernel<<<1, 256, 0, st>>>(K, perm_out, n);
+}
+
 __global__ void max_view_len_kernel(const unsigned long long* views, const uint8_t* valid, int64_t n, unsigned int* out_max) {
   unsigned int m = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)

@@ -124,6 +124,16 @@ struct SortWordArgs {
   int32_t word;   // which 64-bit word of the normalised key (strings / i128 have several); -1 = null rank word
 };
 void launch_sort_word(const SortWordArgs& A, const uint32_t* perm, uint64_t* out, int64_t n, cudaStream_t st);
+// Small inputs (n <= SMALL_SORT_MAX_ROWS): stable sort permutation by direct comparison of up to SMALL_SORT_MAX_KEYS keys
+// in ONE launch (rank = number of rows that order before), same ordering as the key-word radix sort: NULL placement
+// per key, ascending/descending, IEEE total order for floats, bytewise strings with the shorter prefix first.
+static const int SMALL_SORT_MAX_ROWS = 1024;
+static const int SMALL_SORT_MAX_KEYS = 8;
+struct SmallSortKeys {
+  SortWordArgs k[SMALL_SORT_MAX_KEYS];  // `word` unused
+  int n_keys;
+};
+void launch_small_sort(const SmallSortKeys& K, int64_t* perm_out, int64_t n, cudaStream_t st);
 void launch_max_view_len(const unsigned long long* views, const uint8_t* valid, int64_t n, unsigned int* out_max, cudaStream_t st);
 // stable LSD radix sort of (key, val) pairs on 64-bit keys; ping-pong buffers; returns via *result_in_a
 void radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, uint32_t* hist_scratch,

@@ -124,6 +124,7 @@ __device__ __noinline__ i128 div_i128_dev(i128 a, i128 b) { return a / b; }
 __device__ __noinline__ i128 mod_i128_dev(i128 a, i128 b) { return a % b; }
 __device__ __forceinline__ long long f64_order_key(double a) {
   long long x = __double_as_longlong(a);
+  asm volatile("" : "+l"(x));  // integer from here on: no FP neg/abs folding of the bit tricks (NaN payloads)
   return x ^ (long long)((unsigned long long)(x >> 63) >> 1);
 }
 

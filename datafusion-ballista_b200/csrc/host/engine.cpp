@@ -1633,6 +1633,37 @@ struct Runner {
       return out;
     }
     if (n >= ((int64_t)1 << 32)) throw EngineError(B200_ERR_UNSUPPORTED, "sort of more than 2^32 rows");
+    if (n <= SMALL_SORT_MAX_ROWS && keys.size() <= (size_t)SMALL_SORT_MAX_KEYS) {
+      // the tail of a query (ORDER BY over a few groups): one comparison-sort launch, no length read-backs
+      SmallSortKeys K;
+      K.n_keys = (int)keys.size();
+      std::vector<DevColumn> kv;  // keeps the view buffers alive until the launch is enqueued
+      for (size_t ki = 0; ki < keys.size(); ki++) {
+        kv.push_back(as_views(x, kcols[ki]));
+        const DevColumn& kc = kv.back();
+        SortWordArgs& A = K.k[ki];
+        A.data = kc.data;
+        A.valid = kc.valid;
+        A.phys = kc.phys;
+        A.asc = keys[ki].asc;
+        A.nulls_first = keys[ki].nulls_first;
+        A.word = 0;
+      }
+      DevPtr idx = dev_alloc((size_t)n * 8, x.st());
+      launch_small_sort(K, (int64_t*)idx->ptr, n, x.st());
+      x.count();
+      const int64_t m = fetch >= 0 ? std::min<int64_t>(fetch, n) : n;
+      DevBatch proj;
+      proj.n = n;
+      for (size_t c = 0; c < n_in_cols; c++) proj.cols.push_back(in->cols[c]);
+      DevBatchPtr out = gather_batch(x, proj, (const int64_t*)idx->ptr, m, false);
+      CUDA_CHECK(cudaStreamSynchronize(x.st()));
+      if (met) {
+        met->elapsed_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        met->input_rows += (uint64_t)n;
+      }
+      return out;
+    }
     const uint32_t n_blocks = (uint32_t)((n + 2047) / 2048);
     DevPtr ka = dev_alloc((size_t)n * 8, x.st()), kb = dev_alloc((size_t)n * 8, x.st());
     DevPtr va = dev_alloc((size_t)n * 4, x.st()), vb = dev_alloc((size_t)n * 4, x.st());
