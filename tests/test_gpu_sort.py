@@ -63,3 +63,29 @@ def test_sort_orders_match(gpu, oracle, n, ks):
             assert got is None or got.num_rows == 0
             continue
         assert_tables_equal(got, want, sort=False)
+
+
+def test_float_min_max_with_nan_and_signed_zero(gpu, oracle):
+    """MIN/MAX(f64) order by the same IEEE total-order keys as the sorts: NaN above +inf, -0.0 below 0.0"""
+    n = 20000
+    b = _table(n, 77)
+    for e in (gpu, oracle):
+        e.drop_table("st")
+        e.register_batch("st", 0, b.slice(0, n // 2))
+        e.register_batch("st", 1, b.slice(n // 2))
+    c = P.col
+    for keyed in (True, False):
+        gb = [(c("i"), "i")] if keyed else []
+        aggs = [P.agg("min", c("f"), "mn"), P.agg("max", c("f"), "mx"), P.agg("count", c("f"), "n")]
+        s1 = P.aggregate("Partial", gb, aggs, P.scan("st", SCHEMA))
+        part = ([P.field("i", "i32", True)] if keyed else []) + [P.field("mn[min]", "f64", True), P.field("mx[max]", "f64", True), P.field("n[count]", "i64")]
+        faggs = [P.agg("min", None, "mn"), P.agg("max", None, "mx"), P.agg("count", None, "n")]
+        if keyed:
+            st = [Stage(1, P.shuffle_writer(s1, 1, [c(0)], 3)),
+                  Stage(2, P.shuffle_writer(P.aggregate("FinalPartitioned", [(c(0), "i")], faggs, P.shuffle_reader(1, part)), 2))]
+        else:
+            st = [Stage(1, P.shuffle_writer(s1, 1)),
+                  Stage(2, P.shuffle_writer(P.aggregate("Final", [], faggs, P.coalesce_partitions(P.shuffle_reader(1, part))), 2), n_tasks=1)]
+        got = driver.run_stages(gpu, st, f"mm-{keyed}")
+        want = driver.run_stages(oracle, st, f"mm-{keyed}")
+        assert_tables_equal(got, want)
