@@ -252,46 +252,6 @@ void launch_histogram_u32(const uint32_t* ids, int64_t n, uint32_t n_bins, unsig
   histogram_kernel<<<grid_for(n, 256, 8), 256, sm, st>>>(ids, n, n_bins, counts);
 }
 
-// Each CTA claims, per bin, one contiguous chunk of the output for all of its rows (one global
-// atomic per (CTA-chunk, bin)), then ranks its rows inside the chunk with shared-memory atomics.
-__global__ void partition_rank_kernel(const uint32_t* ids, int64_t n, uint32_t n_bins, unsigned long long* cursor, uint32_t* dest) {
-  extern __shared__ unsigned int sh[];  // [n_bins] counts, then [n_bins] base (as 2 x u32)
-  unsigned int* cnt = sh;
-  unsigned long long* base = (unsigned long long*)(sh + ((n_bins + 1) & ~1u));
-  const int64_t chunk = (int64_t)blockDim.x * 16;
-  for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < n; c0 += (int64_t)gridDim.x * chunk) {
-    for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x) cnt[b] = 0;
-    __syncthreads();
-    uint32_t my_rank[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      int64_t i = c0 + (int64_t)k * blockDim.x + threadIdx.x;
-      my_rank[k] = i < n ? atomicAdd(&cnt[ids[i]], 1u) : 0;
-    }
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x) base[b] = cnt[b] ? atomicAdd(&cursor[b], (unsigned long long)cnt[b]) : 0ull;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      int64_t i = c0 + (int64_t)k * blockDim.x + threadIdx.x;
-      if (i < n) dest[i] = (uint32_t)(base[ids[i]] + my_rank[k]);
-    }
-    __syncthreads();
-  }
-}
-__global__ void partition_rank_global_kernel(const uint32_t* ids, int64_t n, unsigned long long* cursor, uint32_t* dest) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dest[i] = (uint32_t)atomicAdd(&cursor[ids[i]], 1ull);
-}
-void launch_partition_rank(const uint32_t* ids, int64_t n, uint32_t n_bins, unsigned long long* cursor, uint32_t* dest, cudaStream_t st) {
-  if (n_bins <= 4096) {
-    size_t sm = ((n_bins + 1) & ~1u) * sizeof(unsigned int) + n_bins * sizeof(unsigned long long);
-    partition_rank_kernel<<<grid_for(n, 256, 16), 256, sm, st>>>(ids, n, n_bins, cursor, dest);
-  } else {
-    partition_rank_global_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(ids, n, cursor, dest);
-  }
-}
-
 template <typename T>
 __global__ void scatter_kernel(const T* in, T* out, const uint32_t* dest, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[dest[i]] = in[i];
@@ -839,6 +799,59 @@ void radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, 
     in_a = !in_a;
   }
   *result_in_a = in_a;
+}
+
+// ---- stable partition placement --------------------------------------------------------------------
+// dest[i] = (rows of lower partitions) + (earlier rows of the same partition): the reference's
+// BatchPartitioner keeps the input order inside every output partition (take() with ascending indices),
+// so do we -- stored partitions are then bit-identical from run to run.
+__global__ void partition_dest_small_kernel(const uint32_t* ids, int n, uint32_t* dest) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = ids[i];
+    uint32_t r = 0;
+    for (int j = 0; j < n; j++) {
+      const uint32_t q = ids[j];
+      r += (q < p || (q == p && j < i)) ? 1u : 0u;
+    }
+    dest[i] = r;
+  }
+}
+__global__ void partition_keys_kernel(const uint32_t* ids, int64_t n, uint64_t* keys, uint32_t* vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = ids[i];
+    vals[i] = (uint32_t)i;
+  }
+}
+__global__ void invert_perm_kernel(const uint32_t* perm, int64_t n, uint32_t* dest) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) dest[perm[k]] = (uint32_t)k;
+}
+uint64_t launch_partition_dest_stable(const uint32_t* ids, int64_t n, uint32_t n_bins, uint32_t* dest, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                                      uint32_t* vals_b, uint32_t* hist_scratch, uint64_t* scan_scratch, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n <= 4096) {
+    partition_dest_small_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ids, (int)n, dest);
+    return 1;
+  }
+  partition_keys_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(ids, n, keys_a, vals_a);
+  uint64_t launches = 1;
+  const int passes = n_bins <= 256 ? 1 : n_bins <= 65536 ? 2 : 4;
+  uint32_t n_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+  uint64_t* offsets = scan_scratch;
+  uint64_t* scan_tmp = scan_scratch + (uint64_t)256 * n_blocks + 1;
+  bool in_a = true;
+  for (int pass = 0; pass < passes; pass++) {
+    uint64_t* kin = in_a ? keys_a : keys_b;
+    uint32_t* vin = in_a ? vals_a : vals_b;
+    uint64_t* kout = in_a ? keys_b : keys_a;
+    uint32_t* vout = in_a ? vals_b : vals_a;
+    radix_hist_kernel<<<n_blocks, RS_BLOCK, 0, st>>>(kin, n, pass * 8, hist_scratch, n_blocks);
+    launch_scan_u32_to_u64(hist_scratch, offsets, (int64_t)256 * n_blocks, scan_tmp, st);
+    radix_scatter_kernel<<<n_blocks, RS_BLOCK, 0, st>>>(kin, vin, kout, vout, n, pass * 8, offsets, n_blocks);
+    launches += 5;
+    in_a = !in_a;
+  }
+  invert_perm_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(in_a ? vals_a : vals_b, n, dest);
+  return launches + 1;
 }
 
 // ------------------------------------------------------------------------------------------------

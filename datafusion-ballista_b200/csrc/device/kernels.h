@@ -56,7 +56,11 @@ void launch_agg_extract(const AggTable& T, const AggExtractArgs& A, cudaStream_t
 void launch_scan_u32_to_u64(const uint32_t* in, uint64_t* out, int64_t n, uint64_t* scratch /* >= n/1024+2 */, cudaStream_t st);
 void launch_histogram_u32(const uint32_t* ids, int64_t n, uint32_t n_bins, unsigned long long* counts, cudaStream_t st);
 // dest[i] = cursor[ids[i]]++  (cursor pre-seeded with the exclusive scan of counts)
-void launch_partition_rank(const uint32_t* ids, int64_t n, uint32_t n_bins, unsigned long long* cursor, uint32_t* dest, cudaStream_t st);
+// stable placement of rows into hash partitions: dest[i] = rows of lower partitions + earlier rows of the same
+// partition (input order kept inside a partition, like the reference's BatchPartitioner).  Scratch as for
+// radix_sort_pairs_u64; returns the number of launches.
+uint64_t launch_partition_dest_stable(const uint32_t* ids, int64_t n, uint32_t n_bins, uint32_t* dest, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b,
+                                      uint32_t* vals_b, uint32_t* hist_scratch, uint64_t* scan_scratch, cudaStream_t st);
 void launch_scatter_fixed(const void* in, void* out, const uint32_t* dest, int64_t n, int width, cudaStream_t st);
 // out[i] = idx[i] >= 0 ? in[idx[i]] : 0 ; valid_out (optional) = idx>=0 && valid_in
 void launch_gather_fixed(const void* in, const uint8_t* valid_in, void* out, uint8_t* valid_out, const int64_t* idx, int64_t n, int width, cudaStream_t st);

@@ -2033,11 +2033,16 @@ struct Runner {
     CUDA_CHECK(cudaStreamSynchronize(x.st()));
     std::vector<int64_t> bounds(P + 1, 0);
     for (uint32_t p = 0; p < P; p++) bounds[p + 1] = bounds[p] + (int64_t)hc[p];
-    DevPtr cursor = dev_alloc((size_t)(P + 1) * 8, x.st());
-    CUDA_CHECK(cudaMemcpyAsync(cursor->ptr, bounds.data(), (size_t)P * 8, cudaMemcpyHostToDevice, x.st()));
     DevPtr dest = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st());
-    launch_partition_rank(pid, n, P, (unsigned long long*)cursor->ptr, (uint32_t*)dest->ptr, x.st());
-    x.count();
+    {
+      const uint32_t n_blocks = (uint32_t)((n + 2047) / 2048) + 1;
+      DevPtr ka = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8, x.st()), kb = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8, x.st());
+      DevPtr va = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st()), vb = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st());
+      DevPtr hist = dev_alloc((size_t)256 * n_blocks * 4 + 64, x.st());
+      DevPtr scan = dev_alloc(((size_t)256 * n_blocks + 1 + (size_t)(256 * n_blocks) / 1024 + 8) * 8, x.st());
+      x.count(launch_partition_dest_stable(pid, n, P, (uint32_t*)dest->ptr, (uint64_t*)ka->ptr, (uint32_t*)va->ptr, (uint64_t*)kb->ptr, (uint32_t*)vb->ptr,
+                                           (uint32_t*)hist->ptr, (uint64_t*)scan->ptr, x.st()));
+    }
     auto st = std::make_shared<DevBatch>();
     st->n = n;
     std::vector<std::vector<int64_t>> chars_per_part;  // [string col][p]
