@@ -71,6 +71,7 @@ struct b200_engine {
   void* pinned_stage = nullptr;              // small pinned buffer for status read-backs
   // ingest narrowing (import_batch): host pool + two pinned staging slots with their device mirrors
   std::unique_ptr<HostPool> pool;
+  std::mutex ingest_mu;                      // one narrowing pipeline at a time (pool and staging slots are shared)
   struct NarrowSlot {
     void* pinned = nullptr;
     void* dev = nullptr;
@@ -239,6 +240,7 @@ static const int64_t NARROW_CHUNK_ROWS = (int64_t)1 << 22;  // 64 MiB of source 
 static const int64_t NARROW_BLOCK_ROWS = (int64_t)1 << 16;  // one pool task
 
 void ingest_decimal_narrowed(b200_engine* e, const uint8_t* src, uint8_t* dst, int64_t n, cudaStream_t st) {
+  std::lock_guard<std::mutex> ingest_guard(e->ingest_mu);
   if (!e->pool) {
     // default pool size: 1.5 x the CPUs this process may use (cgroup quota if there is one; the loops
     // are memory-latency bound, a few more threads than cores help, many more get throttled) --
