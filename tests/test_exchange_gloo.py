@@ -109,3 +109,39 @@ def test_exchange_all_to_all_world2():
     total_before = sum(sum(b.values()) for b in sent.values())
     total_after = sum(len(ks) for _, _, owned, _ in out for pieces in owned.values() for _, ks, _ in pieces)
     assert total_before == total_after
+
+
+def _worker_gather(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ballista_b200 import exchange
+    eng = FakeEngine()
+    # every rank wrote output partition `rank` of stage 2 (what bench.py's final merge gathers onto rank 0)
+    ks = [1000 * rank + j for j in range(3 + rank)]
+    eng.add("job", 2, rank, rank, ks, [f"g{k}" for k in ks])
+    exchange.exchange_stage(eng, "job", 2, world, SCHEMA, rank, world, torch.device("cpu"), owner=lambda p: 0)
+    held = {p: [(fid, bufs[1].view(np.int64).tolist()) for fid, bufs, rows in pieces] for (job, stage, p), pieces in eng.parts.items()}
+    q.put((rank, held))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_exchange_gather_to_rank0_world2():
+    """owner = rank 0 for every partition: the exchange degenerates into the gather the final merge stage needs"""
+    world, port = 2, 29741
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_gather, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=90) for _ in range(world))
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert out[1] == {}                                   # rank 1 keeps nothing
+    assert sorted(out[0]) == [0, 1]                       # rank 0 holds both partitions ...
+    for p in (0, 1):
+        assert out[0][p] == [(p, [1000 * p + j for j in range(3 + p)])]   # ... each as one piece tagged with its sender

@@ -12,3 +12,10 @@ def test_narrowing_matches_definition(tmp_path):
                     os.path.join(ROOT, "datafusion-ballista_b200", "csrc", "host", "host_narrow.cpp"), "-o", exe], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert "fails=0" in out
+
+
+def test_host_pool_runs_every_index_once(tmp_path):
+    exe = str(tmp_path / "pool_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(ROOT, "tests", "native", "pool_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout
+    assert "fails=0" in out
