@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
@@ -700,35 +701,42 @@ OCol eval(const Expr& e, const OBatch& b) {
 // ------------------------------------------------------------------------------------------------
 // Row key encoding (group-by / join keys)
 // ------------------------------------------------------------------------------------------------
+static inline bool encode_key_col(const OCol& c, size_t r, std::string& out) {
+  if (!c.is_valid(r)) {
+    out.push_back('\0');
+    return false;
+  }
+  out.push_back('\1');
+  switch (c.type.pk()) {
+    case PK::Bool:
+    case PK::I64: out.append((const char*)&c.i[r], 8); break;
+    case PK::F64: {
+      double v = c.f[r];
+      if (v == 0.0) v = 0.0;
+      if (v != v) v = std::nan("");
+      out.append((const char*)&v, 8);
+      break;
+    }
+    case PK::I128: out.append((const char*)&c.d[r], 16); break;
+    case PK::Str: {
+      uint32_t len = (uint32_t)c.s[r].size();
+      out.append((const char*)&len, 4);
+      out.append(c.s[r]);
+      break;
+    }
+  }
+  return true;
+}
 bool encode_key(const std::vector<OCol>& keys, size_t r, std::string& out) {  // returns false if any key is NULL
   out.clear();
   bool all_valid = true;
-  for (auto& c : keys) {
-    if (!c.is_valid(r)) {
-      out.push_back('\0');
-      all_valid = false;
-      continue;
-    }
-    out.push_back('\1');
-    switch (c.type.pk()) {
-      case PK::Bool:
-      case PK::I64: out.append((const char*)&c.i[r], 8); break;
-      case PK::F64: {
-        double v = c.f[r];
-        if (v == 0.0) v = 0.0;
-        if (v != v) v = std::nan("");
-        out.append((const char*)&v, 8);
-        break;
-      }
-      case PK::I128: out.append((const char*)&c.d[r], 16); break;
-      case PK::Str: {
-        uint32_t len = (uint32_t)c.s[r].size();
-        out.append((const char*)&len, 4);
-        out.append(c.s[r]);
-        break;
-      }
-    }
-  }
+  for (auto& c : keys) all_valid &= encode_key_col(c, r, out);
+  return all_valid;
+}
+bool encode_key(const std::vector<const OCol*>& keys, size_t r, std::string& out) {  // same, over borrowed columns
+  out.clear();
+  bool all_valid = true;
+  for (auto* c : keys) all_valid &= encode_key_col(*c, r, out);
   return all_valid;
 }
 
@@ -809,21 +817,40 @@ OBatch do_aggregate(const PlanNode& node, const OBatch& in) {
   bool from_states = agg_mode_consumes_states(node.agg_mode);
   bool emit_states = agg_mode_emits_states(node.agg_mode);
   size_t ng = node.group_by.size(), na = node.aggs.size();
-  std::vector<OCol> keys;
-  for (auto& g : node.group_by) keys.push_back(eval(*g.expr, in));
+  // plain column references (keys, aggregate arguments, state columns) are borrowed from `in`; only
+  // computed expressions are materialised (into `store`, a deque so that the addresses stay put)
+  std::deque<OCol> store;
+  auto borrow = [&](const Expr& e) -> const OCol* {
+    if (e.kind == Expr::Col && e.col >= 0 && (size_t)e.col < in.cols.size()) return &in.cols[(size_t)e.col];
+    store.push_back(eval(e, in));
+    return &store.back();
+  };
+  std::vector<const OCol*> keys;
+  for (auto& g : node.group_by) keys.push_back(borrow(*g.expr));
   // inputs per aggregate: raw: [arg]; from states: the state columns
-  std::vector<std::vector<OCol>> ain(na);
+  std::vector<std::vector<const OCol*>> ainp(na);
   size_t sc = ng;
   for (size_t a = 0; a < na; a++) {
     const AggExpr& ae = node.aggs[a];
     if (from_states) {
-      for (int k = 0; k < ae.n_state_cols(); k++) ain[a].push_back(in.cols.at(sc++));
+      for (int k = 0; k < ae.n_state_cols(); k++) ainp[a].push_back(&in.cols.at(sc++));
     } else if (ae.arg) {
-      OCol c = eval(*ae.arg, in);
-      if (ae.fn == AggFn::Avg && !c.type.is_decimal()) c = eval_cast(c, DataType(TypeId::Float64));
-      ain[a].push_back(std::move(c));
+      const OCol* c = borrow(*ae.arg);
+      if (ae.fn == AggFn::Avg && !c->type.is_decimal()) {
+        store.push_back(eval_cast(*c, DataType(TypeId::Float64)));
+        c = &store.back();
+      }
+      ainp[a].push_back(c);
     }
   }
+  struct AinRow {  // keeps the body below reading `ain[a][k]` as a column
+    const std::vector<const OCol*>* v;
+    const OCol& operator[](size_t k) const { return *(*v)[k]; }
+  };
+  struct AinAll {
+    const std::vector<std::vector<const OCol*>>* v;
+    AinRow operator[](size_t a) const { return AinRow{&(*v)[a]}; }
+  } ain{&ainp};
   std::unordered_map<std::string, size_t> index;
   std::vector<size_t> first_row;
   std::vector<std::vector<Acc>> accs;  // [group][agg]
@@ -906,7 +933,7 @@ OBatch do_aggregate(const PlanNode& node, const OBatch& in) {
   out.n = G;
   std::vector<int64_t> fr(first_row.begin(), first_row.end());
   for (size_t g = 0; g < ng; g++) {
-    OCol kc = take(keys[g], fr);
+    OCol kc = take(*keys[g], fr);
     kc.name = node.group_by[g].name;
     out.cols.push_back(std::move(kc));
   }
@@ -1203,18 +1230,38 @@ struct Oracle {
         return out;
       }
       case PlanNode::Filter: {
-        OBatch in = exec(*n.children[0], part, job);
+        // A filter directly over a table scan whose projection is the identity reads the registered
+        // batch in place (no private copy of every column first); only the surviving rows of the
+        // columns the filter's own projection keeps are materialised.  Same values, fewer copies.
+        std::shared_ptr<OBatch> direct;
+        OBatch owned;
+        const PlanNode& ch = *n.children[0];
+        if (ch.op == PlanNode::Scan) {
+          std::lock_guard<std::mutex> g(mu);
+          auto it = tables.find(ch.table);
+          if (it != tables.end()) {
+            auto pit = it->second.find(part);
+            if (pit != it->second.end()) {
+              bool identity = ch.scan_projection.size() == pit->second->cols.size();
+              for (size_t k = 0; identity && k < ch.scan_projection.size(); k++)
+                identity = ch.scan_projection[k] == (int)k && pit->second->cols[k].type == ch.schema[k].type;
+              if (identity) direct = pit->second;
+            }
+          }
+        }
+        if (!direct) owned = exec(ch, part, job);
+        const OBatch& in = direct ? *direct : owned;
         OCol m = eval(*n.predicate, in);
         std::vector<int64_t> idx;
         for (size_t r = 0; r < in.n; r++)
           if (m.is_valid(r) && m.i[r]) idx.push_back((int64_t)r);
         if (n.fetch >= 0 && (size_t)n.fetch < idx.size()) idx.resize((size_t)n.fetch);
-        OBatch out = take(in, idx);
+        OBatch out;
+        out.n = idx.size();
         if (n.has_projection) {
-          OBatch p;
-          p.n = out.n;
-          for (int i : n.projection) p.cols.push_back(out.cols[(size_t)i]);
-          return p;
+          for (int i : n.projection) out.cols.push_back(take(in.cols.at((size_t)i), idx));
+        } else {
+          for (auto& c : in.cols) out.cols.push_back(take(c, idx));
         }
         return out;
       }
@@ -1222,11 +1269,23 @@ struct Oracle {
         OBatch in = exec(*n.children[0], part, job);
         OBatch out;
         out.n = in.n;
-        for (auto& ne : n.exprs) {
-          OCol c = eval(*ne.expr, in);
-          c.name = ne.name;
-          out.cols.push_back(std::move(c));
+        // computed expressions first (they read `in`); then the plain column references, moved out of the
+        // input batch when this is their last use instead of copied
+        out.cols.resize(n.exprs.size());
+        for (size_t k = 0; k < n.exprs.size(); k++)
+          if (n.exprs[k].expr->kind != Expr::Col) out.cols[k] = eval(*n.exprs[k].expr, in);
+        for (size_t k = 0; k < n.exprs.size(); k++) {
+          const Expr& e = *n.exprs[k].expr;
+          if (e.kind != Expr::Col) continue;
+          if ((size_t)e.col >= in.cols.size()) exec_fail("projection column out of range");
+          // every computed expression has already been evaluated; other plain references still need the column
+          bool last = true;
+          for (size_t k2 = k + 1; k2 < n.exprs.size() && last; k2++)
+            last = !(n.exprs[k2].expr->kind == Expr::Col && n.exprs[k2].expr->col == e.col);
+          if (last) out.cols[k] = std::move(in.cols[(size_t)e.col]);
+          else out.cols[k] = in.cols[(size_t)e.col];
         }
+        for (size_t k = 0; k < n.exprs.size(); k++) out.cols[k].name = n.exprs[k].name;
         return out;
       }
       case PlanNode::Aggregate: {
