@@ -363,3 +363,58 @@ def q13(n_partitions: int = 4, pattern: str = "%special%requests%") -> List[Stag
     fin = [P.field("c_count", i64, True), P.field("custdist", i64)]
     st5 = Stage(5, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(4, fin)), 5), n_tasks=1)
     return [st1, st2, st3, st4, st5]
+
+
+Q10_TABLES = {"nation": ["n_nationkey", "n_name"],
+              "customer": ["c_custkey", "c_name", "c_address", "c_nationkey", "c_phone", "c_acctbal", "c_comment"],
+              "orders": ["o_orderkey", "o_custkey", "o_orderdate"],
+              "lineitem": ["l_orderkey", "l_extendedprice", "l_discount", "l_returnflag"]}
+
+
+def q10(n_partitions: int = 4, date_from: str = "1993-10-01", date_to: str = "1994-01-01", flag: str = "R") -> List[Stage]:
+    """benchmarks/queries/q10.sql -- customer |x| nation (broadcast), |x| orders, |x| lineitem; seven group keys (integer,
+    strings, decimal) through the hash-table aggregate; top-20 by revenue."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    st1 = Stage(1, P.shuffle_writer(table_scan("nation", Q10_TABLES["nation"]), 1), n_tasks=1)
+    nat = [P.field("n_nationkey", i64, True), P.field("n_name", "utf8", True)]
+    # S2: nation (broadcast build side) |x| customer -> c_custkey, c_name, c_address, c_phone, c_acctbal, c_comment, n_name
+    s2 = P.hash_join(P.shuffle_reader(1, nat, broadcast=True), table_scan("customer", Q10_TABLES["customer"]), [[c(0), c("c_nationkey")]],
+                     "Inner", "CollectLeft", projection=[2, 3, 4, 6, 7, 8, 1])
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(0)], Pn))
+    cust = [P.field("c_custkey", i64, True), P.field("c_name", "utf8", True), P.field("c_address", "utf8", True), P.field("c_phone", "utf8", True),
+            P.field("c_acctbal", D152, True), P.field("c_comment", "utf8", True), P.field("n_name", "utf8", True)]
+    s3 = P.filter_(P.and_(P.binop(">=", c("o_orderdate"), P.lit_date(date_from)), P.binop("<", c("o_orderdate"), P.lit_date(date_to))),
+                   table_scan("orders", Q10_TABLES["orders"]), projection=[0, 1])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(1)], Pn))
+    ords = [P.field("o_orderkey", i64, True), P.field("o_custkey", i64, True)]
+    # S4: customer' |x| orders' on custkey -> (o_orderkey, customer columns...), re-shuffled on orderkey
+    s4 = P.hash_join(P.shuffle_reader(2, cust), P.shuffle_reader(3, ords), [[c(0), c(1)]], "Inner", "Partitioned",
+                     projection=[7, 0, 1, 2, 3, 4, 5, 6])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    co = [P.field("o_orderkey", i64, True)] + cust
+    s5 = P.filter_(P.binop("=", c("l_returnflag"), P.lit_utf8(flag)), table_scan("lineitem", Q10_TABLES["lineitem"]), projection=[0, 1, 2])
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(0)], Pn))
+    li = [P.field("l_orderkey", i64, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    # S6: (customer, orders) |x| lineitem' on orderkey -> partial aggregate on the seven keys
+    s6 = P.hash_join(P.shuffle_reader(4, co), P.shuffle_reader(5, li), [[c(0), c(0)]], "Inner", "Partitioned",
+                     projection=[1, 2, 5, 4, 7, 3, 6, 9, 10])
+    # columns now: c_custkey, c_name, c_acctbal, c_phone, n_name, c_address, c_comment, l_extendedprice, l_discount
+    gb_names = ["c_custkey", "c_name", "c_acctbal", "c_phone", "n_name", "c_address", "c_comment"]
+    s6 = P.project([(c(i), nme) for i, nme in enumerate(gb_names)] + [(P.binop("*", c(7), one_minus(c(8))), "rev")], s6)
+    gb = [(c(i), nme) for i, nme in enumerate(gb_names)]
+    s6 = P.aggregate("Partial", gb, [P.agg("sum", c(7), "revenue")], s6)
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(i) for i in range(7)], Pn))
+    ktypes = [i64, "utf8", D152, "utf8", "utf8", "utf8", "utf8"]
+    part = [P.field(nme, t, True) for nme, t in zip(gb_names, ktypes)] + [P.field("revenue[sum]", P.dec(38, 4), True)]
+    s7 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "revenue")], P.shuffle_reader(6, part))
+    # select list order: c_custkey, c_name, revenue, c_acctbal, n_name, c_address, c_phone, c_comment
+    s7 = P.project([(c(0), "c_custkey"), (c(1), "c_name"), (c(7), "revenue"), (c(2), "c_acctbal"), (c(4), "n_name"), (c(5), "c_address"),
+                    (c(3), "c_phone"), (c(6), "c_comment")], s7)
+    keys = [P.sort_key(c(2), asc=False)]
+    s7 = P.sort(keys, s7, fetch=20, preserve_partitioning=True)
+    st7 = Stage(7, P.shuffle_writer(s7, 7))
+    fin = [P.field("c_custkey", i64, True), P.field("c_name", "utf8", True), P.field("revenue", P.dec(38, 4), True), P.field("c_acctbal", D152, True),
+           P.field("n_name", "utf8", True), P.field("c_address", "utf8", True), P.field("c_phone", "utf8", True), P.field("c_comment", "utf8", True)]
+    st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, fin), fetch=20), 8), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8]

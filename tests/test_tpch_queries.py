@@ -237,3 +237,33 @@ def test_q13_gpu(gpu, oracle, oracle_lib, msf, parts, P):
     want = driver.run_stages(oracle, st, f"q13-{msf}")
     assert want.num_rows > 1
     assert_tables_equal(got, want, sort=False)
+
+
+# ---- q10: 4-table join, seven group keys (int / strings / decimal), top-20 -------------------------------
+def test_q10_oracle_against_pandas(oracle, oracle_lib):
+    import datetime as dt
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q10_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q10_TABLES}
+    o = df["orders"]
+    lo, hi = o.o_orderdate.min(), o.o_orderdate.max()
+    d0 = lo + (hi - lo) / 4
+    d1 = d0 + dt.timedelta(days=500)
+    flag = "R"   # as in the benchmark query; orders of this window have no 'N' lines yet
+    got = driver.run_stages(oracle, tpch.q10(3, d0.isoformat(), d1.isoformat(), flag), "q10o")
+    o = o[(o.o_orderdate >= d0) & (o.o_orderdate < d1)]
+    li = df["lineitem"][df["lineitem"].l_returnflag == flag]
+    m = df["customer"].merge(df["nation"], left_on="c_nationkey", right_on="n_nationkey").merge(o, left_on="c_custkey", right_on="o_custkey")
+    m = m.merge(li, left_on="o_orderkey", right_on="l_orderkey")
+    want = {}
+    for ck, nm, ab, ph, nn, ad, cm, ext, disc in zip(m.c_custkey, m.c_name, m.c_acctbal, m.c_phone, m.n_name, m.c_address, m.c_comment,
+                                                    m.l_extendedprice, m.l_discount):
+        k = (ck, nm, ab, ph, nn, ad, cm)
+        want[k] = want.get(k, 0) + int(ext.scaleb(2)) * (100 - int(disc.scaleb(2)))
+    assert len(want) > 20
+    top = sorted(want.values(), reverse=True)[:20]
+    rows = got.to_pylist()
+    assert [int(r["revenue"].scaleb(4)) for r in rows] == top          # ORDER BY revenue DESC LIMIT 20
+    for r in rows:
+        k = (r["c_custkey"], r["c_name"], r["c_acctbal"], r["c_phone"], r["n_name"], r["c_address"], r["c_comment"])
+        assert want[k] == int(r["revenue"].scaleb(4))
