@@ -418,3 +418,39 @@ def q10(n_partitions: int = 4, date_from: str = "1993-10-01", date_to: str = "19
            P.field("n_name", "utf8", True), P.field("c_address", "utf8", True), P.field("c_phone", "utf8", True), P.field("c_comment", "utf8", True)]
     st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, fin), fetch=20), 8), n_tasks=1)
     return [st1, st2, st3, st4, st5, st6, st7, st8]
+
+
+Q19_TABLES = {"part": ["p_partkey", "p_brand", "p_size", "p_container"],
+              "lineitem": ["l_partkey", "l_quantity", "l_extendedprice", "l_discount", "l_shipinstruct", "l_shipmode"]}
+Q19_GROUPS = [("Brand#12", ["SM CASE", "SM BOX", "SM PACK", "SM PKG"], 1, 11, 5),
+              ("Brand#23", ["MED BAG", "MED BOX", "MED PKG", "MED PACK"], 10, 20, 10),
+              ("Brand#34", ["LG CASE", "LG BOX", "LG PACK", "LG PKG"], 20, 30, 15)]
+
+
+def q19(n_partitions: int = 4, groups=None, modes=("AIR", "AIR REG"), instruct: str = "DELIVER IN PERSON") -> List[Stage]:
+    """benchmarks/queries/q19.sql -- lineitem |x| part on partkey with the three-way OR of conjunctions as the join's
+    residual filter (IN lists, BETWEEN, decimal compares across both sides); the common factors (ship mode / instruction,
+    p_size >= 1) are pushed below the join as DataFusion does.  groups: [(brand, containers, qty_lo, qty_hi, size_hi)]."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    groups = groups or Q19_GROUPS
+    qty = lambda v: P.lit_dec(int(v) * 100, 15, 2)
+    s1 = P.filter_(P.binop(">=", c("p_size"), P.lit_i32(1)), table_scan("part", Q19_TABLES["part"]))
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    pred = P.and_(P.in_list(c("l_shipmode"), [P.lit_utf8(m) for m in modes]), P.binop("=", c("l_shipinstruct"), P.lit_utf8(instruct)))
+    s2 = P.filter_(pred, table_scan("lineitem", Q19_TABLES["lineitem"]), projection=[0, 1, 2, 3])
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(0)], Pn))
+    pt = [P.field("p_partkey", i64, True), P.field("p_brand", "utf8", True), P.field("p_size", "i32", True), P.field("p_container", "utf8", True)]
+    li = [P.field("l_partkey", i64, True), P.field("l_quantity", D152, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    # residual filter over concat(part[0..3], lineitem[4..7])
+    ors = []
+    for brand, conts, q_lo, q_hi, size_hi in groups:
+        ors.append(P.and_(P.binop("=", c(1), P.lit_utf8(brand)), P.in_list(c(3), [P.lit_utf8(x) for x in conts]),
+                          P.binop(">=", c(5), qty(q_lo)), P.binop("<=", c(5), qty(q_hi)),
+                          P.binop("<=", c(2), P.lit_i32(size_hi))))
+    j = P.hash_join(P.shuffle_reader(1, pt), P.shuffle_reader(2, li), [[c(0), c(0)]], "Inner", "Partitioned", filter=P.or_(*ors), projection=[6, 7])
+    s3 = P.project([(P.binop("*", c(0), one_minus(c(1))), "rev")], j)
+    s3 = P.aggregate("Partial", [], [P.agg("sum", c(0), "revenue")], s3)
+    st3 = Stage(3, P.shuffle_writer(s3, 3))
+    s4 = P.aggregate("Final", [], [P.agg("sum", None, "revenue")], P.coalesce_partitions(P.shuffle_reader(3, [P.field("revenue[sum]", P.dec(38, 4), True)])))
+    return [st1, st2, st3, Stage(4, P.shuffle_writer(s4, 4), n_tasks=1)]

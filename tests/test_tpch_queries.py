@@ -267,3 +267,26 @@ def test_q10_oracle_against_pandas(oracle, oracle_lib):
     for r in rows:
         k = (r["c_custkey"], r["c_name"], r["c_acctbal"], r["c_phone"], r["n_name"], r["c_address"], r["c_comment"])
         assert want[k] == int(r["revenue"].scaleb(4))
+
+
+# ---- q19: join with a three-way OR of conjunctions as residual filter ---------------------------------
+def test_q19_oracle_against_pandas(oracle, oracle_lib):
+    msf, parts = 50, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q19_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q19_TABLES}
+    p, l = df["part"], df["lineitem"]
+    brands = list(p.p_brand.value_counts().index[:3])
+    conts = list(p.p_container.value_counts().index)
+    groups = [(brands[0], conts[0:12], 1, 21, 30), (brands[1], conts[8:24], 10, 35, 40), (brands[2], conts[20:40], 20, 50, 50)]
+    modes, instruct = ("AIR", "REG AIR", "SHIP"), "DELIVER IN PERSON"
+    got = driver.run_stages(oracle, tpch.q19(3, groups, modes, instruct), "q19o")
+    l = l[l.l_shipmode.isin(modes) & (l.l_shipinstruct == instruct)]
+    m = p[p.p_size >= 1].merge(l, left_on="p_partkey", right_on="l_partkey")
+    total, hits = 0, 0
+    for br, sz, ct, q, ext, disc in zip(m.p_brand, m.p_size, m.p_container, m.l_quantity, m.l_extendedprice, m.l_discount):
+        qi = int(q.scaleb(2))
+        if any(br == b and ct in cs and lo * 100 <= qi <= hi * 100 and sz <= sh for b, cs, lo, hi, sh in groups):
+            total += int(ext.scaleb(2)) * (100 - int(disc.scaleb(2)))
+            hits += 1
+    assert hits > 5
+    assert got.column(0).to_pylist() == [D(total).scaleb(-4)]
