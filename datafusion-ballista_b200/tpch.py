@@ -454,3 +454,45 @@ def q19(n_partitions: int = 4, groups=None, modes=("AIR", "AIR REG"), instruct: 
     st3 = Stage(3, P.shuffle_writer(s3, 3))
     s4 = P.aggregate("Final", [], [P.agg("sum", None, "revenue")], P.coalesce_partitions(P.shuffle_reader(3, [P.field("revenue[sum]", P.dec(38, 4), True)])))
     return [st1, st2, st3, Stage(4, P.shuffle_writer(s4, 4), n_tasks=1)]
+
+
+Q18_TABLES = {"customer": ["c_custkey", "c_name"], "orders": ["o_orderkey", "o_custkey", "o_totalprice", "o_orderdate"],
+              "lineitem": ["l_orderkey", "l_quantity"]}
+
+
+def q18(n_partitions: int = 4, threshold: int = 300) -> List[Stage]:
+    """benchmarks/queries/q18.sql -- IN (subquery with GROUP BY ... HAVING sum(l_quantity) > t) as a semi join against a
+    high-cardinality aggregate that is filtered after the aggregation, joined back to customer/orders/lineitem,
+    five group keys, ORDER BY o_totalprice DESC, o_orderdate LIMIT 100."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    # S1: lineitem by orderkey (feeds both the HAVING subquery and the final join)
+    st1 = Stage(1, P.shuffle_writer(table_scan("lineitem", Q18_TABLES["lineitem"]), 1, [c(0)], Pn))
+    li = [P.field("l_orderkey", i64, True), P.field("l_quantity", D152, True)]
+    st2 = Stage(2, P.shuffle_writer(table_scan("customer", Q18_TABLES["customer"]), 2, [c(0)], Pn))
+    cu = [P.field("c_custkey", i64, True), P.field("c_name", "utf8", True)]
+    st3 = Stage(3, P.shuffle_writer(table_scan("orders", Q18_TABLES["orders"]), 3, [c(1)], Pn))
+    od = [P.field("o_orderkey", i64, True), P.field("o_custkey", i64, True), P.field("o_totalprice", D152, True), P.field("o_orderdate", "date32", True)]
+    # S4: customer |x| orders on custkey -> (c_name, c_custkey, o_orderkey, o_orderdate, o_totalprice), re-shuffled on orderkey
+    s4 = P.hash_join(P.shuffle_reader(2, cu), P.shuffle_reader(3, od), [[c(0), c(1)]], "Inner", "Partitioned", projection=[1, 0, 2, 5, 4])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(2)], Pn))
+    co = [P.field("c_name", "utf8", True), P.field("c_custkey", i64, True), P.field("o_orderkey", i64, True), P.field("o_orderdate", "date32", True),
+          P.field("o_totalprice", D152, True)]
+    # S5 (co-partitioned on orderkey): big orders = HAVING sum(l_quantity) > t; semi join; join lineitem back; partial aggregate
+    big = P.aggregate("SinglePartitioned", [(c(0), "l_orderkey")], [P.agg("sum", c(1), "q")], P.shuffle_reader(1, li))
+    big = P.filter_(P.binop(">", c(1), P.lit_dec(int(threshold) * 100, 25, 2)), big, projection=[0])
+    semi = P.hash_join(big, P.shuffle_reader(4, co), [[c(0), c(2)]], "RightSemi", "Partitioned")
+    j = P.hash_join(semi, P.shuffle_reader(1, li), [[c(2), c(0)]], "Inner", "Partitioned", projection=[0, 1, 2, 3, 4, 6])
+    gb_names = ["c_name", "c_custkey", "o_orderkey", "o_orderdate", "o_totalprice"]
+    gb = [(c(i), nme) for i, nme in enumerate(gb_names)]
+    s5 = P.aggregate("Partial", gb, [P.agg("sum", c(5), "sum_qty")], j)
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(i) for i in range(5)], Pn))
+    ktypes = ["utf8", i64, i64, "date32", D152]
+    part = [P.field(nme, t, True) for nme, t in zip(gb_names, ktypes)] + [P.field("sum_qty[sum]", P.dec(25, 2), True)]
+    s6 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "sum_qty")], P.shuffle_reader(5, part))
+    keys = [P.sort_key(c(4), asc=False), P.sort_key(c(3))]
+    s6 = P.sort(keys, s6, fetch=100, preserve_partitioning=True)
+    st6 = Stage(6, P.shuffle_writer(s6, 6))
+    fin = [P.field(nme, t, True) for nme, t in zip(gb_names, ktypes)] + [P.field("sum_qty", P.dec(25, 2), True)]
+    st7 = Stage(7, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(6, fin), fetch=100), 7), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7]

@@ -290,3 +290,26 @@ def test_q19_oracle_against_pandas(oracle, oracle_lib):
             hits += 1
     assert hits > 5
     assert got.column(0).to_pylist() == [D(total).scaleb(-4)]
+
+
+# ---- q18: HAVING subquery as a filtered high-cardinality aggregate + semi join, five group keys, top-100 --------
+def test_q18_oracle_against_pandas(oracle, oracle_lib):
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q18_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q18_TABLES}
+    li = df["lineitem"]
+    per_order = {}
+    for ok, q in zip(li.l_orderkey, li.l_quantity):
+        per_order[ok] = per_order.get(ok, 0) + int(q.scaleb(2))
+    thr = sorted(per_order.values())[-40] // 100       # a threshold that keeps a few dozen orders at this scale
+    got = driver.run_stages(oracle, tpch.q18(3, thr), "q18o")
+    big = {ok for ok, s in per_order.items() if s > thr * 100}
+    assert 10 < len(big) < 100
+    m = df["customer"].merge(df["orders"], left_on="c_custkey", right_on="o_custkey")
+    m = m[m.o_orderkey.isin(big)]
+    want = sorted(((tp, od, nm, ck, ok, per_order[ok]) for nm, ck, ok, od, tp in zip(m.c_name, m.c_custkey, m.o_orderkey, m.o_orderdate, m.o_totalprice)),
+                  key=lambda r: (-r[0], r[1]))
+    rows = got.to_pylist()
+    assert len(rows) == len(want)
+    assert [(r["o_totalprice"], r["o_orderdate"]) for r in rows] == [(w[0], w[1]) for w in want]
+    assert sorted((r["c_name"], r["c_custkey"], r["o_orderkey"], int(r["sum_qty"].scaleb(2))) for r in rows) == sorted((w[2], w[3], w[4], w[5]) for w in want)
