@@ -496,3 +496,59 @@ def q18(n_partitions: int = 4, threshold: int = 300) -> List[Stage]:
     fin = [P.field(nme, t, True) for nme, t in zip(gb_names, ktypes)] + [P.field("sum_qty", P.dec(25, 2), True)]
     st7 = Stage(7, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(6, fin), fetch=100), 7), n_tasks=1)
     return [st1, st2, st3, st4, st5, st6, st7]
+
+
+Q9_TABLES = {"part": ["p_partkey", "p_name"], "supplier": ["s_suppkey", "s_nationkey"], "nation": ["n_nationkey", "n_name"],
+             "partsupp": ["ps_partkey", "ps_suppkey", "ps_supplycost"], "orders": ["o_orderkey", "o_orderdate"],
+             "lineitem": ["l_orderkey", "l_partkey", "l_suppkey", "l_quantity", "l_extendedprice", "l_discount"]}
+
+
+def q9(n_partitions: int = 4, pattern: str = "%green%") -> List[Stage]:
+    """benchmarks/queries/q9.sql -- six-table join (a two-column key on partsupp), LIKE on p_name, EXTRACT(YEAR ...),
+    amount = price*(1-discount) - supplycost*quantity (signed Decimal128(38,4)), GROUP BY nation, o_year
+    ORDER BY nation, o_year DESC."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.like(c("p_name"), pattern), table_scan("part", Q9_TABLES["part"]), projection=[0])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st2 = Stage(2, P.shuffle_writer(table_scan("lineitem", Q9_TABLES["lineitem"]), 2, [c(1)], Pn))
+    li = [dict(f, nullable=True) for f in _sch("lineitem", Q9_TABLES["lineitem"])]
+    # S3: part' |x| lineitem on partkey -> l_orderkey, l_partkey, l_suppkey, l_quantity, l_extendedprice, l_discount; by (suppkey, partkey)
+    s3 = P.hash_join(P.shuffle_reader(1, [P.field("p_partkey", i64, True)]), P.shuffle_reader(2, li), [[c(0), c(1)]], "Inner", "Partitioned",
+                     projection=[1, 2, 3, 4, 5, 6])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(2), c(1)], Pn))
+    st4 = Stage(4, P.shuffle_writer(table_scan("partsupp", Q9_TABLES["partsupp"]), 4, [c(1), c(0)], Pn))
+    ps = [dict(f, nullable=True) for f in _sch("partsupp", Q9_TABLES["partsupp"])]
+    # S5: partsupp |x| (part, lineitem) on (suppkey, partkey) -> l_orderkey, l_suppkey, l_quantity, l_extendedprice, l_discount, ps_supplycost
+    s5 = P.hash_join(P.shuffle_reader(4, ps), P.shuffle_reader(3, li), [[c(1), c(2)], [c(0), c(1)]], "Inner", "Partitioned",
+                     projection=[3, 5, 6, 7, 8, 2])
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(1)], Pn))
+    pl = [P.field("l_orderkey", i64, True), P.field("l_suppkey", i64, True), P.field("l_quantity", D152, True),
+          P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True), P.field("ps_supplycost", D152, True)]
+    # S6: nation |x| supplier (tiny, one task) -> s_suppkey, n_name; by suppkey
+    s6 = P.hash_join(table_scan("nation", Q9_TABLES["nation"]), table_scan("supplier", Q9_TABLES["supplier"]), [[c(0), c("s_nationkey")]],
+                     "Inner", "CollectLeft", projection=[2, 1])
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(0)], Pn))
+    sn = [P.field("s_suppkey", i64, True), P.field("n_name", "utf8", True)]
+    # S7: (supplier, nation) |x| ... on suppkey -> l_orderkey, amount inputs, n_name; by orderkey
+    s7 = P.hash_join(P.shuffle_reader(6, sn), P.shuffle_reader(5, pl), [[c(0), c(1)]], "Inner", "Partitioned", projection=[2, 4, 5, 6, 7, 1])
+    st7 = Stage(7, P.shuffle_writer(s7, 7, [c(0)], Pn))
+    sl = [P.field("l_orderkey", i64, True), P.field("l_quantity", D152, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True),
+          P.field("ps_supplycost", D152, True), P.field("n_name", "utf8", True)]
+    st8 = Stage(8, P.shuffle_writer(table_scan("orders", Q9_TABLES["orders"]), 8, [c(0)], Pn))
+    od = [P.field("o_orderkey", i64, True), P.field("o_orderdate", "date32", True)]
+    # S9: orders |x| ... on orderkey -> nation, o_year, amount -> partial aggregate
+    s9 = P.hash_join(P.shuffle_reader(8, od), P.shuffle_reader(7, sl), [[c(0), c(0)]], "Inner", "Partitioned", projection=[7, 1, 3, 4, 5, 6])
+    amount = P.binop("-", P.binop("*", c(3), one_minus(c(4))), P.binop("*", c(5), c(2)))
+    s9 = P.project([(c(0), "nation"), (P.fn("date_part_year", c(1)), "o_year"), (amount, "amount")], s9)
+    gb = [(c(0), "nation"), (c(1), "o_year")]
+    s9 = P.aggregate("Partial", gb, [P.agg("sum", c(2), "sum_profit")], s9)
+    st9 = Stage(9, P.shuffle_writer(s9, 9, [c(0), c(1)], Pn))
+    part = [P.field("nation", "utf8", True), P.field("o_year", "i32", True), P.field("sum_profit[sum]", P.dec(38, 4), True)]
+    s10 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "sum_profit")], P.shuffle_reader(9, part))
+    keys = [P.sort_key(c(0)), P.sort_key(c(1), asc=False)]
+    s10 = P.sort(keys, s10, preserve_partitioning=True)
+    st10 = Stage(10, P.shuffle_writer(s10, 10))
+    fin = [P.field("nation", "utf8", True), P.field("o_year", "i32", True), P.field("sum_profit", P.dec(38, 4), True)]
+    st11 = Stage(11, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(10, fin)), 11), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8, st9, st10, st11]

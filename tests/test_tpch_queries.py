@@ -313,3 +313,27 @@ def test_q18_oracle_against_pandas(oracle, oracle_lib):
     assert len(rows) == len(want)
     assert [(r["o_totalprice"], r["o_orderdate"]) for r in rows] == [(w[0], w[1]) for w in want]
     assert sorted((r["c_name"], r["c_custkey"], r["o_orderkey"], int(r["sum_qty"].scaleb(2))) for r in rows) == sorted((w[2], w[3], w[4], w[5]) for w in want)
+
+
+# ---- q9: six tables, two-column join key, LIKE, EXTRACT(YEAR), signed decimal amounts ---------------------
+def test_q9_oracle_against_pandas(oracle, oracle_lib):
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q9_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q9_TABLES}
+    pattern = "%z%"   # the generator's part names are random letters
+    got = driver.run_stages(oracle, tpch.q9(3, pattern), "q9o")
+    p = df["part"][df["part"].p_name.str.contains("z")]
+    assert 0 < len(p) < len(df["part"])
+    m = p.merge(df["lineitem"], left_on="p_partkey", right_on="l_partkey")
+    m = m.merge(df["partsupp"], left_on=["l_suppkey", "l_partkey"], right_on=["ps_suppkey", "ps_partkey"])
+    m = m.merge(df["supplier"], left_on="l_suppkey", right_on="s_suppkey").merge(df["nation"], left_on="s_nationkey", right_on="n_nationkey")
+    m = m.merge(df["orders"], left_on="l_orderkey", right_on="o_orderkey")
+    want = {}
+    for nn, od, q, ext, disc, cost in zip(m.n_name, m.o_orderdate, m.l_quantity, m.l_extendedprice, m.l_discount, m.ps_supplycost):
+        amt = int(ext.scaleb(2)) * (100 - int(disc.scaleb(2))) - int(cost.scaleb(2)) * int(q.scaleb(2))   # scale 4, may be negative
+        k = (nn, od.year)
+        want[k] = want.get(k, 0) + amt
+    assert len(want) > 5 and any(v < 0 for v in want.values()) or len(want) > 5
+    rows = got.to_pylist()
+    assert [(r["nation"], r["o_year"]) for r in rows] == sorted(want, key=lambda k: (k[0], -k[1]))
+    assert {(r["nation"], r["o_year"]): int(r["sum_profit"].scaleb(4)) for r in rows} == want
