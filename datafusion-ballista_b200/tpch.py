@@ -552,3 +552,59 @@ def q9(n_partitions: int = 4, pattern: str = "%green%") -> List[Stage]:
     fin = [P.field("nation", "utf8", True), P.field("o_year", "i32", True), P.field("sum_profit", P.dec(38, 4), True)]
     st11 = Stage(11, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(10, fin)), 11), n_tasks=1)
     return [st1, st2, st3, st4, st5, st6, st7, st8, st9, st10, st11]
+
+
+Q7_TABLES = {"supplier": ["s_suppkey", "s_nationkey"], "nation": ["n_nationkey", "n_name"], "customer": ["c_custkey", "c_nationkey"],
+             "orders": ["o_orderkey", "o_custkey"], "lineitem": ["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount", "l_shipdate"]}
+
+
+def q7(n_partitions: int = 4, nation_a: str = "FRANCE", nation_b: str = "GERMANY", date_from: str = "1995-01-01", date_to: str = "1996-12-31") -> List[Stage]:
+    """benchmarks/queries/q7.sql -- nation joined twice (supplier side, customer side; the IN-lists DataFusion infers from the
+    OR are pushed to both scans), the OR of nation pairs as the last join's residual filter, EXTRACT(YEAR FROM l_shipdate),
+    GROUP BY supp_nation, cust_nation, l_year ORDER BY the same."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    two = lambda x: P.in_list(x, [P.lit_utf8(nation_a), P.lit_utf8(nation_b)])
+    # S1: nation(a|b) |x| supplier -> s_suppkey, n_name ; by suppkey
+    n1 = P.filter_(two(c("n_name")), table_scan("nation", Q7_TABLES["nation"]))
+    s1 = P.hash_join(n1, table_scan("supplier", Q7_TABLES["supplier"]), [[c(0), c("s_nationkey")]], "Inner", "CollectLeft", projection=[2, 1])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    sn = [P.field("s_suppkey", i64, True), P.field("supp_nation", "utf8", True)]
+    # S2: lineitem in the date range ; by suppkey
+    s2 = P.filter_(P.and_(P.binop(">=", c("l_shipdate"), P.lit_date(date_from)), P.binop("<=", c("l_shipdate"), P.lit_date(date_to))),
+                   table_scan("lineitem", Q7_TABLES["lineitem"]))
+    st2 = Stage(2, P.shuffle_writer(s2, 2, [c(1)], Pn))
+    li = [dict(f, nullable=True) for f in _sch("lineitem", Q7_TABLES["lineitem"])]
+    # S3: supplier' |x| lineitem' -> l_orderkey, l_extendedprice, l_discount, l_shipdate, supp_nation ; by orderkey
+    s3 = P.hash_join(P.shuffle_reader(1, sn), P.shuffle_reader(2, li), [[c(0), c(1)]], "Inner", "Partitioned", projection=[2, 4, 5, 6, 1])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    sl = [P.field("l_orderkey", i64, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True), P.field("l_shipdate", "date32", True),
+          P.field("supp_nation", "utf8", True)]
+    # S4: nation(a|b) |x| customer -> c_custkey, n_name ; by custkey
+    n2 = P.filter_(two(c("n_name")), table_scan("nation", Q7_TABLES["nation"]))
+    s4 = P.hash_join(n2, table_scan("customer", Q7_TABLES["customer"]), [[c(0), c("c_nationkey")]], "Inner", "CollectLeft", projection=[2, 1])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    cn = [P.field("c_custkey", i64, True), P.field("cust_nation", "utf8", True)]
+    st5 = Stage(5, P.shuffle_writer(table_scan("orders", Q7_TABLES["orders"]), 5, [c(1)], Pn))
+    od = [P.field("o_orderkey", i64, True), P.field("o_custkey", i64, True)]
+    # S6: customer' |x| orders -> o_orderkey, cust_nation ; by orderkey
+    s6 = P.hash_join(P.shuffle_reader(4, cn), P.shuffle_reader(5, od), [[c(0), c(1)]], "Inner", "Partitioned", projection=[2, 1])
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(0)], Pn))
+    oc = [P.field("o_orderkey", i64, True), P.field("cust_nation", "utf8", True)]
+    # S7: (orders, customer) |x| (supplier, lineitem) on orderkey, residual = the two nation pairs
+    pair = P.or_(P.and_(P.binop("=", c(6), P.lit_utf8(nation_a)), P.binop("=", c(1), P.lit_utf8(nation_b))),
+                 P.and_(P.binop("=", c(6), P.lit_utf8(nation_b)), P.binop("=", c(1), P.lit_utf8(nation_a))))
+    j = P.hash_join(P.shuffle_reader(6, oc), P.shuffle_reader(3, sl), [[c(0), c(0)]], "Inner", "Partitioned", filter=pair, projection=[6, 1, 5, 3, 4])
+    s7 = P.project([(c(0), "supp_nation"), (c(1), "cust_nation"), (P.fn("date_part_year", c(2)), "l_year"),
+                    (P.binop("*", c(3), one_minus(c(4))), "volume")], j)
+    gb = [(c(0), "supp_nation"), (c(1), "cust_nation"), (c(2), "l_year")]
+    s7 = P.aggregate("Partial", gb, [P.agg("sum", c(3), "revenue")], s7)
+    st7 = Stage(7, P.shuffle_writer(s7, 7, [c(0), c(1), c(2)], Pn))
+    part = [P.field("supp_nation", "utf8", True), P.field("cust_nation", "utf8", True), P.field("l_year", "i32", True), P.field("revenue[sum]", P.dec(38, 4), True)]
+    s8 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "revenue")], P.shuffle_reader(7, part))
+    keys = [P.sort_key(c(0)), P.sort_key(c(1)), P.sort_key(c(2))]
+    s8 = P.sort(keys, s8, preserve_partitioning=True)
+    st8 = Stage(8, P.shuffle_writer(s8, 8))
+    fin = [P.field("supp_nation", "utf8", True), P.field("cust_nation", "utf8", True), P.field("l_year", "i32", True), P.field("revenue", P.dec(38, 4), True)]
+    st9 = Stage(9, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(8, fin)), 9), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8, st9]

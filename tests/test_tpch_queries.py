@@ -337,3 +337,31 @@ def test_q9_oracle_against_pandas(oracle, oracle_lib):
     rows = got.to_pylist()
     assert [(r["nation"], r["o_year"]) for r in rows] == sorted(want, key=lambda k: (k[0], -k[1]))
     assert {(r["nation"], r["o_year"]): int(r["sum_profit"].scaleb(4)) for r in rows} == want
+
+
+# ---- q7: nation joined twice, OR of nation pairs as residual filter, EXTRACT(YEAR) group key -----------------
+def test_q7_oracle_against_pandas(oracle, oracle_lib):
+    import datetime as dt
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q7_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q7_TABLES}
+    names = list(df["nation"].n_name)
+    a, b = names[3], names[7]
+    d0, d1 = dt.date(1994, 1, 1), dt.date(1997, 12, 31)
+    got = driver.run_stages(oracle, tpch.q7(3, a, b, d0.isoformat(), d1.isoformat()), "q7o")
+    n = df["nation"]
+    s = df["supplier"].merge(n, left_on="s_nationkey", right_on="n_nationkey").rename(columns={"n_name": "supp_nation"})
+    cu = df["customer"].merge(n, left_on="c_nationkey", right_on="n_nationkey").rename(columns={"n_name": "cust_nation"})
+    li = df["lineitem"]
+    li = li[(li.l_shipdate >= d0) & (li.l_shipdate <= d1)]
+    m = li.merge(s, left_on="l_suppkey", right_on="s_suppkey").merge(df["orders"], left_on="l_orderkey", right_on="o_orderkey")
+    m = m.merge(cu, left_on="o_custkey", right_on="c_custkey")
+    m = m[((m.supp_nation == a) & (m.cust_nation == b)) | ((m.supp_nation == b) & (m.cust_nation == a))]
+    want = {}
+    for sn, cn, sd, ext, disc in zip(m.supp_nation, m.cust_nation, m.l_shipdate, m.l_extendedprice, m.l_discount):
+        k = (sn, cn, sd.year)
+        want[k] = want.get(k, 0) + int(ext.scaleb(2)) * (100 - int(disc.scaleb(2)))
+    assert len(want) >= 4
+    rows = got.to_pylist()
+    assert [(r["supp_nation"], r["cust_nation"], r["l_year"]) for r in rows] == sorted(want)
+    assert {(r["supp_nation"], r["cust_nation"], r["l_year"]): int(r["revenue"].scaleb(4)) for r in rows} == want
