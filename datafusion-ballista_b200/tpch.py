@@ -608,3 +608,44 @@ def q7(n_partitions: int = 4, nation_a: str = "FRANCE", nation_b: str = "GERMANY
     fin = [P.field("supp_nation", "utf8", True), P.field("cust_nation", "utf8", True), P.field("l_year", "i32", True), P.field("revenue", P.dec(38, 4), True)]
     st9 = Stage(9, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(8, fin)), 9), n_tasks=1)
     return [st1, st2, st3, st4, st5, st6, st7, st8, st9]
+
+
+Q16_TABLES = {"part": ["p_partkey", "p_brand", "p_type", "p_size"], "partsupp": ["ps_partkey", "ps_suppkey"], "supplier": ["s_suppkey", "s_comment"]}
+
+
+def q16(n_partitions: int = 4, brand: str = "Brand#45", type_prefix: str = "MEDIUM POLISHED%", sizes=(49, 14, 23, 45, 19, 3, 36, 9),
+        complaint: str = "%Customer%Complaints%") -> List[Stage]:
+    """benchmarks/queries/q16.sql -- NOT IN (subquery) as an anti join, <> / NOT LIKE / IN filters, and COUNT(DISTINCT ps_suppkey)
+    in the two-level form DataFusion's SingleDistinctToGroupBy rule produces (group by keys + the distinct column, then count)."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.like(c("s_comment"), complaint), table_scan("supplier", Q16_TABLES["supplier"]), projection=[0])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    pred = P.and_(P.binop("<>", c("p_brand"), P.lit_utf8(brand)), P.like(c("p_type"), type_prefix, negated=True),
+                  P.in_list(c("p_size"), [P.lit_i32(int(v)) for v in sizes]))
+    st2 = Stage(2, P.shuffle_writer(P.filter_(pred, table_scan("part", Q16_TABLES["part"])), 2, [c(0)], Pn))
+    pt = [P.field("p_partkey", i64, True), P.field("p_brand", "utf8", True), P.field("p_type", "utf8", True), P.field("p_size", "i32", True)]
+    st3 = Stage(3, P.shuffle_writer(table_scan("partsupp", Q16_TABLES["partsupp"]), 3, [c(0)], Pn))
+    ps = [P.field("ps_partkey", i64, True), P.field("ps_suppkey", i64, True)]
+    # S4: part' |x| partsupp -> ps_suppkey, p_brand, p_type, p_size ; by suppkey
+    s4 = P.hash_join(P.shuffle_reader(2, pt), P.shuffle_reader(3, ps), [[c(0), c(0)]], "Inner", "Partitioned", projection=[5, 1, 2, 3])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    pp = [P.field("ps_suppkey", i64, True), P.field("p_brand", "utf8", True), P.field("p_type", "utf8", True), P.field("p_size", "i32", True)]
+    # S5: NOT IN complaints: keep probe rows without a match (RightAnti), then the inner level of the distinct count
+    anti = P.hash_join(P.shuffle_reader(1, [P.field("s_suppkey", i64, True)]), P.shuffle_reader(4, pp), [[c(0), c(0)]], "RightAnti", "Partitioned")
+    gb4 = [(c(1), "p_brand"), (c(2), "p_type"), (c(3), "p_size"), (c(0), "ps_suppkey")]
+    s5 = P.aggregate("Partial", gb4, [], anti)
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(0), c(1), c(2), c(3)], Pn))
+    d4 = [P.field("p_brand", "utf8", True), P.field("p_type", "utf8", True), P.field("p_size", "i32", True), P.field("ps_suppkey", i64, True)]
+    s6 = P.aggregate("FinalPartitioned", [(c(0), "p_brand"), (c(1), "p_type"), (c(2), "p_size"), (c(3), "ps_suppkey")], [], P.shuffle_reader(5, d4))
+    gb3 = [(c(0), "p_brand"), (c(1), "p_type"), (c(2), "p_size")]
+    s6 = P.aggregate("Partial", gb3, [P.agg("count", c(3), "supplier_cnt")], s6)
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(0), c(1), c(2)], Pn))
+    part = [P.field("p_brand", "utf8", True), P.field("p_type", "utf8", True), P.field("p_size", "i32", True), P.field("supplier_cnt[count]", i64)]
+    s7 = P.aggregate("FinalPartitioned", gb3, [P.agg("count", None, "supplier_cnt")], P.shuffle_reader(6, part))
+    keys = [P.sort_key(c(3), asc=False), P.sort_key(c(0)), P.sort_key(c(1)), P.sort_key(c(2))]
+    s7 = P.sort(keys, s7, preserve_partitioning=True)
+    st7 = Stage(7, P.shuffle_writer(s7, 7))
+    fin = [P.field("p_brand", "utf8", True), P.field("p_type", "utf8", True), P.field("p_size", "i32", True), P.field("supplier_cnt", i64)]
+    st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, fin)), 8), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8]

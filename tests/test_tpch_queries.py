@@ -365,3 +365,29 @@ def test_q7_oracle_against_pandas(oracle, oracle_lib):
     rows = got.to_pylist()
     assert [(r["supp_nation"], r["cust_nation"], r["l_year"]) for r in rows] == sorted(want)
     assert {(r["supp_nation"], r["cust_nation"], r["l_year"]): int(r["revenue"].scaleb(4)) for r in rows} == want
+
+
+# ---- q16: anti join (NOT IN), NOT LIKE / <> / IN filters, COUNT(DISTINCT) as a two-level aggregate ---------------
+def test_q16_oracle_against_pandas(oracle, oracle_lib):
+    import re
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q16_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q16_TABLES}
+    p = df["part"]
+    brand = p.p_brand.value_counts().index[0]
+    tprefix = p.p_type.iloc[0].split(" ")[0] + " %"
+    sizes = tuple(int(v) for v in p.p_size.value_counts().index[:20])
+    complaint = "%q%x%"
+    got = driver.run_stages(oracle, tpch.q16(3, brand, tprefix, sizes, complaint), "q16o")
+    rx = re.compile("^.*q.*x.*$", re.S)
+    bad = set(df["supplier"][df["supplier"].s_comment.map(lambda s: bool(rx.match(s)))].s_suppkey)
+    assert 0 < len(bad) < len(df["supplier"])
+    pf = p[(p.p_brand != brand) & (~p.p_type.str.startswith(tprefix[:-1])) & p.p_size.isin(sizes)]
+    m = pf.merge(df["partsupp"], left_on="p_partkey", right_on="ps_partkey")
+    m = m[~m.ps_suppkey.isin(bad)]
+    want = m.groupby(["p_brand", "p_type", "p_size"]).ps_suppkey.nunique().to_dict()
+    assert len(want) > 10
+    rows = got.to_pylist()
+    assert {(r["p_brand"], r["p_type"], r["p_size"]): r["supplier_cnt"] for r in rows} == want
+    order = [(-r["supplier_cnt"], r["p_brand"], r["p_type"], r["p_size"]) for r in rows]
+    assert order == sorted(order)
