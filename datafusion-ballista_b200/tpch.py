@@ -649,3 +649,47 @@ def q16(n_partitions: int = 4, brand: str = "Brand#45", type_prefix: str = "MEDI
     fin = [P.field("p_brand", "utf8", True), P.field("p_type", "utf8", True), P.field("p_size", "i32", True), P.field("supplier_cnt", i64)]
     st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, fin)), 8), n_tasks=1)
     return [st1, st2, st3, st4, st5, st6, st7, st8]
+
+
+Q21_TABLES = {"supplier": ["s_suppkey", "s_name", "s_nationkey"], "nation": ["n_nationkey", "n_name"], "orders": ["o_orderkey", "o_orderstatus"],
+              "lineitem": ["l_orderkey", "l_suppkey", "l_commitdate", "l_receiptdate"]}
+
+
+def q21(n_partitions: int = 4, nation: str = "SAUDI ARABIA", status: str = "F") -> List[Stage]:
+    """benchmarks/queries/q21.sql -- EXISTS / NOT EXISTS with inequality correlation (`l2.l_suppkey <> l1.l_suppkey`) as semi /
+    anti joins with residual filters over three readings of lineitem; COUNT(*) GROUP BY s_name, top-100."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    late = P.binop(">", c("l_receiptdate"), c("l_commitdate"))
+    nat = P.filter_(P.binop("=", c("n_name"), P.lit_utf8(nation)), table_scan("nation", Q21_TABLES["nation"]), projection=[0])
+    s1 = P.hash_join(nat, table_scan("supplier", Q21_TABLES["supplier"]), [[c(0), c("s_nationkey")]], "Inner", "CollectLeft", projection=[1, 2])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    sup = [P.field("s_suppkey", i64, True), P.field("s_name", "utf8", True)]
+    st2 = Stage(2, P.shuffle_writer(P.filter_(late, table_scan("lineitem", Q21_TABLES["lineitem"]), projection=[0, 1]), 2, [c(1)], Pn))
+    lk = [P.field("l_orderkey", i64, True), P.field("l_suppkey", i64, True)]
+    # S3: supplier' |x| l1 -> s_name, l_orderkey, l_suppkey ; by orderkey
+    s3 = P.hash_join(P.shuffle_reader(1, sup), P.shuffle_reader(2, lk), [[c(0), c(1)]], "Inner", "Partitioned", projection=[1, 2, 3])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(1)], Pn))
+    t1 = [P.field("s_name", "utf8", True), P.field("l_orderkey", i64, True), P.field("l_suppkey", i64, True)]
+    st4 = Stage(4, P.shuffle_writer(P.filter_(P.binop("=", c("o_orderstatus"), P.lit_utf8(status)), table_scan("orders", Q21_TABLES["orders"]), projection=[0]),
+                                    4, [c(0)], Pn))
+    st5 = Stage(5, P.shuffle_writer(P.project([(c("l_orderkey"), "l_orderkey"), (c("l_suppkey"), "l_suppkey")], table_scan("lineitem", Q21_TABLES["lineitem"])),
+                                    5, [c(0)], Pn))
+    st6 = Stage(6, P.shuffle_writer(P.filter_(late, table_scan("lineitem", Q21_TABLES["lineitem"]), projection=[0, 1]), 6, [c(0)], Pn))
+    # S7, everything co-partitioned on the order key
+    t = P.hash_join(P.shuffle_reader(4, [P.field("o_orderkey", i64, True)]), P.shuffle_reader(3, t1), [[c(0), c(1)]], "Inner", "Partitioned", projection=[1, 2, 3])
+    # EXISTS l2: another supplier has a line in the same order   (filter columns: l2 = 0..1, t = 2..4)
+    other = P.binop("<>", c(1), c(4))
+    t = P.hash_join(P.shuffle_reader(5, lk), t, [[c(0), c(1)]], "RightSemi", "Partitioned", filter=other)
+    # NOT EXISTS l3: no other supplier was late on that order
+    t = P.hash_join(P.shuffle_reader(6, lk), t, [[c(0), c(1)]], "RightAnti", "Partitioned", filter=other)
+    s7 = P.aggregate("Partial", [(c(0), "s_name")], [P.agg("count", None, "numwait")], t)
+    st7 = Stage(7, P.shuffle_writer(s7, 7, [c(0)], Pn))
+    part = [P.field("s_name", "utf8", True), P.field("numwait[count]", i64)]
+    s8 = P.aggregate("FinalPartitioned", [(c(0), "s_name")], [P.agg("count", None, "numwait")], P.shuffle_reader(7, part))
+    keys = [P.sort_key(c(1), asc=False), P.sort_key(c(0))]
+    s8 = P.sort(keys, s8, fetch=100, preserve_partitioning=True)
+    st8 = Stage(8, P.shuffle_writer(s8, 8))
+    fin = [P.field("s_name", "utf8", True), P.field("numwait", i64)]
+    st9 = Stage(9, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(8, fin), fetch=100), 9), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8, st9]

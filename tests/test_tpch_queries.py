@@ -391,3 +391,29 @@ def test_q16_oracle_against_pandas(oracle, oracle_lib):
     assert {(r["p_brand"], r["p_type"], r["p_size"]): r["supplier_cnt"] for r in rows} == want
     order = [(-r["supplier_cnt"], r["p_brand"], r["p_type"], r["p_size"]) for r in rows]
     assert order == sorted(order)
+
+
+# ---- q21: EXISTS / NOT EXISTS with `<>` correlation: semi and anti joins with residual filters ---------------
+def test_q21_oracle_against_python(oracle, oracle_lib):
+    msf, parts = 20, 2
+    load_tables(oracle, oracle_lib, msf, tpch.Q21_TABLES, parts)
+    df = {t: table_df(oracle, t, oracle.n_table_partitions(t)) for t in tpch.Q21_TABLES}
+    sup = df["supplier"].merge(df["nation"], left_on="s_nationkey", right_on="n_nationkey")
+    nation = sup.n_name.value_counts().index[0]
+    status = df["orders"].o_orderstatus.value_counts().index[0]
+    got = driver.run_stages(oracle, tpch.q21(3, nation, status), "q21o")
+    li = df["lineitem"]
+    supp_of, late_of = {}, {}
+    for ok, sk, cd, rd in zip(li.l_orderkey, li.l_suppkey, li.l_commitdate, li.l_receiptdate):
+        supp_of.setdefault(ok, set()).add(sk)
+        if rd > cd:
+            late_of.setdefault(ok, set()).add(sk)
+    good_orders = set(df["orders"][df["orders"].o_orderstatus == status].o_orderkey)
+    name_of = {sk: nm for sk, nm, nn in zip(sup.s_suppkey, sup.s_name, sup.n_name) if nn == nation}
+    want = {}
+    for ok, sk, cd, rd in zip(li.l_orderkey, li.l_suppkey, li.l_commitdate, li.l_receiptdate):
+        if rd > cd and sk in name_of and ok in good_orders and (supp_of[ok] - {sk}) and not (late_of.get(ok, set()) - {sk}):
+            want[name_of[sk]] = want.get(name_of[sk], 0) + 1
+    assert len(want) > 3
+    top = sorted(((-v, k) for k, v in want.items()))[:100]
+    assert [(-r["numwait"], r["s_name"]) for r in got.to_pylist()] == top
