@@ -772,7 +772,7 @@ inline PlanPtr parse_plan(const Json& j) {
     PlanNode* l = parse_child("left");
     PlanNode* r = parse_child("right");
     n->join_type = parse_join_type(j.get_str("join_type", "Inner"));
-    n->partition_mode = smj ? std::string("Partitioned") : j.get_str("mode", "CollectLeft");
+    n->partition_mode = smj ? std::string("Partitioned") : j.get_str("mode", "Partitioned");
     n->null_equals_null = j.get_bool("null_equals_null", false);
     const Json& on = j.at("on");
     for (size_t i = 0; i < on.size(); i++) {

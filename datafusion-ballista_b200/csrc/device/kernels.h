@@ -79,6 +79,42 @@ struct GatherCols {
   int n;
 };
 void launch_gather_multi(const GatherCols& cols, const int64_t* idx, int64_t n, cudaStream_t st);
+// ---- one-pass stable radix partition + exchange / export packing (shuffle.cu) ---------------------
+static const int PART_MAX_STR_COLS = 16;
+static const uint32_t PART_MAX_FANOUT = 4096;   // per-warp counters of the scatter kernel must fit shared memory
+struct PartStrCol {
+  const void* data;       // views (16 B/row) or Arrow int32 offsets
+  const uint8_t* valid;
+  int is_view;
+  int _pad;
+};
+struct PartStrCols {
+  PartStrCol c[PART_MAX_STR_COLS];
+  int n;
+};
+uint32_t partition_n_tiles(int64_t n);
+// tile_hist: [P][n_tiles] u32 (may be nullptr when only totals are wanted); counts: [P] u64, pre-zeroed;
+// str_bytes: [sc.n][P] u64, pre-zeroed; pid == nullptr means "everything goes to partition 0"
+cudaError_t launch_partition_hist(const uint32_t* pid, int64_t n, uint32_t P, uint32_t* tile_hist, unsigned long long* counts, const PartStrCols& sc,
+                                  unsigned long long* str_bytes, cudaStream_t st);
+// offsets: exclusive scan of tile_hist (partition-major); cols: every column to move (validity bytes as their own
+// width-1 entries; only in/out/width are used); dest_out (optional): the destination row of every input row
+cudaError_t launch_partition_scatter(const uint32_t* pid, int64_t n, uint32_t P, const uint64_t* offsets, const GatherCols& cols, uint32_t* dest_out,
+                                     cudaStream_t st);
+enum PackKind : int32_t { PK_COPY = 0, PK_STR_VIEWS = 1, PK_STR_UTF8 = 2, PK_BITMAP = 3 };
+struct PackJob {
+  const void* src;        // bytes / views / int32 offsets (already positioned at the slice's first row)
+  const uint8_t* valid;   // strings: validity bytes of the slice or nullptr
+  const uint8_t* chars;   // PK_STR_UTF8: chars base the offsets are relative to
+  void* dst;              // PK_COPY: destination; strings: int32 offsets out (rows + 1, starting at 0)
+  void* dst2;             // strings: characters out
+  uint64_t bytes;         // PK_COPY: bytes to copy; strings: capacity of the character area
+  int64_t rows;           // strings, PK_BITMAP
+  int32_t kind;
+  int32_t _pad;
+};
+void launch_pack_jobs(const PackJob* jobs_dev, int n_jobs, cudaStream_t st);
+
 // ingest: int32 / int64 (width 4 / 8) -> sign-extended 16-byte Decimal128 values
 void launch_widen_to_i128(const void* in, int width, void* out, int64_t n, cudaStream_t st);
 // out[i] = in[i] - in[0] for i < n_plus_1; first_last[0..1] = in[0], in[n_plus_1 - 1] (device memory)

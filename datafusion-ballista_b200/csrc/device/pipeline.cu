@@ -19,6 +19,8 @@
 //  * everything else (division, casts, LIKE, string compares, generic group keys) runs in rolled
 //    per-row __noinline__ paths that exist once in the binary.
 #include <cuda_runtime.h>
+
+#include <mutex>
 #include <stdint.h>
 
 #include "../common/hash.hpp"
@@ -1409,7 +1411,21 @@ __device__ __forceinline__ void store_out_i64(void* data, uint8_t phys, unsigned
   }
 }
 
-__device__ __forceinline__ void sink_materialize(const Lane L, const uint32_t active, uint32_t* warp_tot /*[VM_R][32]*/, unsigned long long* tile_base_sh) {
+// Output position of a tile = rows kept by all EARLIER tiles (decoupled look-back over one 64-bit word per tile:
+// {flag:2, count:62}; flag 1 = this tile's own count, 2 = inclusive prefix), so FilterExec / ProjectionExec keep
+// the input row order across tiles like their DataFusion counterparts (both are order-preserving operators).
+// Tiles are dealt round-robin to co-resident CTAs that walk their tiles in increasing order, so a tile only ever
+// waits for tiles that are already running.
+__device__ __forceinline__ unsigned long long tile_ld_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tile_st_release(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sink_materialize(const Lane L, const uint32_t active, uint32_t* warp_tot /*[VM_R][32]*/, unsigned long long* tile_base_sh,
+                                                 const int64_t t, const int64_t n_tiles) {
   const int lane = L.tid & 31, warp = L.tid >> 5, nwarps = L.B >> 5;
   uint32_t lane_pre[VM_R];
 #pragma unroll
@@ -1431,7 +1447,33 @@ __device__ __forceinline__ void sink_materialize(const Lane L, const uint32_t ac
     }
     pos[r] = mine + lane_pre[r];
   }
-  if (L.tid == 0) *tile_base_sh = run ? atomicAdd(&PROG.status->out_rows, (unsigned long long)run) : 0ull;
+  if (warp == 0) {
+    const unsigned long long F_AGG = 1ull << 62, F_PFX = 2ull << 62, CNT = (1ull << 62) - 1;
+    unsigned long long* ts = PROG.tile_state;
+    if (lane == 0 && t > 0) tile_st_release(&ts[t], F_AGG | (unsigned long long)run);
+    unsigned long long excl = 0;
+    for (int64_t p = t - 1; p >= 0; p -= 32) {
+      const int64_t q = p - lane;
+      unsigned long long v = F_PFX;  // before the first tile: an (empty) inclusive prefix
+      if (q >= 0) {
+        do {
+          v = tile_ld_acquire(&ts[q]);
+        } while ((v >> 62) == 0);
+      }
+      const uint32_t pf = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+      const int first = pf ? __ffs(pf) - 1 : 32;
+      unsigned long long c = (lane <= first) ? (v & CNT) : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+      excl += c;
+      if (pf) break;
+    }
+    if (lane == 0) {
+      tile_st_release(&ts[t], F_PFX | (excl + (unsigned long long)run));
+      *tile_base_sh = excl;
+      if (t == n_tiles - 1) PROG.status->out_rows = excl + (unsigned long long)run;
+    }
+  }
   __syncthreads();
   if (run == 0) return;
   const unsigned long long base = *tile_base_sh;
@@ -2097,7 +2139,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
     mbar_fence_init();
   }
   const int n_instr = PROG.n_instr;
-  if (tid < n_instr) decode_micro(tid, &mops[tid]);
+  for (int pc = tid; pc < n_instr; pc += B) decode_micro(pc, &mops[pc]);
   if (SINK == SINK_AGG_REG && tid >= 64 && tid < 64 + PROG.n_acc) decode_acc(tid - 64, &accops[tid - 64]);
   if (SINK == SINK_AGG_REG && tid < VM_REG_GROUPS) {
     gtable.state[tid] = 0;
@@ -2165,7 +2207,7 @@ __global__ void __launch_bounds__(512, 1) pipeline_kernel() {
       active = run_program(L, active, mops, n_instr);
     }
     if (SINK == SINK_MATERIALIZE) {
-      sink_materialize(L, active, warp_tot, &tile_base_sh);
+      sink_materialize(L, active, warp_tot, &tile_base_sh, t, n_tiles);
     } else if (SINK == SINK_AGG_GLOBAL) {
       active = sink_agg_global(L, active);
       live_rows += __popc(active);
@@ -2211,10 +2253,47 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------------
 // Host launcher
 // ------------------------------------------------------------------------------------------------
+// The running program lives in __constant__ memory, one copy per device.  Up to `concurrent_tasks` host threads
+// (and possibly several streams) drive one engine (cpu_bound_executor.rs:94-131), so {upload, launch} is one
+// critical section per device, and the upload additionally waits (on the device) for the previous pipeline
+// kernel of ANY stream: a pipeline kernel occupies every SM anyway, so nothing is lost by running them one
+// after the other, while all the small kernels around them still overlap freely.
+struct ProgramGate {
+  std::mutex mu;
+  cudaEvent_t last = nullptr;
+};
+static ProgramGate g_gate[64];
+
+struct GateLock {
+  ProgramGate& g;
+  cudaStream_t st;
+  cudaError_t err = cudaSuccess;
+  GateLock(cudaStream_t s) : g(g_gate[current_device() & 63]), st(s) {
+    g.mu.lock();
+    if (!g.last) err = cudaEventCreateWithFlags(&g.last, cudaEventDisableTiming);
+    else err = cudaStreamWaitEvent(st, g.last, 0);
+  }
+  ~GateLock() {
+    if (g.last) cudaEventRecord(g.last, st);
+    g.mu.unlock();
+  }
+  static int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+  }
+};
+
 template <int SINK, int G, bool ADD_ONLY>
 static cudaError_t launch_one(int grid, int block, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(pipeline_kernel<SINK, G, ADD_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  // the opt-in to large dynamic shared memory is per (function, device) and sticky: raise it only when needed
+  static size_t granted[64] = {0};
+  const int dev = GateLock::current_device() & 63;
+  if (smem > granted[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pipeline_kernel<SINK, G, ADD_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    granted[dev] = smem;
+  }
   pipeline_kernel<SINK, G, ADD_ONLY><<<grid, block, smem, st>>>();
   return cudaGetLastError();
 }
@@ -2229,8 +2308,9 @@ bool pipeline_add_only(const Program& P, int grid, int block) {
 }
 
 cudaError_t launch_pipeline(const Program& P, int reg_groups, int grid, int block, size_t smem, cudaStream_t st) {
-  // stream-ordered upload of the program into constant memory (the previous kernel on `st` is done
-  // before this copy executes)
+  GateLock gate(st);
+  if (gate.err != cudaSuccess) return gate.err;
+  // stream-ordered upload of the program into constant memory
   cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(Program), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   const bool add_only = pipeline_add_only(P, grid, block);
@@ -2252,6 +2332,8 @@ bool fused_rows_ok(const Program& P, int grid, int block, int rows_per_thread) {
 
 cudaError_t launch_fused_pipeline(const Program& P, const FusedSpec& F, FusedShape shape, int reg_groups, int grid, int block, size_t smem, cudaStream_t st,
                                   int* is_static) {
+  GateLock gate(st);
+  if (gate.err != cudaSuccess) return gate.err;
   cudaError_t e = cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(Program), 0, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbolAsync(c_fused, &F, sizeof(FusedSpec), 0, cudaMemcpyHostToDevice, st);

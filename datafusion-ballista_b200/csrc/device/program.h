@@ -15,8 +15,8 @@ namespace b200 {
 static const int VM_R = 2;            // rows per thread per tile (register-blocked)
 static const int VM_MAX_COLS = 24;    // source columns of one pipeline
 static const int VM_MAX_REGS = 40;    // VM value registers (shared-memory resident)
-static const int VM_MAX_IMMS = 40;
-static const int VM_MAX_INSTR = 112;
+static const int VM_MAX_IMMS = 128;
+static const int VM_MAX_INSTR = 224;
 static const int VM_MAX_OUT = 32;     // materialize sink output columns
 static const int VM_MAX_KEYS = 8;     // group-by / hash key columns
 static const int VM_MAX_ACC = 16;     // physical accumulators of an aggregate sink
@@ -184,6 +184,7 @@ struct Program {
   AggTable table;
   unsigned long long* acc_hi;   // register sink: high 64-bit words [cta][thread][group][acc], pre-zeroed
   RunStatus* status;
+  unsigned long long* tile_state;  // materialize sink: one look-back word per tile, zeroed before the launch
   int64_t n_rows;
 };
 

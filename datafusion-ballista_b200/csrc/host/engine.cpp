@@ -11,6 +11,7 @@
 // DataFusion 53.1 [EXT]) is executed by the CUDA kernels in csrc/device.  There is no CPU path:
 // every operator either runs on the GPU or fails with B200_ERR_UNSUPPORTED.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,7 @@
 #include "../device/kernels.h"
 #include "host_pool.hpp"
 #include "lower.hpp"
+#include "nccl_dyn.hpp"
 
 using namespace b200;
 
@@ -35,6 +37,8 @@ struct Piece {
   int64_t file_id;
   DevBatchPtr batch;
   int64_t r0, r1;
+  int32_t src_rank = 0;               // which executor's map task produced it (exchange)
+  std::vector<int64_t> str_bytes;     // per Utf8 column of the batch: character bytes of rows [r0, r1); empty = unknown
 };
 struct ShuffleKey {
   std::string job;
@@ -63,8 +67,8 @@ struct b200_engine {
   std::mutex mu;
   std::map<std::string, std::map<int, DevBatchPtr>> tables;
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
-  uint64_t launches = 0;
-  uint64_t n_fused = 0, n_fused_static = 0, n_vm = 0;  // pipelines per kernel family (b200_engine_counter)
+  std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0};  // pipelines per kernel family (b200_engine_counter)
   int64_t batch_size = 8192;
   std::map<std::string, std::string> config;
   std::map<std::string, int> agg_hint;       // plan fingerprint -> sink that worked (0 reg, >0 log2 cap)
@@ -78,7 +82,12 @@ struct b200_engine {
     cudaEvent_t done = nullptr;
     bool used = false;
   } nslot[2];
-  uint64_t narrowed_bytes_saved = 0;         // PCIe bytes not sent thanks to narrowing (b200_engine_counter)
+  ncclComm_t comm = nullptr;                 // exchange communicator (b200_engine_comm_init); nullptr = single executor
+  std::mutex comm_mu;                        // one collective at a time
+  uint64_t exch_sent_bytes = 0, exch_recv_bytes = 0;
+  std::mutex export_mu;                      // small-result export arena (pinned), one export at a time
+  uint8_t* export_arena = nullptr;
+  std::atomic<uint64_t> narrowed_bytes_saved{0};         // PCIe bytes not sent thanks to narrowing (b200_engine_counter)
 };
 
 struct b200_stage {
@@ -96,6 +105,23 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // Small helpers
 // ------------------------------------------------------------------------------------------------
+// Per-thread read-back arena: scalars the host needs from the device (row counts, status words, string
+// byte totals) are queued as asynchronous copies into one pinned buffer and become readable after the next
+// Exec::sync().  Checks that only have to hold before the task RETURNS (arithmetic-overflow flags of kernels
+// whose output size is already known) are deferred to that same synchronisation instead of costing their own.
+struct TaskCtx {
+  uint8_t* arena = nullptr;
+  size_t pos = 0;
+  bool drained = true;
+  std::vector<std::function<void()>> checks;
+};
+static const size_t TASK_ARENA_BYTES = (size_t)1 << 16;
+inline TaskCtx& task_ctx() {
+  static thread_local TaskCtx t;
+  if (!t.arena && cudaHostAlloc((void**)&t.arena, TASK_ARENA_BYTES, cudaHostAllocDefault) != cudaSuccess) t.arena = nullptr;
+  return t;
+}
+
 struct Exec {
   b200_engine* e;
   b200_stage* s;
@@ -104,28 +130,92 @@ struct Exec {
   void check_cancel() const {
     if (cancel && *cancel) throw EngineError(B200_ERR_CANCELLED, "task cancelled");
   }
-  void count(uint64_t n = 1) const { e->launches += n; }
+  void count(uint64_t n = 1) const { e->launches.fetch_add(n, std::memory_order_relaxed); }
   OpMetrics* m(const PlanNode* n) const {
     if (!s) return nullptr;
     auto it = s->metric_index.find(n);
     return it == s->metric_index.end() ? nullptr : &s->metrics[(size_t)it->second];
   }
+  // queue a device->host copy of `bytes` bytes; the returned pointer is readable after sync()
+  const void* fetch_bytes(const void* dptr, size_t bytes) const {
+    TaskCtx& t = task_ctx();
+    if (!t.arena) throw EngineError(B200_ERR_OOM, "pinned read-back arena unavailable");
+    if (t.drained) {
+      t.pos = 0;
+      t.drained = false;
+    }
+    const size_t at = (t.pos + 15) & ~(size_t)15;
+    if (at + bytes > TASK_ARENA_BYTES) {  // rare: flush what is queued, then start over
+      sync();
+      return fetch_bytes(dptr, bytes);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(t.arena + at, dptr, bytes, cudaMemcpyDeviceToHost, st()));
+    t.pos = at + bytes;
+    return t.arena + at;
+  }
+  // pinned host scratch for an asynchronous host->device upload; valid until the next sync()
+  void* stage_bytes(size_t bytes) const {
+    TaskCtx& t = task_ctx();
+    if (!t.arena) throw EngineError(B200_ERR_OOM, "pinned staging arena unavailable");
+    if (t.drained) {
+      t.pos = 0;
+      t.drained = false;
+    }
+    size_t at = (t.pos + 15) & ~(size_t)15;
+    if (at + bytes > TASK_ARENA_BYTES) {
+      sync();
+      t.pos = 0;
+      t.drained = false;
+      at = 0;
+      if (bytes > TASK_ARENA_BYTES) throw EngineError(B200_ERR_INVALID, "staging request larger than the arena");
+    }
+    t.pos = at + bytes;
+    return t.arena + at;
+  }
+  template <class T>
+  const T* fetch(const void* dptr) const {
+    return (const T*)fetch_bytes(dptr, sizeof(T));
+  }
+  void defer(std::function<void()> fn) const { task_ctx().checks.push_back(std::move(fn)); }
+  // wait for everything enqueued so far, then run the deferred checks (they may throw)
+  void sync() const {
+    TaskCtx& t = task_ctx();
+    cudaError_t se = cudaStreamSynchronize(st());
+    t.drained = true;
+    std::vector<std::function<void()>> cs;
+    cs.swap(t.checks);
+    CUDA_CHECK(se);
+    for (auto& c : cs) c();
+    check_cancel();
+  }
+  // drop deferred checks without running them (error unwinding)
+  static void abandon() {
+    TaskCtx& t = task_ctx();
+    t.checks.clear();
+    t.drained = true;
+  }
+  template <class T>
+  T get(const void* dptr) const {
+    const T* p = fetch<T>(dptr);
+    sync();
+    return *p;
+  }
 };
 
-template <class T>
-T d2h_value(const void* dptr, cudaStream_t st) {
-  // small read-backs (row counts, string lengths, status words) land in a per-thread pinned slot: a
-  // pageable destination would make the "async" copy a staged, slower one
-  static thread_local void* slot = nullptr;
-  static_assert(sizeof(T) <= 64, "d2h_value is for scalars");
-  if (!slot && cudaHostAlloc(&slot, 64, cudaHostAllocDefault) != cudaSuccess) slot = nullptr;
-  T v;
-  void* dst = slot ? slot : (void*)&v;
-  CUDA_CHECK(cudaMemcpyAsync(dst, dptr, sizeof(T), cudaMemcpyDeviceToHost, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));
-  if (slot) memcpy(&v, slot, sizeof(T));
-  return v;
-}
+// B200_TIMING=1: host wall time of the phases of a task (diagnostic; stderr)
+struct ScopeTimer {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  bool on;
+  explicit ScopeTimer(const char* n) : name(n) {
+    static const bool enabled = getenv("B200_TIMING") != nullptr;
+    on = enabled;
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  ~ScopeTimer() {
+    if (on) fprintf(stderr, "[b200-time] %s host_ms=%.3f\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
 
 uint64_t next_pow2(uint64_t v) {
   uint64_t p = 1;
@@ -151,6 +241,62 @@ DevColumn make_out_column(const std::string& name, const DataType& t, Phys phys,
   return c;
 }
 
+// A batch of small copy / string-conversion jobs executed by ONE kernel (shuffle.cu pack_jobs_kernel): the tail of
+// a query moves a handful of rows through a dozen columns and is bound by launch count, not bytes.
+struct PackList {
+  std::vector<PackJob> jobs;
+  void copy(const void* src, void* dst, uint64_t bytes) {
+    if (!bytes) return;
+    PackJob j;
+    memset(&j, 0, sizeof j);
+    j.kind = PK_COPY;
+    j.src = src;
+    j.dst = dst;
+    j.bytes = bytes;
+    jobs.push_back(j);
+  }
+  // string column slice (views or Arrow offsets positioned at the first row) -> offsets (rows + 1, from 0) + chars
+  void bitmap(const uint8_t* bytes, int64_t rows, void* bitmap_out, void* zero_count_out) {
+    PackJob j;
+    memset(&j, 0, sizeof j);
+    j.kind = PK_BITMAP;
+    j.src = bytes;
+    j.dst = bitmap_out;
+    j.dst2 = zero_count_out;
+    j.rows = rows;
+    jobs.push_back(j);
+  }
+  void strings(const DevColumn& c, void* offsets_out, void* chars_out, uint64_t chars_cap = ~0ull) {
+    PackJob j;
+    memset(&j, 0, sizeof j);
+    j.bytes = chars_cap;
+    j.kind = c.phys == PH_STRVIEW ? PK_STR_VIEWS : PK_STR_UTF8;
+    j.src = c.data;
+    j.valid = c.valid;
+    j.chars = c.chars;
+    j.dst = offsets_out;
+    j.dst2 = chars_out;
+    j.rows = c.n;
+    jobs.push_back(j);
+  }
+  void run(const Exec& x, std::vector<DevPtr>* keep = nullptr) {
+    if (jobs.empty()) return;
+    const size_t bytes = jobs.size() * sizeof(PackJob);
+    DevPtr d = dev_alloc(bytes, x.st());
+    if (bytes <= TASK_ARENA_BYTES / 4) {
+      void* h = x.stage_bytes(bytes);
+      memcpy(h, jobs.data(), bytes);
+      CUDA_CHECK(cudaMemcpyAsync(d->ptr, h, bytes, cudaMemcpyHostToDevice, x.st()));
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(d->ptr, jobs.data(), bytes, cudaMemcpyHostToDevice, x.st()));  // pageable: staged by the driver before returning
+    }
+    launch_pack_jobs((const PackJob*)d->ptr, (int)jobs.size(), x.st());
+    x.count();
+    if (keep) keep->push_back(d);
+    jobs.clear();
+  }
+};
+
 // strings as views (needed for gather / scatter / sort / join); zero-copy for non-strings
 DevColumn as_views(const Exec& x, const DevColumn& c) {
   if (c.phys != PH_UTF8) return c;
@@ -166,16 +312,39 @@ DevColumn as_views(const Exec& x, const DevColumn& c) {
 }
 
 // views -> Arrow Utf8 (offsets + chars), contiguous
-DevColumn as_utf8(const Exec& x, const DevColumn& c) {
+DevColumn as_utf8(const Exec& x, const DevColumn& c, int64_t known_total = -1) {
   if (c.phys != PH_STRVIEW) return c;
   const int64_t n = c.n;
+  if (known_total >= 0 && n <= 4096) {
+    // small column whose character count the host already knows: offsets + chars in ONE launch, no read-back
+    DevPtr offsets = dev_alloc((size_t)(n + 1) * 4, x.st());
+    DevPtr chars = dev_alloc((size_t)known_total + 16, x.st());
+    PackList pl;
+    pl.strings(c, offsets->ptr, chars->ptr);
+    pl.run(x);
+    DevColumn o;
+    o.name = c.name;
+    o.type = c.type;
+    o.nullable = c.nullable;
+    o.phys = PH_UTF8;
+    o.n = n;
+    o.data = (const uint8_t*)offsets->ptr;
+    o.chars = (const uint8_t*)chars->ptr;
+    o.chars_bytes = known_total;
+    o.valid = c.valid;
+    o.keep.push_back(offsets);
+    o.keep.push_back(chars);
+    if (c.valid)
+      for (auto& k : c.keep) o.keep.push_back(k);
+    return o;
+  }
   DevPtr lens = dev_alloc((size_t)(n + 1) * 4, x.st());
   DevPtr offs64 = dev_alloc((size_t)(n + 2) * 8, x.st());
   DevPtr scratch = dev_alloc((size_t)(n / 1024 + 4) * 8, x.st());
   launch_view_lengths((const unsigned long long*)c.data, c.valid, (uint32_t*)lens->ptr, n, x.st());
   launch_scan_u32_to_u64((const uint32_t*)lens->ptr, (uint64_t*)offs64->ptr, n, (uint64_t*)scratch->ptr, x.st());
   x.count(4);
-  uint64_t total = d2h_value<uint64_t>((const uint64_t*)offs64->ptr + n, x.st());
+  uint64_t total = known_total >= 0 ? (uint64_t)known_total : x.get<uint64_t>((const uint64_t*)offs64->ptr + n);
   if (total > 0x7FFFFFFFull) throw EngineError(B200_ERR_UNSUPPORTED, "string column exceeds 2 GiB (LargeUtf8 not supported)");
   DevPtr offsets = dev_alloc((size_t)(n + 1) * 4, x.st());
   DevPtr chars = dev_alloc((size_t)total + 16, x.st());
@@ -380,78 +549,92 @@ DevBatchPtr import_batch(b200_engine* e, ArrowArray* arr, ArrowSchema* sch) {
 // ------------------------------------------------------------------------------------------------
 // Arrow export (HBM -> host)
 // ------------------------------------------------------------------------------------------------
-// Small results (the tail of most queries is a handful of rows): every buffer is copied asynchronously
-// into one pinned arena and the stream is synchronised twice in total (fixed-size parts, then string
-// bytes) instead of once per buffer.
+// Small results (the tail of most queries is a handful of rows): ONE kernel packs every buffer of the batch
+// (bitmaps + null counts, fixed-width values, string offsets and characters) into a device arena, one copy
+// brings the arena to pinned host memory, one synchronisation in total.  Character areas are sized optimistically;
+// a column that needs more sends the batch down the general path.
 static const int64_t SMALL_EXPORT_ROWS = 4096;
-static const size_t SMALL_EXPORT_ARENA = (size_t)4 << 20;
+static const size_t SMALL_EXPORT_ARENA = (size_t)1 << 20;
+static const size_t SMALL_EXPORT_CHARS = (size_t)32 << 10;  // per string column
 
 bool export_batch_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
   const int64_t n = r1 - r0;
-  static thread_local uint8_t* arena = nullptr;
-  if (!arena && cudaHostAlloc((void**)&arena, SMALL_EXPORT_ARENA, cudaHostAllocDefault) != cudaSuccess) {
-    arena = nullptr;
+  std::lock_guard<std::mutex> eg(x.e->export_mu);
+  if (!x.e->export_arena && cudaHostAlloc((void**)&x.e->export_arena, SMALL_EXPORT_ARENA, cudaHostAllocDefault) != cudaSuccess) {
+    x.e->export_arena = nullptr;
     return false;
   }
+  uint8_t* arena = x.e->export_arena;
   cudaStream_t st = x.st();
-  struct Slot { size_t validity = 0, count = 0, data = 0, chars = 0; DevColumn u; bool has_valid = false; };
+  struct Slot { size_t validity = 0, count = 0, data = 0, chars = 0, chars_cap = 0; bool has_valid = false; };
   std::vector<Slot> slots(b.cols.size());
   std::vector<HostCol> hcs(b.cols.size());
+  std::vector<DevColumn> cs(b.cols.size());
   size_t pos = 0;
   auto take = [&](size_t bytes) {
     size_t p = pos;
     pos += (bytes + 63) & ~(size_t)63;
     return p;
   };
-  // phase 1: validity bitmaps, null counts, fixed-width data / offsets
   for (size_t ci = 0; ci < b.cols.size(); ci++) {
-    DevColumn c = slice_column(b.cols[ci], r0, r1);
+    cs[ci] = slice_column(b.cols[ci], r0, r1);
+    const DevColumn& c = cs[ci];
     HostCol& h = hcs[ci];
     Slot& sl = slots[ci];
     h.name = c.name;
     h.type = c.type;
     h.nullable = true;
     h.n = n;
-    size_t need = (size_t)(n + 7) / 8 + 64 + (size_t)(n + 1) * 16 + 128;
-    if (pos + need > SMALL_EXPORT_ARENA / 2) return false;  // leave room for the string bytes
     if (c.valid && n) {
       sl.has_valid = true;
-      DevPtr bm = dev_alloc((size_t)(n + 7) / 8 + 16, st);
-      DevPtr cnt = dev_alloc(8, st);
-      CUDA_CHECK(cudaMemsetAsync(cnt->ptr, 0, 8, st));
-      launch_bytes_to_bitmap(c.valid, (uint8_t*)bm->ptr, n, (unsigned long long*)cnt->ptr, st);
-      x.count();
       sl.validity = take((size_t)(n + 7) / 8);
       sl.count = take(8);
-      CUDA_CHECK(cudaMemcpyAsync(arena + sl.validity, bm->ptr, (size_t)(n + 7) / 8, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(arena + sl.count, cnt->ptr, 8, cudaMemcpyDeviceToHost, st));
     }
     if (c.type.id == TypeId::Bool) {
       h.data.assign((size_t)(n + 7) / 8, 0);
-      if (n) {
-        DevPtr bm = dev_alloc((size_t)(n + 7) / 8 + 16, st);
-        launch_bytes_to_bitmap(c.data, (uint8_t*)bm->ptr, n, nullptr, st);
-        x.count();
-        sl.data = take(h.data.size());
-        CUDA_CHECK(cudaMemcpyAsync(arena + sl.data, bm->ptr, h.data.size(), cudaMemcpyDeviceToHost, st));
-      }
+      sl.data = take(h.data.size());
     } else if (c.type.id == TypeId::Utf8) {
-      sl.u = c.phys == PH_STRVIEW ? as_utf8(x, c) : c;
       h.data.resize((size_t)(n + 1) * 4);
       sl.data = take(h.data.size());
-      CUDA_CHECK(cudaMemcpyAsync(arena + sl.data, sl.u.data, h.data.size(), cudaMemcpyDeviceToHost, st));
+      sl.chars_cap = (c.phys == PH_UTF8 && c.chars_bytes >= 0) ? (size_t)c.chars_bytes : SMALL_EXPORT_CHARS;
+      sl.chars = take(sl.chars_cap);
     } else {
       h.data.resize((size_t)n * c.width());
       sl.data = take(h.data.size());
-      if (n) CUDA_CHECK(cudaMemcpyAsync(arena + sl.data, c.data, h.data.size(), cudaMemcpyDeviceToHost, st));
+    }
+    if (pos > SMALL_EXPORT_ARENA) return false;
+  }
+  if (pos == 0) {
+    export_record_batch(std::move(hcs), n, out, out_schema);
+    return true;
+  }
+  DevPtr dev = dev_alloc(pos, st);
+  uint8_t* d = (uint8_t*)dev->ptr;
+  PackList pl;
+  for (size_t ci = 0; ci < b.cols.size(); ci++) {
+    const DevColumn& c = cs[ci];
+    const Slot& sl = slots[ci];
+    if (sl.has_valid) pl.bitmap(c.valid, n, d + sl.validity, d + sl.count);
+    if (c.type.id == TypeId::Bool) {
+      if (n) pl.bitmap(c.data, n, d + sl.data, nullptr);
+    } else if (c.type.id == TypeId::Utf8) {
+      pl.strings(c, d + sl.data, d + sl.chars, sl.chars_cap);
+    } else if (n) {
+      pl.copy(c.data, d + sl.data, (uint64_t)n * c.width());
     }
   }
-  CUDA_CHECK(cudaStreamSynchronize(st));
-  // phase 2: string bytes (their range is known only now)
-  bool any_chars = false;
+  pl.run(x);
+  CUDA_CHECK(cudaMemcpyAsync(arena, d, pos, cudaMemcpyDeviceToHost, st));
+  x.sync();
+  for (size_t ci = 0; ci < b.cols.size(); ci++)
+    if (hcs[ci].type.id == TypeId::Utf8) {
+      int32_t total = 0;
+      memcpy(&total, arena + slots[ci].data + (size_t)n * 4, 4);
+      if ((size_t)total > slots[ci].chars_cap) return false;  // optimistic character area too small: general path
+    }
   for (size_t ci = 0; ci < b.cols.size(); ci++) {
     HostCol& h = hcs[ci];
-    Slot& sl = slots[ci];
+    const Slot& sl = slots[ci];
     if (sl.has_valid) {
       unsigned long long nulls = 0;
       memcpy(&nulls, arena + sl.count, 8);
@@ -460,28 +643,9 @@ bool export_batch_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1
     }
     if (!h.data.empty()) memcpy(h.data.data(), arena + sl.data, h.data.size());
     if (h.type.id == TypeId::Utf8) {
-      int32_t* off = (int32_t*)h.data.data();
-      const int32_t first = off[0], last = off[n];
-      h.extra.resize((size_t)(last - first));
-      if (last > first) {
-        if (pos + h.extra.size() > SMALL_EXPORT_ARENA) {  // long strings: straight into the vector
-          CUDA_CHECK(cudaMemcpyAsync(h.extra.data(), sl.u.chars + first, h.extra.size(), cudaMemcpyDeviceToHost, st));
-          CUDA_CHECK(cudaStreamSynchronize(st));
-          sl.chars = (size_t)-1;
-        } else {
-          sl.chars = take(h.extra.size());
-          CUDA_CHECK(cudaMemcpyAsync(arena + sl.chars, sl.u.chars + first, h.extra.size(), cudaMemcpyDeviceToHost, st));
-          any_chars = true;
-        }
-      }
-      for (int64_t i = 0; i <= n; i++) off[i] -= first;
+      const int32_t total = ((const int32_t*)h.data.data())[n];
+      h.extra.assign(arena + sl.chars, arena + sl.chars + (size_t)total);
     }
-  }
-  if (any_chars) {
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    for (size_t ci = 0; ci < b.cols.size(); ci++)
-      if (hcs[ci].type.id == TypeId::Utf8 && !hcs[ci].extra.empty() && slots[ci].chars != (size_t)-1)
-        memcpy(hcs[ci].extra.data(), arena + slots[ci].chars, hcs[ci].extra.size());
   }
   export_record_batch(std::move(hcs), n, out, out_schema);
   return true;
@@ -507,7 +671,7 @@ void export_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, Arro
       x.count();
       h.validity.resize((size_t)(n + 7) / 8);
       CUDA_CHECK(cudaMemcpyAsync(h.validity.data(), bm->ptr, h.validity.size(), cudaMemcpyDeviceToHost, st));
-      h.null_count = (int64_t)d2h_value<unsigned long long>(cnt->ptr, st);
+      h.null_count = (int64_t)x.get<unsigned long long>(cnt->ptr);
       if (h.null_count == 0) h.validity.clear();
     }
     if (c.type.id == TypeId::Bool) {
@@ -556,11 +720,35 @@ struct FusedPlan {
   size_t smem = 0;
 };
 
-RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedPlan* fused = nullptr) {
+static void throw_run_error(unsigned int error) {
+  if (error == 1) throw EngineError(B200_ERR_EXECUTION, "Arithmetic overflow");
+  if (error == 2) throw EngineError(B200_ERR_EXECUTION, "Divide by zero");
+  if (error) throw EngineError(B200_ERR_EXECUTION, "execution error in expression");
+}
+
+static bool program_filters(const Program& P) {
+  for (int i = 0; i < P.n_instr; i++)
+    if (P.code[i].op == OP_FILTER || (P.code[i].flags & IF_FILTER)) return true;
+  return false;
+}
+
+// Enqueues the pipeline kernel.  wait == true: synchronises, checks the status word and returns it
+// (`extra_fetch`, if given, is a device word read back in the same synchronisation).  wait == false:
+// the caller already knows the output size; the status check (and the kernel time for the metrics)
+// is deferred to the task's next synchronisation.
+RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedPlan* fused = nullptr, bool wait = true, OpMetrics* met = nullptr,
+                          const unsigned int* extra_fetch = nullptr, unsigned int* extra_out = nullptr) {
   Program& P = pb.prog;
   DevPtr dstat = dev_alloc(sizeof(RunStatus), x.st());
   CUDA_CHECK(cudaMemsetAsync(dstat->ptr, 0, sizeof(RunStatus), x.st()));
   P.status = (RunStatus*)dstat->ptr;
+  DevPtr tstate;
+  if (P.sink == SINK_MATERIALIZE) {
+    const int64_t nt = (P.n_rows + (int64_t)pb.block * VM_R - 1) / ((int64_t)pb.block * VM_R);
+    tstate = dev_alloc((size_t)std::max<int64_t>(nt, 1) * 8, x.st());
+    CUDA_CHECK(cudaMemsetAsync(tstate->ptr, 0, (size_t)std::max<int64_t>(nt, 1) * 8, x.st()));
+    P.tile_state = (unsigned long long*)tstate->ptr;
+  }
   int grid;
   if (fused) {
     const int64_t warp_tile = 32 * fused->spec.rows_per_thread, nw = fused->block / 32;
@@ -618,15 +806,34 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
   CUDA_CHECK(cudaEventRecord(e1, x.st()));
   x.count();
   RunOutcome o;
-  CUDA_CHECK(cudaMemcpyAsync(&o.status, dstat->ptr, sizeof(RunStatus), cudaMemcpyDeviceToHost, x.st()));
-  cudaError_t se = cudaStreamSynchronize(x.st());
-  if (se == cudaSuccess) cudaEventElapsedTime(&o.ms, e0, e1);
+  const RunStatus* hs = x.fetch<RunStatus>(dstat->ptr);
+  const unsigned int* he = extra_fetch ? x.fetch<unsigned int>(extra_fetch) : nullptr;
+  if (!wait) {
+    x.defer([hs, e0, e1, met, dstat, tstate]() {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      if (met) met->elapsed_ns += (uint64_t)(ms * 1e6);
+      throw_run_error(hs->error);
+    });
+    memset(&o.status, 0, sizeof o.status);
+    return o;
+  }
+  try {
+    x.sync();
+  } catch (...) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    throw;
+  }
+  o.status = *hs;
+  if (he && extra_out) *extra_out = *he;
+  cudaEventElapsedTime(&o.ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  CUDA_CHECK(se);
-  if (o.status.error == 1) throw EngineError(B200_ERR_EXECUTION, "Arithmetic overflow");
-  if (o.status.error == 2) throw EngineError(B200_ERR_EXECUTION, "Divide by zero");
-  if (o.status.error) throw EngineError(B200_ERR_EXECUTION, "execution error in expression");
+  if (met) met->elapsed_ns += (uint64_t)(o.ms * 1e6);
+  throw_run_error(o.status.error);
   return o;
 }
 
@@ -658,8 +865,10 @@ DevBatchPtr run_materialize(const Exec& x, PipelineBuilder& pb, const std::vecto
     out->cols.push_back(oc);
   }
   pb.finalize_layout(4096);
-  RunOutcome r = launch_program(x, pb, 1);
-  out->n = (int64_t)r.status.out_rows;
+  // without a filter every input row comes out: no need to wait for the row count
+  const bool filters = program_filters(P);
+  RunOutcome r = launch_program(x, pb, 1, nullptr, filters, met);
+  out->n = filters ? (int64_t)r.status.out_rows : src->n;
   uint64_t wbytes = 0;
   for (auto& c : out->cols) {
     c.n = out->n;
@@ -675,7 +884,6 @@ DevBatchPtr run_materialize(const Exec& x, PipelineBuilder& pb, const std::vecto
     for (auto& c : out->cols)
       if (c.phys == PH_STRVIEW) c.keep.push_back(k);
   if (met) {
-    met->elapsed_ns += (uint64_t)(r.ms * 1e6);
     met->bytes_read += source_bytes(pb);
     met->bytes_written += wbytes;
     met->launches += 1;
@@ -1235,6 +1443,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   AggLowered L;
   TableMem tm;
   RunOutcome ro;
+  unsigned int n_groups = 0;
   for (;;) {
     x.check_cancel();
     pbp = make_pb();
@@ -1281,11 +1490,8 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     }
     FusedPlan fspec;
     const bool use_fused = level == 0 && match_fused(P, fspec);
-    ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr);
-    if (met) {
-      met->elapsed_ns += (uint64_t)(ro.ms * 1e6);
-      met->launches += 2;
-    }
+    ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr, true, met, tm.T.n_groups, &n_groups);
+    if (met) met->launches += 2;
     if (ro.status.pack_overflow) {
       pack_mode = pack_mode == 2 ? 1 : 0;
       continue;
@@ -1299,7 +1505,6 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     x.e->agg_hint[hint_key] = level * 4 + pack_mode;
   }
   PipelineBuilder& pb = *pbp;
-  unsigned int n_groups = d2h_value<unsigned int>(tm.T.n_groups, x.st());
   // extraction
   auto out = std::make_shared<DevBatch>();
   out->n = n_groups;
@@ -1344,8 +1549,13 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   }
   launch_agg_extract(tm.T, A, x.st());
   x.count();
-  unsigned int err = d2h_value<unsigned int>(A.error, x.st());
-  if (err) throw EngineError(B200_ERR_EXECUTION, "Arithmetic overflow");
+  {
+    // the extraction's overflow flag (decimal AVG / SUM precision) only has to be seen before the task returns
+    const unsigned int* herr = x.fetch<unsigned int>(A.error);
+    x.defer([herr, counter]() {
+      if (*herr) throw EngineError(B200_ERR_EXECUTION, "Arithmetic overflow");
+    });
+  }
   for (size_t c = 0; c < out->cols.size() && c < node.schema.size(); c++) out->cols[c].name = node.schema[c].name;
   if (met) {
     met->bytes_read += source_bytes(pb);
@@ -1402,6 +1612,9 @@ struct Runner {
       for (auto& c : b.cols) out->cols.push_back(slice_column(c, parts[0].second.first, parts[0].second.second));
       return out;
     }
+    // few rows (the tail of a query, reduce side of a small shuffle): all copies in one kernel launch
+    const bool batched = total <= 65536;
+    PackList pl;
     for (size_t ci = 0; ci < schema.size(); ci++) {
       bool any_valid = false;
       for (auto& p : parts) any_valid |= p.first->cols[ci].valid != nullptr;
@@ -1416,9 +1629,11 @@ struct Runner {
         DevColumn sc = slice_column(p.first->cols[ci], r0, r1);
         if (sc.type != t) throw EngineError(B200_ERR_INVALID, "concat: type mismatch in column " + schema[ci].name);
         DevColumn v = as_views(x, sc);
-        CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.data + pos * oc.width(), v.data, (size_t)n * oc.width(), cudaMemcpyDeviceToDevice, x.st()));
+        if (batched) pl.copy(v.data, (uint8_t*)oc.data + pos * oc.width(), (uint64_t)n * oc.width());
+        else CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.data + pos * oc.width(), v.data, (size_t)n * oc.width(), cudaMemcpyDeviceToDevice, x.st()));
         if (any_valid) {
-          if (v.valid) CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.valid + pos, v.valid, (size_t)n, cudaMemcpyDeviceToDevice, x.st()));
+          if (v.valid && batched) pl.copy(v.valid, (uint8_t*)oc.valid + pos, (uint64_t)n);
+          else if (v.valid) CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.valid + pos, v.valid, (size_t)n, cudaMemcpyDeviceToDevice, x.st()));
           else CUDA_CHECK(cudaMemsetAsync((uint8_t*)oc.valid + pos, 1, (size_t)n, x.st()));
         }
         if (ph == PH_STRVIEW)
@@ -1427,6 +1642,7 @@ struct Runner {
       }
       out->cols.push_back(oc);
     }
+    pl.run(x);
     return out;
   }
 
@@ -1659,7 +1875,6 @@ struct Runner {
       proj.n = n;
       for (size_t c = 0; c < n_in_cols; c++) proj.cols.push_back(in->cols[c]);
       DevBatchPtr out = gather_batch(x, proj, (const int64_t*)idx->ptr, m, false);
-      CUDA_CHECK(cudaStreamSynchronize(x.st()));
       if (met) {
         met->elapsed_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         met->input_rows += (uint64_t)n;
@@ -1684,11 +1899,12 @@ struct Runner {
         CUDA_CHECK(cudaMemsetAsync(mx->ptr, 0, 16, x.st()));
         launch_max_view_len((const unsigned long long*)kc.data, kc.valid, n, (unsigned int*)mx->ptr, x.st());
         x.count();
-        unsigned int maxlen = d2h_value<unsigned int>(mx->ptr, x.st());
+        unsigned int maxlen = x.get<unsigned int>(mx->ptr);
         n_words = (int)(maxlen / 7) + 1;
       }
       // least significant word first; the NULL-rank word is the most significant
       for (int w = n_words - 1; w >= (kc.valid ? -1 : 0); w--) {
+        x.check_cancel();
         SortWordArgs A;
         A.data = kc.data;
         A.valid = kc.valid;
@@ -1766,6 +1982,13 @@ struct Runner {
     }
     const size_t nk = lk.size();
     if (nk > (size_t)VM_MAX_KEYS) throw EngineError(B200_ERR_UNSUPPORTED, "too many join keys");
+    // CollectLeft replays the whole build side in every probe task; a join type that also EMITS build rows
+    // (unmatched or semi/anti) would then emit them once per task.  DataFusion shares a visited bitmap across
+    // the probe partitions of one process; tasks here are independent, so those shapes are only legal with a
+    // single probe partition.
+    if (collect_left && (n.join_type == JoinType::Left || n.join_type == JoinType::Full || n.join_type == JoinType::LeftSemi || n.join_type == JoinType::LeftAnti) &&
+        n_partitions(*n.children[1]) > 1)
+      throw EngineError(B200_ERR_UNSUPPORTED, "CollectLeft hash join that emits build-side rows over more than one probe partition: plan it as Partitioned");
     JoinSide L = prepare_side(*n.children[0], part, collect_left, lk, n.null_equals_null, met);
     JoinSide R = prepare_side(*n.children[1], part, false, rk, n.null_equals_null, met);
     const int64_t nb = L.batch->n, np = R.batch->n;
@@ -1791,19 +2014,22 @@ struct Runner {
     DevPtr heads = dev_alloc((size_t)n_buckets * 4, x.st());
     CUDA_CHECK(cudaMemsetAsync(heads->ptr, 0xFF, (size_t)n_buckets * 4, x.st()));
     DevPtr next = dev_alloc((size_t)std::max<int64_t>(nb, 1) * 4, x.st());
+    x.check_cancel();
     launch_join_build(lh, nullptr, nb, (int32_t*)heads->ptr, n_buckets, (int32_t*)next->ptr, x.st());
     x.count();
+    x.check_cancel();
     DevPtr counts = dev_alloc((size_t)(np + 1) * 4, x.st());
     DevPtr offs = dev_alloc((size_t)(np + 2) * 8, x.st());
     DevPtr scratch = dev_alloc((size_t)(np / 1024 + 4) * 8, x.st());
     launch_join_probe_count(K, lh, (const int32_t*)heads->ptr, n_buckets, (const int32_t*)next->ptr, rh, nullptr, np, (uint32_t*)counts->ptr, nullptr, x.st());
     launch_scan_u32_to_u64((const uint32_t*)counts->ptr, (uint64_t*)offs->ptr, np, (uint64_t*)scratch->ptr, x.st());
     x.count(4);
-    int64_t n_pairs = (int64_t)d2h_value<uint64_t>((const uint64_t*)offs->ptr + np, x.st());
+    int64_t n_pairs = (int64_t)x.get<uint64_t>((const uint64_t*)offs->ptr + np);
     DevPtr bi = dev_alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, x.st()), pi = dev_alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, x.st());
     launch_join_probe_write(K, lh, (const int32_t*)heads->ptr, n_buckets, (const int32_t*)next->ptr, rh, nullptr, np, (const uint64_t*)offs->ptr, (int64_t*)bi->ptr, (int64_t*)pi->ptr, x.st());
     x.count();
 
+    x.check_cancel();
     DevBatch Lp, Rp;  // payload-only views
     Lp.n = nb;
     Rp.n = np;
@@ -1849,7 +2075,7 @@ struct Runner {
       launch_flag_to_u32(marks, want ? 1 : 0, (uint32_t*)f->ptr, nrows, x.st());
       launch_scan_u32_to_u64((const uint32_t*)f->ptr, (uint64_t*)o->ptr, nrows, (uint64_t*)sc->ptr, x.st());
       x.count(4);
-      *n_sel = (int64_t)d2h_value<uint64_t>((const uint64_t*)o->ptr + nrows, x.st());
+      *n_sel = (int64_t)x.get<uint64_t>((const uint64_t*)o->ptr + nrows);
       DevPtr idx = dev_alloc((size_t)std::max<int64_t>(*n_sel, 1) * 8, x.st());
       launch_select_indices((const uint32_t*)f->ptr, (const uint64_t*)o->ptr, (int64_t*)idx->ptr, nrows, x.st());
       x.count();
@@ -1945,11 +2171,45 @@ struct Runner {
     return t;
   }
 
+  // character bytes of every Utf8 column of `b` (rows [0, b.n)), one read-back for all of them; known values are reused
+  std::vector<int64_t> string_bytes(const DevBatch& b) {
+    std::vector<int64_t> out;
+    PartStrCols sc;
+    sc.n = 0;
+    std::vector<size_t> unknown;
+    for (auto& c : b.cols) {
+      if (c.type.id != TypeId::Utf8) continue;
+      if (c.phys == PH_UTF8 && c.chars_bytes >= 0) {
+        out.push_back(c.chars_bytes);
+        continue;
+      }
+      out.push_back(-1);
+      if (b.n == 0) {
+        out.back() = 0;
+        continue;
+      }
+      if (sc.n == PART_MAX_STR_COLS) throw EngineError(B200_ERR_UNSUPPORTED, "more than 16 string columns in one shuffle output");
+      sc.c[sc.n++] = PartStrCol{c.data, c.valid, c.phys == PH_STRVIEW ? 1 : 0, 0};
+      unknown.push_back(out.size() - 1);
+    }
+    if (sc.n) {
+      DevPtr acc = dev_alloc((size_t)(1 + sc.n) * 8, x.st());
+      CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, (size_t)(1 + sc.n) * 8, x.st()));
+      CUDA_CHECK(launch_partition_hist(nullptr, b.n, 1, nullptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + 1, x.st()));
+      x.count();
+      const unsigned long long* h = (const unsigned long long*)x.fetch_bytes((const unsigned long long*)acc->ptr + 1, (size_t)sc.n * 8);
+      x.sync();
+      for (size_t k = 0; k < unknown.size(); k++) out[unknown[k]] = (int64_t)h[k];
+    }
+    return out;
+  }
+
   std::vector<b200_shuffle_write_partition> execute_stage(const PlanNode& root, int input_partition) {
     if (root.op != PlanNode::ShuffleWriter) throw EngineError(B200_ERR_INVALID, "stage plan root must be a ShuffleWriterExec");
     OpMetrics* met = x.m(&root);
     const PlanNode& child = *root.children[0];
     const int64_t bs = x.e->batch_size;
+    const int32_t my_rank = x.e->rank;
     auto nbatches = [&](uint64_t rows) { return (rows + (uint64_t)bs - 1) / (uint64_t)bs; };
     std::vector<b200_shuffle_write_partition> res;
     // no repartitioning; also hash partitioning into ONE partition (hash % 1 == 0 for every row), which
@@ -1957,25 +2217,21 @@ struct Runner {
     const bool single = root.n_out_partitions == 1;
     if (root.n_out_partitions == 0 || single) {
       DevBatchPtr in = exec(child, input_partition);
-      // canonical Arrow layout for stored partitions (strings contiguous)
+      // stored as produced: strings stay views into kept-alive character buffers; they are laid out as Arrow
+      // Utf8 only when the partition leaves the device (export) or the GPU (exchange)
       auto st = std::make_shared<DevBatch>();
       st->n = in->n;
-      std::vector<int64_t> cb;
       for (size_t c = 0; c < in->cols.size(); c++) {
         DevColumn col = in->cols[c];
         col.name = root.schema[c].name;
-        if (col.type.id == TypeId::Utf8) {
-          if (col.phys == PH_STRVIEW) col = as_utf8(x, col);
-          if (col.chars_bytes < 0) {
-            int32_t o0 = d2h_value<int32_t>(col.data, x.st());
-            int32_t o1 = d2h_value<int32_t>(col.data + 4 * col.n, x.st());
-            col.chars_bytes = o1 - o0;
-          }
-          cb.push_back(col.chars_bytes);
-        }
         st->cols.push_back(col);
       }
-      CUDA_CHECK(cudaStreamSynchronize(x.st()));
+      std::vector<int64_t> cb;
+      {
+        ScopeTimer t2("writer: string bytes + final sync");
+        cb = string_bytes(*st);
+        x.sync();  // deferred status checks of this task's kernels
+      }
       b200_shuffle_write_partition w{};
       w.partition_id = single ? 0u : (uint64_t)input_partition;
       w.num_rows = (uint64_t)st->n;
@@ -1988,12 +2244,12 @@ struct Runner {
         auto& v = x.e->shuffle[ShuffleKey{job, root.stage_id, single ? 0 : input_partition}];
         if (single) {
           const int64_t fid = (int64_t)input_partition;
-          v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == fid; }), v.end());
-          if (st->n > 0) v.push_back(Piece{fid, st, 0, st->n});
+          v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == fid && pc.src_rank == my_rank; }), v.end());
+          if (st->n > 0) v.push_back(Piece{fid, st, 0, st->n, my_rank, cb});
           else if (v.empty()) x.e->shuffle.erase(ShuffleKey{job, root.stage_id, 0});
         } else {
           v.clear();
-          v.push_back(Piece{-1, st, 0, st->n});
+          v.push_back(Piece{-1, st, 0, st->n, my_rank, cb});
         }
       }
       if (met) {
@@ -2004,12 +2260,17 @@ struct Runner {
       if (!(single && st->n == 0)) res.push_back(w);  // only partitions with rows are reported
       return res;
     }
-    // hash repartition: pid = hash(keys) % P fused into the child's pipeline, then rank + scatter
+    // hash repartition: pid = hash(keys) % P computed by the child's pipeline kernel, then ONE stable radix
+    // partition pass (per-tile histogram -> scan -> ranked scatter of every column)
     const uint32_t P = (uint32_t)root.n_out_partitions;
+    if (P > PART_MAX_FANOUT) throw EngineError(B200_ERR_UNSUPPORTED, "more than 4096 output partitions in one shuffle");
     size_t n_payload = 0;
+    std::vector<int> direct;       // payload column -> source column index when it is forwarded untouched, else -1
+    DevBatchPtr srcb;
     DevBatchPtr mat = with_chain(child, input_partition, false, [&](const BuilderFactory& mk, DevBatchPtr& src) {
       auto pbp = mk();
       PipelineBuilder& pb = *pbp;
+      srcb = src;
       std::vector<ColRef> outs = named_cols(pb, root.schema);
       n_payload = outs.size();
       std::vector<ColRef> keys;
@@ -2021,78 +2282,106 @@ struct Runner {
       ColRef h = pb.hash_of(keys);
       ColRef pid = pb.mod_u64(h, P);
       pid.name = "__pid";
-      outs.push_back(pid);
-      return run_materialize(x, pb, outs, src, met);
+      // columns the chain forwards untouched are scattered straight from the source batch (each byte moves
+      // once); only computed columns and the partition id are materialised first
+      direct.assign(n_payload, -1);
+      std::vector<ColRef> mouts;
+      if (!program_filters(pb.prog))
+        for (size_t c = 0; c < n_payload; c++) direct[c] = pb.source_index(outs[c]);
+      for (size_t c = 0; c < n_payload; c++)
+        if (direct[c] < 0) mouts.push_back(outs[c]);
+      mouts.push_back(pid);
+      return run_materialize(x, pb, mouts, src, met);
     });
     const int64_t n = mat->n;
-    const uint32_t* pid = (const uint32_t*)mat->cols[n_payload].data;
-    DevPtr counts = dev_alloc((size_t)(P + 1) * 8, x.st());
-    CUDA_CHECK(cudaMemsetAsync(counts->ptr, 0, (size_t)(P + 1) * 8, x.st()));
-    launch_histogram_u32(pid, n, P, (unsigned long long*)counts->ptr, x.st());
-    x.count();
-    std::vector<unsigned long long> hc(P);
-    CUDA_CHECK(cudaMemcpyAsync(hc.data(), counts->ptr, (size_t)P * 8, cudaMemcpyDeviceToHost, x.st()));
-    CUDA_CHECK(cudaStreamSynchronize(x.st()));
-    std::vector<int64_t> bounds(P + 1, 0);
-    for (uint32_t p = 0; p < P; p++) bounds[p + 1] = bounds[p] + (int64_t)hc[p];
-    DevPtr dest = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st());
+    if (n >= ((int64_t)1 << 32)) throw EngineError(B200_ERR_UNSUPPORTED, "more than 2^32 rows in one shuffle-writer task");
+    const uint32_t* pid = (const uint32_t*)mat->cols.back().data;
+    std::vector<DevColumn> pay;
     {
-      const uint32_t n_blocks = (uint32_t)((n + 2047) / 2048) + 1;
-      DevPtr ka = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8, x.st()), kb = dev_alloc((size_t)std::max<int64_t>(n, 1) * 8, x.st());
-      DevPtr va = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st()), vb = dev_alloc((size_t)std::max<int64_t>(n, 1) * 4, x.st());
-      DevPtr hist = dev_alloc((size_t)256 * n_blocks * 4 + 64, x.st());
-      DevPtr scan = dev_alloc(((size_t)256 * n_blocks + 1 + (size_t)(256 * n_blocks) / 1024 + 8) * 8, x.st());
-      x.count(launch_partition_dest_stable(pid, n, P, (uint32_t*)dest->ptr, (uint64_t*)ka->ptr, (uint32_t*)va->ptr, (uint64_t*)kb->ptr, (uint32_t*)vb->ptr,
-                                           (uint32_t*)hist->ptr, (uint64_t*)scan->ptr, x.st()));
+      size_t mi = 0;
+      for (size_t c = 0; c < n_payload; c++) {
+        DevColumn col = direct[c] >= 0 ? as_views(x, srcb->cols[(size_t)direct[c]]) : mat->cols[mi++];
+        col.name = root.schema[c].name;
+        pay.push_back(col);
+      }
+    }
+    // histogram (+ string bytes per partition for ShuffleWritePartition.num_bytes)
+    PartStrCols sc;
+    sc.n = 0;
+    for (auto& c : pay)
+      if (c.type.id == TypeId::Utf8) {
+        if (sc.n == PART_MAX_STR_COLS) throw EngineError(B200_ERR_UNSUPPORTED, "more than 16 string columns in one shuffle output");
+        sc.c[sc.n++] = PartStrCol{c.data, c.valid, c.phys == PH_STRVIEW ? 1 : 0, 0};
+      }
+    if ((size_t)P * (1 + sc.n) * 4 > 200 * 1024) throw EngineError(B200_ERR_UNSUPPORTED, "shuffle fan-out x string columns exceeds the histogram's shared memory");
+    const uint32_t n_tiles = partition_n_tiles(n);
+    const size_t acc_words = (size_t)P * (1 + sc.n);
+    DevPtr acc = dev_alloc(acc_words * 8, x.st());
+    CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, acc_words * 8, x.st()));
+    DevPtr tile_hist = dev_alloc((size_t)std::max<uint64_t>((uint64_t)P * n_tiles, 1) * 4 + 64, x.st());
+    CUDA_CHECK(launch_partition_hist(pid, n, P, (uint32_t*)tile_hist->ptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + P, x.st()));
+    x.count();
+    const unsigned long long* hc = (const unsigned long long*)x.fetch_bytes(acc->ptr, acc_words * 8);
+    // while the counts travel: scan the per-tile histogram and scatter
+    const int64_t hn = (int64_t)P * n_tiles;
+    DevPtr offs = dev_alloc((size_t)(hn + 2) * 8, x.st());
+    DevPtr scratch = dev_alloc((size_t)(hn / 1024 + 4) * 8, x.st());
+    if (hn > 0) {
+      launch_scan_u32_to_u64((const uint32_t*)tile_hist->ptr, (uint64_t*)offs->ptr, hn, (uint64_t*)scratch->ptr, x.st());
+      x.count(3);
     }
     auto st = std::make_shared<DevBatch>();
     st->n = n;
-    std::vector<std::vector<int64_t>> chars_per_part;  // [string col][p]
-    for (size_t c = 0; c < n_payload; c++) {
-      const DevColumn& sc = mat->cols[c];
-      DevColumn oc = make_out_column(root.schema[c].name, sc.type, sc.phys, n, sc.valid != nullptr, x.st());
-      oc.n = n;
-      launch_scatter_fixed(sc.data, (void*)oc.data, (const uint32_t*)dest->ptr, n, sc.width(), x.st());
-      x.count();
-      if (sc.valid) {
-        launch_scatter_fixed(sc.valid, (void*)oc.valid, (const uint32_t*)dest->ptr, n, 1, x.st());
-        x.count();
+    {
+      GatherCols gc;
+      gc.n = 0;
+      auto flush = [&]() {
+        if (gc.n && n > 0) {
+          CUDA_CHECK(launch_partition_scatter(pid, n, P, (const uint64_t*)offs->ptr, gc, nullptr, x.st()));
+          x.count();
+        }
+        gc.n = 0;
+      };
+      auto add = [&](const void* in, void* out, int width) {
+        GatherCol& g = gc.c[gc.n++];
+        memset(&g, 0, sizeof g);
+        g.in = in;
+        g.out = out;
+        g.width = width;
+        if (gc.n == GATHER_MAX_COLS) flush();
+      };
+      for (size_t c = 0; c < n_payload; c++) {
+        const DevColumn& scn = pay[c];
+        DevColumn oc = make_out_column(root.schema[c].name, scn.type, scn.phys, n, scn.valid != nullptr, x.st());
+        oc.n = n;
+        add(scn.data, (void*)oc.data, scn.width());
+        if (scn.valid) add(scn.valid, (void*)oc.valid, 1);
+        for (auto& k : scn.keep) oc.keep.push_back(k);
+        st->cols.push_back(oc);
       }
-      for (auto& k : sc.keep) oc.keep.push_back(k);
-      if (oc.phys == PH_STRVIEW) {
-        DevColumn u = as_utf8(x, oc);
-        // chars per partition from the offsets at the partition boundaries
-        std::vector<int32_t> offs(P + 1);
-        DevPtr bidx = dev_alloc((size_t)(P + 1) * 8, x.st());
-        CUDA_CHECK(cudaMemcpyAsync(bidx->ptr, bounds.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, x.st()));
-        DevPtr bo = dev_alloc((size_t)(P + 1) * 4, x.st());
-        launch_gather_fixed(u.data, nullptr, bo->ptr, nullptr, (const int64_t*)bidx->ptr, P + 1, 4, x.st());
-        x.count();
-        CUDA_CHECK(cudaMemcpyAsync(offs.data(), bo->ptr, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, x.st()));
-        CUDA_CHECK(cudaStreamSynchronize(x.st()));
-        std::vector<int64_t> cp(P);
-        for (uint32_t p = 0; p < P; p++) cp[p] = offs[p + 1] - offs[p];
-        chars_per_part.push_back(cp);
-        oc = u;
-      }
-      st->cols.push_back(oc);
+      flush();
     }
-    CUDA_CHECK(cudaStreamSynchronize(x.st()));
+    x.sync();
+    std::vector<int64_t> bounds(P + 1, 0);
+    for (uint32_t p = 0; p < P; p++) bounds[p + 1] = bounds[p] + (int64_t)hc[p];
+    std::vector<std::vector<int64_t>> chars_per_part((size_t)sc.n, std::vector<int64_t>(P));  // [string col][p]
+    for (int c = 0; c < sc.n; c++)
+      for (uint32_t p = 0; p < P; p++) chars_per_part[(size_t)c][p] = (int64_t)hc[(size_t)P * (1 + c) + p];
     uint64_t total_bytes = 0;
     {
       std::lock_guard<std::mutex> g(x.e->mu);
       for (uint32_t p = 0; p < P; p++) {
         auto& v = x.e->shuffle[ShuffleKey{job, root.stage_id, (int64_t)p}];
         // a re-run of the same map task replaces its previous output (task retry)
-        v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == input_partition; }), v.end());
+        v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == input_partition && pc.src_rank == my_rank; }), v.end());
         const int64_t rows = bounds[p + 1] - bounds[p];
         if (rows == 0) {
           if (v.empty()) x.e->shuffle.erase(ShuffleKey{job, root.stage_id, (int64_t)p});
           continue;  // only partitions with rows are reported (sort_shuffle/writer.rs:357-369)
         }
-        v.push_back(Piece{input_partition, st, bounds[p], bounds[p + 1]});
         std::vector<int64_t> cb;
         for (auto& cp : chars_per_part) cb.push_back(cp[p]);
+        v.push_back(Piece{input_partition, st, bounds[p], bounds[p + 1], my_rank, cb});
         b200_shuffle_write_partition w{};
         w.partition_id = p;
         w.num_rows = (uint64_t)rows;
@@ -2110,6 +2399,350 @@ struct Runner {
       met->bytes_read += total_bytes;
     }
     return res;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Exchange between the box's GPU executors (ShuffleReaderExec's remote fetch, shuffle_reader.rs:522-602 /
+// client.rs:143-220, as an all-to-all-v over NVLink).  Gang collective: every executor of the communicator calls
+// it for the same (job, stage) after its map tasks finished.
+//
+// Round 1: every pair exchanges one fixed-size slot = [header | inline payload].  The header lists, per piece,
+// (partition, file id, rows, byte size of every column buffer) -- the ShuffleWritePartition / PartitionLocation
+// metadata the reference sends through the scheduler -- so no separate size collective is needed, and messages
+// of up to EXCH_INLINE bytes (the partial-aggregate states of q1: a few hundred bytes) are complete after it.
+// Round 2 (only for pairs whose payload is larger): grouped ncclSend/ncclRecv straight from the stored column
+// slices into the receiver's final column buffers -- no packing copy on either side.
+// ------------------------------------------------------------------------------------------------
+static const uint64_t EXCH_MAGIC = 0xB200E8C4A11ull;
+static const size_t EXCH_INLINE = 16 << 10;
+enum ExchangeMode { EXCH_HASH = 0, EXCH_GATHER = 1, EXCH_BROADCAST = 2 };
+
+struct ExchEntry {
+  int64_t partition, file_id, rows;
+  std::vector<uint64_t> sizes;  // 3 per column: validity bytes, data bytes, chars bytes
+};
+
+#define NCCL_CHECK(expr)                                                                                              \
+  do {                                                                                                                \
+    ncclResult_t _r = (expr);                                                                                         \
+    if (_r != 0) throw EngineError(B200_ERR_CUDA, std::string("NCCL error: ") + NcclApi::get().GetErrorString(_r) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+struct Exchange {
+  Exec x;
+  Runner r;
+  b200_engine* e;
+  std::string job;
+  int64_t stage;
+  int P, mode, root;
+  Schema schema;
+  size_t ncols;
+
+  bool goes_to(int p, int d) const {
+    if (mode == EXCH_BROADCAST) return true;
+    if (mode == EXCH_GATHER) return d == root;
+    return p % e->world == d;
+  }
+  int n_owned(int d) const {
+    int k = 0;
+    for (int p = 0; p < P; p++) k += goes_to(p, d) ? 1 : 0;
+    return k;
+  }
+  size_t entry_bytes() const { return (3 + 3 * ncols) * 8; }
+  size_t hdr_bytes(int d) const { return (32 + (size_t)n_owned(d) * entry_bytes() + 255) & ~(size_t)255; }
+  size_t slot_bytes() const {
+    size_t h = 0;
+    for (int d = 0; d < e->world; d++) h = std::max(h, hdr_bytes(d));
+    return h + EXCH_INLINE;
+  }
+  static uint64_t al16(uint64_t v) { return (v + 15) & ~15ull; }
+
+  void run(uint64_t* sent_out, uint64_t* recv_out) {
+    NcclApi& N = NcclApi::get();
+    const int W = e->world, me = e->rank;
+    // ---- local pieces: one (coalesced) piece per partition ------------------------------------------------
+    struct Local {
+      int p;
+      Piece piece;
+    };
+    std::vector<Local> locals;
+    {
+      std::vector<std::pair<int, std::vector<Piece>>> snap;
+      {
+        std::lock_guard<std::mutex> g(e->mu);
+        for (int p = 0; p < P; p++) {
+          auto it = e->shuffle.find(ShuffleKey{job, stage, (int64_t)p});
+          if (it == e->shuffle.end()) continue;
+          std::vector<Piece> mine;
+          for (auto& pc : it->second)
+            if (pc.src_rank == me && pc.r1 > pc.r0) mine.push_back(pc);
+          if (!mine.empty()) snap.push_back({p, mine});
+        }
+      }
+      for (auto& kv : snap) {
+        if (kv.second.size() == 1) {
+          locals.push_back(Local{kv.first, kv.second[0]});
+          continue;
+        }
+        std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>> v;
+        for (auto& pc : kv.second) v.push_back({pc.batch, {pc.r0, pc.r1}});
+        Piece c;
+        c.file_id = kv.second[0].file_id;
+        c.batch = r.concat_slices(v, schema);
+        c.r0 = 0;
+        c.r1 = c.batch->n;
+        c.src_rank = me;
+        bool known = true;
+        for (auto& pc : kv.second) known &= !pc.str_bytes.empty() || pc.batch->cols.empty();
+        if (known && !kv.second[0].str_bytes.empty()) {
+          c.str_bytes.assign(kv.second[0].str_bytes.size(), 0);
+          for (auto& pc : kv.second)
+            for (size_t k = 0; k < c.str_bytes.size(); k++) c.str_bytes[k] += pc.str_bytes[k];
+        }
+        locals.push_back(Local{kv.first, c});
+      }
+    }
+    // string bytes of every outgoing slice must be known on the host (they normally are: the writer recorded them)
+    for (auto& L : locals) {
+      size_t n_str = 0;
+      for (auto& c : L.piece.batch->cols) n_str += c.type.id == TypeId::Utf8 ? 1 : 0;
+      if (L.piece.batch->cols.size() != ncols) throw EngineError(B200_ERR_INVALID, "exchange: stored partition does not match the given schema");
+      if (n_str && L.piece.str_bytes.size() != n_str) {
+        DevBatch sl;
+        sl.n = L.piece.r1 - L.piece.r0;
+        for (auto& c : L.piece.batch->cols) sl.cols.push_back(slice_column(c, L.piece.r0, L.piece.r1));
+        L.piece.str_bytes = r.string_bytes(sl);
+      }
+    }
+    if (W <= 1) {
+      *sent_out = *recv_out = 0;
+      return;
+    }
+    if (!e->comm) throw EngineError(B200_ERR_INVALID, "exchange: communicator not initialised (b200_engine_comm_init)");
+    const size_t slot = slot_bytes();
+    DevPtr sendbuf = dev_alloc(slot * W, x.st()), recvbuf = dev_alloc(slot * W, x.st());
+    // ---- compose headers and the payload layout per destination -----------------------------------------------
+    struct Out {
+      std::vector<ExchEntry> entries;
+      std::vector<const Local*> src;
+      uint64_t payload = 0;
+      bool inl = true;
+    };
+    std::vector<Out> outs((size_t)W);
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      Out& o = outs[(size_t)d];
+      for (auto& L : locals) {
+        if (!goes_to(L.p, d)) continue;
+        ExchEntry en;
+        en.partition = L.p;
+        en.file_id = L.piece.file_id;
+        en.rows = L.piece.r1 - L.piece.r0;
+        size_t si = 0;
+        for (auto& c : L.piece.batch->cols) {
+          en.sizes.push_back(c.valid ? (uint64_t)en.rows : 0);
+          if (c.type.id == TypeId::Utf8) {
+            en.sizes.push_back((uint64_t)(en.rows + 1) * 4);
+            en.sizes.push_back((uint64_t)L.piece.str_bytes[si++]);
+          } else {
+            en.sizes.push_back((uint64_t)en.rows * c.width());
+            en.sizes.push_back(0);
+          }
+        }
+        for (uint64_t b : en.sizes) o.payload += al16(b);
+        o.entries.push_back(en);
+        o.src.push_back(&L);
+      }
+      o.inl = o.payload <= EXCH_INLINE;
+    }
+    // headers -> one staging block -> device; inline payloads packed by the same kernel that places the headers
+    size_t hdr_total = 0;
+    std::vector<size_t> hdr_at((size_t)W, 0);
+    for (int d = 0; d < W; d++) {
+      hdr_at[(size_t)d] = hdr_total;
+      hdr_total += d == me ? 0 : hdr_bytes(d);
+    }
+    uint8_t* hstage = (uint8_t*)x.stage_bytes(hdr_total ? hdr_total : 16);
+    memset(hstage, 0, hdr_total);
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      const Out& o = outs[(size_t)d];
+      uint64_t* h = (uint64_t*)(hstage + hdr_at[(size_t)d]);
+      h[0] = EXCH_MAGIC;
+      h[1] = o.entries.size();
+      h[2] = o.inl ? 1 : 0;
+      h[3] = o.payload;
+      uint64_t* q = h + 4;
+      for (auto& en : o.entries) {
+        *q++ = (uint64_t)en.partition;
+        *q++ = (uint64_t)en.file_id;
+        *q++ = (uint64_t)en.rows;
+        for (uint64_t b : en.sizes) *q++ = b;
+      }
+    }
+    DevPtr hdev = dev_alloc(hdr_total + 16, x.st());
+    if (hdr_total) CUDA_CHECK(cudaMemcpyAsync(hdev->ptr, hstage, hdr_total, cudaMemcpyHostToDevice, x.st()));
+    PackList pl;
+    std::vector<DevColumn> keep_cols;  // converted string columns of large messages, alive until the sends are enqueued
+    struct SendOp { const void* ptr; uint64_t bytes; int peer; };
+    std::vector<SendOp> sends;
+    uint64_t sent = 0;
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      const Out& o = outs[(size_t)d];
+      uint8_t* sl = (uint8_t*)sendbuf->ptr + (size_t)d * slot;
+      pl.copy((const uint8_t*)hdev->ptr + hdr_at[(size_t)d], sl, hdr_bytes(d));
+      uint8_t* cur = sl + hdr_bytes(d);
+      sent += o.payload;
+      for (size_t k = 0; k < o.entries.size(); k++) {
+        const Piece& pc = o.src[k]->piece;
+        const ExchEntry& en = o.entries[k];
+        size_t si = 0;
+        for (size_t c = 0; c < ncols; c++) {
+          DevColumn col = slice_column(pc.batch->cols[c], pc.r0, pc.r1);
+          const uint64_t bv = en.sizes[3 * c], bd = en.sizes[3 * c + 1], bc = en.sizes[3 * c + 2];
+          if (o.inl) {
+            if (bv) pl.copy(col.valid, cur, bv);
+            cur += al16(bv);
+            if (col.type.id == TypeId::Utf8) {
+              pl.strings(col, cur, cur + al16(bd), bc);
+            } else if (bd) {
+              pl.copy(col.data, cur, bd);
+            }
+            cur += al16(bd) + al16(bc);
+          } else {
+            if (bv) sends.push_back(SendOp{col.valid, bv, d});
+            if (col.type.id == TypeId::Utf8) {
+              DevColumn u = col.phys == PH_STRVIEW ? as_utf8(x, col, (int64_t)pc.str_bytes[si]) : col;
+              const uint8_t* chars = u.chars;
+              if (col.phys != PH_STRVIEW) {
+                // Arrow slice: the receiver wants offsets that start at 0
+                DevPtr ro = dev_alloc((size_t)(u.n + 1) * 4 + 64, x.st());
+                DevPtr fl = dev_alloc(16, x.st());
+                launch_rebase_offsets((const int32_t*)u.data, u.n + 1, (int32_t*)ro->ptr, (int32_t*)fl->ptr, x.st());
+                x.count();
+                // first offset of the slice: needed on the host to position the chars pointer
+                const int32_t first = x.get<int32_t>(fl->ptr);
+                chars = u.chars + first;
+                u.data = (const uint8_t*)ro->ptr;
+                u.keep.push_back(ro);
+              }
+              keep_cols.push_back(u);
+              sends.push_back(SendOp{u.data, bd, d});
+              if (bc) sends.push_back(SendOp{chars, bc, d});
+            } else if (bd) {
+              sends.push_back(SendOp{col.data, bd, d});
+            }
+          }
+          if (col.type.id == TypeId::Utf8) si++;
+        }
+      }
+    }
+    pl.run(x);
+    // ---- round 1: fixed-size slots ---------------------------------------------------------------------------
+    std::lock_guard<std::mutex> cg(e->comm_mu);
+    NCCL_CHECK(N.GroupStart());
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      NCCL_CHECK(N.Send((const uint8_t*)sendbuf->ptr + (size_t)d * slot, slot, kNcclUint8, d, e->comm, x.st()));
+      NCCL_CHECK(N.Recv((uint8_t*)recvbuf->ptr + (size_t)d * slot, slot, kNcclUint8, d, e->comm, x.st()));
+    }
+    NCCL_CHECK(N.GroupEnd());
+    x.count(1);
+    // incoming headers: every peer used hdr_bytes(me)
+    const size_t hb = hdr_bytes(me);
+    std::vector<const uint64_t*> rh((size_t)W, nullptr);
+    for (int d = 0; d < W; d++)
+      if (d != me) rh[(size_t)d] = (const uint64_t*)x.fetch_bytes((const uint8_t*)recvbuf->ptr + (size_t)d * slot, hb);
+    x.sync();
+    // ---- parse, allocate, round 2 ------------------------------------------------------------------------------
+    struct RecvOp { void* ptr; uint64_t bytes; int peer; };
+    std::vector<RecvOp> recvs;
+    struct Incoming { int p; Piece piece; };
+    std::vector<Incoming> incoming;
+    uint64_t recvd = 0;
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      const uint64_t* h = rh[(size_t)d];
+      if (h[0] != EXCH_MAGIC) throw EngineError(B200_ERR_CUDA, "exchange: bad header from rank " + std::to_string(d));
+      const uint64_t n_ent = h[1];
+      const bool inl = h[2] != 0;
+      recvd += h[3];
+      if (32 + n_ent * entry_bytes() > hb) throw EngineError(B200_ERR_INVALID, "exchange: header overflow");
+      const uint64_t* q = h + 4;
+      const uint8_t* cur = (const uint8_t*)recvbuf->ptr + (size_t)d * slot + hb;
+      for (uint64_t k = 0; k < n_ent; k++) {
+        const int64_t part = (int64_t)*q++, fid = (int64_t)*q++, rows = (int64_t)*q++;
+        auto b = std::make_shared<DevBatch>();
+        b->n = rows;
+        std::vector<int64_t> sb;
+        for (size_t c = 0; c < ncols; c++) {
+          const uint64_t bv = *q++, bd = *q++, bc = *q++;
+          DevColumn col;
+          col.name = schema[c].name;
+          col.type = schema[c].type;
+          col.phys = phys_of(col.type);
+          col.n = rows;
+          col.nullable = bv != 0;
+          auto place = [&](uint64_t bytes) -> const uint8_t* {
+            if (inl) {
+              const uint8_t* ptr = cur;
+              cur += al16(bytes);
+              col.keep.push_back(recvbuf);
+              return ptr;
+            }
+            DevPtr dp = dev_alloc((size_t)bytes + 64, x.st());
+            col.keep.push_back(dp);
+            if (bytes) recvs.push_back(RecvOp{dp->ptr, bytes, d});
+            return (const uint8_t*)dp->ptr;
+          };
+          const uint8_t* pv = place(bv);
+          if (bv) col.valid = pv;
+          col.data = place(bd);
+          if (col.type.id == TypeId::Utf8) {
+            col.chars = place(bc);
+            col.chars_bytes = (int64_t)bc;
+            sb.push_back((int64_t)bc);
+          } else if (inl) {
+            cur += al16(bc);
+          }
+          b->cols.push_back(col);
+        }
+        Incoming in;
+        in.p = (int)part;
+        in.piece.file_id = fid;
+        in.piece.batch = b;
+        in.piece.r0 = 0;
+        in.piece.r1 = rows;
+        in.piece.src_rank = d;
+        in.piece.str_bytes = sb;
+        incoming.push_back(in);
+      }
+    }
+    if (!sends.empty() || !recvs.empty()) {
+      NCCL_CHECK(N.GroupStart());
+      for (auto& so : sends) NCCL_CHECK(N.Send(so.ptr, so.bytes, kNcclUint8, so.peer, e->comm, x.st()));
+      for (auto& ro : recvs) NCCL_CHECK(N.Recv(ro.ptr, ro.bytes, kNcclUint8, ro.peer, e->comm, x.st()));
+      NCCL_CHECK(N.GroupEnd());
+      x.count(1);
+    }
+    // ---- install ---------------------------------------------------------------------------------------------
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      for (int p = 0; p < P; p++) {
+        if (goes_to(p, me)) continue;
+        e->shuffle.erase(ShuffleKey{job, stage, (int64_t)p});  // handed over to its owner
+      }
+      for (auto& in : incoming) {
+        auto& v = e->shuffle[ShuffleKey{job, stage, (int64_t)in.p}];
+        v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.src_rank == in.piece.src_rank && pc.file_id == in.piece.file_id; }), v.end());
+        v.push_back(in.piece);
+        std::stable_sort(v.begin(), v.end(), [](const Piece& a, const Piece& b) { return a.src_rank != b.src_rank ? a.src_rank < b.src_rank : a.file_id < b.file_id; });
+      }
+    }
+    *sent_out = sent;
+    *recv_out = recvd;
   }
 };
 
@@ -2196,6 +2829,8 @@ void b200_engine_destroy(b200_engine* e) {
     if (sl.dev) cudaFree(sl.dev);
     if (sl.done) cudaEventDestroy(sl.done);
   }
+  if (e->comm && NcclApi::get().ok()) NcclApi::get().CommDestroy(e->comm);
+  if (e->export_arena) cudaFreeHost(e->export_arena);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -2311,7 +2946,7 @@ int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, in
         launch_tpch_str_len(t, c, msf, row_begin, n, (uint32_t*)lens->ptr, st);
         launch_scan_u32_to_u64((const uint32_t*)lens->ptr, (uint64_t*)offs64->ptr, n, (uint64_t*)scratch->ptr, st);
         e->launches += 4;
-        uint64_t total = d2h_value<uint64_t>((const uint64_t*)offs64->ptr + n, st);
+        uint64_t total = Exec{e, nullptr, nullptr}.get<uint64_t>((const uint64_t*)offs64->ptr + n);
         if (total > 0x7FFFFFFFull) throw EngineError(B200_ERR_UNSUPPORTED, "generated string column exceeds 2 GiB; use more partitions");
         DevPtr offsets = dev_alloc((size_t)(n + 1) * 4 + 64, st);
         DevPtr chars = dev_alloc((size_t)total + 64, st);
@@ -2337,6 +2972,11 @@ int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, in
   });
 }
 
+int64_t b200_tpch_table_rows(const char* table, int64_t msf) {
+  const int t = table ? table_id(table) : -1;
+  return t < 0 ? -1 : tpch::table_rows(t, msf);
+}
+
 int b200_engine_export_table(b200_engine* e, const char* table, int partition, struct ArrowArray* out, struct ArrowSchema* out_schema) {
   return guard([&] {
     CUDA_CHECK(cudaSetDevice(e->device));
@@ -2353,6 +2993,7 @@ int b200_engine_export_table(b200_engine* e, const char* table, int partition, s
 }
 
 int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, const char* plan_json, uint64_t plan_len, b200_stage** out) {
+  ScopeTimer tm("stage_prepare");
   return guard([&] {
     if (!e || !plan_json || !out) throw EngineError(B200_ERR_INVALID, "null argument");
     Json j = parse_json(plan_json, plan_len ? (size_t)plan_len : strlen(plan_json));
@@ -2372,6 +3013,7 @@ int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, con
 }
 
 int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag, b200_shuffle_write_partition* out, int cap, int* n_out) {
+  ScopeTimer tm("stage_execute");
   return guard([&] {
     if (!s || !n_out) throw EngineError(B200_ERR_INVALID, "null argument");
     CUDA_CHECK(cudaSetDevice(s->eng->device));
@@ -2382,6 +3024,23 @@ int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_
       res = r.execute_stage(*s->plan, input_partition);
     } catch (...) {
       cudaStreamSynchronize(s->eng->stream);
+      Exec::abandon();
+      // a cancelled or failed task leaves nothing behind (Executor::cancel_task drops the future together with
+      // its partial outputs, executor.rs:217-237): remove whatever this task already stored
+      {
+        std::lock_guard<std::mutex> g(s->eng->mu);
+        for (auto it = s->eng->shuffle.begin(); it != s->eng->shuffle.end();) {
+          if (it->first.job == s->job_id && it->first.stage == s->stage_id) {
+            auto& v = it->second;
+            v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return (pc.file_id == input_partition || (pc.file_id < 0 && it->first.part == input_partition)) && pc.src_rank == s->eng->rank; }), v.end());
+            if (v.empty()) {
+              it = s->eng->shuffle.erase(it);
+              continue;
+            }
+          }
+          ++it;
+        }
+      }
       throw;
     }
     if ((int)res.size() > cap) throw EngineError(B200_ERR_INVALID, "output array too small");
@@ -2410,6 +3069,7 @@ int b200_stage_metrics(b200_stage* s, b200_operator_metrics* out, int cap, int* 
 void b200_stage_release(b200_stage* s) { delete s; }
 
 int b200_partition_export(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  ScopeTimer tm("partition_export");
   return guard([&] {
     CUDA_CHECK(cudaSetDevice(e->device));
     std::vector<std::pair<DevBatchPtr, std::pair<int64_t, int64_t>>> pieces;
@@ -2588,6 +3248,62 @@ int b200_remove_stage_data(b200_engine* e, const char* job_id, int64_t stage_id)
     for (auto it = e->shuffle.begin(); it != e->shuffle.end();) {
       if (it->first.job == job_id && it->first.stage == stage_id) it = e->shuffle.erase(it);
       else ++it;
+    }
+  });
+}
+
+int b200_comm_unique_id(void* out, uint64_t cap) {
+  return guard([&] {
+    if (!out || cap < sizeof(ncclUniqueId)) throw EngineError(B200_ERR_INVALID, "b200_comm_unique_id needs a 128-byte buffer");
+    NcclApi& N = NcclApi::get();
+    if (!N.ok()) throw EngineError(B200_ERR_CUDA, "libnccl not available: " + N.error);
+    ncclUniqueId id;
+    NCCL_CHECK(N.GetUniqueId(&id));
+    memcpy(out, &id, sizeof id);
+  });
+}
+
+int b200_engine_comm_init(b200_engine* e, const void* nccl_id, uint64_t id_bytes) {
+  return guard([&] {
+    if (!e || !nccl_id || id_bytes < sizeof(ncclUniqueId)) throw EngineError(B200_ERR_INVALID, "b200_engine_comm_init: bad arguments");
+    if (e->world <= 1) return;  // a single executor exchanges nothing
+    NcclApi& N = NcclApi::get();
+    if (!N.ok()) throw EngineError(B200_ERR_CUDA, "libnccl not available: " + N.error);
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->comm_mu);
+    if (e->comm) {
+      N.CommDestroy(e->comm);
+      e->comm = nullptr;
+    }
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof id);
+    NCCL_CHECK(N.CommInitRank(&e->comm, e->world, id, e->rank));
+  });
+}
+
+int b200_exchange_stage(b200_engine* e, const char* job_id, int64_t stage_id, int n_out_partitions, int mode, int root, const char* schema_json,
+                        b200_exchange_stats* stats) {
+  return guard([&] {
+    if (!e || !job_id || !schema_json) throw EngineError(B200_ERR_INVALID, "null argument");
+    if (mode < 0 || mode > 2 || n_out_partitions < 0 || root < 0 || root >= std::max(e->world, 1)) throw EngineError(B200_ERR_INVALID, "b200_exchange_stage: bad mode / root");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    Json j = parse_json(schema_json, strlen(schema_json));
+    Exec x{e, nullptr, nullptr};
+    Exchange ex{x, Runner{x, job_id}, e, job_id, stage_id, n_out_partitions, mode, root, parse_schema(j), 0};
+    ex.ncols = ex.schema.size();
+    uint64_t sent = 0, recvd = 0;
+    try {
+      ex.run(&sent, &recvd);
+    } catch (...) {
+      cudaStreamSynchronize(e->stream);
+      Exec::abandon();
+      throw;
+    }
+    e->exch_sent_bytes += sent;
+    e->exch_recv_bytes += recvd;
+    if (stats) {
+      stats->sent_bytes = sent;
+      stats->recv_bytes = recvd;
     }
   });
 }

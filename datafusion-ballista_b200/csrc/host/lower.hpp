@@ -297,6 +297,14 @@ class PipelineBuilder {
     if (c.op.kind != OPD_NONE) return c.op;
     return use_source(c.op.idx);
   }
+  // index of the source-batch column this reference forwards untouched, or -1 for a computed value
+  int source_index(const ColRef& c) const {
+    if (c.op.kind == OPD_NONE) return (int)c.op.idx;
+    if (c.op.kind == OPD_COL)
+      for (size_t i = 0; i < src_map_.size(); i++)
+        if (src_map_[i] == (int)c.op.idx) return (int)i;
+    return -1;
+  }
   void pin(const ColRef& c) {
     if (c.op.kind == OPD_REG) pins_[c.op.idx]++;
   }
@@ -347,7 +355,7 @@ class PipelineBuilder {
         roff = (roff + 15u) & ~15u;
       }
       prog.regs_bytes = (roff + 127u) & ~127u;
-      const uint32_t budget = 216 * 1024;
+      const uint32_t budget = 208 * 1024;  // dynamic part; ~16 KB of static shared memory (decoded micro-ops) come on top
       int S = prog.stage_bytes ? (int)((budget - prog.regs_bytes) / prog.stage_bytes) : VM_MAX_STAGES;
       if (prog.regs_bytes >= budget) S = 0;
       if (S > VM_MAX_STAGES) S = VM_MAX_STAGES;
@@ -384,6 +392,7 @@ class PipelineBuilder {
   std::map<int, int> pins_;
   std::map<int, bool> reg_free_;
   std::map<int, bool> reg_nullable_;
+  std::map<std::string, int> string_imms_;
 
   VInstr blank(uint8_t op, uint8_t t) {
     VInstr i;
@@ -404,6 +413,8 @@ class PipelineBuilder {
     return prog.n_imms++;
   }
   int string_imm(const std::string& s) {
+    auto it = string_imms_.find(s);  // the same literal appears many times in IN lists / OR-ed conjunctions (q19)
+    if (it != string_imms_.end()) return it->second;
     DevPtr p = dev_alloc(s.size() + 16, st_);
     if (!s.empty()) CUDA_CHECK(cudaMemcpyAsync(p->ptr, s.data(), s.size(), cudaMemcpyHostToDevice, st_));
     keep.push_back(p);
@@ -411,7 +422,9 @@ class PipelineBuilder {
     memset(&d, 0, sizeof d);
     d.lo = (uint64_t)p->ptr;
     d.hi = s.size();
-    return add_imm(d);
+    const int idx = add_imm(d);
+    string_imms_[s] = idx;
+    return idx;
   }
   Operand use_source(int src_idx) {
     if (src_map_[(size_t)src_idx] < 0) {

@@ -74,3 +74,91 @@ def run_stages(engine, stages: List[Stage], job_id: str = "job", collect: bool =
     if not batches:
         return None
     return pa.Table.from_batches(batches)
+
+
+# ---- one executor per GPU (gang-scheduled stages + NVLink exchange inside the library) ------------------------
+REPLICATED_TABLES = {"nation", "region"}   # dimension tables every executor holds in full
+
+
+def _readers_of(node: dict, stage_id: int, under_merge: bool = False):
+    """(broadcast?, under a merge / coalesce?, schema) of every ShuffleReaderExec of `stage_id` below `node`."""
+    out = []
+    op = node.get("op")
+    if op in ("ShuffleReaderExec", "UnresolvedShuffleExec") and node["stage_id"] == stage_id:
+        out.append((bool(node.get("broadcast")), under_merge, node["schema"]))
+    merge = under_merge or op in ("CoalescePartitionsExec", "SortPreservingMergeExec", "GlobalLimitExec")
+    for k in ("input", "left", "right"):
+        if k in node:
+            out += _readers_of(node[k], stage_id, merge)
+    return out
+
+
+def run_stages_distributed(engine, stages: List[Stage], job_id: str, rank: int, world: int, collect: bool = True,
+                           on_stage=None) -> Optional[pa.Table]:
+    """The same walk as run_stages with one executor per GPU: every rank runs the tasks whose input lives in its HBM,
+    and after each stage the engines exchange the stage's output partitions (b200_exchange_stage) according to how
+    the consuming stage reads them -- hash repartition (partition p -> rank p % world), merge / single-task consumer
+    (everything -> rank 0) or broadcast build side (everything -> everyone).  Returns the result on rank 0."""
+    from .engine import EXCHANGE_BROADCAST, EXCHANGE_GATHER, EXCHANGE_HASH
+    out_parts: Dict[int, int] = {}
+    placement: Dict[int, str] = {}   # stage id -> "hash" | "root" | "all"
+    for si, st in enumerate(stages):
+        root = st.plan
+        kind, what = _probe_side_leaf(root["input"])
+        if st.n_tasks == 1:
+            tasks = [0] if rank == 0 else []
+            n_keys = 1
+        elif kind == "table":
+            n_local = engine.n_table_partitions(what)
+            tasks = list(range(n_local)) if (what not in REPLICATED_TABLES or rank == 0) else []
+            n_keys = n_local
+        else:
+            n_up = out_parts[what]
+            where = placement[what]
+            if where == "hash":
+                tasks = [p for p in range(n_up) if p % world == rank]
+            elif where == "root":
+                tasks = list(range(n_up)) if rank == 0 else []
+            else:
+                tasks = list(range(n_up)) if rank == 0 else []
+            n_keys = n_up
+        qse = engine.create_query_stage_exec(job_id, st.stage_id, st.json(job_id))
+        for p in tasks:
+            qse.execute_query_stage(p)
+        qse.release()
+        part = root.get("partitioning")
+        n_out = part["n"] if part else n_keys
+        out_parts[st.stage_id] = n_out
+        # how do later stages read this one?
+        readers = []
+        for later in stages[si + 1:]:
+            rs = _readers_of(later.plan["input"], st.stage_id)
+            readers += [(b, m or later.n_tasks == 1, sch) for (b, m, sch) in rs]
+        if not readers:
+            placement[st.stage_id] = "root"
+            last_schema = None
+            mode = None
+        else:
+            bcast = any(r[0] for r in readers)
+            merged = all(r[1] for r in readers)
+            schema = readers[0][2]
+            if bcast:
+                mode, placement[st.stage_id] = EXCHANGE_BROADCAST, "all"
+            elif part and not merged:
+                mode, placement[st.stage_id] = EXCHANGE_HASH, "hash"
+            else:
+                mode, placement[st.stage_id] = EXCHANGE_GATHER, "root"
+            if world > 1:
+                stats = engine.exchange_stage(job_id, st.stage_id, n_out, schema, mode, 0)
+                if on_stage is not None:
+                    on_stage(st.stage_id, mode, stats)
+    if not collect or rank != 0:
+        return None
+    last = stages[-1]
+    batches = []
+    for p in range(out_parts[last.stage_id]):
+        if engine.partition_rows(job_id, last.stage_id, p) >= 0:
+            batches.append(engine.partition_export(job_id, last.stage_id, p))
+    if not batches:
+        return None
+    return pa.Table.from_batches(batches)

@@ -40,6 +40,14 @@ class OperatorMetrics(C.Structure):
                 ("kernel_launches", C.c_uint64)]
 
 
+class ExchangeStats(C.Structure):
+    _fields_ = [("sent_bytes", C.c_uint64), ("recv_bytes", C.c_uint64)]
+
+
+EXCHANGE_HASH, EXCHANGE_GATHER, EXCHANGE_BROADCAST = 0, 1, 2
+NCCL_ID_BYTES = 128
+
+
 class DeviceBuffer(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("bytes", C.c_uint64)]
 
@@ -61,9 +69,10 @@ EXPORTED_SYMBOLS = [
     "b200_engine_create", "b200_engine_destroy", "b200_last_error", "b200_engine_set_stream",
     "b200_engine_synchronize", "b200_engine_kernel_launches", "b200_engine_counter", "b200_engine_set_config",
     "b200_engine_register_batch", "b200_engine_drop_table", "b200_engine_tpch_generate",
-    "b200_engine_export_table", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
+    "b200_engine_export_table", "b200_tpch_table_rows", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
+    "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage",
     "b200_version",
 ]
 
@@ -95,6 +104,8 @@ def load_library():
     L.b200_engine_drop_table.argtypes = [vp, cp]
     L.b200_engine_tpch_generate.argtypes = [vp, cp, i64, ci, i64, i64, cp]
     L.b200_engine_export_table.argtypes = [vp, cp, ci, vp, vp]
+    L.b200_tpch_table_rows.argtypes = [cp, i64]
+    L.b200_tpch_table_rows.restype = i64
     L.b200_stage_prepare.argtypes = [vp, cp, i64, cp, u64, C.POINTER(vp)]
     L.b200_stage_execute.argtypes = [vp, ci, vp, C.POINTER(ShuffleWritePartition), ci, C.POINTER(ci)]
     L.b200_stage_metrics.argtypes = [vp, C.POINTER(OperatorMetrics), ci, C.POINTER(ci)]
@@ -108,6 +119,9 @@ def load_library():
     L.b200_remove_job_data.argtypes = [vp, cp]
     L.b200_remove_stage_data.argtypes = [vp, cp, i64]
     L.b200_device_gather.argtypes = [vp, C.POINTER(DeviceBuffer), ci, vp, u64]
+    L.b200_comm_unique_id.argtypes = [vp, u64]
+    L.b200_engine_comm_init.argtypes = [vp, vp, u64]
+    L.b200_exchange_stage.argtypes = [vp, cp, i64, ci, ci, ci, cp, C.POINTER(ExchangeStats)]
     L.b200_host_alloc_pinned.argtypes = [u64]
     L.b200_host_alloc_pinned.restype = vp
     L.b200_host_free_pinned.argtypes = [vp]
@@ -136,14 +150,17 @@ def _check(rc):
 class QueryStageExecutor:
     def __init__(self, engine: "GpuExecutionEngine", handle, job_id: str, stage_id: int):
         self.engine, self.h, self.job_id, self.stage_id = engine, handle, job_id, stage_id
+        self._cap = 8192   # >= the largest shuffle fan-out the engine accepts (4096)
+        self._out = (ShuffleWritePartition * self._cap)()
 
     def execute_query_stage(self, input_partition: int, cancel_flag=None) -> List[ShuffleWritePartition]:
-        cap = 65536
-        out = (ShuffleWritePartition * cap)()
+        cap = self._cap
+        out = self._out
         n = C.c_int(0)
         cf = C.addressof(cancel_flag) if cancel_flag is not None else None
         _check(load_library().b200_stage_execute(self.h, input_partition, cf, out, cap, C.byref(n)))
-        return [out[i] for i in range(n.value)]
+        res = [ShuffleWritePartition.from_buffer_copy(out[i]) for i in range(n.value)]
+        return res
 
     def collect_plan_metrics(self) -> List[dict]:
         cap = 256
@@ -216,6 +233,28 @@ class GpuExecutionEngine:
         _check(load_library().b200_engine_tpch_generate(self.h, table.encode(), msf, partition, row_begin, row_end, csv))
         self._parts.setdefault(table, set()).add(partition)
 
+    @staticmethod
+    def tpch_table_rows(table: str, msf: int) -> int:
+        return load_library().b200_tpch_table_rows(table.encode(), msf)
+
+    def tpch_load(self, tables: dict, msf: int, rank: int = 0, world: int = 1, parts: int = 1, replicated=("nation", "region")) -> dict:
+        """Generate this executor's share of the given TPC-H tables in HBM: rows [rank, rank+1) / world of every
+        table, split into `parts` input partitions; the small dimension tables are replicated in full.
+        Returns {table: global row count}."""
+        rows = {}
+        for t, cols in tables.items():
+            n = self.tpch_table_rows(t, msf)
+            rows[t] = n
+            self.drop_table(t)
+            if t in replicated or n < 1000:
+                self.tpch_generate(t, msf, 0, 0, n, cols)
+                continue
+            lo, hi = n * rank // world, n * (rank + 1) // world
+            step = (hi - lo + parts - 1) // parts
+            for p in range(parts):
+                self.tpch_generate(t, msf, p, min(hi, lo + p * step), min(hi, lo + (p + 1) * step), cols)
+        return rows
+
     def export_table(self, table: str, partition: int) -> pa.RecordBatch:
         arr, sch = ArrowArray(), ArrowSchema()
         _check(load_library().b200_engine_export_table(self.h, table.encode(), partition, C.addressof(arr), C.addressof(sch)))
@@ -266,6 +305,27 @@ class GpuExecutionEngine:
             arr[i].ptr = p
             arr[i].bytes = b
         _check(load_library().b200_device_gather(self.h, arr, len(bufs), dst_ptr, dst_bytes))
+
+    # -- exchange between the box's GPU executors (NCCL inside the library) -------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes generated by ONE executor and handed to every executor's comm_init (b200_comm_unique_id)."""
+        buf = C.create_string_buffer(NCCL_ID_BYTES)
+        _check(load_library().b200_comm_unique_id(buf, NCCL_ID_BYTES))
+        return buf.raw
+
+    def comm_init(self, nccl_id: bytes) -> None:
+        buf = C.create_string_buffer(nccl_id, len(nccl_id))
+        _check(load_library().b200_engine_comm_init(self.h, buf, len(nccl_id)))
+
+    def exchange_stage(self, job_id: str, stage_id: int, n_out_partitions: int, schema, mode: int = EXCHANGE_HASH, root: int = 0) -> dict:
+        """Collective: move every output partition of (job, stage) to the executor(s) that will read it
+        (b200_exchange_stage).  `schema`: the stage's output schema (list of {"name", "type"} dicts)."""
+        import json as _json
+        st = ExchangeStats()
+        sj = schema if isinstance(schema, str) else _json.dumps(schema)
+        _check(load_library().b200_exchange_stage(self.h, job_id.encode(), stage_id, n_out_partitions, mode, root, sj.encode(), C.byref(st)))
+        return {"sent_bytes": st.sent_bytes, "recv_bytes": st.recv_bytes}
 
     def remove_job_data(self, job_id: str) -> None:
         _check(load_library().b200_remove_job_data(self.h, job_id.encode()))

@@ -233,9 +233,14 @@ class Stage:
         self.stage_id = stage_id
         self.plan = plan
         self.n_tasks = n_tasks  # None: as many as the leaf has partitions (driver decides)
+        self._json = None
 
     def json(self, job_id: str) -> str:
-        p = dict(self.plan)
-        p["job_id"] = job_id
-        p["stage_id"] = self.stage_id
-        return dumps(p)
+        # serialised once; the job id is patched into the cached text (a stage is prepared once per task, and the
+        # harness runs the same stage plans under a fresh job id every benchmark step)
+        if self._json is None:
+            p = dict(self.plan)
+            p["job_id"] = "\x00JOB\x00"
+            p["stage_id"] = self.stage_id
+            self._json = dumps(p)
+        return self._json.replace("\\u0000JOB\\u0000", json.dumps(job_id)[1:-1])

@@ -49,10 +49,20 @@ def col_index(table: str, name: str) -> int:
     raise KeyError(name)
 
 
+# table -> the columns it is registered with, when that is a superset of what a query references (None: exactly the
+# query's columns, the projection is the identity)
+TABLE_LAYOUT: dict = {}
+
+
 def table_scan(table: str, columns: List[str]) -> dict:
-    """DataSourceExec with projection push-down; the table must be registered with exactly `columns`
-    (the harness generates only the referenced columns), so the projection is the identity."""
+    """DataSourceExec with projection push-down.  By default the table is registered with exactly `columns`
+    (the harness generates only the referenced columns); with TABLE_LAYOUT[table] set, the scan carries the
+    projection indices into the registered layout."""
     sch = [f for name in columns for f in SCHEMAS[table] if f["name"] == name]
+    layout = TABLE_LAYOUT.get(table)
+    if layout is not None:
+        full = [f for name in layout for f in SCHEMAS[table] if f["name"] == name]
+        return P.scan(table, full, projection=[layout.index(name) for name in columns])
     return P.scan(table, sch)
 
 

@@ -93,6 +93,8 @@ int b200_engine_drop_table(b200_engine* e, const char* table);
  * Rows [row_begin,row_end) of the table at milli-scale-factor `msf` become partition `partition`. */
 int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, int partition,
                               int64_t row_begin, int64_t row_end, const char* columns_csv);
+/* Rows of a synthetic TPC-H table at milli-scale-factor `msf` (-1: unknown table). */
+int64_t b200_tpch_table_rows(const char* table, int64_t msf);
 /* Read a registered table partition back to the host (test/diagnostic). */
 int b200_engine_export_table(b200_engine* e, const char* table, int partition,
                              struct ArrowArray* out, struct ArrowSchema* out_schema);
@@ -147,6 +149,32 @@ int b200_remove_job_data(b200_engine* e, const char* job_id);
 /* Drop every stored partition of one stage (used by the exchange step once the pieces have been
  * handed to their owning GPUs; the reference deletes map outputs the same way on stage rollback). */
 int b200_remove_stage_data(b200_engine* e, const char* job_id, int64_t stage_id);
+
+/* ---- exchange between the box's GPU executors ------------------------------------------------
+ * Stands behind ShuffleReaderExec's remote fetch (shuffle_reader.rs:522-602 -> BallistaClient::fetch_partition,
+ * client.rs:143-220 -> BallistaFlightService::do_get / do_action, flight_service.rs:88-306): with one executor per GPU
+ * of one box the same bytes move as an all-to-all-v over NVLink (grouped ncclSend / ncclRecv issued by this
+ * library on the engine's stream).  NCCL is bound with dlopen; an engine with world == 1 never loads it.
+ *   b200_comm_unique_id: 128 bytes (ncclUniqueId) generated by ONE executor; the host side distributes them to the
+ *     others (in Ballista: a task property set by the scheduler; in the harness: any broadcast).
+ *   b200_engine_comm_init: collective over the `world` engines created with ranks 0..world-1.
+ *   b200_exchange_stage: collective, after every executor finished its map tasks of (job, stage).  Afterwards each
+ *     output partition's pieces live in the HBM of the executor(s) that will run its reduce task:
+ *       B200_EXCHANGE_HASH       partition p -> executor p % world        (hash repartition, planner.rs:194-256)
+ *       B200_EXCHANGE_GATHER     every partition -> executor `root`       (CoalescePartitions / SortPreservingMerge)
+ *       B200_EXCHANGE_BROADCAST  every partition -> every executor        (broadcast join build side,
+ *                                                                          planner.rs:142-183, shuffle_reader.rs:121-144)
+ *     schema_json: the stage's output schema (same JSON as b200_partition_import_device). */
+#define B200_NCCL_ID_BYTES 128
+enum { B200_EXCHANGE_HASH = 0, B200_EXCHANGE_GATHER = 1, B200_EXCHANGE_BROADCAST = 2 };
+typedef struct b200_exchange_stats {
+  uint64_t sent_bytes;   /* payload bytes this executor sent to peers */
+  uint64_t recv_bytes;   /* payload bytes it received */
+} b200_exchange_stats;
+int b200_comm_unique_id(void* out, uint64_t cap);
+int b200_engine_comm_init(b200_engine* e, const void* nccl_id, uint64_t id_bytes);
+int b200_exchange_stage(b200_engine* e, const char* job_id, int64_t stage_id, int n_out_partitions, int mode, int root,
+                        const char* schema_json, b200_exchange_stats* stats);
 
 /* ---- pinned host staging (harness side of "RecordBatches are pinned and DMA'd") ------------- */
 void* b200_host_alloc_pinned(uint64_t bytes);

@@ -29,7 +29,11 @@ def oracle(oracle_lib):
 @pytest.fixture(scope="session")
 def gpu_engine_session():
     import ballista_b200 as bb
-    e = bb.GpuExecutionEngine(0)
+    try:
+        e = bb.GpuExecutionEngine(0)
+    except bb.engine.B200Error as ex:
+        # no CUDA device here: the engine has no CPU path, so the gpu-marked tests cannot run at all
+        pytest.skip(f"no usable CUDA device: {ex}")
     yield e
     e.close()
 
