@@ -148,6 +148,20 @@ void launch_join_probe_count(const JoinKeys& K, const uint64_t* build_hash, cons
 void launch_join_probe_write(const JoinKeys& K, const uint64_t* build_hash, const int32_t* heads, uint64_t n_buckets, const int32_t* next,
                              const uint64_t* probe_hash, const uint8_t* probe_ok, int64_t n_probe, const uint64_t* offsets,
                              int64_t* out_build_idx, int64_t* out_probe_idx, cudaStream_t st);
+// ---- single-pass join (join.cu) -----------------------------------------------------------------
+struct JoinNode {   // one per build row
+  uint64_t tag;     // exact mode: 64-bit image of the (single, integer-like) key; else the row hash
+  int32_t next;     // previous head of the bucket, -1 = end of chain
+  uint32_t _pad;
+};
+// exact == true: one integer-like key column, tag = key (build_hash / probe_hash unused)
+void launch_join_build2(const JoinKeys& K, bool exact, const uint64_t* build_hash, int64_t n_build, int32_t* heads /* pre-set to -1 */, uint64_t n_buckets,
+                        JoinNode* nodes, cudaStream_t st);
+// mode bit 0: emit (build row, probe row) pairs -- *counter (pre-zeroed) ends up with the total number of pairs, of
+// which the first `cap` were written; bit 1: probe_mark[j] = 1 for probe rows with a match; bit 2: build_mark[i] = 1
+void launch_join_probe2(const JoinKeys& K, bool exact, int mode, const JoinNode* nodes, const int32_t* heads, uint64_t n_buckets, const uint64_t* probe_hash,
+                        int64_t n_probe, unsigned long long* counter, uint64_t cap, int64_t* out_build_idx, int64_t* out_probe_idx, uint8_t* probe_mark,
+                        uint8_t* build_mark, cudaStream_t st);
 // compaction helpers: indices of rows whose flag byte == want
 void launch_flag_to_u32(const uint8_t* flags, uint8_t want, uint32_t* out, int64_t n, cudaStream_t st);
 void launch_select_indices(const uint32_t* flag01, const uint64_t* offs, int64_t* out_idx, int64_t n, cudaStream_t st);

@@ -82,6 +82,13 @@ struct b200_engine {
     cudaEvent_t done = nullptr;
     bool used = false;
   } nslot[2];
+  // per-kernel device timing (b200.metrics.kernel_timing = on): CUDA event pairs on the launching stream, resolved
+  // when the statistics are read (b200_engine_kernel_stats)
+  bool kernel_timing = false;
+  struct KernelSample { std::string name; cudaEvent_t e0, e1; uint64_t bytes; };
+  std::vector<KernelSample> ksamples;
+  struct KernelStat { double ms = 0; uint64_t launches = 0, bytes = 0; };
+  std::map<std::string, KernelStat> kstats;
   ncclComm_t comm = nullptr;                 // exchange communicator (b200_engine_comm_init); nullptr = single executor
   std::mutex comm_mu;                        // one collective at a time
   uint64_t exch_sent_bytes = 0, exch_recv_bytes = 0;
@@ -199,6 +206,31 @@ struct Exec {
     const T* p = fetch<T>(dptr);
     sync();
     return *p;
+  }
+};
+
+// Brackets one kernel (or one short sequence) with CUDA events when kernel timing is on; `bytes` = algorithmic bytes
+// (SURVEY.md 8(d) formulas) so that achieved GB/s per kernel family can be reported next to the HBM roofline.
+struct KernelTimer {
+  b200_engine* e;
+  cudaStream_t st;
+  b200_engine::KernelSample ks;
+  bool on;
+  KernelTimer(const Exec& x, const char* name, uint64_t bytes) : e(x.e), st(x.st()), on(x.e->kernel_timing) {
+    if (!on) return;
+    ks.name = name;
+    ks.bytes = bytes;
+    if (cudaEventCreate(&ks.e0) != cudaSuccess || cudaEventCreate(&ks.e1) != cudaSuccess) {
+      on = false;
+      return;
+    }
+    cudaEventRecord(ks.e0, st);
+  }
+  ~KernelTimer() {
+    if (!on) return;
+    cudaEventRecord(ks.e1, st);
+    std::lock_guard<std::mutex> g(e->mu);
+    e->ksamples.push_back(ks);
   }
 };
 
@@ -374,6 +406,9 @@ DevBatchPtr gather_batch(const Exec& x, const DevBatch& in, const int64_t* idx, 
   gc.n = 0;
   auto flush = [&]() {
     if (gc.n) {
+      uint64_t b = 8;
+      for (int k = 0; k < gc.n; k++) b += 2ull * (uint64_t)gc.c[k].width;
+      KernelTimer kt(x, "gather", (uint64_t)n_out * b);
       launch_gather_multi(gc, idx, n_out, x.st());
       x.count();
       gc.n = 0;
@@ -773,6 +808,11 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
     }
     for (int i = 0; i < P.n_regs; i++) fprintf(stderr, "[b200]   reg %d: vk=%d off=%u valid_off=%u\n", i, P.regs[i].vk, P.regs[i].smem_off, P.regs[i].valid_off);
   }
+  uint64_t kt_bytes = 0;
+  for (int i = 0; i < P.n_cols; i++) kt_bytes += (uint64_t)P.cols[i].width * (uint64_t)P.n_rows;
+  if (P.sink == SINK_MATERIALIZE)
+    for (int j = 0; j < P.n_out; j++) kt_bytes += (uint64_t)phys_width((Phys)P.out[j].phys) * (uint64_t)P.n_rows;  // upper bound: every row kept
+  KernelTimer kt(x, fused ? "pipeline_fused_agg" : P.sink == SINK_MATERIALIZE ? "pipeline_materialize" : P.sink == SINK_AGG_REG ? "pipeline_agg_reg" : "pipeline_agg_global", kt_bytes);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
@@ -1946,17 +1986,50 @@ struct Runner {
   }
 
   // ---- hash join --------------------------------------------------------------------------------
-  struct JoinSide {
-    DevBatchPtr batch;  // [payload columns..., key columns..., hash, ok]
-    size_t n_payload;
+  // Evaluates `outs` of a pipeline: columns the chain forwards untouched (and that no filter compacts) are taken
+  // from the source batch as they are, only computed columns go through the materialising kernel.
+  struct Mixed {
+    std::vector<DevColumn> cols;  // one per entry of `outs`
+    int64_t n = 0;
   };
-  JoinSide prepare_side(const PlanNode& child, int part, bool all, const std::vector<ExprPtr>& key_exprs, bool null_equals_null, OpMetrics* met) {
+  Mixed materialize_mixed(PipelineBuilder& pb, const std::vector<ColRef>& outs, const DevBatchPtr& src, OpMetrics* met) {
+    Mixed m;
+    const bool filters = program_filters(pb.prog);
+    std::vector<int> direct(outs.size(), -1);
+    std::vector<ColRef> mouts;
+    for (size_t c = 0; c < outs.size(); c++) {
+      if (!filters) direct[c] = pb.source_index(outs[c]);
+      if (direct[c] < 0) mouts.push_back(outs[c]);
+    }
+    DevBatchPtr mat;
+    m.n = src->n;
+    if (!mouts.empty()) {
+      mat = run_materialize(x, pb, mouts, src, met);
+      m.n = mat->n;
+    }
+    size_t mi = 0;
+    for (size_t c = 0; c < outs.size(); c++) {
+      DevColumn col = direct[c] >= 0 ? src->cols[(size_t)direct[c]] : mat->cols[mi++];
+      col.name = outs[c].name;
+      m.cols.push_back(col);
+    }
+    return m;
+  }
+
+  struct JoinSide {
+    DevBatch payload;              // output columns of the side
+    std::vector<DevColumn> keys;   // evaluated join keys (strings as views)
+    const uint64_t* hash = nullptr;
+    DevColumn hash_col;
+    int64_t n = 0;
+  };
+  JoinSide prepare_side(const PlanNode& child, int part, bool all, const std::vector<ExprPtr>& key_exprs, bool need_hash, OpMetrics* met) {
     JoinSide js;
-    js.batch = with_chain(child, part, all, [&](const BuilderFactory& mk, DevBatchPtr& src) {
+    with_chain(child, part, all, [&](const BuilderFactory& mk, DevBatchPtr& src) {
       auto pbp = mk();
       PipelineBuilder& pb = *pbp;
       std::vector<ColRef> outs = named_cols(pb, child.schema);
-      js.n_payload = outs.size();
+      const size_t n_payload = outs.size();
       std::vector<ColRef> keys;
       for (auto& ke : key_exprs) {
         ColRef k = pb.compile(*ke);
@@ -1964,13 +2037,31 @@ struct Runner {
         keys.push_back(k);
       }
       for (auto& k : keys) outs.push_back(k);
-      ColRef h = pb.hash_of(keys);
-      h.name = "__hash";
-      outs.push_back(h);
-      return run_materialize(x, pb, outs, src, met);
+      if (need_hash) {
+        ColRef h = pb.hash_of(keys);
+        h.name = "__hash";
+        outs.push_back(h);
+      }
+      Mixed m = materialize_mixed(pb, outs, src, met);
+      js.n = m.n;
+      js.payload.n = m.n;
+      for (size_t c = 0; c < n_payload; c++) js.payload.cols.push_back(m.cols[c]);
+      for (size_t k = 0; k < keys.size(); k++) js.keys.push_back(as_views(x, m.cols[n_payload + k]));
+      if (need_hash) {
+        js.hash_col = m.cols.back();
+        js.hash = (const uint64_t*)js.hash_col.data;
+      }
+      return src;
     });
-    (void)null_equals_null;
     return js;
+  }
+
+  static bool exact_key(const DataType& t) {
+    switch (t.id) {
+      case TypeId::Int8: case TypeId::Int16: case TypeId::Int32: case TypeId::Int64: case TypeId::UInt8: case TypeId::UInt16: case TypeId::UInt32:
+      case TypeId::UInt64: case TypeId::Date32: case TypeId::Timestamp: return true;
+      default: return false;
+    }
   }
 
   DevBatchPtr exec_join(const PlanNode& n, int part, OpMetrics* met) {
@@ -1989,57 +2080,92 @@ struct Runner {
     if (collect_left && (n.join_type == JoinType::Left || n.join_type == JoinType::Full || n.join_type == JoinType::LeftSemi || n.join_type == JoinType::LeftAnti) &&
         n_partitions(*n.children[1]) > 1)
       throw EngineError(B200_ERR_UNSUPPORTED, "CollectLeft hash join that emits build-side rows over more than one probe partition: plan it as Partitioned");
-    JoinSide L = prepare_side(*n.children[0], part, collect_left, lk, n.null_equals_null, met);
-    JoinSide R = prepare_side(*n.children[1], part, false, rk, n.null_equals_null, met);
-    const int64_t nb = L.batch->n, np = R.batch->n;
+    // one integer-like key: the table is keyed by the key itself (no hash column, no second look at the keys)
+    const bool exact = nk == 1 && exact_key(lk[0]->type) && lk[0]->type.id == rk[0]->type.id;
+    JoinSide L = prepare_side(*n.children[0], part, collect_left, lk, !exact, met);
+    JoinSide R = prepare_side(*n.children[1], part, false, rk, !exact, met);
+    const int64_t nb = L.n, np = R.n;
     if (nb >= ((int64_t)1 << 31)) throw EngineError(B200_ERR_UNSUPPORTED, "hash join build side exceeds 2^31 rows");
     auto t0 = std::chrono::steady_clock::now();
     JoinKeys K;
     memset(&K, 0, sizeof K);
     K.n_keys = (int)nk;
     K.null_equals_null = n.null_equals_null ? 1 : 0;
-    // rows with a NULL key never match (unless null_equals_null): ok = AND of key validity
-    DevPtr l_ok, r_ok;
-    auto key_col = [&](JoinSide& s, size_t k) -> DevColumn& { return s.batch->cols[s.n_payload + k]; };
+    uint64_t key_bytes_b = 0, key_bytes_p = 0;
     for (size_t k = 0; k < nk; k++) {
-      DevColumn& b = key_col(L, k);
-      DevColumn& p = key_col(R, k);
+      const DevColumn& b = L.keys[k];
+      const DevColumn& p = R.keys[k];
       if (b.phys != p.phys) throw EngineError(B200_ERR_UNSUPPORTED, "join key physical types differ (" + b.type.str() + " vs " + p.type.str() + "): add casts");
       K.build[k] = KeyCol{b.data, b.valid, (uint8_t)b.phys, (uint8_t)b.width()};
       K.probe[k] = KeyCol{p.data, p.valid, (uint8_t)p.phys, (uint8_t)p.width()};
+      key_bytes_b += (uint64_t)b.width();
+      key_bytes_p += (uint64_t)p.width();
     }
-    const uint64_t* lh = (const uint64_t*)L.batch->cols[L.n_payload + nk].data;
-    const uint64_t* rh = (const uint64_t*)R.batch->cols[R.n_payload + nk].data;
-    uint64_t n_buckets = next_pow2((uint64_t)std::max<int64_t>(nb, 1) * 2);
+    const bool exact_ok = exact && !(n.null_equals_null && (L.keys[0].valid || R.keys[0].valid));
+    if (exact && !exact_ok) throw EngineError(B200_ERR_UNSUPPORTED, "null_equals_null join on a nullable integer key");
+    x.check_cancel();
+    const uint64_t n_buckets = next_pow2((uint64_t)std::max<int64_t>(nb, 1) * 2);
     DevPtr heads = dev_alloc((size_t)n_buckets * 4, x.st());
-    CUDA_CHECK(cudaMemsetAsync(heads->ptr, 0xFF, (size_t)n_buckets * 4, x.st()));
-    DevPtr next = dev_alloc((size_t)std::max<int64_t>(nb, 1) * 4, x.st());
+    DevPtr nodes = dev_alloc((size_t)std::max<int64_t>(nb, 1) * sizeof(JoinNode), x.st());
+    {
+      KernelTimer kt(x, "join_build", (uint64_t)nb * (key_bytes_b + sizeof(JoinNode)) + n_buckets * 4);
+      CUDA_CHECK(cudaMemsetAsync(heads->ptr, 0xFF, (size_t)n_buckets * 4, x.st()));
+      launch_join_build2(K, exact, L.hash, nb, (int32_t*)heads->ptr, n_buckets, (JoinNode*)nodes->ptr, x.st());
+      x.count();
+    }
     x.check_cancel();
-    launch_join_build(lh, nullptr, nb, (int32_t*)heads->ptr, n_buckets, (int32_t*)next->ptr, x.st());
-    x.count();
+    const bool has_filter = n.join_filter != nullptr;
+    const JoinType jt = n.join_type;
+    const bool semi_anti = jt == JoinType::LeftSemi || jt == JoinType::LeftAnti || jt == JoinType::RightSemi || jt == JoinType::RightAnti;
+    const bool left_outer = jt == JoinType::Left || jt == JoinType::Full, right_outer = jt == JoinType::Right || jt == JoinType::Full;
+    const bool want_bmark = jt == JoinType::LeftSemi || jt == JoinType::LeftAnti || left_outer;
+    const bool want_pmark = jt == JoinType::RightSemi || jt == JoinType::RightAnti || right_outer;
+    // with a residual filter the marks must come from the pairs that survive it
+    const bool need_pairs = has_filter || !semi_anti;
+    int mode = need_pairs ? 1 : 0;
+    DevPtr bmark, pmark;
+    if (!has_filter && want_bmark) {
+      bmark = dev_alloc((size_t)std::max<int64_t>(nb, 1), x.st());
+      CUDA_CHECK(cudaMemsetAsync(bmark->ptr, 0, (size_t)std::max<int64_t>(nb, 1), x.st()));
+      mode |= 4;
+    }
+    if (!has_filter && want_pmark) {
+      pmark = dev_alloc((size_t)std::max<int64_t>(np, 1), x.st());
+      CUDA_CHECK(cudaMemsetAsync(pmark->ptr, 0, (size_t)std::max<int64_t>(np, 1), x.st()));
+      mode |= 2;
+    }
+    int64_t n_pairs = 0;
+    DevPtr bi, pi;
+    if (mode) {
+      DevPtr counter = dev_alloc(16, x.st());
+      uint64_t cap = need_pairs ? (uint64_t)std::max<int64_t>(np + nb / 8 + 1024, 1) : 0;
+      for (int attempt = 0;; attempt++) {
+        if (need_pairs) {
+          bi = dev_alloc((size_t)std::max<uint64_t>(cap, 1) * 8, x.st());
+          pi = dev_alloc((size_t)std::max<uint64_t>(cap, 1) * 8, x.st());
+        }
+        CUDA_CHECK(cudaMemsetAsync(counter->ptr, 0, 16, x.st()));
+        {
+          KernelTimer kt(x, "join_probe", (uint64_t)np * (key_bytes_p + 4 + sizeof(JoinNode)));
+          launch_join_probe2(K, exact, mode, (const JoinNode*)nodes->ptr, (const int32_t*)heads->ptr, n_buckets, R.hash, np, (unsigned long long*)counter->ptr, cap,
+                             need_pairs ? (int64_t*)bi->ptr : nullptr, need_pairs ? (int64_t*)pi->ptr : nullptr, pmark ? (uint8_t*)pmark->ptr : nullptr,
+                             bmark ? (uint8_t*)bmark->ptr : nullptr, x.st());
+          x.count();
+        }
+        if (!need_pairs) break;
+        n_pairs = (int64_t)x.get<unsigned long long>(counter->ptr);
+        if ((uint64_t)n_pairs <= cap) break;
+        if (attempt) throw EngineError(B200_ERR_EXECUTION, "hash join: pair count changed between passes");
+        cap = (uint64_t)n_pairs;  // many-to-many join: run again with the exact size
+      }
+    }
     x.check_cancel();
-    DevPtr counts = dev_alloc((size_t)(np + 1) * 4, x.st());
-    DevPtr offs = dev_alloc((size_t)(np + 2) * 8, x.st());
-    DevPtr scratch = dev_alloc((size_t)(np / 1024 + 4) * 8, x.st());
-    launch_join_probe_count(K, lh, (const int32_t*)heads->ptr, n_buckets, (const int32_t*)next->ptr, rh, nullptr, np, (uint32_t*)counts->ptr, nullptr, x.st());
-    launch_scan_u32_to_u64((const uint32_t*)counts->ptr, (uint64_t*)offs->ptr, np, (uint64_t*)scratch->ptr, x.st());
-    x.count(4);
-    int64_t n_pairs = (int64_t)x.get<uint64_t>((const uint64_t*)offs->ptr + np);
-    DevPtr bi = dev_alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, x.st()), pi = dev_alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, x.st());
-    launch_join_probe_write(K, lh, (const int32_t*)heads->ptr, n_buckets, (const int32_t*)next->ptr, rh, nullptr, np, (const uint64_t*)offs->ptr, (int64_t*)bi->ptr, (int64_t*)pi->ptr, x.st());
-    x.count();
-
-    x.check_cancel();
-    DevBatch Lp, Rp;  // payload-only views
-    Lp.n = nb;
-    Rp.n = np;
-    for (size_t c = 0; c < L.n_payload; c++) Lp.cols.push_back(L.batch->cols[c]);
-    for (size_t c = 0; c < R.n_payload; c++) Rp.cols.push_back(R.batch->cols[c]);
-
-    const int64_t* bidx = (const int64_t*)bi->ptr;
-    const int64_t* pidx = (const int64_t*)pi->ptr;
+    const int64_t* bidx = need_pairs ? (const int64_t*)bi->ptr : nullptr;
+    const int64_t* pidx = need_pairs ? (const int64_t*)pi->ptr : nullptr;
+    const DevBatch& Lp = L.payload;
+    const DevBatch& Rp = R.payload;
     DevPtr fbi, fpi;  // filtered pair lists
-    if (n.join_filter && n_pairs > 0) {
+    if (has_filter && n_pairs > 0) {
       // evaluate the residual filter on the candidate pairs, carrying the pair indices through
       DevBatchPtr lg = gather_batch(x, Lp, bidx, n_pairs, false), rg = gather_batch(x, Rp, pidx, n_pairs, false);
       auto cat = std::make_shared<DevBatch>();
@@ -2081,7 +2207,8 @@ struct Runner {
       x.count();
       return idx;
     };
-    auto marks_of = [&](const int64_t* idx, int64_t nrows) {
+    auto marks_of = [&](const int64_t* idx, int64_t nrows, const DevPtr& from_probe) {
+      if (!has_filter && from_probe) return from_probe;  // the probe pass already marked them
       DevPtr m = dev_alloc((size_t)std::max<int64_t>(nrows, 1), x.st());
       CUDA_CHECK(cudaMemsetAsync(m->ptr, 0, (size_t)std::max<int64_t>(nrows, 1), x.st()));
       if (n_pairs > 0) {
@@ -2091,20 +2218,20 @@ struct Runner {
       return m;
     };
     DevBatchPtr out;
-    switch (n.join_type) {
+    switch (jt) {
       case JoinType::LeftSemi:
       case JoinType::LeftAnti: {
-        DevPtr m = marks_of(bidx, nb);
+        DevPtr m = marks_of(bidx, nb, bmark);
         int64_t ns = 0;
-        DevPtr idx = flags_to_indices((const uint8_t*)m->ptr, nb, n.join_type == JoinType::LeftSemi, &ns);
+        DevPtr idx = flags_to_indices((const uint8_t*)m->ptr, nb, jt == JoinType::LeftSemi, &ns);
         out = gather_batch(x, Lp, (const int64_t*)idx->ptr, ns, false);
         break;
       }
       case JoinType::RightSemi:
       case JoinType::RightAnti: {
-        DevPtr m = marks_of(pidx, np);
+        DevPtr m = marks_of(pidx, np, pmark);
         int64_t ns = 0;
-        DevPtr idx = flags_to_indices((const uint8_t*)m->ptr, np, n.join_type == JoinType::RightSemi, &ns);
+        DevPtr idx = flags_to_indices((const uint8_t*)m->ptr, np, jt == JoinType::RightSemi, &ns);
         out = gather_batch(x, Rp, (const int64_t*)idx->ptr, ns, false);
         break;
       }
@@ -2112,36 +2239,67 @@ struct Runner {
         // inner pairs (+ unmatched rows for outer joins, index -1 on the missing side)
         int64_t extra_l = 0, extra_r = 0;
         DevPtr ul, ur;
-        const bool left_outer = n.join_type == JoinType::Left || n.join_type == JoinType::Full;
-        const bool right_outer = n.join_type == JoinType::Right || n.join_type == JoinType::Full;
         if (left_outer) {
-          DevPtr m = marks_of(bidx, nb);
+          DevPtr m = marks_of(bidx, nb, bmark);
           ul = flags_to_indices((const uint8_t*)m->ptr, nb, false, &extra_l);
         }
         if (right_outer) {
-          DevPtr m = marks_of(pidx, np);
+          DevPtr m = marks_of(pidx, np, pmark);
           ur = flags_to_indices((const uint8_t*)m->ptr, np, false, &extra_r);
         }
         const int64_t total = n_pairs + extra_l + extra_r;
-        DevPtr li = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8, x.st()), ri = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8, x.st());
-        if (n_pairs) {
-          CUDA_CHECK(cudaMemcpyAsync(li->ptr, bidx, (size_t)n_pairs * 8, cudaMemcpyDeviceToDevice, x.st()));
-          CUDA_CHECK(cudaMemcpyAsync(ri->ptr, pidx, (size_t)n_pairs * 8, cudaMemcpyDeviceToDevice, x.st()));
+        const int64_t* li_p = bidx;
+        const int64_t* ri_p = pidx;
+        DevPtr li, ri;
+        if (extra_l || extra_r) {
+          li = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8, x.st());
+          ri = dev_alloc((size_t)std::max<int64_t>(total, 1) * 8, x.st());
+          if (n_pairs) {
+            CUDA_CHECK(cudaMemcpyAsync(li->ptr, bidx, (size_t)n_pairs * 8, cudaMemcpyDeviceToDevice, x.st()));
+            CUDA_CHECK(cudaMemcpyAsync(ri->ptr, pidx, (size_t)n_pairs * 8, cudaMemcpyDeviceToDevice, x.st()));
+          }
+          if (extra_l) {
+            CUDA_CHECK(cudaMemcpyAsync((int64_t*)li->ptr + n_pairs, ul->ptr, (size_t)extra_l * 8, cudaMemcpyDeviceToDevice, x.st()));
+            CUDA_CHECK(cudaMemsetAsync((int64_t*)ri->ptr + n_pairs, 0xFF, (size_t)extra_l * 8, x.st()));
+          }
+          if (extra_r) {
+            CUDA_CHECK(cudaMemsetAsync((int64_t*)li->ptr + n_pairs + extra_l, 0xFF, (size_t)extra_r * 8, x.st()));
+            CUDA_CHECK(cudaMemcpyAsync((int64_t*)ri->ptr + n_pairs + extra_l, ur->ptr, (size_t)extra_r * 8, cudaMemcpyDeviceToDevice, x.st()));
+          }
+          li_p = (const int64_t*)li->ptr;
+          ri_p = (const int64_t*)ri->ptr;
         }
-        if (extra_l) {
-          CUDA_CHECK(cudaMemcpyAsync((int64_t*)li->ptr + n_pairs, ul->ptr, (size_t)extra_l * 8, cudaMemcpyDeviceToDevice, x.st()));
-          CUDA_CHECK(cudaMemsetAsync((int64_t*)ri->ptr + n_pairs, 0xFF, (size_t)extra_l * 8, x.st()));
+        // only the columns the join's projection keeps are gathered
+        std::vector<int> want;
+        const size_t nl = Lp.cols.size(), nr = Rp.cols.size();
+        if (n.has_projection) want = n.projection;
+        else
+          for (size_t c = 0; c < nl + nr; c++) want.push_back((int)c);
+        DevBatch Ls, Rs;
+        Ls.n = nb;
+        Rs.n = np;
+        std::vector<std::pair<int, size_t>> where;  // per wanted column: (side, index inside the side's gathered batch)
+        for (int idx : want) {
+          if ((size_t)idx < nl) {
+            where.push_back({0, Ls.cols.size()});
+            Ls.cols.push_back(Lp.cols[(size_t)idx]);
+          } else {
+            where.push_back({1, Rs.cols.size()});
+            Rs.cols.push_back(Rp.cols.at((size_t)idx - nl));
+          }
         }
-        if (extra_r) {
-          CUDA_CHECK(cudaMemsetAsync((int64_t*)li->ptr + n_pairs + extra_l, 0xFF, (size_t)extra_r * 8, x.st()));
-          CUDA_CHECK(cudaMemcpyAsync((int64_t*)ri->ptr + n_pairs + extra_l, ur->ptr, (size_t)extra_r * 8, cudaMemcpyDeviceToDevice, x.st()));
-        }
-        DevBatchPtr lg = gather_batch(x, Lp, (const int64_t*)li->ptr, total, right_outer);
-        DevBatchPtr rg = gather_batch(x, Rp, (const int64_t*)ri->ptr, total, left_outer);
+        KernelTimer kt(x, "join_gather", 0);
+        DevBatchPtr lg = gather_batch(x, Ls, li_p, total, right_outer);
+        DevBatchPtr rg = gather_batch(x, Rs, ri_p, total, left_outer);
         out = std::make_shared<DevBatch>();
         out->n = total;
-        for (auto& c : lg->cols) out->cols.push_back(c);
-        for (auto& c : rg->cols) out->cols.push_back(c);
+        for (auto& w : where) out->cols.push_back(w.first == 0 ? lg->cols[w.second] : rg->cols[w.second]);
+        for (size_t c = 0; c < out->cols.size() && c < n.schema.size(); c++) out->cols[c].name = n.schema[c].name;
+        if (met) {
+          met->elapsed_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+          met->input_rows += (uint64_t)(nb + np);
+        }
+        return out;
       }
     }
     if (n.has_projection) {
@@ -2151,7 +2309,6 @@ struct Runner {
       out = p;
     }
     for (size_t c = 0; c < out->cols.size() && c < n.schema.size(); c++) out->cols[c].name = n.schema[c].name;
-    CUDA_CHECK(cudaStreamSynchronize(x.st()));
     if (met) {
       met->elapsed_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
       met->input_rows += (uint64_t)(nb + np);
@@ -2319,8 +2476,13 @@ struct Runner {
     DevPtr acc = dev_alloc(acc_words * 8, x.st());
     CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, acc_words * 8, x.st()));
     DevPtr tile_hist = dev_alloc((size_t)std::max<uint64_t>((uint64_t)P * n_tiles, 1) * 4 + 64, x.st());
-    CUDA_CHECK(launch_partition_hist(pid, n, P, (uint32_t*)tile_hist->ptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + P, x.st()));
-    x.count();
+    uint64_t row_bytes = 0;
+    for (auto& c : pay) row_bytes += (uint64_t)c.width() + (c.valid ? 1 : 0);
+    {
+      KernelTimer kt(x, "partition_hist", (uint64_t)n * 4);
+      CUDA_CHECK(launch_partition_hist(pid, n, P, (uint32_t*)tile_hist->ptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + P, x.st()));
+      x.count();
+    }
     const unsigned long long* hc = (const unsigned long long*)x.fetch_bytes(acc->ptr, acc_words * 8);
     // while the counts travel: scan the per-tile histogram and scatter
     const int64_t hn = (int64_t)P * n_tiles;
@@ -2337,6 +2499,9 @@ struct Runner {
       gc.n = 0;
       auto flush = [&]() {
         if (gc.n && n > 0) {
+          uint64_t b = 0;
+          for (int k = 0; k < gc.n; k++) b += (uint64_t)gc.c[k].width;
+          KernelTimer kt(x, "partition_scatter", (uint64_t)n * (2 * b + 4));
           CUDA_CHECK(launch_partition_scatter(pid, n, P, (const uint64_t*)offs->ptr, gc, nullptr, x.st()));
           x.count();
         }
@@ -2862,6 +3027,7 @@ int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
     std::lock_guard<std::mutex> g(e->mu);
     e->config[key] = value;
     if (std::string(key) == "datafusion.execution.batch_size") e->batch_size = std::max<int64_t>(1, atoll(value));
+    if (std::string(key) == "b200.metrics.kernel_timing") e->kernel_timing = std::string(value) == "on" || std::string(value) == "1" || std::string(value) == "true";
   });
 }
 
@@ -3249,6 +3415,39 @@ int b200_remove_stage_data(b200_engine* e, const char* job_id, int64_t stage_id)
       if (it->first.job == job_id && it->first.stage == stage_id) it = e->shuffle.erase(it);
       else ++it;
     }
+  });
+}
+
+int b200_engine_kernel_stats(b200_engine* e, b200_kernel_stat* out, int cap, int* n_out, int reset) {
+  return guard([&] {
+    if (!e || !n_out) throw EngineError(B200_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    std::lock_guard<std::mutex> g(e->mu);
+    for (auto& ks : e->ksamples) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ks.e0, ks.e1) == cudaSuccess) {
+        auto& st = e->kstats[ks.name];
+        st.ms += ms;
+        st.launches++;
+        st.bytes += ks.bytes;
+      }
+      cudaEventDestroy(ks.e0);
+      cudaEventDestroy(ks.e1);
+    }
+    e->ksamples.clear();
+    int k = 0;
+    for (auto& kv : e->kstats) {
+      if (k >= cap) break;
+      memset(&out[k], 0, sizeof out[k]);
+      snprintf(out[k].name, sizeof out[k].name, "%s", kv.first.c_str());
+      out[k].elapsed_ns = (uint64_t)(kv.second.ms * 1e6);
+      out[k].launches = kv.second.launches;
+      out[k].algorithmic_bytes = kv.second.bytes;
+      k++;
+    }
+    *n_out = k;
+    if (reset) e->kstats.clear();
   });
 }
 

@@ -40,6 +40,10 @@ class OperatorMetrics(C.Structure):
                 ("kernel_launches", C.c_uint64)]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("elapsed_ns", C.c_uint64), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
+
+
 class ExchangeStats(C.Structure):
     _fields_ = [("sent_bytes", C.c_uint64), ("recv_bytes", C.c_uint64)]
 
@@ -72,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "b200_engine_export_table", "b200_tpch_table_rows", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
-    "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage",
+    "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_engine_kernel_stats",
     "b200_version",
 ]
 
@@ -119,6 +123,7 @@ def load_library():
     L.b200_remove_job_data.argtypes = [vp, cp]
     L.b200_remove_stage_data.argtypes = [vp, cp, i64]
     L.b200_device_gather.argtypes = [vp, C.POINTER(DeviceBuffer), ci, vp, u64]
+    L.b200_engine_kernel_stats.argtypes = [vp, C.POINTER(KernelStat), ci, C.POINTER(ci), ci]
     L.b200_comm_unique_id.argtypes = [vp, u64]
     L.b200_engine_comm_init.argtypes = [vp, vp, u64]
     L.b200_exchange_stage.argtypes = [vp, cp, i64, ci, ci, ci, cp, C.POINTER(ExchangeStats)]
@@ -216,6 +221,15 @@ class GpuExecutionEngine:
     def counter(self, name: str) -> int:
         """Pipelines run per kernel family: 'fused', 'fused_static', 'vm' (b200_engine_counter)."""
         return load_library().b200_engine_counter(self.h, name.encode())
+
+    def kernel_stats(self, reset: bool = False) -> dict:
+        """{kernel family: {"ms", "launches", "bytes"}} while b200.metrics.kernel_timing is on (b200_engine_kernel_stats)."""
+        cap = 128
+        out = (KernelStat * cap)()
+        n = C.c_int(0)
+        _check(load_library().b200_engine_kernel_stats(self.h, out, cap, C.byref(n), 1 if reset else 0))
+        return {out[i].name.decode(): {"ms": out[i].elapsed_ns / 1e6, "launches": out[i].launches, "bytes": out[i].algorithmic_bytes}
+                for i in range(n.value)}
 
     # -- leaf inputs ---------------------------------------------------------------------------
     def register_batch(self, table: str, partition: int, batch: pa.RecordBatch) -> None:

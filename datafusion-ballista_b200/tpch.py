@@ -703,3 +703,327 @@ def q21(n_partitions: int = 4, nation: str = "SAUDI ARABIA", status: str = "F") 
     fin = [P.field("s_name", "utf8", True), P.field("numwait", i64)]
     st9 = Stage(9, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(8, fin), fetch=100), 9), n_tasks=1)
     return [st1, st2, st3, st4, st5, st6, st7, st8, st9]
+
+
+# ---- q14: join + SUM(CASE WHEN p_type LIKE 'PROMO%' ...) / SUM(...) in fp64 (the 100.00 literal is a Float64) ----------
+Q14_TABLES = {"lineitem": ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"], "part": ["p_partkey", "p_type"]}
+D384 = P.dec(38, 4)
+
+
+def q14(n_partitions: int = 4, date_from: str = "1995-09-01", date_to: str = "1995-10-01", prefix: str = "PROMO%") -> List[Stage]:
+    """benchmarks/queries/q14.sql."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.and_(P.binop(">=", c("l_shipdate"), P.lit_date(date_from)), P.binop("<", c("l_shipdate"), P.lit_date(date_to))),
+                   table_scan("lineitem", Q14_TABLES["lineitem"]), projection=[0, 1, 2])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st2 = Stage(2, P.shuffle_writer(table_scan("part", Q14_TABLES["part"]), 2, [c(0)], Pn))
+    li = [P.field("l_partkey", i64, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    pt = [P.field("p_partkey", i64, True), P.field("p_type", "utf8", True)]
+    j = P.hash_join(P.shuffle_reader(2, pt), P.shuffle_reader(1, li), [[c(0), c(0)]], "Inner", "Partitioned", projection=[1, 3, 4])
+    vol = P.binop("*", c(1), one_minus(c(2)))
+    s3 = P.project([(P.case([[P.like(c(0), prefix), vol]], P.lit_dec(0, 38, 4)), "promo"), (vol, "rev")], j)
+    s3 = P.aggregate("Partial", [], [P.agg("sum", c(0), "promo"), P.agg("sum", c(1), "rev")], s3)
+    st3 = Stage(3, P.shuffle_writer(s3, 3))
+    part = [P.field("promo[sum]", D384, True), P.field("rev[sum]", D384, True)]
+    s4 = P.aggregate("Final", [], [P.agg("sum", None, "promo"), P.agg("sum", None, "rev")], P.coalesce_partitions(P.shuffle_reader(3, part)))
+    s4 = P.project([(P.binop("/", P.binop("*", P.lit_f64(100.0), P.cast(c(0), "f64")), P.cast(c(1), "f64")), "promo_revenue")], s4)
+    return [st1, st2, st3, Stage(4, P.shuffle_writer(s4, 4), n_tasks=1)]
+
+
+# ---- q8: eight-table join, CASE inside SUM, decimal division ------------------------------------------------------
+Q8_TABLES = {"part": ["p_partkey", "p_type"], "supplier": ["s_suppkey", "s_nationkey"],
+             "lineitem": ["l_orderkey", "l_partkey", "l_suppkey", "l_extendedprice", "l_discount"],
+             "orders": ["o_orderkey", "o_custkey", "o_orderdate"], "customer": ["c_custkey", "c_nationkey"],
+             "nation": ["n_nationkey", "n_name", "n_regionkey"], "region": ["r_regionkey", "r_name"]}
+
+
+def q8(n_partitions: int = 4, nation: str = "BRAZIL", region: str = "AMERICA", ptype: str = "ECONOMY ANODIZED STEEL",
+       date_from: str = "1995-01-01", date_to: str = "1996-12-31") -> List[Stage]:
+    """benchmarks/queries/q8.sql -- market share: SUM(CASE WHEN nation = X THEN volume ELSE 0 END) / SUM(volume) per o_year
+    (Decimal128(38,4) / Decimal128(38,4) -> Decimal128(38,8) [EXT])."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.binop("=", c("p_type"), P.lit_utf8(ptype)), table_scan("part", Q8_TABLES["part"]), projection=[0])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st2 = Stage(2, P.shuffle_writer(table_scan("lineitem", Q8_TABLES["lineitem"]), 2, [c(1)], Pn))
+    li = [dict(f, nullable=True) for f in _sch("lineitem", Q8_TABLES["lineitem"])]
+    # S3: part' |x| lineitem -> l_orderkey, l_suppkey, l_extendedprice, l_discount ; by orderkey
+    s3 = P.hash_join(P.shuffle_reader(1, [P.field("p_partkey", i64, True)]), P.shuffle_reader(2, li), [[c(0), c(1)]], "Inner", "Partitioned", projection=[1, 3, 4, 5])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    pl = [P.field("l_orderkey", i64, True), P.field("l_suppkey", i64, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    s4 = P.filter_(P.and_(P.binop(">=", c("o_orderdate"), P.lit_date(date_from)), P.binop("<=", c("o_orderdate"), P.lit_date(date_to))),
+                   table_scan("orders", Q8_TABLES["orders"]))
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    od = [P.field("o_orderkey", i64, True), P.field("o_custkey", i64, True), P.field("o_orderdate", "date32", True)]
+    # S5: orders' |x| (part, lineitem) on orderkey -> o_custkey, o_orderdate, l_suppkey, l_extendedprice, l_discount ; by custkey
+    s5 = P.hash_join(P.shuffle_reader(4, od), P.shuffle_reader(3, pl), [[c(0), c(0)]], "Inner", "Partitioned", projection=[1, 2, 4, 5, 6])
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(0)], Pn))
+    ol = [P.field("o_custkey", i64, True), P.field("o_orderdate", "date32", True), P.field("l_suppkey", i64, True),
+          P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    # S6: customers of the region: region' |x| nation |x| customer -> c_custkey ; by custkey
+    reg = P.filter_(P.binop("=", c("r_name"), P.lit_utf8(region)), table_scan("region", Q8_TABLES["region"]), projection=[0])
+    n1 = P.hash_join(reg, table_scan("nation", Q8_TABLES["nation"]), [[c(0), c("n_regionkey")]], "Inner", "CollectLeft", projection=[1])
+    s6 = P.hash_join(n1, table_scan("customer", Q8_TABLES["customer"]), [[c(0), c("c_nationkey")]], "Inner", "CollectLeft", projection=[1])
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(0)], Pn))
+    # S7: customers' |x| ... on custkey -> o_orderdate, l_suppkey, l_extendedprice, l_discount ; by suppkey
+    s7 = P.hash_join(P.shuffle_reader(6, [P.field("c_custkey", i64, True)]), P.shuffle_reader(5, ol), [[c(0), c(0)]], "Inner", "Partitioned", projection=[2, 3, 4, 5])
+    st7 = Stage(7, P.shuffle_writer(s7, 7, [c(1)], Pn))
+    t7 = [P.field("o_orderdate", "date32", True), P.field("l_suppkey", i64, True), P.field("l_extendedprice", D152, True), P.field("l_discount", D152, True)]
+    # S8: nation n2 |x| supplier -> s_suppkey, n_name ; by suppkey
+    n2 = P.project([(c("n_nationkey"), "n_nationkey"), (c("n_name"), "n_name")], table_scan("nation", Q8_TABLES["nation"]))
+    s8 = P.hash_join(n2, table_scan("supplier", Q8_TABLES["supplier"]), [[c(0), c("s_nationkey")]], "Inner", "CollectLeft", projection=[2, 1])
+    st8 = Stage(8, P.shuffle_writer(s8, 8, [c(0)], Pn))
+    sn = [P.field("s_suppkey", i64, True), P.field("n_name", "utf8", True)]
+    # S9: -> o_year, volume, nation -> partial aggregate
+    s9 = P.hash_join(P.shuffle_reader(8, sn), P.shuffle_reader(7, t7), [[c(0), c(1)]], "Inner", "Partitioned", projection=[1, 2, 4, 5])
+    vol = P.binop("*", c(2), one_minus(c(3)))
+    s9 = P.project([(P.fn("date_part_year", c(1)), "o_year"), (P.case([[P.binop("=", c(0), P.lit_utf8(nation)), vol]], P.lit_dec(0, 38, 4)), "nat_volume"),
+                    (vol, "volume")], s9)
+    gb = [(c(0), "o_year")]
+    s9 = P.aggregate("Partial", gb, [P.agg("sum", c(1), "nat"), P.agg("sum", c(2), "tot")], s9)
+    st9 = Stage(9, P.shuffle_writer(s9, 9, [c(0)], Pn))
+    part = [P.field("o_year", "i32", True), P.field("nat[sum]", D384, True), P.field("tot[sum]", D384, True)]
+    s10 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "nat"), P.agg("sum", None, "tot")], P.shuffle_reader(9, part))
+    s10 = P.project([(c(0), "o_year"), (P.binop("/", c(1), c(2)), "mkt_share")], s10)
+    keys = [P.sort_key(c(0))]
+    s10 = P.sort(keys, s10, preserve_partitioning=True)
+    st10 = Stage(10, P.shuffle_writer(s10, 10))
+    fin = [P.field("o_year", "i32", True), P.field("mkt_share", P.dec(38, 8), True)]
+    st11 = Stage(11, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(10, fin)), 11), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8, st9, st10, st11]
+
+
+def _with_const_key(plan, n_cols: int):
+    """plan + a constant Int64 column: a scalar subquery's single row joins every row through it."""
+    return P.project([(P.col(i), f"c{i}") for i in range(n_cols)] + [(P.lit_i64(1), "__one")], plan)
+
+
+# ---- q11: HAVING sum > (scalar subquery) * 0.0001 -- the scalar joins as a broadcast one-row build side ---------------
+Q11_TABLES = {"partsupp": ["ps_partkey", "ps_suppkey", "ps_availqty", "ps_supplycost"], "supplier": ["s_suppkey", "s_nationkey"],
+              "nation": ["n_nationkey", "n_name"]}
+
+
+def q11(n_partitions: int = 4, nation: str = "GERMANY", fraction: float = 0.0001) -> List[Stage]:
+    """benchmarks/queries/q11.sql -- value = SUM(ps_supplycost * ps_availqty) per part (Decimal128(15,2) x Int32->Decimal128(10,0)
+    = Decimal128(26,2), SUM -> (36,2)); the threshold is fp64 because 0.0001 is a Float64 literal."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    nat = P.filter_(P.binop("=", c("n_name"), P.lit_utf8(nation)), table_scan("nation", Q11_TABLES["nation"]), projection=[0])
+    s1 = P.hash_join(nat, table_scan("supplier", Q11_TABLES["supplier"]), [[c(0), c("s_nationkey")]], "Inner", "CollectLeft", projection=[1])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st2 = Stage(2, P.shuffle_writer(table_scan("partsupp", Q11_TABLES["partsupp"]), 2, [c(1)], Pn))
+    ps = [dict(f, nullable=True) for f in _sch("partsupp", Q11_TABLES["partsupp"])]
+    s3 = P.hash_join(P.shuffle_reader(1, [P.field("s_suppkey", i64, True)]), P.shuffle_reader(2, ps), [[c(0), c(1)]], "Inner", "Partitioned", projection=[1, 3, 4])
+    s3 = P.project([(c(0), "ps_partkey"), (P.binop("*", c(2), P.cast(c(1), P.dec(10, 0))), "v")], s3)
+    gb = [(c(0), "ps_partkey")]
+    s3 = P.aggregate("Partial", gb, [P.agg("sum", c(1), "value")], s3)
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    D362 = P.dec(36, 2)
+    part = [P.field("ps_partkey", i64, True), P.field("value[sum]", D362, True)]
+    s4 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "value")], P.shuffle_reader(3, part))
+    st4 = Stage(4, P.shuffle_writer(s4, 4))
+    pv = [P.field("ps_partkey", i64, True), P.field("value", D362, True)]
+    s5 = P.aggregate("Partial", [], [P.agg("sum", c(1), "total")], P.shuffle_reader(4, pv))
+    st5 = Stage(5, P.shuffle_writer(s5, 5))
+    s6 = P.aggregate("Final", [], [P.agg("sum", None, "total")], P.coalesce_partitions(P.shuffle_reader(5, [P.field("total[sum]", P.dec(38, 2), True)])))
+    s6 = P.project([(P.binop("*", P.cast(c(0), "f64"), P.lit_f64(fraction)), "thr"), (P.lit_i64(1), "__one")], s6)
+    st6 = Stage(6, P.shuffle_writer(s6, 6), n_tasks=1)
+    thr = [P.field("thr", "f64", True), P.field("__one", i64, True)]
+    probe = _with_const_key(P.shuffle_reader(4, pv), 2)
+    # filter columns: thr, __one | c0 (ps_partkey), c1 (value), __one
+    j = P.hash_join(P.shuffle_reader(6, thr, broadcast=True), probe, [[c(1), c(2)]], "Inner", "CollectLeft",
+                    filter=P.binop(">", P.cast(c(3), "f64"), c(0)), projection=[2, 3])
+    j = P.project([(c(0), "ps_partkey"), (c(1), "value")], j)
+    keys = [P.sort_key(c(1), asc=False)]
+    st7 = Stage(7, P.shuffle_writer(P.sort(keys, j, preserve_partitioning=True), 7))
+    st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, pv)), 8), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8]
+
+
+# ---- q15: the revenue0 view evaluated once, its MAX joined back as a one-row build side --------------------------
+Q15_TABLES = {"lineitem": ["l_suppkey", "l_extendedprice", "l_discount", "l_shipdate"], "supplier": ["s_suppkey", "s_name", "s_address", "s_phone"]}
+
+
+def q15(n_partitions: int = 4, date_from: str = "1996-01-01", date_to: str = "1996-04-01") -> List[Stage]:
+    """benchmarks/queries/q15.sql (CREATE VIEW revenue0 ...; SELECT ...; DROP VIEW -- benchmarks/src/bin/tpch.rs:720-749 runs the
+    three statements; the view is inlined here)."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.and_(P.binop(">=", c("l_shipdate"), P.lit_date(date_from)), P.binop("<", c("l_shipdate"), P.lit_date(date_to))),
+                   table_scan("lineitem", Q15_TABLES["lineitem"]), projection=[0, 1, 2])
+    s1 = P.project([(c(0), "supplier_no"), (P.binop("*", c(1), one_minus(c(2))), "rev")], s1)
+    gb = [(c(0), "supplier_no")]
+    s1 = P.aggregate("Partial", gb, [P.agg("sum", c(1), "total_revenue")], s1)
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    part = [P.field("supplier_no", i64, True), P.field("total_revenue[sum]", D384, True)]
+    s2 = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "total_revenue")], P.shuffle_reader(1, part))
+    st2 = Stage(2, P.shuffle_writer(s2, 2))
+    rv = [P.field("supplier_no", i64, True), P.field("total_revenue", D384, True)]
+    st3 = Stage(3, P.shuffle_writer(P.aggregate("Partial", [], [P.agg("max", c(1), "m")], P.shuffle_reader(2, rv)), 3))
+    s4 = P.aggregate("Final", [], [P.agg("max", None, "m")], P.coalesce_partitions(P.shuffle_reader(3, [P.field("m[max]", D384, True)])))
+    s4 = P.project([(c(0), "m"), (P.lit_i64(1), "__one")], s4)
+    st4 = Stage(4, P.shuffle_writer(s4, 4), n_tasks=1)
+    mx = [P.field("m", D384, True), P.field("__one", i64, True)]
+    # filter columns: m, __one | c0 (supplier_no), c1 (total_revenue), __one
+    j = P.hash_join(P.shuffle_reader(4, mx, broadcast=True), _with_const_key(P.shuffle_reader(2, rv), 2), [[c(1), c(2)]], "Inner", "CollectLeft",
+                    filter=P.binop("=", c(3), c(0)), projection=[2, 3])
+    st5 = Stage(5, P.shuffle_writer(j, 5, [c(0)], Pn))
+    st6 = Stage(6, P.shuffle_writer(table_scan("supplier", Q15_TABLES["supplier"]), 6, [c(0)], Pn))
+    sp = [dict(f, nullable=True) for f in _sch("supplier", Q15_TABLES["supplier"])]
+    rj = [P.field("c0", i64, True), P.field("c1", D384, True)]
+    s7 = P.hash_join(P.shuffle_reader(5, rj), P.shuffle_reader(6, sp), [[c(0), c(0)]], "Inner", "Partitioned", projection=[2, 3, 4, 5, 1])
+    s7 = P.project([(c(0), "s_suppkey"), (c(1), "s_name"), (c(2), "s_address"), (c(3), "s_phone"), (c(4), "total_revenue")], s7)
+    keys = [P.sort_key(c(0))]
+    st7 = Stage(7, P.shuffle_writer(P.sort(keys, s7, preserve_partitioning=True), 7))
+    fin = [P.field("s_suppkey", i64, True), P.field("s_name", "utf8", True), P.field("s_address", "utf8", True), P.field("s_phone", "utf8", True),
+           P.field("total_revenue", D384, True)]
+    st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, fin)), 8), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8]
+
+
+# ---- q2: correlated MIN subquery decorrelated into a per-part aggregate joined back -------------------------------
+Q2_TABLES = {"part": ["p_partkey", "p_mfgr", "p_type", "p_size"],
+             "supplier": ["s_suppkey", "s_name", "s_address", "s_nationkey", "s_phone", "s_acctbal", "s_comment"],
+             "partsupp": ["ps_partkey", "ps_suppkey", "ps_supplycost"], "nation": ["n_nationkey", "n_name", "n_regionkey"],
+             "region": ["r_regionkey", "r_name"]}
+
+
+def q2(n_partitions: int = 4, size: int = 15, type_suffix: str = "%BRASS", region: str = "EUROPE") -> List[Stage]:
+    """benchmarks/queries/q2.sql -- minimum-cost supplier of the region per part, top 100 by s_acctbal DESC, n_name, s_name, p_partkey."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    reg = P.filter_(P.binop("=", c("r_name"), P.lit_utf8(region)), table_scan("region", Q2_TABLES["region"]), projection=[0])
+    nat = P.hash_join(reg, table_scan("nation", Q2_TABLES["nation"]), [[c(0), c("n_regionkey")]], "Inner", "CollectLeft", projection=[1, 2])
+    # nation'(n_nationkey, n_name) |x| supplier -> s_suppkey, s_name, s_address, s_phone, s_acctbal, s_comment, n_name ; by suppkey
+    s1 = P.hash_join(nat, table_scan("supplier", Q2_TABLES["supplier"]), [[c(0), c("s_nationkey")]], "Inner", "CollectLeft", projection=[2, 3, 4, 6, 7, 8, 1])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    sup = [P.field("s_suppkey", i64, True), P.field("s_name", "utf8", True), P.field("s_address", "utf8", True), P.field("s_phone", "utf8", True),
+           P.field("s_acctbal", D152, True), P.field("s_comment", "utf8", True), P.field("n_name", "utf8", True)]
+    st2 = Stage(2, P.shuffle_writer(table_scan("partsupp", Q2_TABLES["partsupp"]), 2, [c(1)], Pn))
+    ps = [dict(f, nullable=True) for f in _sch("partsupp", Q2_TABLES["partsupp"])]
+    # S3: suppliers of the region |x| partsupp -> ps_partkey, ps_supplycost, s_acctbal, s_name, n_name, s_address, s_phone, s_comment ; by partkey
+    s3 = P.hash_join(P.shuffle_reader(1, sup), P.shuffle_reader(2, ps), [[c(0), c(1)]], "Inner", "Partitioned", projection=[7, 9, 4, 1, 6, 2, 3, 5])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    e = [P.field("ps_partkey", i64, True), P.field("ps_supplycost", D152, True), P.field("s_acctbal", D152, True), P.field("s_name", "utf8", True),
+         P.field("n_name", "utf8", True), P.field("s_address", "utf8", True), P.field("s_phone", "utf8", True), P.field("s_comment", "utf8", True)]
+    s4 = P.filter_(P.and_(P.binop("=", c("p_size"), P.lit_i32(size)), P.like(c("p_type"), type_suffix)), table_scan("part", Q2_TABLES["part"]), projection=[0, 1])
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0)], Pn))
+    pt = [P.field("p_partkey", i64, True), P.field("p_mfgr", "utf8", True)]
+    # S5 (everything co-partitioned on the part key): min cost per part, joined back with `cost = min`
+    m = P.aggregate("SinglePartitioned", [(c(0), "ps_partkey")], [P.agg("min", c(1), "min_cost")], P.shuffle_reader(3, e))
+    j1 = P.hash_join(P.shuffle_reader(4, pt), P.shuffle_reader(3, e), [[c(0), c(0)]], "Inner", "Partitioned", projection=[0, 1, 3, 4, 5, 6, 7, 8, 9])
+    # filter columns: ps_partkey, min_cost | p_partkey, p_mfgr, cost, s_acctbal, s_name, n_name, s_address, s_phone, s_comment
+    j2 = P.hash_join(m, j1, [[c(0), c(0)]], "Inner", "Partitioned", filter=P.binop("=", c(4), c(1)), projection=[5, 6, 7, 2, 3, 8, 9, 10])
+    s5 = P.project([(c(0), "s_acctbal"), (c(1), "s_name"), (c(2), "n_name"), (c(3), "p_partkey"), (c(4), "p_mfgr"), (c(5), "s_address"),
+                    (c(6), "s_phone"), (c(7), "s_comment")], j2)
+    keys = [P.sort_key(c(0), asc=False), P.sort_key(c(2)), P.sort_key(c(1)), P.sort_key(c(3))]
+    st5 = Stage(5, P.shuffle_writer(P.sort(keys, s5, fetch=100, preserve_partitioning=True), 5))
+    fin = [P.field("s_acctbal", D152, True), P.field("s_name", "utf8", True), P.field("n_name", "utf8", True), P.field("p_partkey", i64, True),
+           P.field("p_mfgr", "utf8", True), P.field("s_address", "utf8", True), P.field("s_phone", "utf8", True), P.field("s_comment", "utf8", True)]
+    st6 = Stage(6, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(5, fin), fetch=100), 6), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6]
+
+
+# ---- q20: nested IN subqueries as semi joins, correlated SUM as a two-key aggregate joined with an fp64 residual ----
+Q20_TABLES = {"supplier": ["s_suppkey", "s_name", "s_address", "s_nationkey"], "nation": ["n_nationkey", "n_name"],
+              "partsupp": ["ps_partkey", "ps_suppkey", "ps_availqty"], "part": ["p_partkey", "p_name"],
+              "lineitem": ["l_partkey", "l_suppkey", "l_quantity", "l_shipdate"]}
+
+
+def q20(n_partitions: int = 4, pattern: str = "forest%", nation: str = "CANADA", date_from: str = "1994-01-01", date_to: str = "1995-01-01") -> List[Stage]:
+    """benchmarks/queries/q20.sql -- `ps_availqty > 0.5 * SUM(l_quantity)`: 0.5 is a Float64 literal, so both sides compare as fp64."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    s1 = P.filter_(P.like(c("p_name"), pattern), table_scan("part", Q20_TABLES["part"]), projection=[0])
+    st1 = Stage(1, P.shuffle_writer(s1, 1, [c(0)], Pn))
+    st2 = Stage(2, P.shuffle_writer(table_scan("partsupp", Q20_TABLES["partsupp"]), 2, [c(0)], Pn))
+    ps = [dict(f, nullable=True) for f in _sch("partsupp", Q20_TABLES["partsupp"])]
+    s3 = P.hash_join(P.shuffle_reader(1, [P.field("p_partkey", i64, True)]), P.shuffle_reader(2, ps), [[c(0), c(0)]], "RightSemi", "Partitioned")
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0), c(1)], Pn))
+    s4 = P.filter_(P.and_(P.binop(">=", c("l_shipdate"), P.lit_date(date_from)), P.binop("<", c("l_shipdate"), P.lit_date(date_to))),
+                   table_scan("lineitem", Q20_TABLES["lineitem"]), projection=[0, 1, 2])
+    gb = [(c(0), "l_partkey"), (c(1), "l_suppkey")]
+    s4 = P.aggregate("Partial", gb, [P.agg("sum", c(2), "q")], s4)
+    st4 = Stage(4, P.shuffle_writer(s4, 4, [c(0), c(1)], Pn))
+    part = [P.field("l_partkey", i64, True), P.field("l_suppkey", i64, True), P.field("q[sum]", P.dec(25, 2), True)]
+    agg = P.aggregate("FinalPartitioned", gb, [P.agg("sum", None, "q")], P.shuffle_reader(4, part))
+    # filter columns: l_partkey, l_suppkey, q | ps_partkey, ps_suppkey, ps_availqty
+    j = P.hash_join(agg, P.shuffle_reader(3, ps), [[c(0), c(0)], [c(1), c(1)]], "Inner", "Partitioned",
+                    filter=P.binop(">", P.cast(c(5), "f64"), P.binop("*", P.lit_f64(0.5), P.cast(c(2), "f64"))), projection=[4])
+    st5 = Stage(5, P.shuffle_writer(j, 5, [c(0)], Pn))
+    nat = P.filter_(P.binop("=", c("n_name"), P.lit_utf8(nation)), table_scan("nation", Q20_TABLES["nation"]), projection=[0])
+    s6 = P.hash_join(nat, table_scan("supplier", Q20_TABLES["supplier"]), [[c(0), c("s_nationkey")]], "Inner", "CollectLeft", projection=[1, 2, 3])
+    st6 = Stage(6, P.shuffle_writer(s6, 6, [c(0)], Pn))
+    sp = [P.field("s_suppkey", i64, True), P.field("s_name", "utf8", True), P.field("s_address", "utf8", True)]
+    s7 = P.hash_join(P.shuffle_reader(5, [P.field("ps_suppkey", i64, True)]), P.shuffle_reader(6, sp), [[c(0), c(0)]], "RightSemi", "Partitioned")
+    s7 = P.project([(c(1), "s_name"), (c(2), "s_address")], s7)
+    keys = [P.sort_key(c(0))]
+    st7 = Stage(7, P.shuffle_writer(P.sort(keys, s7, preserve_partitioning=True), 7))
+    fin = [P.field("s_name", "utf8", True), P.field("s_address", "utf8", True)]
+    st8 = Stage(8, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(7, fin)), 8), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7, st8]
+
+
+# ---- q22: substring, uncorrelated scalar AVG (one-row build side), NOT EXISTS as an anti join -----------------------
+Q22_TABLES = {"customer": ["c_custkey", "c_phone", "c_acctbal"], "orders": ["o_custkey"]}
+
+
+def q22(n_partitions: int = 4, codes=("13", "31", "23", "29", "30", "18", "17")) -> List[Stage]:
+    """benchmarks/queries/q22.sql."""
+    c, Pn = P.col, n_partitions
+    i64 = "i64"
+    code = P.fn("substr", c("c_phone"), P.lit_i64(1), P.lit_i64(2))
+    in_codes = P.in_list(code, [P.lit_utf8(v) for v in codes])
+    cust = table_scan("customer", Q22_TABLES["customer"])
+    s1 = P.filter_(P.and_(in_codes, P.binop(">", c("c_acctbal"), P.lit_dec(0, 15, 2))), cust, projection=[2])
+    st1 = Stage(1, P.shuffle_writer(P.aggregate("Partial", [], [P.agg("avg", c(0), "a")], s1), 1))
+    st_avg = [P.field("a[count]", "u64", True), P.field("a[sum]", P.dec(25, 2), True)]
+    s2 = P.aggregate("Final", [], [P.agg("avg", None, "a", D152)], P.coalesce_partitions(P.shuffle_reader(1, st_avg)))
+    s2 = P.project([(c(0), "a"), (P.lit_i64(1), "__one")], s2)
+    st2 = Stage(2, P.shuffle_writer(s2, 2), n_tasks=1)
+    av = [P.field("a", P.dec(19, 6), True), P.field("__one", i64, True)]
+    s3 = P.filter_(in_codes, cust)
+    s3 = P.project([(c(0), "c_custkey"), (P.fn("substr", c(1), P.lit_i64(1), P.lit_i64(2)), "cntrycode"), (c(2), "c_acctbal"), (P.lit_i64(1), "__one")], s3)
+    # filter columns: a, __one | c_custkey, cntrycode, c_acctbal, __one
+    s3 = P.hash_join(P.shuffle_reader(2, av, broadcast=True), s3, [[c(1), c(3)]], "Inner", "CollectLeft", filter=P.binop(">", c(4), c(0)), projection=[2, 3, 4])
+    st3 = Stage(3, P.shuffle_writer(s3, 3, [c(0)], Pn))
+    cu = [P.field("c_custkey", i64, True), P.field("cntrycode", "utf8", True), P.field("c_acctbal", D152, True)]
+    st4 = Stage(4, P.shuffle_writer(table_scan("orders", Q22_TABLES["orders"]), 4, [c(0)], Pn))
+    s5 = P.hash_join(P.shuffle_reader(4, [P.field("o_custkey", i64, True)]), P.shuffle_reader(3, cu), [[c(0), c(0)]], "RightAnti", "Partitioned")
+    gb = [(c(1), "cntrycode")]
+    s5 = P.aggregate("Partial", gb, [P.agg("count", None, "numcust"), P.agg("sum", c(2), "totacctbal")], s5)
+    st5 = Stage(5, P.shuffle_writer(s5, 5, [c(0)], Pn))
+    part = [P.field("cntrycode", "utf8", True), P.field("numcust[count]", i64), P.field("totacctbal[sum]", P.dec(25, 2), True)]
+    s6 = P.aggregate("FinalPartitioned", [(c(0), "cntrycode")], [P.agg("count", None, "numcust"), P.agg("sum", None, "totacctbal")], P.shuffle_reader(5, part))
+    keys = [P.sort_key(c(0))]
+    st6 = Stage(6, P.shuffle_writer(P.sort(keys, s6, preserve_partitioning=True), 6))
+    fin = [P.field("cntrycode", "utf8", True), P.field("numcust", i64), P.field("totacctbal", P.dec(25, 2), True)]
+    st7 = Stage(7, P.shuffle_writer(P.sort_preserving_merge(keys, P.shuffle_reader(6, fin)), 7), n_tasks=1)
+    return [st1, st2, st3, st4, st5, st6, st7]
+
+
+# ---- registry: query name -> (tables it scans with the columns it references, stage-plan builder) -------------
+QUERIES = {
+    "q1": ({"lineitem": Q1_COLUMNS}, q1), "q3": (Q3_TABLES, q3), "q4": (Q4_TABLES, q4), "q5": (Q5_TABLES, q5),
+    "q6": ({"lineitem": Q6_COLUMNS}, q6), "q7": (Q7_TABLES, q7), "q9": (Q9_TABLES, q9), "q10": (Q10_TABLES, q10),
+    "q12": (Q12_TABLES, q12), "q13": (Q13_TABLES, q13), "q16": (Q16_TABLES, q16), "q17": (Q17_TABLES, q17),
+    "q18": (Q18_TABLES, q18), "q19": (Q19_TABLES, q19), "q21": (Q21_TABLES, q21),
+    "q2": (Q2_TABLES, q2), "q8": (Q8_TABLES, q8), "q11": (Q11_TABLES, q11), "q14": (Q14_TABLES, q14), "q15": (Q15_TABLES, q15),
+    "q20": (Q20_TABLES, q20), "q22": (Q22_TABLES, q22),
+}
+
+
+def union_tables(names) -> dict:
+    """{table: [columns]} covering every query in `names` (each table registered once, scans carry projections)."""
+    out: dict = {}
+    for n in names:
+        for t, cols in QUERIES[n][0].items():
+            out.setdefault(t, [])
+            out[t] += [c for c in cols if c not in out[t]]
+    return out
+
+
+def base_rows(name: str, rows_of: dict) -> int:
+    """Base-table rows a query scans (the numerator of the rows/s metric)."""
+    return sum(rows_of[t] for t in QUERIES[name][0])

@@ -79,6 +79,16 @@ uint64_t b200_engine_kernel_launches(b200_engine* e);
  * "vm" (tile VM pipeline_kernel); "ingest_bytes_saved": host->device bytes NOT sent because
  * Decimal128 values were narrowed on the host and widened on the device.  Unknown names return 0. */
 uint64_t b200_engine_counter(b200_engine* e, const char* name);
+/* Per-kernel-family device time (CUDA events on the launching stream) and algorithmic bytes, accumulated since the
+ * last reset while the config key "b200.metrics.kernel_timing" is "on" (radix partition, join build / probe,
+ * group-by, sort passes, ...): the measurement behind the per-operator roofline figures. */
+typedef struct b200_kernel_stat {
+  char name[48];
+  uint64_t elapsed_ns;
+  uint64_t launches;
+  uint64_t algorithmic_bytes;
+} b200_kernel_stat;
+int b200_engine_kernel_stats(b200_engine* e, b200_kernel_stat* out, int cap, int* n_out, int reset);
 /* session config (TaskDefinition.props), e.g. "datafusion.execution.batch_size" */
 int b200_engine_set_config(b200_engine* e, const char* key, const char* value);
 
