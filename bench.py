@@ -35,6 +35,10 @@ SF10_MSF = 10000
 ROWS_SF10 = 59_986_052
 BYTES_PER_ROW = 78  # Arrow layout of the 7 referenced columns
 METRIC = "tpch_q1_rows_per_sec"
+try:
+    START_AFFINITY = os.sched_getaffinity(0)
+except Exception:  # pragma: no cover
+    START_AFFINITY = None
 
 
 def log(*a):
@@ -404,6 +408,10 @@ def run_b200(args):
     # ---- parity of the TIMED path's result with the CPU oracle on the same (global) table: untimed ----
     parity = {"checked": False}
     if rank == 0 and not args.no_parity:
+        try:
+            os.sched_setaffinity(0, START_AFFINITY)
+        except Exception:
+            pass
         threads = usable_cpus()
         need = total_rows * 100
         if host_mem_available() > need * 1.3:
@@ -451,8 +459,13 @@ def run_b200(args):
                                 "recv_bytes_per_step_rank0": exch["recv"] / args.steps}
         if e2e:
             line["e2e"] = e2e
-        # CPU baseline beside it (rank 0): bounded sample of the same workload
+        # CPU baseline beside it (rank 0): bounded sample of the same workload, on every CPU this process started with
+        # (creating the engine bound this thread to the GPU's NUMA node)
         if not args.no_cpu_baseline:
+            try:
+                os.sched_setaffinity(0, START_AFFINITY)
+            except Exception:
+                pass
             threads = usable_cpus()
             rows = ROWS_SF10 // 4
             t, _ = cpu_q1(SF10_MSF, 0, rows, threads, steps=2, warmup=1)

@@ -79,42 +79,6 @@ struct GatherCols {
   int n;
 };
 void launch_gather_multi(const GatherCols& cols, const int64_t* idx, int64_t n, cudaStream_t st);
-// ---- one-pass stable radix partition + exchange / export packing (shuffle.cu) ---------------------
-static const int PART_MAX_STR_COLS = 16;
-static const uint32_t PART_MAX_FANOUT = 4096;   // per-warp counters of the scatter kernel must fit shared memory
-struct PartStrCol {
-  const void* data;       // views (16 B/row) or Arrow int32 offsets
-  const uint8_t* valid;
-  int is_view;
-  int _pad;
-};
-struct PartStrCols {
-  PartStrCol c[PART_MAX_STR_COLS];
-  int n;
-};
-uint32_t partition_n_tiles(int64_t n);
-// tile_hist: [P][n_tiles] u32 (may be nullptr when only totals are wanted); counts: [P] u64, pre-zeroed;
-// str_bytes: [sc.n][P] u64, pre-zeroed; pid == nullptr means "everything goes to partition 0"
-cudaError_t launch_partition_hist(const uint32_t* pid, int64_t n, uint32_t P, uint32_t* tile_hist, unsigned long long* counts, const PartStrCols& sc,
-                                  unsigned long long* str_bytes, cudaStream_t st);
-// offsets: exclusive scan of tile_hist (partition-major); cols: every column to move (validity bytes as their own
-// width-1 entries; only in/out/width are used); dest_out (optional): the destination row of every input row
-cudaError_t launch_partition_scatter(const uint32_t* pid, int64_t n, uint32_t P, const uint64_t* offsets, const GatherCols& cols, uint32_t* dest_out,
-                                     cudaStream_t st);
-enum PackKind : int32_t { PK_COPY = 0, PK_STR_VIEWS = 1, PK_STR_UTF8 = 2, PK_BITMAP = 3 };
-struct PackJob {
-  const void* src;        // bytes / views / int32 offsets (already positioned at the slice's first row)
-  const uint8_t* valid;   // strings: validity bytes of the slice or nullptr
-  const uint8_t* chars;   // PK_STR_UTF8: chars base the offsets are relative to
-  void* dst;              // PK_COPY: destination; strings: int32 offsets out (rows + 1, starting at 0)
-  void* dst2;             // strings: characters out
-  uint64_t bytes;         // PK_COPY: bytes to copy; strings: capacity of the character area
-  int64_t rows;           // strings, PK_BITMAP
-  int32_t kind;
-  int32_t _pad;
-};
-void launch_pack_jobs(const PackJob* jobs_dev, int n_jobs, cudaStream_t st);
-
 // ingest: int32 / int64 (width 4 / 8) -> sign-extended 16-byte Decimal128 values
 void launch_widen_to_i128(const void* in, int width, void* out, int64_t n, cudaStream_t st);
 // out[i] = in[i] - in[0] for i < n_plus_1; first_last[0..1] = in[0], in[n_plus_1 - 1] (device memory)
@@ -141,6 +105,52 @@ struct JoinKeys {
   int n_keys;
   int null_equals_null;
 };
+// ---- one-pass stable radix partition + exchange / export packing (shuffle.cu) ---------------------
+static const int PART_MAX_STR_COLS = 16;
+static const uint32_t PART_MAX_FANOUT = 4096;   // per-warp counters of the scatter kernel must fit shared memory
+struct PartStrCol {
+  const void* data;       // views (16 B/row) or Arrow int32 offsets
+  const uint8_t* valid;
+  int is_view;
+  int _pad;
+};
+struct PartStrCols {
+  PartStrCol c[PART_MAX_STR_COLS];
+  int n;
+};
+// Where a row's partition id comes from: a materialised uint32 column (computed by the child's pipeline kernel), or --
+// when the shuffle keys are plain integer-like columns -- the key columns themselves: the partition kernels then apply the
+// row hash of csrc/common/hash.hpp (first key sets, later keys combine, NULL skips) and `% P` on the fly, and the
+// materialising pass disappears.
+struct PidSrc {
+  const uint32_t* pid;
+  KeyCol keys[VM_MAX_KEYS];
+  int n_keys;
+  int _pad;
+};
+uint32_t partition_n_tiles(int64_t n);
+// tile_hist: [P][n_tiles] u32 (may be nullptr when only totals are wanted); counts: [P] u64, pre-zeroed;
+// str_bytes: [sc.n][P] u64, pre-zeroed; pid.pid == nullptr && pid.n_keys == 0 means "everything goes to partition 0"
+cudaError_t launch_partition_hist(const PidSrc& pid, int64_t n, uint32_t P, uint32_t* tile_hist, unsigned long long* counts, const PartStrCols& sc,
+                                  unsigned long long* str_bytes, cudaStream_t st);
+// offsets: exclusive scan of tile_hist (partition-major); cols: every column to move (validity bytes as their own
+// width-1 entries; only in/out/width are used); dest_out (optional): the destination row of every input row
+cudaError_t launch_partition_scatter(const PidSrc& pid, int64_t n, uint32_t P, const uint64_t* offsets, const GatherCols& cols, uint32_t* dest_out,
+                                     cudaStream_t st);
+enum PackKind : int32_t { PK_COPY = 0, PK_STR_VIEWS = 1, PK_STR_UTF8 = 2, PK_BITMAP = 3 };
+struct PackJob {
+  const void* src;        // bytes / views / int32 offsets (already positioned at the slice's first row)
+  const uint8_t* valid;   // strings: validity bytes of the slice or nullptr
+  const uint8_t* chars;   // PK_STR_UTF8: chars base the offsets are relative to
+  void* dst;              // PK_COPY: destination; strings: int32 offsets out (rows + 1, starting at 0)
+  void* dst2;             // strings: characters out
+  uint64_t bytes;         // PK_COPY: bytes to copy; strings: capacity of the character area
+  int64_t rows;           // strings, PK_BITMAP
+  int32_t kind;
+  int32_t _pad;
+};
+void launch_pack_jobs(const PackJob* jobs_dev, int n_jobs, cudaStream_t st);
+
 void launch_join_build(const uint64_t* build_hash, const uint8_t* build_ok, int64_t n_build, int32_t* heads, uint64_t n_buckets, int32_t* next, cudaStream_t st);
 // pass 1: counts per probe row (+ marks); pass 2: write pairs at offsets
 void launch_join_probe_count(const JoinKeys& K, const uint64_t* build_hash, const int32_t* heads, uint64_t n_buckets, const int32_t* next,
@@ -148,6 +158,27 @@ void launch_join_probe_count(const JoinKeys& K, const uint64_t* build_hash, cons
 void launch_join_probe_write(const JoinKeys& K, const uint64_t* build_hash, const int32_t* heads, uint64_t n_buckets, const int32_t* next,
                              const uint64_t* probe_hash, const uint8_t* probe_ok, int64_t n_probe, const uint64_t* offsets,
                              int64_t* out_build_idx, int64_t* out_probe_idx, cudaStream_t st);
+// ---- high-cardinality group-by over plain columns (groupby.cu) ---------------------------------------
+static const int GB_MAX_ACC = 8;
+struct GroupBySpec {
+  FusedCol cols[FUSED_MAX_COLS];   // data + width of every referenced column (no validity, 4 / 8 / 16 bytes wide)
+  int n_cols;
+  int n_filters;
+  int f_col[FUSED_MAX_FILTERS], f_op[FUSED_MAX_FILTERS];   // op: 0 EQ 1 NE 2 LT 3 LE 4 GT 5 GE
+  int64_t f_imm[FUSED_MAX_FILTERS];
+  int n_keys;                       // 1 or 2 (two keys: both must lie in [0, 2^32), checked per row)
+  int key_col[2];
+  int n_prod;                       // decimal products: kind 0 a*(lit-b), 1 a*(lit+b), 2 a*b; a_src 1 = previous product
+  int p_kind[2], p_a_src[2], p_a_col[2], p_b_col[2];
+  int64_t p_lit[2];
+  int n_acc;
+  int a_src[GB_MAX_ACC], a_col[GB_MAX_ACC];   // src: 0 column, 1 / 2 product, 3 COUNT
+  int64_t n_rows;
+  AggTable table;
+  RunStatus* status;
+};
+cudaError_t launch_groupby(const GroupBySpec& S, int sm_count, cudaStream_t st);
+
 // ---- single-pass join (join.cu) -----------------------------------------------------------------
 struct JoinNode {   // one per build row
   uint64_t tag;     // exact mode: 64-bit image of the (single, integer-like) key; else the row hash
@@ -194,6 +225,31 @@ void radix_sort_pairs_u64(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, 
                           uint64_t* scan_scratch, cudaStream_t st, bool* result_in_a, uint64_t* launches);
 void launch_iota_u32(uint32_t* out, int64_t n, cudaStream_t st);
 void launch_u32_to_i64(const uint32_t* in, int64_t* out, int64_t n, cudaStream_t st);
+
+// ---- Parquet page decode (parquet.cu) ----------------------------------------------------------------
+enum PqOutKind : int32_t { PQ_OUT_I32 = 0, PQ_OUT_I64 = 1, PQ_OUT_F64 = 2, PQ_OUT_DEC128 = 3, PQ_OUT_STRVIEW = 4, PQ_OUT_BOOL8 = 5 };
+struct PqPage {
+  const uint8_t* data;      // page payload in HBM (after the Thrift page header)
+  uint32_t n_values;        // values including NULLs (dictionary pages: entries)
+  uint32_t def_off, def_len;  // definition-level section inside the payload; len 0 = required column / no levels
+  uint32_t val_off, val_len;  // values section
+  uint32_t encoding;        // 0 PLAIN, 1 dictionary indices
+  int64_t row0;             // first row of the page inside the column (dictionary pages: first entry in the dictionary array)
+  int64_t dict_base;        // data pages: first entry of their chunk's dictionary
+};
+struct PqColumn {
+  int32_t phys;             // parquet physical type (pq::PhysType)
+  int32_t type_length;      // FIXED_LEN_BYTE_ARRAY
+  int32_t out_kind;         // PqOutKind
+  int32_t _pad;
+  void* dict;               // decoded dictionary entries (output type; byte arrays as 16-byte views)
+};
+void launch_pq_levels(const PqPage* pages, int n_pages, uint8_t* valid, uint32_t* nonnull, unsigned long long* total_nonnull, cudaStream_t st);
+void launch_pq_page_scan(const uint32_t* nonnull, int n_pages, unsigned long long* dense_base, cudaStream_t st);
+void launch_pq_dict(const PqColumn& C, const PqPage* dict_pages, int n_dicts, cudaStream_t st);
+void launch_pq_values(const PqColumn& C, const PqPage* pages, int n_pages, const unsigned long long* dense_base, const uint32_t* nonnull, void* out, cudaStream_t st);
+void launch_pq_expand(const PqPage* pages, int n_pages, const unsigned long long* dense_base, const uint8_t* valid, const void* dense, void* out, int width,
+                      cudaStream_t st);
 
 // ---- synthetic TPC-H input ----------------------------------------------------------------------
 void launch_tpch_fixed(int table, int col, int kind, int64_t msf, int64_t row0, int64_t n, void* out, cudaStream_t st);

@@ -152,7 +152,7 @@ struct RunStatus {
   unsigned long long out_rows;   // materialize sink: rows written
   unsigned long long in_active;  // rows that passed all filters
   unsigned int pack_overflow;    // OP_STR_PACK8 met a string longer than 7 bytes: re-lower without packing
-  unsigned int _pad;
+  unsigned int _pad;             // (keeps the struct 8-byte aligned; the group-by kernel reports "outside my pattern" through pack_overflow too)
 };
 
 struct Program {

@@ -12,7 +12,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../common/hash.hpp"
 #include "kernels.h"
+#include "keyimg.cuh"
 
 namespace b200 {
 
@@ -20,6 +22,15 @@ static const int PT_BLOCK = 256;                      // 8 warps
 static const int PT_WARPS = PT_BLOCK / 32;
 static const int PT_ROUNDS = 8;                       // rows per thread
 static const int PT_TILE = PT_BLOCK * PT_ROUNDS;      // 2048 rows per tile; warp w owns rows [w*256, (w+1)*256)
+
+__device__ __forceinline__ uint32_t pid_of(const PidSrc& ps, int64_t i, uint32_t P) {
+  if (ps.pid) return ps.pid[i];
+  if (ps.n_keys == 0) return 0u;
+  uint64_t h = jkey_valid(ps.keys[0], i) ? hash_i64((int64_t)jkey_image(ps.keys[0], i)) : 0ull;
+  for (int k = 1; k < ps.n_keys; k++)
+    if (jkey_valid(ps.keys[k], i)) h = combine_hashes(hash_i64((int64_t)jkey_image(ps.keys[k], i)), h);
+  return (uint32_t)(h % (uint64_t)P);
+}
 
 __device__ __forceinline__ uint32_t str_len_of(const PartStrCol& c, int64_t i) {
   if (c.valid && !c.valid[i]) return 0u;
@@ -30,7 +41,7 @@ __device__ __forceinline__ uint32_t str_len_of(const PartStrCol& c, int64_t i) {
 
 // tile_hist[p * n_tiles + tile] = rows of partition p in the tile; counts[p] += the same;
 // str_bytes[c * P + p] += string bytes of column c that go to partition p (ShuffleWritePartition.num_bytes)
-__global__ void __launch_bounds__(PT_BLOCK) part_tile_hist_kernel(const uint32_t* __restrict__ pid, int64_t n, uint32_t P, uint32_t n_tiles, uint32_t* __restrict__ tile_hist,
+__global__ void __launch_bounds__(PT_BLOCK) part_tile_hist_kernel(const PidSrc pid, int64_t n, uint32_t P, uint32_t n_tiles, uint32_t* __restrict__ tile_hist,
                                                                  unsigned long long* __restrict__ counts, PartStrCols sc, unsigned long long* __restrict__ str_bytes) {
   extern __shared__ unsigned int sh[];  // [P] counts, then [n_str][P] byte sums (as 2 x u32: lo/hi not needed: < 2^32 per tile)
   const int n_str = sc.n;
@@ -42,7 +53,7 @@ __global__ void __launch_bounds__(PT_BLOCK) part_tile_hist_kernel(const uint32_t
   for (int r = 0; r < PT_ROUNDS; r++) {
     const int64_t i = t0 + warp * (PT_TILE / PT_WARPS) + r * 32 + lane;
     if (i < n) {
-      const uint32_t p = pid ? pid[i] : 0u;
+      const uint32_t p = pid_of(pid, i, P);
       atomicAdd(&sh[p], 1u);
       for (int c = 0; c < n_str; c++) {
         const uint32_t len = str_len_of(sc.c[c], i);
@@ -77,7 +88,7 @@ __device__ __forceinline__ void scatter_rows(const GatherCol& c, const int64_t (
 
 // offsets[p * n_tiles + tile] = first output row of (partition p, tile); the rank of a row inside its
 // (p, tile) group is its stable position: rows of earlier warps, earlier rounds, lower lanes first.
-__global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_kernel(const uint32_t* __restrict__ pid, int64_t n, uint32_t P, uint32_t n_tiles,
+__global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_kernel(const PidSrc pid, int64_t n, uint32_t P, uint32_t n_tiles,
                                                                     const uint64_t* __restrict__ offsets, GatherCols cols, uint32_t* __restrict__ dest_out) {
   extern __shared__ unsigned int sh[];  // [PT_WARPS][P] per-warp counts -> per-warp bases
   for (uint32_t b = threadIdx.x; b < P * PT_WARPS; b += PT_BLOCK) sh[b] = 0;
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_kernel(const uint3
   for (int r = 0; r < PT_ROUNDS; r++) {
     row[r] = t0 + warp * (PT_TILE / PT_WARPS) + r * 32 + lane;
     const bool live = row[r] < n;
-    p[r] = live ? (pid ? pid[row[r]] : 0u) : 0xFFFFFFFFu;
+    p[r] = live ? pid_of(pid, row[r], P) : 0xFFFFFFFFu;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, p[r]);
     uint32_t base = 0;
     if (live) base = mine[p[r]];
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_kernel(const uint3
 size_t partition_scatter_smem(uint32_t P) { return (size_t)P * PT_WARPS * sizeof(unsigned int); }
 uint32_t partition_n_tiles(int64_t n) { return (uint32_t)((n + PT_TILE - 1) / PT_TILE); }
 
-cudaError_t launch_partition_hist(const uint32_t* pid, int64_t n, uint32_t P, uint32_t* tile_hist, unsigned long long* counts, const PartStrCols& sc,
+cudaError_t launch_partition_hist(const PidSrc& pid, int64_t n, uint32_t P, uint32_t* tile_hist, unsigned long long* counts, const PartStrCols& sc,
                                   unsigned long long* str_bytes, cudaStream_t st) {
   const uint32_t nt = partition_n_tiles(n);
   if (nt == 0) return cudaSuccess;
@@ -151,7 +162,7 @@ cudaError_t launch_partition_hist(const uint32_t* pid, int64_t n, uint32_t P, ui
   return cudaGetLastError();
 }
 
-cudaError_t launch_partition_scatter(const uint32_t* pid, int64_t n, uint32_t P, const uint64_t* offsets, const GatherCols& cols, uint32_t* dest_out,
+cudaError_t launch_partition_scatter(const PidSrc& pid, int64_t n, uint32_t P, const uint64_t* offsets, const GatherCols& cols, uint32_t* dest_out,
                                      cudaStream_t st) {
   const uint32_t nt = partition_n_tiles(n);
   if (nt == 0) return cudaSuccess;

@@ -10,8 +10,11 @@
 // The operator tree below the writer (FilterExec/ProjectionExec/AggregateExec/HashJoinExec/SortExec,
 // DataFusion 53.1 [EXT]) is executed by the CUDA kernels in csrc/device.  There is no CPU path:
 // every operator either runs on the GPU or fails with B200_ERR_UNSUPPORTED.
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -26,6 +29,7 @@
 #include "host_pool.hpp"
 #include "lower.hpp"
 #include "nccl_dyn.hpp"
+#include "parquet_meta.hpp"
 
 using namespace b200;
 
@@ -68,7 +72,7 @@ struct b200_engine {
   std::map<std::string, std::map<int, DevBatchPtr>> tables;
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
   std::atomic<uint64_t> launches{0};
-  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0};  // pipelines per kernel family (b200_engine_counter)
+  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0}, n_groupby{0};  // pipelines per kernel family (b200_engine_counter)
   int64_t batch_size = 8192;
   std::map<std::string, std::string> config;
   std::map<std::string, int> agg_hint;       // plan fingerprint -> sink that worked (0 reg, >0 log2 cap)
@@ -771,8 +775,10 @@ static bool program_filters(const Program& P) {
 // (`extra_fetch`, if given, is a device word read back in the same synchronisation).  wait == false:
 // the caller already knows the output size; the status check (and the kernel time for the metrics)
 // is deferred to the task's next synchronisation.
+bool match_groupby(const Program& P, GroupBySpec& S);
+
 RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedPlan* fused = nullptr, bool wait = true, OpMetrics* met = nullptr,
-                          const unsigned int* extra_fetch = nullptr, unsigned int* extra_out = nullptr) {
+                          const unsigned int* extra_fetch = nullptr, unsigned int* extra_out = nullptr, const GroupBySpec* gb = nullptr) {
   Program& P = pb.prog;
   DevPtr dstat = dev_alloc(sizeof(RunStatus), x.st());
   CUDA_CHECK(cudaMemsetAsync(dstat->ptr, 0, sizeof(RunStatus), x.st()));
@@ -812,13 +818,19 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
   for (int i = 0; i < P.n_cols; i++) kt_bytes += (uint64_t)P.cols[i].width * (uint64_t)P.n_rows;
   if (P.sink == SINK_MATERIALIZE)
     for (int j = 0; j < P.n_out; j++) kt_bytes += (uint64_t)phys_width((Phys)P.out[j].phys) * (uint64_t)P.n_rows;  // upper bound: every row kept
-  KernelTimer kt(x, fused ? "pipeline_fused_agg" : P.sink == SINK_MATERIALIZE ? "pipeline_materialize" : P.sink == SINK_AGG_REG ? "pipeline_agg_reg" : "pipeline_agg_global", kt_bytes);
+  KernelTimer kt(x, gb ? "groupby_hash_agg" : fused ? "pipeline_fused_agg" : P.sink == SINK_MATERIALIZE ? "pipeline_materialize" : P.sink == SINK_AGG_REG ? "pipeline_agg_reg" : "pipeline_agg_global", kt_bytes);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, x.st()));
   cudaError_t le;
-  if (fused) {
+  if (gb) {
+    GroupBySpec S = *gb;
+    S.status = P.status;
+    S.table = P.table;
+    le = launch_groupby(S, x.e->sm_count, x.st());
+    x.e->n_groupby++;
+  } else if (fused) {
     int is_static = 0;
     le = launch_fused_pipeline(P, fused->spec, fused->shape, reg_groups, grid, fused->block, fused->smem, x.st(), &is_static);
     x.e->n_fused++;
@@ -1417,6 +1429,97 @@ bool match_fused(const Program& P, FusedPlan& FP) {
   return true;
 }
 
+// Recognise scan -> integer/date/decimal compares against literals -> up to two decimal products -> one or two integer-like
+// key COLUMNS -> COUNT / SUM accumulators in a lowered aggregate program: the shape the dedicated high-cardinality kernel
+// (groupby.cu) runs without the tile VM.  Hash instructions of the general key path are ignored (the kernel hashes the
+// key image itself).
+bool match_groupby(const Program& P, GroupBySpec& S) {
+  memset(&S, 0, sizeof S);
+  if (getenv("B200_NO_GROUPBY")) return false;
+  if (P.n_keys < 1 || P.n_keys > 2 || P.n_acc > GB_MAX_ACC || P.n_cols > FUSED_MAX_COLS || P.n_cols == 0) return false;
+  for (int c = 0; c < P.n_cols; c++) {
+    const ColDesc& cd = P.cols[c];
+    if (cd.valid) return false;
+    if (!(cd.phys == PH_I32 || cd.phys == PH_I64 || cd.phys == PH_U64 || cd.phys == PH_DEC128)) return false;
+    S.cols[c].data = cd.data;
+    S.cols[c].width = cd.width;
+  }
+  S.n_cols = P.n_cols;
+  auto col_of = [&](const Operand& o, int* out) -> bool {
+    if (o.kind != OPD_COL || o.idx >= (unsigned)P.n_cols) return false;
+    *out = (int)o.idx;
+    return true;
+  };
+  int prod_reg[2] = {-1, -1};
+  for (int i = 0; i < P.n_instr; i++) {
+    const VInstr& v = P.code[i];
+    switch (v.op) {
+      case OP_HASH:
+      case OP_HASH_COMBINE: break;  // the general path's row hash: not needed
+      case OP_CMP_EQ: case OP_CMP_NE: case OP_CMP_LT: case OP_CMP_LE: case OP_CMP_GT: case OP_CMP_GE: {
+        if (!(v.flags & IF_FILTER) || (v.flags & IF_NULLCHK) || v.t != VK_I64 || v.aux == PH_U64) return false;
+        if (S.n_filters >= FUSED_MAX_FILTERS) return false;
+        Operand col = v.a, imm = v.b;
+        uint8_t op = v.op;
+        if (v.a.kind == OPD_IMM && v.b.kind == OPD_COL) {
+          col = v.b;
+          imm = v.a;
+          op = v.op == OP_CMP_LT ? OP_CMP_GT : v.op == OP_CMP_LE ? OP_CMP_GE : v.op == OP_CMP_GT ? OP_CMP_LT : v.op == OP_CMP_GE ? OP_CMP_LE : v.op;
+        }
+        if (imm.kind != OPD_IMM || P.imms[imm.idx].is_null) return false;
+        if (!col_of(col, &S.f_col[S.n_filters])) return false;
+        S.f_op[S.n_filters] = (int)op - (int)OP_CMP_EQ;
+        S.f_imm[S.n_filters] = (int64_t)P.imms[imm.idx].lo;
+        S.n_filters++;
+        break;
+      }
+      case OP_DEC_MUL_LIT_MINUS: case OP_DEC_MUL_LIT_PLUS: case OP_MUL: {
+        if ((v.flags & IF_NULLCHK) || (v.op == OP_MUL && v.t != VK_I128)) return false;
+        if (S.n_prod >= 2 || v.dst.kind != OPD_REG) return false;
+        const int j = S.n_prod;
+        S.p_kind[j] = v.op == OP_DEC_MUL_LIT_MINUS ? 0 : v.op == OP_DEC_MUL_LIT_PLUS ? 1 : 2;
+        if (v.a.kind == OPD_REG && j == 1 && (int)v.a.idx == prod_reg[0]) S.p_a_src[j] = 1;
+        else if (!col_of(v.a, &S.p_a_col[j])) return false;
+        if (!col_of(v.b, &S.p_b_col[j])) return false;
+        if (S.p_kind[j] != 2) {
+          const uint64_t lo = P.imms[v.imm].lo, hi = P.imms[v.imm].hi;
+          if (hi != (uint64_t)((int64_t)lo >> 63)) return false;
+          S.p_lit[j] = (int64_t)lo;
+        }
+        prod_reg[S.n_prod++] = v.dst.idx;
+        break;
+      }
+      default: return false;
+    }
+  }
+  S.n_keys = P.n_keys;
+  for (int k = 0; k < P.n_keys; k++) {
+    if (!col_of(P.keys[k], &S.key_col[k])) return false;
+    if (P.cols[S.key_col[k]].phys == PH_DEC128) return false;
+  }
+  S.n_acc = P.n_acc;
+  for (int a = 0; a < P.n_acc; a++) {
+    const AccDesc& ad = P.acc[a];
+    if (ad.kind == ACC_COUNT_STAR || (ad.kind == ACC_COUNT && !ad.nullable)) {
+      S.a_src[a] = 3;
+      continue;
+    }
+    if (ad.kind != ACC_SUM_I128 || ad.nullable) return false;
+    if (ad.src.kind == OPD_REG) {
+      if ((int)ad.src.idx == prod_reg[0]) S.a_src[a] = 1;
+      else if ((int)ad.src.idx == prod_reg[1]) S.a_src[a] = 2;
+      else return false;
+    } else if (col_of(ad.src, &S.a_col[a])) {
+      S.a_src[a] = 0;
+    } else {
+      return false;
+    }
+  }
+  S.n_rows = P.n_rows;
+  S.table = P.table;
+  return true;
+}
+
 struct TableMem {
   AggTable T;
   std::vector<DevPtr> keep;
@@ -1484,6 +1587,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   TableMem tm;
   RunOutcome ro;
   unsigned int n_groups = 0;
+  bool gb_bailed = false;
   for (;;) {
     x.check_cancel();
     pbp = make_pb();
@@ -1507,6 +1611,9 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     }
     const bool reg_ok = (int)L.accs.size() <= VM_REG_ACC;
     if (!reg_ok && level == 0) level = 1;
+    // up to a few million input rows a table sized for "every row its own group" is cheap: no capacity ladder
+    const bool small_input = src->n <= ((int64_t)1 << 22);
+    if (level > 0 && small_input) level = 8;
     uint64_t cap;
     int reg_groups = 0;
     if (level == 0) {
@@ -1530,8 +1637,14 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     }
     FusedPlan fspec;
     const bool use_fused = level == 0 && match_fused(P, fspec);
-    ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr, true, met, tm.T.n_groups, &n_groups);
+    GroupBySpec gspec;
+    const bool use_gb = level > 0 && !gb_bailed && match_groupby(P, gspec);
+    ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr, true, met, tm.T.n_groups, &n_groups, use_gb ? &gspec : nullptr);
     if (met) met->launches += 2;
+    if (ro.status.pack_overflow && use_gb) {
+      gb_bailed = true;  // operands outside the dedicated kernel's ranges: same table size on the general sink
+      continue;
+    }
     if (ro.status.pack_overflow) {
       pack_mode = pack_mode == 2 ? 1 : 0;
       continue;
@@ -1541,8 +1654,15 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     level++;
   }
   {
+    // remember the smallest table class that holds this many groups (not the level that happened to be used: a small
+    // input jumps straight to a table sized for its row count)
+    int learnt = level;
+    if (level > 0) {
+      learnt = 1;
+      while (learnt < 7 && ((uint64_t)1 << (12 + 4 * learnt)) < (uint64_t)n_groups * 2) learnt++;
+    }
     std::lock_guard<std::mutex> g(x.e->mu);
-    x.e->agg_hint[hint_key] = level * 4 + pack_mode;
+    x.e->agg_hint[hint_key] = learnt * 4 + pack_mode;
   }
   PipelineBuilder& pb = *pbp;
   // extraction
@@ -2352,7 +2472,9 @@ struct Runner {
     if (sc.n) {
       DevPtr acc = dev_alloc((size_t)(1 + sc.n) * 8, x.st());
       CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, (size_t)(1 + sc.n) * 8, x.st()));
-      CUDA_CHECK(launch_partition_hist(nullptr, b.n, 1, nullptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + 1, x.st()));
+      PidSrc none;
+      memset(&none, 0, sizeof none);
+      CUDA_CHECK(launch_partition_hist(none, b.n, 1, nullptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + 1, x.st()));
       x.count();
       const unsigned long long* h = (const unsigned long long*)x.fetch_bytes((const unsigned long long*)acc->ptr + 1, (size_t)sc.n * 8);
       x.sync();
@@ -2422,12 +2544,15 @@ struct Runner {
     const uint32_t P = (uint32_t)root.n_out_partitions;
     if (P > PART_MAX_FANOUT) throw EngineError(B200_ERR_UNSUPPORTED, "more than 4096 output partitions in one shuffle");
     size_t n_payload = 0;
-    std::vector<int> direct;       // payload column -> source column index when it is forwarded untouched, else -1
-    DevBatchPtr srcb;
-    DevBatchPtr mat = with_chain(child, input_partition, false, [&](const BuilderFactory& mk, DevBatchPtr& src) {
+    std::vector<DevColumn> pay;   // payload columns (strings as views)
+    PidSrc ps;
+    memset(&ps, 0, sizeof ps);
+    std::vector<DevColumn> key_keep;
+    DevBatchPtr mat_keep;
+    int64_t n = 0;
+    with_chain(child, input_partition, false, [&](const BuilderFactory& mk, DevBatchPtr& src) {
       auto pbp = mk();
       PipelineBuilder& pb = *pbp;
-      srcb = src;
       std::vector<ColRef> outs = named_cols(pb, root.schema);
       n_payload = outs.size();
       std::vector<ColRef> keys;
@@ -2436,32 +2561,37 @@ struct Runner {
         pb.pin(k);
         keys.push_back(k);
       }
-      ColRef h = pb.hash_of(keys);
-      ColRef pid = pb.mod_u64(h, P);
-      pid.name = "__pid";
-      // columns the chain forwards untouched are scattered straight from the source batch (each byte moves
-      // once); only computed columns and the partition id are materialised first
-      direct.assign(n_payload, -1);
-      std::vector<ColRef> mouts;
-      if (!program_filters(pb.prog))
-        for (size_t c = 0; c < n_payload; c++) direct[c] = pb.source_index(outs[c]);
-      for (size_t c = 0; c < n_payload; c++)
-        if (direct[c] < 0) mouts.push_back(outs[c]);
-      mouts.push_back(pid);
-      return run_materialize(x, pb, mouts, src, met);
-    });
-    const int64_t n = mat->n;
-    if (n >= ((int64_t)1 << 32)) throw EngineError(B200_ERR_UNSUPPORTED, "more than 2^32 rows in one shuffle-writer task");
-    const uint32_t* pid = (const uint32_t*)mat->cols.back().data;
-    std::vector<DevColumn> pay;
-    {
-      size_t mi = 0;
+      // shuffle keys that are plain integer-like columns of an unfiltered input: the partition kernels hash them on
+      // the fly; otherwise the pipeline kernel materialises the partition id next to the computed payload columns
+      bool direct_keys = !program_filters(pb.prog) && !keys.empty() && keys.size() <= (size_t)VM_MAX_KEYS;
+      for (auto& k : keys) direct_keys = direct_keys && pb.source_index(k) >= 0 && exact_key(k.type);
+      if (direct_keys) {
+        for (auto& k : keys) {
+          const DevColumn& kc = src->cols[(size_t)pb.source_index(k)];
+          ps.keys[ps.n_keys++] = KeyCol{kc.data, kc.valid, (uint8_t)kc.phys, (uint8_t)kc.width()};
+          key_keep.push_back(kc);
+        }
+      } else {
+        ColRef h = pb.hash_of(keys);
+        ColRef pid = pb.mod_u64(h, P);
+        pid.name = "__pid";
+        outs.push_back(pid);
+      }
+      Mixed m = materialize_mixed(pb, outs, src, met);
+      n = m.n;
       for (size_t c = 0; c < n_payload; c++) {
-        DevColumn col = direct[c] >= 0 ? as_views(x, srcb->cols[(size_t)direct[c]]) : mat->cols[mi++];
+        DevColumn col = as_views(x, m.cols[c]);
         col.name = root.schema[c].name;
         pay.push_back(col);
       }
-    }
+      if (!direct_keys) {
+        key_keep.push_back(m.cols.back());
+        ps.pid = (const uint32_t*)m.cols.back().data;
+      }
+      return src;
+    });
+    if (n >= ((int64_t)1 << 32)) throw EngineError(B200_ERR_UNSUPPORTED, "more than 2^32 rows in one shuffle-writer task");
+    const PidSrc& pid = ps;
     // histogram (+ string bytes per partition for ShuffleWritePartition.num_bytes)
     PartStrCols sc;
     sc.n = 0;
@@ -2479,7 +2609,9 @@ struct Runner {
     uint64_t row_bytes = 0;
     for (auto& c : pay) row_bytes += (uint64_t)c.width() + (c.valid ? 1 : 0);
     {
-      KernelTimer kt(x, "partition_hist", (uint64_t)n * 4);
+      uint64_t kb = pid.pid ? 4 : 0;
+      for (int k = 0; k < pid.n_keys; k++) kb += pid.keys[k].width;
+      KernelTimer kt(x, "partition_hist", (uint64_t)n * kb);
       CUDA_CHECK(launch_partition_hist(pid, n, P, (uint32_t*)tile_hist->ptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + P, x.st()));
       x.count();
     }
@@ -2911,6 +3043,256 @@ struct Exchange {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Parquet scan: DataSourceExec + ParquetSource with the page decode on the device
+// (ballista/core/proto/datafusion.proto:1058-1077; registration path benchmarks/src/bin/tpch.rs:684-693).
+// The host parses the footer and the page headers (parquet_meta.hpp), ships the raw bytes of the REQUESTED column chunks
+// to HBM (projection push-down: other columns never cross the bus) and csrc/device/parquet.cu decodes them.
+// ------------------------------------------------------------------------------------------------
+struct PqHostColumn {
+  pq::SchemaElement se;
+  int leaf = -1;
+  bool optional = false;
+  std::vector<PqPage> pages, dicts;
+  int64_t rows = 0, dict_entries = 0;
+  DevPtr raw;  // the column's chunks, back to back
+};
+
+static DataType pq_arrow_type(const pq::SchemaElement& se, int* out_kind) {
+  const bool is_decimal = se.logical == 5 || se.converted == 5;
+  const bool is_date = se.logical == 6 || se.converted == 6;
+  switch (se.type) {
+    case pq::T_BOOLEAN: *out_kind = PQ_OUT_BOOL8; return DataType(TypeId::Bool);
+    case pq::T_INT32:
+      if (is_decimal) { *out_kind = PQ_OUT_DEC128; return DataType::decimal(se.precision, se.scale); }
+      *out_kind = PQ_OUT_I32;
+      return DataType(is_date ? TypeId::Date32 : TypeId::Int32);
+    case pq::T_INT64:
+      if (is_decimal) { *out_kind = PQ_OUT_DEC128; return DataType::decimal(se.precision, se.scale); }
+      *out_kind = PQ_OUT_I64;
+      return DataType(TypeId::Int64);
+    case pq::T_DOUBLE: *out_kind = PQ_OUT_F64; return DataType(TypeId::Float64);
+    case pq::T_BYTE_ARRAY: *out_kind = PQ_OUT_STRVIEW; return DataType(TypeId::Utf8);
+    case pq::T_FLBA:
+      if (is_decimal && se.type_length >= 1 && se.type_length <= 16) { *out_kind = PQ_OUT_DEC128; return DataType::decimal(se.precision, se.scale); }
+      break;
+    default: break;
+  }
+  throw EngineError(B200_ERR_UNSUPPORTED, "parquet column '" + se.name + "': physical/logical type not supported by the device scan");
+}
+
+DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vector<std::string>& want) {
+  ScopeTimer tm("parquet_scan");
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw EngineError(B200_ERR_NOT_FOUND, "cannot open " + path);
+  fseek(f, 0, SEEK_END);
+  const size_t fsize = (size_t)ftell(f);
+  fseek(f, 0, SEEK_SET);
+  struct Pinned {
+    uint8_t* p = nullptr;
+    ~Pinned() {
+      if (p) cudaFreeHost(p);
+    }
+  } file;
+  if (cudaHostAlloc((void**)&file.p, fsize + 64, cudaHostAllocDefault) != cudaSuccess) {
+    fclose(f);
+    throw EngineError(B200_ERR_OOM, "pinned staging for the parquet file");
+  }
+  const size_t got = fread(file.p, 1, fsize, f);
+  fclose(f);
+  if (got != fsize) throw EngineError(B200_ERR_INVALID, "short read on " + path);
+  pq::FileMeta fm;
+  try {
+    fm = pq::read_file_meta(file.p, fsize);
+  } catch (const std::runtime_error& ex) {
+    throw EngineError(B200_ERR_INVALID, ex.what());
+  }
+  if (fm.schema.empty()) throw EngineError(B200_ERR_INVALID, "parquet: empty schema");
+  const size_t n_leaves = fm.schema.size() - 1;
+  if ((size_t)fm.schema[0].num_children != n_leaves) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: nested schemas are not supported by the device scan");
+  std::vector<PqHostColumn> cols;
+  std::vector<std::string> names = want;
+  if (names.empty())
+    for (size_t i = 1; i < fm.schema.size(); i++) names.push_back(fm.schema[i].name);
+  for (auto& nm : names) {
+    PqHostColumn c;
+    for (size_t i = 1; i < fm.schema.size(); i++)
+      if (fm.schema[i].name == nm) c.leaf = (int)i - 1;
+    if (c.leaf < 0) throw EngineError(B200_ERR_INVALID, "parquet: no column named " + nm);
+    c.se = fm.schema[(size_t)c.leaf + 1];
+    if (c.se.num_children) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: nested column " + nm);
+    if (c.se.repetition == 2) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: repeated column " + nm);
+    c.optional = c.se.repetition == 1;
+    cols.push_back(c);
+  }
+  cudaStream_t st = x.st();
+  int64_t n_rows = 0;
+  for (auto& rg : fm.row_groups) n_rows += rg.num_rows;
+  // ---- raw bytes to HBM + page tables ---------------------------------------------------------------------------------
+  for (auto& c : cols) {
+    size_t total = 0;
+    for (auto& rg : fm.row_groups) {
+      if ((size_t)c.leaf >= rg.columns.size()) throw EngineError(B200_ERR_INVALID, "parquet: row group without column " + c.se.name);
+      total += (size_t)rg.columns[(size_t)c.leaf].total_compressed;
+    }
+    c.raw = dev_alloc(total + 64, st);
+    size_t dpos = 0;
+    for (auto& rg : fm.row_groups) {
+      const pq::ColumnChunkMeta& cm = rg.columns[(size_t)c.leaf];
+      if (cm.codec != 0) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: column " + c.se.name + " is compressed (codec " + std::to_string(cm.codec) + "); the device scan reads UNCOMPRESSED pages");
+      int64_t start = cm.data_page_offset;
+      if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
+      if (start < 0 || (size_t)start + (size_t)cm.total_compressed > fsize) throw EngineError(B200_ERR_INVALID, "parquet: column chunk outside the file");
+      CUDA_CHECK(cudaMemcpyAsync((uint8_t*)c.raw->ptr + dpos, file.p + start, (size_t)cm.total_compressed, cudaMemcpyHostToDevice, st));
+      const uint8_t* hp = file.p + start;
+      const uint8_t* hend = hp + cm.total_compressed;
+      const uint8_t* dbase = (const uint8_t*)c.raw->ptr + dpos;
+      int64_t chunk_dict_base = c.dict_entries, chunk_values = 0;
+      while (hp < hend && chunk_values < cm.num_values) {
+        pq::PageHeader h;
+        try {
+          h = pq::read_page_header(hp, hend);
+        } catch (const std::runtime_error& ex) {
+          throw EngineError(B200_ERR_INVALID, ex.what());
+        }
+        const uint8_t* payload = hp + h.header_bytes;
+        if (payload + h.compressed_size > hend) throw EngineError(B200_ERR_INVALID, "parquet: page overruns its chunk");
+        PqPage pg;
+        memset(&pg, 0, sizeof pg);
+        pg.data = dbase + (payload - (file.p + start));
+        pg.n_values = (uint32_t)h.num_values;
+        if (h.type == pq::P_DICTIONARY) {
+          if (h.encoding != pq::E_PLAIN && h.encoding != pq::E_PLAIN_DICTIONARY) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: dictionary page encoding");
+          pg.val_off = 0;
+          pg.val_len = (uint32_t)h.compressed_size;
+          pg.row0 = c.dict_entries;
+          chunk_dict_base = c.dict_entries;
+          c.dict_entries += h.num_values;
+          c.dicts.push_back(pg);
+        } else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
+          uint32_t off = 0;
+          if (h.type == pq::P_DATA) {
+            if (c.optional) {
+              if (h.def_encoding != pq::E_RLE) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: definition levels not RLE encoded");
+              uint32_t len;
+              memcpy(&len, payload, 4);
+              pg.def_off = 4;
+              pg.def_len = len;
+              off = 4 + len;
+            }
+          } else {
+            pg.def_off = (uint32_t)h.rep_bytes;
+            pg.def_len = c.optional ? (uint32_t)h.def_bytes : 0;
+            off = (uint32_t)(h.rep_bytes + h.def_bytes);
+          }
+          if (off > (uint32_t)h.compressed_size) throw EngineError(B200_ERR_INVALID, "parquet: level section overruns the page");
+          pg.val_off = off;
+          pg.val_len = (uint32_t)h.compressed_size - off;
+          if (h.encoding == pq::E_PLAIN) pg.encoding = 0;
+          else if (h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY) pg.encoding = 1;
+          else throw EngineError(B200_ERR_UNSUPPORTED, "parquet: column " + c.se.name + " uses encoding " + std::to_string(h.encoding) + " (supported: PLAIN, RLE_DICTIONARY)");
+          pg.row0 = c.rows;
+          pg.dict_base = chunk_dict_base;
+          c.rows += h.num_values;
+          chunk_values += h.num_values;
+          c.pages.push_back(pg);
+        }  // index pages etc.: skipped
+        hp = payload + h.compressed_size;
+      }
+      dpos += (size_t)cm.total_compressed;
+    }
+    if (c.rows != n_rows) throw EngineError(B200_ERR_INVALID, "parquet: column " + c.se.name + " has " + std::to_string(c.rows) + " values, the file " + std::to_string(n_rows) + " rows");
+  }
+  // ---- decode ------------------------------------------------------------------------------------------------------------
+  struct ColWork {
+    PqColumn pc;
+    DataType type;
+    DevPtr d_pages, d_dicts, valid, nonnull, dense_base, total, dict, out;
+    const unsigned long long* h_total = nullptr;
+    int width = 0;
+  };
+  std::vector<ColWork> work(cols.size());
+  auto upload = [&](const std::vector<PqPage>& v) {
+    DevPtr d = dev_alloc(std::max<size_t>(v.size(), 1) * sizeof(PqPage), st);
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(d->ptr, v.data(), v.size() * sizeof(PqPage), cudaMemcpyHostToDevice, st));  // pageable: staged before returning
+    return d;
+  };
+  for (size_t ci = 0; ci < cols.size(); ci++) {
+    PqHostColumn& c = cols[ci];
+    ColWork& w = work[ci];
+    memset(&w.pc, 0, sizeof w.pc);
+    int kind = 0;
+    w.type = pq_arrow_type(c.se, &kind);
+    w.pc.phys = c.se.type;
+    w.pc.type_length = c.se.type_length;
+    w.pc.out_kind = kind;
+    w.width = kind == PQ_OUT_I32 ? 4 : (kind == PQ_OUT_I64 || kind == PQ_OUT_F64) ? 8 : kind == PQ_OUT_BOOL8 ? 1 : 16;
+    w.d_pages = upload(c.pages);
+    w.d_dicts = upload(c.dicts);
+    if (c.dict_entries) {
+      w.dict = dev_alloc((size_t)c.dict_entries * (size_t)w.width + 64, st);
+      w.pc.dict = w.dict->ptr;
+      launch_pq_dict(w.pc, (const PqPage*)w.d_dicts->ptr, (int)c.dicts.size(), st);
+      x.count();
+    }
+    if (c.optional) {
+      w.valid = dev_alloc((size_t)std::max<int64_t>(n_rows, 1) + 64, st);
+      w.nonnull = dev_alloc(std::max<size_t>(c.pages.size(), 1) * 4, st);
+      w.dense_base = dev_alloc(std::max<size_t>(c.pages.size(), 1) * 8, st);
+      w.total = dev_alloc(16, st);
+      CUDA_CHECK(cudaMemsetAsync(w.total->ptr, 0, 16, st));
+      launch_pq_levels((const PqPage*)w.d_pages->ptr, (int)c.pages.size(), (uint8_t*)w.valid->ptr, (uint32_t*)w.nonnull->ptr, (unsigned long long*)w.total->ptr, st);
+      launch_pq_page_scan((const uint32_t*)w.nonnull->ptr, (int)c.pages.size(), (unsigned long long*)w.dense_base->ptr, st);
+      x.count(2);
+      w.h_total = x.fetch<unsigned long long>(w.total->ptr);
+    }
+  }
+  x.sync();  // one read-back for all nullable columns: which of them really contain NULLs
+  auto out = std::make_shared<DevBatch>();
+  out->n = n_rows;
+  for (size_t ci = 0; ci < cols.size(); ci++) {
+    PqHostColumn& c = cols[ci];
+    ColWork& w = work[ci];
+    const bool has_nulls = c.optional && (int64_t)*w.h_total != n_rows;
+    w.out = dev_alloc((size_t)std::max<int64_t>(n_rows, 1) * (size_t)w.width + 64, st);
+    {
+      KernelTimer kt(x, "parquet_decode_values", (uint64_t)n_rows * (uint64_t)w.width);
+      if (!has_nulls) {
+        launch_pq_values(w.pc, (const PqPage*)w.d_pages->ptr, (int)c.pages.size(), nullptr, nullptr, w.out->ptr, st);
+        x.count();
+      } else {
+        DevPtr dense = dev_alloc((size_t)std::max<int64_t>(n_rows, 1) * (size_t)w.width + 64, st);
+        launch_pq_values(w.pc, (const PqPage*)w.d_pages->ptr, (int)c.pages.size(), (const unsigned long long*)w.dense_base->ptr, (const uint32_t*)w.nonnull->ptr, dense->ptr, st);
+        launch_pq_expand((const PqPage*)w.d_pages->ptr, (int)c.pages.size(), (const unsigned long long*)w.dense_base->ptr, (const uint8_t*)w.valid->ptr, dense->ptr,
+                         w.out->ptr, w.width, st);
+        x.count(2);
+      }
+    }
+    DevColumn col;
+    col.name = c.se.name;
+    col.type = w.type;
+    col.n = n_rows;
+    col.nullable = has_nulls;
+    col.phys = w.pc.out_kind == PQ_OUT_STRVIEW ? PH_STRVIEW : phys_of(w.type);
+    col.data = (const uint8_t*)w.out->ptr;
+    col.keep.push_back(w.out);
+    if (has_nulls) {
+      col.valid = (const uint8_t*)w.valid->ptr;
+      col.keep.push_back(w.valid);
+    }
+    if (col.phys == PH_STRVIEW) {
+      // registered tables use the canonical Arrow layout (offsets + contiguous characters): the views into the raw pages
+      // are compacted once, here, and the raw pages are released
+      col.keep.push_back(c.raw);
+      if (w.dict) col.keep.push_back(w.dict);
+      col = as_utf8(x, col);
+    }
+    out->cols.push_back(col);
+  }
+  x.sync();
+  return out;
+}
+
 void collect_nodes(const PlanNode& n, b200_stage* s) {
   s->metric_index[&n] = (int)s->metrics.size();
   OpMetrics m;
@@ -2956,6 +3338,50 @@ extern "C" {
 const char* b200_version(void) { return "b200exec 0.1 sm_100a"; }
 const char* b200_last_error(void) { return g_err.c_str(); }
 
+// Ingest is a host<->GPU pipeline (pinned staging, a pool of narrowing threads, DMA): it only reaches the PCIe rate when
+// the host side runs on the NUMA node the GPU hangs off -- across the socket interconnect the same copies run at about
+// half speed.  The thread that creates the engine (and every thread it starts later, e.g. the ingest pool) is therefore
+// bound to the CPUs of the GPU's node; pinned buffers it allocates afterwards are first-touched there.
+// B200_NUMA_BIND=0 keeps the caller's affinity.
+static void bind_to_gpu_numa_node(int device) {
+  const char* env = getenv("B200_NUMA_BIND");
+  if (env && env[0] == '0') return;
+  char busid[64] = {0};
+  if (cudaDeviceGetPCIBusId(busid, sizeof busid, device) != cudaSuccess) return;
+  for (char* c = busid; *c; c++) *c = (char)tolower(*c);
+  char path[256];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", busid);
+  int node = -1;
+  if (FILE* f = fopen(path, "r")) {
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  if (node < 0) return;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  char list[4096] = {0};
+  const size_t got = fread(list, 1, sizeof list - 1, f);
+  fclose(f);
+  if (!got) return;
+  cpu_set_t want, cur, both;
+  CPU_ZERO(&want);
+  for (char* p = list; *p;) {
+    char* end = nullptr;
+    long a = strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    if (*end == '-') b = strtol(end + 1, &end, 10);
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET((int)c, &want);
+    p = (*end == ',') ? end + 1 : end;
+    if (*end != ',' ) break;
+  }
+  if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+  CPU_AND(&both, &want, &cur);
+  if (CPU_COUNT(&both) == 0) return;
+  sched_setaffinity(0, sizeof both, &both);
+}
+
 int b200_engine_create(int device, uint64_t pool_bytes, int rank, int world, b200_engine** out) {
   return guard([&] {
     if (!out) throw EngineError(B200_ERR_INVALID, "null out pointer");
@@ -2965,6 +3391,7 @@ int b200_engine_create(int device, uint64_t pool_bytes, int rank, int world, b20
       throw EngineError(B200_ERR_CUDA, std::string("no CUDA device available: the B200 engine has no CPU path (") + cudaGetErrorString(ce) + ")");
     if (device < 0 || device >= ndev) throw EngineError(B200_ERR_INVALID, "bad device ordinal");
     CUDA_CHECK(cudaSetDevice(device));
+    bind_to_gpu_numa_node(device);
     auto* e = new b200_engine();
     e->device = device;
     e->rank = rank;
@@ -3018,6 +3445,7 @@ uint64_t b200_engine_counter(b200_engine* e, const char* name) {
   if (n == "fused") return e->n_fused;
   if (n == "fused_static") return e->n_fused_static;
   if (n == "vm") return e->n_vm;
+  if (n == "groupby") return e->n_groupby;
   if (n == "ingest_bytes_saved") return e->narrowed_bytes_saved;
   return 0;
 }
@@ -3027,6 +3455,7 @@ int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
     std::lock_guard<std::mutex> g(e->mu);
     e->config[key] = value;
     if (std::string(key) == "datafusion.execution.batch_size") e->batch_size = std::max<int64_t>(1, atoll(value));
+    if (std::string(key) == "b200.agg.reset_hints") e->agg_hint.clear();  // forget which aggregate strategy each plan shape needed
     if (std::string(key) == "b200.metrics.kernel_timing") e->kernel_timing = std::string(value) == "on" || std::string(value) == "1" || std::string(value) == "true";
   });
 }
@@ -3138,6 +3567,93 @@ int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, in
   });
 }
 
+// Host-only view of what the device scan would be handed: schema, row counts and the page inventory of every column
+// (JSON).  No CUDA call: used by the CPU tests to pin the Thrift footer / page-header reader against pyarrow's metadata.
+int b200_parquet_describe(const char* path, char* out, uint64_t cap) {
+  return guard([&] {
+    if (!path || !out || cap < 2) throw EngineError(B200_ERR_INVALID, "bad argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) throw EngineError(B200_ERR_NOT_FOUND, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END);
+    const size_t fsize = (size_t)ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf(fsize);
+    const size_t got = fread(buf.data(), 1, fsize, f);
+    fclose(f);
+    if (got != fsize) throw EngineError(B200_ERR_INVALID, "short read");
+    pq::FileMeta fm;
+    try {
+      fm = pq::read_file_meta(buf.data(), fsize);
+    } catch (const std::runtime_error& ex) {
+      throw EngineError(B200_ERR_INVALID, ex.what());
+    }
+    std::string j = "{\"num_rows\":" + std::to_string(fm.num_rows) + ",\"row_groups\":" + std::to_string(fm.row_groups.size()) + ",\"columns\":[";
+    for (size_t i = 1; i < fm.schema.size(); i++) {
+      const pq::SchemaElement& se = fm.schema[i];
+      int64_t data_pages = 0, dict_pages = 0, values = 0, dict_encoded = 0, codec = 0;
+      for (auto& rg : fm.row_groups) {
+        if (i - 1 >= rg.columns.size()) continue;
+        const pq::ColumnChunkMeta& cm = rg.columns[i - 1];
+        codec = cm.codec;
+        int64_t start = cm.data_page_offset;
+        if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
+        const uint8_t* hp = buf.data() + start;
+        const uint8_t* hend = hp + cm.total_compressed;
+        int64_t seen = 0;
+        while (hp < hend && seen < cm.num_values) {
+          pq::PageHeader h = pq::read_page_header(hp, hend);
+          if (h.type == pq::P_DICTIONARY) dict_pages++;
+          else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
+            data_pages++;
+            seen += h.num_values;
+            values += h.num_values;
+            if (h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY) dict_encoded++;
+          }
+          hp += h.header_bytes + (size_t)h.compressed_size;
+        }
+      }
+      if (i > 1) j += ",";
+      j += "{\"name\":\"" + se.name + "\",\"physical\":" + std::to_string(se.type) + ",\"type_length\":" + std::to_string(se.type_length) + ",\"optional\":" +
+           (se.repetition == 1 ? "true" : "false") + ",\"logical\":" + std::to_string(se.logical) + ",\"converted\":" + std::to_string(se.converted) +
+           ",\"precision\":" + std::to_string(se.precision) + ",\"scale\":" + std::to_string(se.scale) + ",\"codec\":" + std::to_string(codec) +
+           ",\"values\":" + std::to_string(values) + ",\"data_pages\":" + std::to_string(data_pages) + ",\"dict_pages\":" + std::to_string(dict_pages) +
+           ",\"dict_encoded_pages\":" + std::to_string(dict_encoded) + "}";
+    }
+    j += "]}";
+    if (j.size() + 1 > cap) throw EngineError(B200_ERR_INVALID, "description buffer too small");
+    memcpy(out, j.c_str(), j.size() + 1);
+  });
+}
+
+int b200_engine_register_parquet(b200_engine* e, const char* table, int partition, const char* path, const char* columns_csv) {
+  return guard([&] {
+    if (!e || !table || !path) throw EngineError(B200_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::vector<std::string> cols;
+    if (columns_csv && *columns_csv) {
+      std::string sct(columns_csv);
+      size_t p = 0;
+      while (p <= sct.size()) {
+        size_t q = sct.find(',', p);
+        if (q == std::string::npos) q = sct.size();
+        if (q > p) cols.push_back(sct.substr(p, q - p));
+        p = q + 1;
+      }
+    }
+    Exec x{e, nullptr, nullptr};
+    DevBatchPtr b;
+    try {
+      b = scan_parquet(x, path, cols);
+    } catch (...) {
+      cudaStreamSynchronize(e->stream);
+      Exec::abandon();
+      throw;
+    }
+    std::lock_guard<std::mutex> g(e->mu);
+    e->tables[table][partition] = b;
+  });
+}
+
 int64_t b200_tpch_table_rows(const char* table, int64_t msf) {
   const int t = table ? table_id(table) : -1;
   return t < 0 ? -1 : tpch::table_rows(t, msf);
@@ -3171,7 +3687,18 @@ int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, con
     s->job_id = job_id ? job_id : plan->job_id;
     s->stage_id = stage_id;
     plan->stage_id = stage_id;
-    s->fingerprint = s->job_id.substr(0, s->job_id.find('#')) + ":" + std::to_string(stage_id) + ":" + std::to_string(mix64(hash_bytes((const uint8_t*)plan_json, (uint32_t)strlen(plan_json))));
+    {
+      // strategy hints (which aggregate sink / table size worked) are remembered per plan SHAPE: the job id is taken out
+      // of the hashed text so that the next job that runs the same stage plan starts from what the last one learnt
+      std::string shape(plan_json, plan_len ? (size_t)plan_len : strlen(plan_json));
+      const std::string tag = "\"job_id\":\"";
+      size_t at = shape.find(tag);
+      if (at != std::string::npos) {
+        size_t end = shape.find('"', at + tag.size());
+        if (end != std::string::npos) shape.erase(at + tag.size(), end - at - tag.size());
+      }
+      s->fingerprint = std::to_string(stage_id) + ":" + std::to_string(mix64(hash_bytes((const uint8_t*)shape.data(), (uint32_t)shape.size())));
+    }
     collect_nodes(*plan, s);
     s->plan = std::move(plan);
     *out = s;

@@ -72,7 +72,7 @@ class ArrowArray(C.Structure):
 EXPORTED_SYMBOLS = [
     "b200_engine_create", "b200_engine_destroy", "b200_last_error", "b200_engine_set_stream",
     "b200_engine_synchronize", "b200_engine_kernel_launches", "b200_engine_counter", "b200_engine_set_config",
-    "b200_engine_register_batch", "b200_engine_drop_table", "b200_engine_tpch_generate",
+    "b200_engine_register_batch", "b200_engine_register_parquet", "b200_parquet_describe", "b200_engine_drop_table", "b200_engine_tpch_generate",
     "b200_engine_export_table", "b200_tpch_table_rows", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
@@ -105,6 +105,8 @@ def load_library():
     L.b200_engine_counter.restype = u64
     L.b200_engine_set_config.argtypes = [vp, cp, cp]
     L.b200_engine_register_batch.argtypes = [vp, cp, ci, vp, vp]
+    L.b200_engine_register_parquet.argtypes = [vp, cp, ci, cp, cp]
+    L.b200_parquet_describe.argtypes = [cp, vp, u64]
     L.b200_engine_drop_table.argtypes = [vp, cp]
     L.b200_engine_tpch_generate.argtypes = [vp, cp, i64, ci, i64, i64, cp]
     L.b200_engine_export_table.argtypes = [vp, cp, ci, vp, vp]
@@ -150,6 +152,15 @@ class B200Error(RuntimeError):
 def _check(rc):
     if rc != 0:
         raise B200Error(rc, load_library().b200_last_error().decode(errors="replace"))
+
+
+def parquet_describe(path: str) -> dict:
+    """What the device Parquet scan's host-side metadata reader sees in `path` (b200_parquet_describe; no GPU needed)."""
+    import json as _json
+    cap = 1 << 20
+    buf = C.create_string_buffer(cap)
+    _check(load_library().b200_parquet_describe(path.encode(), buf, cap))
+    return _json.loads(buf.value.decode())
 
 
 class QueryStageExecutor:
@@ -236,6 +247,12 @@ class GpuExecutionEngine:
         arr, sch = ArrowArray(), ArrowSchema()
         batch._export_to_c(C.addressof(arr), C.addressof(sch))
         _check(load_library().b200_engine_register_batch(self.h, table.encode(), partition, C.addressof(arr), C.addressof(sch)))
+        self._parts.setdefault(table, set()).add(partition)
+
+    def register_parquet(self, table: str, partition: int, path: str, columns: Optional[List[str]] = None) -> None:
+        """Scan a Parquet file into a table partition with the page decode on the device (b200_engine_register_parquet)."""
+        csv = ",".join(columns).encode() if columns else None
+        _check(load_library().b200_engine_register_parquet(self.h, table.encode(), partition, path.encode(), csv))
         self._parts.setdefault(table, set()).add(partition)
 
     def drop_table(self, table: str) -> None:

@@ -98,6 +98,14 @@ int b200_engine_set_config(b200_engine* e, const char* key, const char* value);
  * The engine releases `batch` / `schema` when the copy has been issued. */
 int b200_engine_register_batch(b200_engine* e, const char* table, int partition,
                                struct ArrowArray* batch, struct ArrowSchema* schema);
+/* DataSourceExec + ParquetSource leaf (datafusion.proto:1058-1077; tpch.rs:684-693 registers TPC-H tables this way): the
+ * file's requested column chunks cross the bus ENCODED and are decoded on the device (PLAIN / RLE_DICTIONARY pages V1+V2,
+ * definition levels, INT32 / INT64 / DOUBLE / BOOLEAN / BYTE_ARRAY / FIXED_LEN_BYTE_ARRAY with DECIMAL / DATE / STRING
+ * annotations, flat schemas, UNCOMPRESSED codec).  columns_csv = NULL: every column.  Replaces the table partition. */
+int b200_engine_register_parquet(b200_engine* e, const char* table, int partition, const char* path, const char* columns_csv);
+/* Host-only: JSON description (schema, rows, page inventory per column) of a Parquet file as the scan's metadata reader
+ * sees it.  No CUDA call. */
+int b200_parquet_describe(const char* path, char* out, uint64_t cap);
 int b200_engine_drop_table(b200_engine* e, const char* table);
 /* Synthetic TPC-H-shaped table generated directly in HBM (bench/test input; columns = NULL: all).
  * Rows [row_begin,row_end) of the table at milli-scale-factor `msf` become partition `partition`. */

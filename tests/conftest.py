@@ -40,4 +40,7 @@ def gpu_engine_session():
 
 @pytest.fixture()
 def gpu(gpu_engine_session):
+    # the engine remembers, per plan shape, which aggregate strategy the data needed last time; tests that assert which
+    # kernel ran must not depend on what an earlier test fed the same plan
+    gpu_engine_session.set_config("b200.agg.reset_hints", "1")
     return gpu_engine_session
