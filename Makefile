@@ -5,7 +5,7 @@ PKG       := datafusion-ballista_b200
 SRC       := $(PKG)/csrc
 OUT       := $(PKG)/lib
 NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-function
-OBJS      := $(OUT)/pipeline.o $(OUT)/kernels.o $(OUT)/shuffle.o $(OUT)/join.o $(OUT)/groupby.o $(OUT)/parquet.o $(OUT)/engine.o $(OUT)/host_narrow.o
+OBJS      := $(OUT)/pipeline.o $(OUT)/kernels.o $(OUT)/shuffle.o $(OUT)/join.o $(OUT)/groupby.o $(OUT)/parquet.o $(OUT)/filter.o $(OUT)/engine.o $(OUT)/host_narrow.o
 CXX       ?= g++
 COMMON    := $(wildcard $(SRC)/common/*.hpp) $(wildcard $(SRC)/device/*.h) $(wildcard $(SRC)/device/*.cuh) $(wildcard $(SRC)/host/*.hpp) include/b200exec.h include/b200_arrow_abi.h
 
@@ -15,6 +15,9 @@ $(OUT)/pipeline.o: $(SRC)/device/pipeline.cu $(COMMON)
 	@mkdir -p $(OUT)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(OUT)/kernels.o: $(SRC)/device/kernels.cu $(COMMON)
+	@mkdir -p $(OUT)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(OUT)/filter.o: $(SRC)/device/filter.cu $(COMMON)
 	@mkdir -p $(OUT)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(OUT)/parquet.o: $(SRC)/device/parquet.cu $(COMMON)

@@ -235,7 +235,7 @@ def run_reference(args):
         return
     threads = usable_cpus()
     if args.workload != "q1":
-        print(json.dumps({"impl": "reference", "unavailable": f"CPU arm implemented for the q1 headline workload only (asked: {args.workload})"}), flush=True)
+        emit({"impl": "reference", "unavailable": f"CPU arm implemented for the q1 headline workload only (asked: {args.workload})"})
         return
     rows = ROWS_SF10  # the FULL configs[1] table, like the GPU arm's per-GPU share
     times, _ = cpu_q1(SF10_MSF, 0, rows, threads, args.steps, args.warmup)
@@ -251,7 +251,7 @@ def run_reference(args):
                          "sample": f"q1 over all {rows} lineitem rows of SF10 per step, {threads} map tasks on {threads} threads"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- GPU arm ----------------------------------------------------------------------------------------
@@ -471,7 +471,7 @@ def run_b200(args):
             t, _ = cpu_q1(SF10_MSF, 0, rows, threads, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": rows * len(t) / sum(t), "unit": "rows/s", "cores": threads, "kind": "port",
                                     "sample": f"q1 over {rows} lineitem rows (SF2.5), {threads} threads, 2 timed passes", "note": PORT_NOTE}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -625,7 +625,7 @@ def run_workload(args):
             "gpu_launches": launches, "clocks": clocks,
             "parity_checked": bool(parity.get("checked") and parity.get("equal")), "parity": parity, "self_consistent_at_full_scale": consistent,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -690,7 +690,25 @@ def measure_e2e(eng, bb, pa, torch, dist, step, rank, world, device, steps):
                     "Decimal128 sign-extension bytes, H2D of h2d_bytes_per_step, device widens) -> 3 stages (+ exchanges) -> b200_partition_export (D2H)"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process' real stdout; everything else a library prints there (NCCL's version banner,
+    torchrun notices) was redirected to stderr when the run started."""
+    txt = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, txt.encode())
+    else:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

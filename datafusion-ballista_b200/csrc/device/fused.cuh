@@ -811,6 +811,11 @@ constexpr FusedShapeDesc kShapeQ1 = {1, {4}, {3 /*LE*/}, 2, {1, 1}, {4, 4}, 1, 2
 // TPC-H q6 (benchmarks/queries/q6.sql): date range, discount BETWEEN, quantity <; count + sum(price*disc)
 constexpr FusedShapeDesc kShapeQ6 = {5, {4, 4, 16, 16, 16}, {5 /*GE*/, 2 /*LT*/, 5, 3 /*LE*/, 2}, 0, {0, 0}, {0, 0}, 0, 1, {2, 0}, {0, 0}, {16, 0}, {16, 0}, 2,
                                      {3, 1}, {0, 0}};
+// the same query when the two key columns carry pre-packed 4-byte images (registered tables, engine.cpp prepack_short_strings):
+// the keys are plain 32-bit integer tile columns, no offsets / character gathers
+constexpr FusedShapeDesc kShapeQ1P = {1, {4}, {3 /*LE*/}, 2, {0, 0}, {4, 4}, 1, 2, {0, 1}, {0, 1}, {16, 0}, {16, 16}, 6,
+                                      {3, 0, 0, 1, 2, 0}, {0, 16, 16, 0, 0, 16}};
+constexpr FusedShape kQ1P = fused_shape_encode(kShapeQ1P);
 constexpr FusedShape kQ1 = fused_shape_encode(kShapeQ1);
 constexpr FusedShape kQ6 = fused_shape_encode(kShapeQ6);
 
@@ -835,6 +840,7 @@ static cudaError_t launch_fused(const FusedSpec& F, FusedShape shape, int reg_gr
   const int R = F.rows_per_thread;
   *is_static = 1;
   if (reg_groups > 1 && shape.a == kQ1.a && shape.b == kQ1.b) return launch_fused_variant<VM_REG_GROUPS, kQ1.a, kQ1.b>(R, grid, block, smem, st);
+  if (reg_groups > 1 && shape.a == kQ1P.a && shape.b == kQ1P.b) return launch_fused_variant<VM_REG_GROUPS, kQ1P.a, kQ1P.b>(R, grid, block, smem, st);
   if (reg_groups <= 1 && shape.a == kQ6.a && shape.b == kQ6.b) return launch_fused_variant<1, kQ6.a, kQ6.b>(R, grid, block, smem, st);
   *is_static = 0;
   if (reg_groups > 1) return launch_fused_variant<VM_REG_GROUPS, 0, 0>(R, grid, block, smem, st);

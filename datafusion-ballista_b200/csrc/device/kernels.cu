@@ -371,6 +371,25 @@ __global__ void utf8_to_views_kernel(const int32_t* offsets, const uint8_t* char
 void launch_utf8_to_views(const int32_t* offsets, const uint8_t* chars, unsigned long long* views, int64_t n, cudaStream_t st) {
   utf8_to_views_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(offsets, chars, views, n);
 }
+// 32-bit images (len << 24 | up to 3 bytes, first character in the low byte: the OP_STR_PACK8 image) of a Utf8 column whose
+// strings are all at most 3 bytes long -- the companion the fused aggregate kernel reads instead of offsets + characters
+__global__ void prepack3_kernel(const int32_t* offsets, const uint8_t* chars, int64_t n, uint32_t* out, unsigned int* too_long) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t o0 = offsets[i];
+    const uint32_t len = (uint32_t)(offsets[i + 1] - o0);
+    uint32_t v = 0;
+    if (len > 3) {
+      *too_long = 1u;
+    } else {
+      for (uint32_t k = 0; k < len; k++) v |= (uint32_t)chars[o0 + k] << (8 * k);
+      v |= len << 24;
+    }
+    out[i] = v;
+  }
+}
+void launch_prepack3(const int32_t* offsets, const uint8_t* chars, int64_t n, uint32_t* out, unsigned int* too_long, cudaStream_t st) {
+  prepack3_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(offsets, chars, n, out, too_long);
+}
 __global__ void view_lengths_kernel(const unsigned long long* views, const uint8_t* valid, uint32_t* lens, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     lens[i] = (valid && !valid[i]) ? 0u : (uint32_t)views[2 * i + 1];

@@ -87,6 +87,7 @@ void launch_iota_i64(int64_t* out, int64_t n, cudaStream_t st);
 
 // ---- strings / validity ------------------------------------------------------------------------
 void launch_utf8_to_views(const int32_t* offsets, const uint8_t* chars, unsigned long long* views, int64_t n, cudaStream_t st);
+void launch_prepack3(const int32_t* offsets, const uint8_t* chars, int64_t n, uint32_t* out, unsigned int* too_long, cudaStream_t st);
 void launch_view_lengths(const unsigned long long* views, const uint8_t* valid, uint32_t* lens, int64_t n, cudaStream_t st);
 void launch_views_to_utf8(const unsigned long long* views, const uint8_t* valid, const uint64_t* offs64, int32_t* offsets_out, uint8_t* chars_out, int64_t n, cudaStream_t st);
 void launch_bitmap_to_bytes(const uint8_t* bitmap, int64_t bit_offset, uint8_t* bytes, int64_t n, cudaStream_t st);
@@ -158,6 +159,41 @@ void launch_join_probe_count(const JoinKeys& K, const uint64_t* build_hash, cons
 void launch_join_probe_write(const JoinKeys& K, const uint64_t* build_hash, const int32_t* heads, uint64_t n_buckets, const int32_t* next,
                              const uint64_t* probe_hash, const uint8_t* probe_ok, int64_t n_probe, const uint64_t* offsets,
                              int64_t* out_build_idx, int64_t* out_probe_idx, cudaStream_t st);
+// ---- FilterExec + column projection without the tile VM (filter.cu) ------------------------------------------
+static const int FF_MAX_COLS = 16, FF_MAX_OPS = 48, FF_MAX_IMMS = 40, FF_MAX_OUT = 24;
+enum FfOpKind : uint8_t { FF_CMP = 0, FF_AND = 1, FF_OR = 2, FF_NOT = 3, FF_FILTER_REG = 4 };
+struct FfCol {
+  const void* data;       // values / Arrow offsets / views
+  const uint8_t* chars;   // PH_UTF8
+  uint8_t phys, width;
+  uint8_t _pad[6];
+};
+struct FfOp {
+  uint8_t kind;           // FfOpKind
+  uint8_t cmp;            // FF_CMP: 0 EQ 1 NE 2 LT 3 LE 4 GT 5 GE
+  uint8_t vt;             // FF_CMP: 0 signed 64-bit, 1 signed 128-bit, 2 string (EQ / NE), 3 unsigned 64-bit
+  uint8_t filter;         // 1: the result ANDs into the row's pass flag instead of landing in a register
+  uint8_t dst;            // bool register (bit of the per-row register word)
+  uint8_t a, b;           // FF_CMP: column or immediate index; logic: bool registers
+  uint8_t a_imm, b_imm;   // FF_CMP: operand is an immediate
+  uint8_t _pad[3];
+};
+struct FfImm {
+  uint64_t lo, hi;        // integers: two's complement 128-bit; strings: device pointer, length
+};
+struct FastFilterSpec {
+  FfCol cols[FF_MAX_COLS];
+  FfOp ops[FF_MAX_OPS];
+  FfImm imms[FF_MAX_IMMS];
+  int n_cols, n_ops, n_out, _pad;
+  uint8_t out_col[FF_MAX_OUT];
+  void* out_data[FF_MAX_OUT];
+  int64_t n_rows;
+  unsigned long long* tile_state;   // one look-back word per 1024-row tile, zeroed
+  RunStatus* status;
+};
+cudaError_t launch_fast_filter(const FastFilterSpec& S, int sm_count, cudaStream_t st);
+
 // ---- high-cardinality group-by over plain columns (groupby.cu) ---------------------------------------
 static const int GB_MAX_ACC = 8;
 struct GroupBySpec {
@@ -233,7 +269,7 @@ struct PqPage {
   uint32_t n_values;        // values including NULLs (dictionary pages: entries)
   uint32_t def_off, def_len;  // definition-level section inside the payload; len 0 = required column / no levels
   uint32_t val_off, val_len;  // values section
-  uint32_t encoding;        // 0 PLAIN, 1 dictionary indices
+  uint32_t encoding;        // 0 PLAIN, 1 dictionary indices, 2 RLE (BOOLEAN values)
   int64_t row0;             // first row of the page inside the column (dictionary pages: first entry in the dictionary array)
   int64_t dict_base;        // data pages: first entry of their chunk's dictionary
 };

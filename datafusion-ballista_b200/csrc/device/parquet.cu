@@ -228,6 +228,12 @@ __global__ void __launch_bounds__(128) pq_values_kernel(const PqColumn C, const 
     pq_hybrid_decode(p, end, bw, n, lane, [&](uint32_t i, uint32_t idx) { pq_store_from_dict(C, out, base + i, dbase + idx); });
     return;
   }
+  if (pg.encoding == 2) {  // RLE-encoded BOOLEAN values (data page V2 writers): 4-byte length, then hybrid runs of width 1
+    if (p + 4 > end) return;
+    p += 4;
+    pq_hybrid_decode(p, end, 1, n, lane, [&](uint32_t i, uint32_t v) { ((uint8_t*)out)[base + i] = (uint8_t)(v & 1); });
+    return;
+  }
   if (C.phys == 6) {  // PLAIN BYTE_ARRAY
     if (lane == 0) {
       unsigned long long* views = (unsigned long long*)out + 2 * base;

@@ -72,7 +72,7 @@ struct b200_engine {
   std::map<std::string, std::map<int, DevBatchPtr>> tables;
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
   std::atomic<uint64_t> launches{0};
-  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0}, n_groupby{0};  // pipelines per kernel family (b200_engine_counter)
+  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0}, n_groupby{0}, n_fastfilter{0};  // pipelines per kernel family (b200_engine_counter)
   int64_t batch_size = 8192;
   std::map<std::string, std::string> config;
   std::map<std::string, int> agg_hint;       // plan fingerprint -> sink that worked (0 reg, >0 log2 cap)
@@ -401,6 +401,36 @@ DevColumn as_utf8(const Exec& x, const DevColumn& c, int64_t known_total = -1) {
   if (c.valid)
     for (auto& k : c.keep) o.keep.push_back(k);  // validity lives in the old allocations
   return o;
+}
+
+// Registered tables: every Utf8 column whose strings are all at most 3 bytes long (TPC-H flags, status, ...) gets a
+// companion of 4-byte key images (len << 24 | bytes).  An aggregate that groups by such a column then streams 4 bytes per
+// row through the same TMA ring as its other operands instead of gathering characters behind the offsets.
+void prepack_short_strings(const Exec& x, DevBatch& b) {
+  struct Cand { size_t col; DevPtr img, flag; const unsigned int* h; };
+  std::vector<Cand> cands;
+  for (size_t ci = 0; ci < b.cols.size(); ci++) {
+    DevColumn& c = b.cols[ci];
+    if (c.phys != PH_UTF8 || c.valid || c.pk32 || c.n == 0) continue;
+    if (c.chars_bytes < 0 || c.chars_bytes > 3 * c.n) continue;  // some string must be longer
+    Cand cd;
+    cd.col = ci;
+    cd.img = dev_alloc((size_t)c.n * 4 + 64, x.st());
+    cd.flag = dev_alloc(16, x.st());
+    CUDA_CHECK(cudaMemsetAsync(cd.flag->ptr, 0, 16, x.st()));
+    launch_prepack3((const int32_t*)c.data, c.chars, c.n, (uint32_t*)cd.img->ptr, (unsigned int*)cd.flag->ptr, x.st());
+    x.count();
+    cd.h = x.fetch<unsigned int>(cd.flag->ptr);
+    cands.push_back(cd);
+  }
+  if (cands.empty()) return;
+  x.sync();
+  for (auto& cd : cands) {
+    if (*cd.h) continue;
+    DevColumn& c = b.cols[cd.col];
+    c.pk32 = (const uint32_t*)cd.img->ptr;
+    c.keep.push_back(cd.img);
+  }
 }
 
 DevBatchPtr gather_batch(const Exec& x, const DevBatch& in, const int64_t* idx, int64_t n_out, bool may_be_null) {
@@ -776,16 +806,19 @@ static bool program_filters(const Program& P) {
 // the caller already knows the output size; the status check (and the kernel time for the metrics)
 // is deferred to the task's next synchronisation.
 bool match_groupby(const Program& P, GroupBySpec& S);
+bool match_fast_filter(const Program& P, FastFilterSpec& S);
 
 RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedPlan* fused = nullptr, bool wait = true, OpMetrics* met = nullptr,
-                          const unsigned int* extra_fetch = nullptr, unsigned int* extra_out = nullptr, const GroupBySpec* gb = nullptr) {
+                          const unsigned int* extra_fetch = nullptr, unsigned int* extra_out = nullptr, const GroupBySpec* gb = nullptr,
+                          const FastFilterSpec* ff = nullptr) {
   Program& P = pb.prog;
   DevPtr dstat = dev_alloc(sizeof(RunStatus), x.st());
   CUDA_CHECK(cudaMemsetAsync(dstat->ptr, 0, sizeof(RunStatus), x.st()));
   P.status = (RunStatus*)dstat->ptr;
   DevPtr tstate;
   if (P.sink == SINK_MATERIALIZE) {
-    const int64_t nt = (P.n_rows + (int64_t)pb.block * VM_R - 1) / ((int64_t)pb.block * VM_R);
+    const int64_t tile_rows = ff ? 1024 : (int64_t)pb.block * VM_R;
+    const int64_t nt = (P.n_rows + tile_rows - 1) / tile_rows;
     tstate = dev_alloc((size_t)std::max<int64_t>(nt, 1) * 8, x.st());
     CUDA_CHECK(cudaMemsetAsync(tstate->ptr, 0, (size_t)std::max<int64_t>(nt, 1) * 8, x.st()));
     P.tile_state = (unsigned long long*)tstate->ptr;
@@ -818,13 +851,19 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
   for (int i = 0; i < P.n_cols; i++) kt_bytes += (uint64_t)P.cols[i].width * (uint64_t)P.n_rows;
   if (P.sink == SINK_MATERIALIZE)
     for (int j = 0; j < P.n_out; j++) kt_bytes += (uint64_t)phys_width((Phys)P.out[j].phys) * (uint64_t)P.n_rows;  // upper bound: every row kept
-  KernelTimer kt(x, gb ? "groupby_hash_agg" : fused ? "pipeline_fused_agg" : P.sink == SINK_MATERIALIZE ? "pipeline_materialize" : P.sink == SINK_AGG_REG ? "pipeline_agg_reg" : "pipeline_agg_global", kt_bytes);
+  KernelTimer kt(x, ff ? "filter_compact" : gb ? "groupby_hash_agg" : fused ? "pipeline_fused_agg" : P.sink == SINK_MATERIALIZE ? "pipeline_materialize" : P.sink == SINK_AGG_REG ? "pipeline_agg_reg" : "pipeline_agg_global", kt_bytes);
   cudaEvent_t e0, e1;
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, x.st()));
   cudaError_t le;
-  if (gb) {
+  if (ff) {
+    FastFilterSpec S = *ff;
+    S.status = P.status;
+    S.tile_state = P.tile_state;
+    le = launch_fast_filter(S, x.e->sm_count, x.st());
+    x.e->n_fastfilter++;
+  } else if (gb) {
     GroupBySpec S = *gb;
     S.status = P.status;
     S.table = P.table;
@@ -919,7 +958,9 @@ DevBatchPtr run_materialize(const Exec& x, PipelineBuilder& pb, const std::vecto
   pb.finalize_layout(4096);
   // without a filter every input row comes out: no need to wait for the row count
   const bool filters = program_filters(P);
-  RunOutcome r = launch_program(x, pb, 1, nullptr, filters, met);
+  FastFilterSpec ffs;
+  const bool use_ff = filters && match_fast_filter(P, ffs);
+  RunOutcome r = launch_program(x, pb, 1, nullptr, filters, met, nullptr, nullptr, nullptr, use_ff ? &ffs : nullptr);
   out->n = filters ? (int64_t)r.status.out_rows : src->n;
   uint64_t wbytes = 0;
   for (auto& c : out->cols) {
@@ -1201,21 +1242,30 @@ bool match_fused(const Program& P, FusedPlan& FP) {
   uint32_t fused_off[VM_MAX_COLS];
   uint32_t cur = 0, tx = 0, tx_utf8 = 0;
   bool aligned = true;
+  // short-string keys with a pre-packed companion (prepack_short_strings) are read as 4-byte integer key columns
+  bool prepacked[VM_MAX_COLS] = {false};
+  if (!getenv("B200_NO_PREPACK"))
+    for (int i = 0; i < P.n_instr; i++) {
+      const VInstr& v = P.code[i];
+      if (v.op == OP_STR_PACK8 && v.a.kind == OPD_COL && v.imm == 24 && v.aux <= 3 && P.cols[v.a.idx].phys == PH_UTF8 && P.cols[v.a.idx].packed32 &&
+          (((uintptr_t)P.cols[v.a.idx].packed32) & 15) == 0)
+        prepacked[v.a.idx] = true;
+    }
   for (int c = 0; c < P.n_cols; c++) {
     const ColDesc& cd = P.cols[c];
     if (cd.valid) return false;
     FusedCol& fc = F.cols[c];
-    fc.data = cd.data;
-    fc.width = cd.width;
-    fc.utf8 = cd.phys == PH_UTF8 ? 1u : 0u;
-    fc.tile_bytes = TR * cd.width + (fc.utf8 ? 16u : 0u);
+    fc.data = prepacked[c] ? cd.packed32 : cd.data;
+    fc.width = prepacked[c] ? 4 : cd.width;
+    fc.utf8 = (cd.phys == PH_UTF8 && !prepacked[c]) ? 1u : 0u;
+    fc.tile_bytes = TR * fc.width + (fc.utf8 ? 16u : 0u);
     if (fc.tile_bytes & 15u) return false;
     fc.off = cur;
     fused_off[c] = cur;
     cur += fc.tile_bytes;
     if (fc.utf8) tx_utf8 += fc.tile_bytes;
     else tx += fc.tile_bytes;
-    if (((uintptr_t)cd.data & 15) != 0) aligned = false;
+    if (((uintptr_t)fc.data & 15) != 0) aligned = false;
   }
   F.n_cols = P.n_cols;
   F.rows_per_thread = R;
@@ -1311,6 +1361,13 @@ bool match_fused(const Program& P, FusedPlan& FP) {
         PackInfo pi;
         pi.reg = v.dst.idx;
         memset(&pi.k, 0, sizeof pi.k);
+        if (prepacked[v.a.idx]) {  // the image is already in the tile: an integer key column of width 4
+          pi.k.kind = 0;
+          pi.k.off = fused_off[v.a.idx];
+          pi.k.w = 4;
+          packs.push_back(pi);
+          break;
+        }
         pi.k.kind = 1;
         pi.k.off = fused_off[v.a.idx];
         pi.k.chars = P.cols[v.a.idx].chars;
@@ -1520,6 +1577,116 @@ bool match_groupby(const Program& P, GroupBySpec& S) {
   return true;
 }
 
+// Recognise a materialising program that only FILTERS (comparisons of plain columns with literals or with each other,
+// combined with AND / OR / NOT) and forwards plain columns: the shape the dedicated FilterExec kernel (filter.cu) runs
+// without the tile VM.  LIKE, arithmetic, casts, NULL-aware compares or computed outputs keep the VM.
+bool match_fast_filter(const Program& P, FastFilterSpec& S) {
+  if (P.sink != SINK_MATERIALIZE || getenv("B200_NO_FASTFILTER")) return false;
+  if (P.n_cols > FF_MAX_COLS || P.n_cols == 0 || P.n_instr > FF_MAX_OPS || P.n_instr == 0 || P.n_imms > FF_MAX_IMMS || P.n_out > FF_MAX_OUT || P.n_regs > 64) return false;
+  memset(&S, 0, sizeof S);
+  auto int_phys = [](uint8_t ph) { return ph == PH_I8 || ph == PH_I16 || ph == PH_I32 || ph == PH_I64 || ph == PH_U8 || ph == PH_U16 || ph == PH_U32 || ph == PH_U64; };
+  for (int c = 0; c < P.n_cols; c++) {
+    const ColDesc& cd = P.cols[c];
+    if (cd.valid) return false;
+    if (!(int_phys(cd.phys) || cd.phys == PH_DEC128 || cd.phys == PH_UTF8 || cd.phys == PH_STRVIEW || cd.phys == PH_F64 || cd.phys == PH_F32 || cd.phys == PH_BOOL8)) return false;
+    S.cols[c].data = cd.data;
+    S.cols[c].chars = cd.chars;
+    S.cols[c].phys = cd.phys;
+    S.cols[c].width = cd.width;
+  }
+  S.n_cols = P.n_cols;
+  for (int i = 0; i < P.n_imms; i++) {
+    S.imms[i].lo = P.imms[i].lo;
+    S.imms[i].hi = P.imms[i].hi;
+  }
+  auto bool_reg = [&](const Operand& o, uint8_t* out) {
+    if (o.kind != OPD_REG || o.vk != VK_BOOL || o.idx >= 64) return false;
+    *out = (uint8_t)o.idx;
+    return true;
+  };
+  bool any_filter = false;
+  for (int i = 0; i < P.n_instr; i++) {
+    const VInstr& v = P.code[i];
+    FfOp& op = S.ops[S.n_ops];
+    memset(&op, 0, sizeof op);
+    if (v.flags & IF_NULLCHK) return false;
+    switch (v.op) {
+      case OP_CMP_EQ: case OP_CMP_NE: case OP_CMP_LT: case OP_CMP_LE: case OP_CMP_GT: case OP_CMP_GE: {
+        op.kind = FF_CMP;
+        op.cmp = (uint8_t)(v.op - OP_CMP_EQ);
+        if (!(v.t == VK_I64 || v.t == VK_I128 || v.t == VK_STR)) return false;
+        if (v.t == VK_STR && !(v.op == OP_CMP_EQ || v.op == OP_CMP_NE)) return false;
+        bool wide = v.t == VK_I128;
+        const Operand* ops2[2] = {&v.a, &v.b};
+        uint8_t idx[2], is_imm[2];
+        for (int k = 0; k < 2; k++) {
+          const Operand& o = *ops2[k];
+          if (o.kind == OPD_IMM) {
+            if (o.idx >= (unsigned)P.n_imms || P.imms[o.idx].is_null) return false;
+            idx[k] = (uint8_t)o.idx;
+            is_imm[k] = 1;
+          } else if (o.kind == OPD_COL) {
+            if (o.idx >= (unsigned)P.n_cols) return false;
+            const uint8_t ph = P.cols[o.idx].phys;
+            if (v.t == VK_STR) {
+              if (!(ph == PH_UTF8 || ph == PH_STRVIEW)) return false;
+            } else {
+              if (!(int_phys(ph) || ph == PH_DEC128)) return false;
+              wide = wide || ph == PH_DEC128;
+            }
+            idx[k] = (uint8_t)o.idx;
+            is_imm[k] = 0;
+          } else {
+            return false;
+          }
+        }
+        op.a = idx[0];
+        op.b = idx[1];
+        op.a_imm = is_imm[0];
+        op.b_imm = is_imm[1];
+        op.vt = v.t == VK_STR ? 2 : (wide ? 1 : (v.aux == PH_U64 ? 3 : 0));
+        if (wide && v.aux == PH_U64) return false;
+        // a 64-bit immediate compared as 128 bits needs its sign extension in `hi`
+        for (int k = 0; k < 2; k++)
+          if (op.vt == 1 && is_imm[k] && v.t != VK_I128) S.imms[idx[k]].hi = (uint64_t)((int64_t)S.imms[idx[k]].lo >> 63);
+        if (v.flags & IF_FILTER) op.filter = 1;
+        else if (!bool_reg(v.dst, &op.dst)) return false;
+        break;
+      }
+      case OP_AND:
+      case OP_OR:
+        op.kind = v.op == OP_AND ? FF_AND : FF_OR;
+        if (!bool_reg(v.a, &op.a) || !bool_reg(v.b, &op.b) || !bool_reg(v.dst, &op.dst)) return false;
+        break;
+      case OP_NOT:
+        op.kind = FF_NOT;
+        if (!bool_reg(v.a, &op.a) || !bool_reg(v.dst, &op.dst)) return false;
+        break;
+      case OP_FILTER:
+        op.kind = FF_FILTER_REG;
+        op.filter = 1;
+        if (!bool_reg(v.a, &op.a)) return false;
+        break;
+      default: return false;
+    }
+    any_filter = any_filter || op.filter;
+    S.n_ops++;
+  }
+  if (!any_filter) return false;
+  for (int j = 0; j < P.n_out; j++) {
+    const OutCol& oc = P.out[j];
+    if (oc.src.kind != OPD_COL || oc.src.idx >= (unsigned)P.n_cols || oc.valid) return false;
+    const uint8_t ph = P.cols[oc.src.idx].phys;
+    const bool str = ph == PH_UTF8 || ph == PH_STRVIEW;
+    if (str ? oc.phys != PH_STRVIEW : (oc.phys != ph)) return false;
+    S.out_col[j] = (uint8_t)oc.src.idx;
+    S.out_data[j] = oc.data;
+  }
+  S.n_out = P.n_out;
+  S.n_rows = P.n_rows;
+  return true;
+}
+
 struct TableMem {
   AggTable T;
   std::vector<DevPtr> keep;
@@ -1590,6 +1757,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   bool gb_bailed = false;
   for (;;) {
     x.check_cancel();
+    ScopeTimer t_iter("  agg: lower+alloc+launch+sync");
     pbp = make_pb();
     PipelineBuilder& pb = *pbp;
     L = AggLowered();
@@ -1626,7 +1794,10 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       else cap = std::min<uint64_t>(next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2), (uint64_t)1 << std::min(40, 12 + 4 * level));
       if (cap < 16) cap = 16;
     }
-    tm = alloc_table(x, cap, n_keys, L.accs);
+    {
+      ScopeTimer t_alloc("    agg: alloc_table");
+      tm = alloc_table(x, cap, n_keys, L.accs);
+    }
     P.table = tm.T;
     pb.finalize_layout((size_t)VM_REG_ACC * 512 * 16 + 256);
     if (level == 0) {
@@ -1639,7 +1810,10 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     const bool use_fused = level == 0 && match_fused(P, fspec);
     GroupBySpec gspec;
     const bool use_gb = level > 0 && !gb_bailed && match_groupby(P, gspec);
-    ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr, true, met, tm.T.n_groups, &n_groups, use_gb ? &gspec : nullptr);
+    {
+      ScopeTimer t_l("    agg: launch_program (incl. sync)");
+      ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr, true, met, tm.T.n_groups, &n_groups, use_gb ? &gspec : nullptr);
+    }
     if (met) met->launches += 2;
     if (ro.status.pack_overflow && use_gb) {
       gb_bailed = true;  // operands outside the dedicated kernel's ranges: same table size on the general sink
@@ -1666,6 +1840,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   }
   PipelineBuilder& pb = *pbp;
   // extraction
+  ScopeTimer t_ex("  agg: extract");
   auto out = std::make_shared<DevBatch>();
   out->n = n_groups;
   AggExtractArgs A;
@@ -2563,14 +2738,12 @@ struct Runner {
       }
       // shuffle keys that are plain integer-like columns of an unfiltered input: the partition kernels hash them on
       // the fly; otherwise the pipeline kernel materialises the partition id next to the computed payload columns
-      bool direct_keys = !program_filters(pb.prog) && !keys.empty() && keys.size() <= (size_t)VM_MAX_KEYS;
-      for (auto& k : keys) direct_keys = direct_keys && pb.source_index(k) >= 0 && exact_key(k.type);
+      // integer-like shuffle keys travel as columns (forwarded untouched, or compacted with the payload when the chain
+      // filters) and the partition kernels hash them on the fly; other key types get a materialised partition id
+      bool direct_keys = !keys.empty() && keys.size() <= (size_t)VM_MAX_KEYS;
+      for (auto& k : keys) direct_keys = direct_keys && exact_key(k.type) && (k.op.kind == OPD_NONE || k.op.kind == OPD_COL);
       if (direct_keys) {
-        for (auto& k : keys) {
-          const DevColumn& kc = src->cols[(size_t)pb.source_index(k)];
-          ps.keys[ps.n_keys++] = KeyCol{kc.data, kc.valid, (uint8_t)kc.phys, (uint8_t)kc.width()};
-          key_keep.push_back(kc);
-        }
+        for (auto& k : keys) outs.push_back(k);
       } else {
         ColRef h = pb.hash_of(keys);
         ColRef pid = pb.mod_u64(h, P);
@@ -2584,7 +2757,13 @@ struct Runner {
         col.name = root.schema[c].name;
         pay.push_back(col);
       }
-      if (!direct_keys) {
+      if (direct_keys) {
+        for (size_t k = 0; k < keys.size(); k++) {
+          const DevColumn& kc = m.cols[n_payload + k];
+          ps.keys[ps.n_keys++] = KeyCol{kc.data, kc.valid, (uint8_t)kc.phys, (uint8_t)kc.width()};
+          key_keep.push_back(kc);
+        }
+      } else {
         key_keep.push_back(m.cols.back());
         ps.pid = (const uint32_t*)m.cols.back().data;
       }
@@ -3190,6 +3369,7 @@ DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vect
           pg.val_len = (uint32_t)h.compressed_size - off;
           if (h.encoding == pq::E_PLAIN) pg.encoding = 0;
           else if (h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY) pg.encoding = 1;
+          else if (h.encoding == pq::E_RLE && c.se.type == pq::T_BOOLEAN) pg.encoding = 2;
           else throw EngineError(B200_ERR_UNSUPPORTED, "parquet: column " + c.se.name + " uses encoding " + std::to_string(h.encoding) + " (supported: PLAIN, RLE_DICTIONARY)");
           pg.row0 = c.rows;
           pg.dict_base = chunk_dict_base;
@@ -3289,6 +3469,7 @@ DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vect
     }
     out->cols.push_back(col);
   }
+  prepack_short_strings(x, *out);
   x.sync();
   return out;
 }
@@ -3446,6 +3627,7 @@ uint64_t b200_engine_counter(b200_engine* e, const char* name) {
   if (n == "fused_static") return e->n_fused_static;
   if (n == "vm") return e->n_vm;
   if (n == "groupby") return e->n_groupby;
+  if (n == "fastfilter") return e->n_fastfilter;
   if (n == "ingest_bytes_saved") return e->narrowed_bytes_saved;
   return 0;
 }
@@ -3465,6 +3647,7 @@ int b200_engine_register_batch(b200_engine* e, const char* table, int partition,
     CUDA_CHECK(cudaSetDevice(e->device));
     DevBatchPtr b = import_batch(e, batch, schema);
     Exec x{e, nullptr, nullptr};
+    prepack_short_strings(x, *b);
     DevBatchPtr prev;
     {
       std::lock_guard<std::mutex> g(e->mu);
@@ -3561,6 +3744,7 @@ int b200_engine_tpch_generate(b200_engine* e, const char* table, int64_t msf, in
       }
       b->cols.push_back(col);
     }
+    prepack_short_strings(Exec{e, nullptr, nullptr}, *b);
     CUDA_CHECK(cudaStreamSynchronize(st));
     std::lock_guard<std::mutex> g(e->mu);
     e->tables[table][partition] = b;

@@ -40,6 +40,20 @@ def test_q1(gpu, oracle, oracle_lib, msf, parts, P):
     assert_tables_equal(got, want, sort=False)  # ORDER BY l_returnflag, l_linestatus
 
 
+def test_q1_without_prepacked_keys(gpu, oracle, oracle_lib, monkeypatch):
+    """The same query with the key columns read as Arrow offsets + characters (the path a table takes whose short-string
+    companion images do not exist, e.g. a key column with a string longer than 3 bytes)."""
+    monkeypatch.setenv("B200_NO_PREPACK", "1")
+    for e in (gpu, oracle):
+        e.drop_table("lineitem")
+        _load(e, oracle_lib, "lineitem", 20, tpch.Q1_COLUMNS, 2)
+    s0 = gpu.counter("fused_static")
+    got = driver.run_stages(gpu, tpch.q1(4), "q1-noprepack")
+    assert gpu.counter("fused_static") >= s0 + 2
+    want = driver.run_stages(oracle, tpch.q1(4), "q1-noprepack")
+    assert_tables_equal(got, want, sort=False)
+
+
 @pytest.mark.parametrize("msf,parts", [(10, 2), (50, 5)])
 def test_q6(gpu, oracle, oracle_lib, msf, parts):
     for e in (gpu, oracle):

@@ -1,0 +1,90 @@
+"""One big instance of one operator, so that `ncu -k regex:<kernel> -c 1` lands on a representative launch, and so that the
+engine's own CUDA-event timing (b200_engine_kernel_stats) can be read for the same launch without a profiler attached.
+
+  python tools/op_probe.py join|partition|groupby|groupby_small|filter|parquet|q1 [msf]
+
+  join       orders (build, 15 M rows at SF10) |x| lineitem (probe, 60 M rows) on the order key      -> join_build2 / join_probe2
+  partition  lineitem (4 columns, 48 B/row) hash-repartitioned on l_orderkey into 8 partitions       -> part_tile_hist / part_tile_scatter
+  groupby    lineitem GROUP BY l_partkey, AVG(l_quantity) (2 M groups at SF10; q17's inner aggregate)  -> groupby_kernel
+  groupby_small  lineitem GROUP BY l_suppkey, SUM/COUNT (100 k groups: table resident in L2)
+  filter     q3's lineitem filter (l_shipdate > date) forwarding 3 columns                            -> fast_filter_kernel
+  parquet    lineitem q1 columns written by pyarrow (uncompressed), scanned by the device decoder      -> pq_values_kernel
+  q1         stage 1 of q1                                                                             -> fused_kernel
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ballista_b200 as bb
+from ballista_b200 import plan as P, tpch
+
+op = sys.argv[1]
+msf = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
+reps = int(os.environ.get("REPS", "2"))
+eng = bb.GpuExecutionEngine(0)
+eng.set_config("b200.metrics.kernel_timing", "on")
+c = P.col
+D152 = P.dec(15, 2)
+
+
+def load(table, cols):
+    n = eng.tpch_table_rows(table, msf)
+    eng.drop_table(table)
+    eng.tpch_generate(table, msf, 0, 0, n, cols)
+    return n
+
+
+def run(stages, tasks):
+    for r in range(reps):
+        job = f"probe{r}"
+        for st, nt in zip(stages, tasks):
+            q = eng.create_query_stage_exec(job, st.stage_id, st.json(job))
+            for p in range(nt):
+                q.execute_query_stage(p)
+            q.release()
+        eng.synchronize()
+        eng.remove_job_data(job)
+
+
+if op == "join":
+    load("orders", ["o_orderkey", "o_custkey"])
+    load("lineitem", ["l_orderkey", "l_extendedprice"])
+    j = P.hash_join(tpch.table_scan("orders", ["o_orderkey", "o_custkey"]), tpch.table_scan("lineitem", ["l_orderkey", "l_extendedprice"]),
+                    [[c(0), c(0)]], "Inner", "Partitioned", projection=[1, 3])
+    s = P.aggregate("Partial", [], [P.agg("sum", c(1), "s"), P.agg("count", None, "n")], j)
+    run([P.Stage(1, P.shuffle_writer(s, 1))], [1])
+elif op == "partition":
+    cols = tpch.Q5_TABLES["lineitem"]
+    load("lineitem", cols)
+    run([P.Stage(1, P.shuffle_writer(tpch.table_scan("lineitem", cols), 1, [c(0)], 8))], [1])
+elif op in ("groupby", "groupby_small"):
+    key = "l_partkey" if op == "groupby" else "l_suppkey"
+    load("lineitem", [key, "l_quantity"])
+    s = P.aggregate("Partial", [(c(0), key)], [P.agg("avg", c(1), "a")], tpch.table_scan("lineitem", [key, "l_quantity"]))
+    run([P.Stage(1, P.shuffle_writer(s, 1))], [1])
+elif op == "filter":
+    cols = ["l_orderkey", "l_extendedprice", "l_discount", "l_shipdate"]
+    load("lineitem", cols)
+    f = P.filter_(P.binop(">", c("l_shipdate"), P.lit_date("1995-03-15")), tpch.table_scan("lineitem", cols), projection=[0, 1, 2])
+    run([P.Stage(1, P.shuffle_writer(f, 1))], [1])
+elif op == "parquet":
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    m = min(msf, 2000)
+    n = eng.tpch_table_rows("lineitem", m)
+    eng.tpch_generate("lineitem", m, 0, 0, n, tpch.Q1_COLUMNS)
+    host = pa.Table.from_batches([eng.export_table("lineitem", 0)])
+    path = "/tmp/lineitem_probe.parquet"
+    pq.write_table(host, path, compression="NONE")
+    print("parquet file bytes", os.path.getsize(path), "arrow bytes", host.nbytes, file=sys.stderr)
+    for r in range(reps):
+        eng.register_parquet("lineitem_pq", 0, path, tpch.Q1_COLUMNS)
+elif op == "q1":
+    load("lineitem", tpch.Q1_COLUMNS)
+    run([tpch.q1(1)[0]], [1])
+else:
+    raise SystemExit(__doc__)
+print(json.dumps({op: eng.kernel_stats()}, indent=1))
+eng.close()
