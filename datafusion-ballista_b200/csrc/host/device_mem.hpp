@@ -36,16 +36,49 @@ struct EngineError : std::runtime_error {
                             std::to_string(__LINE__));                                                        \
   } while (0)
 
+// Small allocations (status words, offsets of a few rows, literal pools, the 4-row batches at the tail of a query) are
+// carved out of per-thread 2 MB chunks instead of each paying a cudaMallocAsync / cudaFreeAsync pair: a stage issues
+// dozens of them, and at the tail of a query the driver calls cost more than the kernels.  A chunk is stream-ordered
+// like the allocations it replaces (allocated and freed on the stream that uses it) and lives until the last
+// sub-allocation is released.
+struct ArenaChunk {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaStream_t stream = nullptr;
+  ~ArenaChunk() {
+    if (base) cudaFreeAsync(base, stream);
+  }
+};
+static const size_t ARENA_CHUNK_BYTES = (size_t)2 << 20;
+static const size_t ARENA_MAX_ALLOC = (size_t)64 << 10;
+
 struct DevAlloc {
   void* ptr = nullptr;
   size_t bytes = 0;
   cudaStream_t stream = nullptr;
+  std::shared_ptr<ArenaChunk> chunk;  // set for arena sub-allocations
   DevAlloc(size_t n, cudaStream_t st) : bytes(n), stream(st) {
-    size_t padded = ((n + 255) & ~(size_t)255) + 256;
+    const size_t padded = ((n + 255) & ~(size_t)255) + 256;
+    if (padded <= ARENA_MAX_ALLOC) {
+      static thread_local std::shared_ptr<ArenaChunk> cur;
+      if (!cur || cur->stream != st || cur->used + padded > cur->cap) {
+        auto c = std::make_shared<ArenaChunk>();
+        void* p = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&p, ARENA_CHUNK_BYTES, st));
+        c->base = (uint8_t*)p;
+        c->cap = ARENA_CHUNK_BYTES;
+        c->stream = st;
+        cur = c;
+      }
+      ptr = cur->base + cur->used;
+      cur->used += padded;
+      chunk = cur;
+      return;
+    }
     CUDA_CHECK(cudaMallocAsync(&ptr, padded, st));
   }
   ~DevAlloc() {
-    if (ptr) cudaFreeAsync(ptr, stream);
+    if (ptr && !chunk) cudaFreeAsync(ptr, stream);
   }
   DevAlloc(const DevAlloc&) = delete;
   DevAlloc& operator=(const DevAlloc&) = delete;

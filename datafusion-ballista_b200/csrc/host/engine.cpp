@@ -11,6 +11,7 @@
 // DataFusion 53.1 [EXT]) is executed by the CUDA kernels in csrc/device.  There is no CPU path:
 // every operator either runs on the GPU or fails with B200_ERR_UNSUPPORTED.
 #include <sched.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <atomic>
@@ -30,6 +31,7 @@
 #include "lower.hpp"
 #include "nccl_dyn.hpp"
 #include "parquet_meta.hpp"
+#include "arrow_ipc.hpp"
 
 using namespace b200;
 
@@ -626,7 +628,7 @@ static const int64_t SMALL_EXPORT_ROWS = 4096;
 static const size_t SMALL_EXPORT_ARENA = (size_t)1 << 20;
 static const size_t SMALL_EXPORT_CHARS = (size_t)32 << 10;  // per string column
 
-bool export_batch_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
+bool download_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, std::vector<HostCol>& hcs_out) {
   const int64_t n = r1 - r0;
   std::lock_guard<std::mutex> eg(x.e->export_mu);
   if (!x.e->export_arena && cudaHostAlloc((void**)&x.e->export_arena, SMALL_EXPORT_ARENA, cudaHostAllocDefault) != cudaSuccess) {
@@ -674,7 +676,7 @@ bool export_batch_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1
     if (pos > SMALL_EXPORT_ARENA) return false;
   }
   if (pos == 0) {
-    export_record_batch(std::move(hcs), n, out, out_schema);
+    hcs_out = std::move(hcs);
     return true;
   }
   DevPtr dev = dev_alloc(pos, st);
@@ -716,14 +718,16 @@ bool export_batch_small(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1
       h.extra.assign(arena + sl.chars, arena + sl.chars + (size_t)total);
     }
   }
-  export_record_batch(std::move(hcs), n, out, out_schema);
+  hcs_out = std::move(hcs);
   return true;
 }
 
-void export_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
+// rows [r0, r1) of a device batch as host columns (Arrow buffers: bitmaps, values, offsets + characters)
+std::vector<HostCol> download_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1) {
   const int64_t n = r1 - r0;
-  if (n <= SMALL_EXPORT_ROWS && export_batch_small(x, b, r0, r1, out, out_schema)) return;
   std::vector<HostCol> hcs;
+  if (n <= SMALL_EXPORT_ROWS && download_small(x, b, r0, r1, hcs)) return hcs;
+  hcs.clear();
   cudaStream_t st = x.st();
   for (auto& c0 : b.cols) {
     DevColumn c = slice_column(c0, r0, r1);
@@ -770,7 +774,12 @@ void export_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, Arro
     }
     hcs.push_back(std::move(h));
   }
-  export_record_batch(std::move(hcs), n, out, out_schema);
+  return hcs;
+}
+
+void export_batch(const Exec& x, const DevBatch& b, int64_t r0, int64_t r1, ArrowArray* out, ArrowSchema* out_schema) {
+  std::vector<HostCol> hcs = download_batch(x, b, r0, r1);
+  export_record_batch(std::move(hcs), r1 - r0, out, out_schema);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1740,14 +1749,17 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   }
   const std::string hint_key = (x.s ? x.s->fingerprint : std::string("?")) + "#" + std::to_string(node_idx);
   int level = 0;
+  bool had_hint = false;
   {
     std::lock_guard<std::mutex> g(x.e->mu);
     auto it = x.e->agg_hint.find(hint_key);
     if (it != x.e->agg_hint.end()) {
       level = it->second / 4;
       pack_mode = std::min(pack_mode, it->second % 4);
+      had_hint = true;
     }
   }
+  bool sampled = false;
   // strategy ladder: register sink (<= 4 groups) -> global table of growing capacity; packed keys -> plain keys
   std::unique_ptr<PipelineBuilder> pbp;
   AggLowered L;
@@ -1805,6 +1817,26 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       DevPtr hi = dev_alloc(hi_bytes, x.st());
       tm.keep.push_back(hi);
       P.acc_hi = (unsigned long long*)hi->ptr;
+    }
+    // First sight of a large integer-keyed aggregate: group the first 16 K rows on the hash kernel to learn whether the
+    // 4-group register sink can apply at all and which table class to start with, instead of discovering it by running
+    // (and abandoning) full passes up the capacity ladder.
+    if (!sampled && !had_hint && level == 0 && n_keys > 0 && src->n > ((int64_t)1 << 20)) {
+      sampled = true;
+      GroupBySpec probe;
+      const int64_t sample_rows = 16384;
+      TableMem stm = alloc_table(x, 65536, n_keys, L.accs);
+      P.table = stm.T;
+      if (match_groupby(P, probe)) {
+        probe.n_rows = sample_rows;
+        unsigned int seen = 0;
+        RunOutcome so = launch_program(x, pb, 0, nullptr, true, nullptr, stm.T.n_groups, &seen, &probe);
+        if (!so.status.pack_overflow && (so.status.overflow || seen > (unsigned)VM_REG_GROUPS)) {
+          level = (so.status.overflow || (int64_t)seen * 2 > sample_rows) ? 3 : 2;  // (nearly) every row its own group: 16 M slots; else 1 M
+          continue;
+        }
+      }
+      P.table = tm.T;
     }
     FusedPlan fspec;
     const bool use_fused = level == 0 && match_fused(P, fspec);
@@ -4215,6 +4247,255 @@ int b200_exchange_stage(b200_engine* e, const char* job_id, int64_t stage_id, in
       stats->sent_bytes = sent;
       stats->recv_bytes = recvd;
     }
+  });
+}
+
+// ---- the reference's shuffle file format: Arrow IPC streams with LZ4_FRAME bodies (csrc/host/arrow_ipc.hpp) ----------------
+static std::vector<HostCol> host_cols_from_arrow(ArrowArray* arr, ArrowSchema* sch, int64_t* n_rows) {
+  std::vector<ImportedCol> ics = import_record_batch(arr, sch, n_rows);
+  const int64_t n = *n_rows;
+  std::vector<HostCol> out;
+  for (auto& ic : ics) {
+    HostCol h;
+    h.name = ic.name;
+    h.type = ic.type;
+    h.nullable = ic.nullable;
+    h.n = n;
+    if (ic.large_offsets) throw EngineError(B200_ERR_UNSUPPORTED, "LargeUtf8 columns are not supported");
+    auto bit = [](const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; };
+    if (ic.null_count > 0 && ic.validity) {
+      h.validity.assign((size_t)((n + 7) / 8), 0);
+      for (int64_t i = 0; i < n; i++)
+        if (bit(ic.validity, i + ic.offset)) h.validity[(size_t)(i >> 3)] |= (uint8_t)(1u << (i & 7));
+        else h.null_count++;
+      if (h.null_count == 0) h.validity.clear();
+    }
+    if (ic.type.id == TypeId::Null) {
+      h.null_count = n;
+    } else if (ic.type.id == TypeId::Bool) {
+      h.data.assign((size_t)((n + 7) / 8), 0);
+      for (int64_t i = 0; i < n; i++)
+        if (bit(ic.data, i + ic.offset)) h.data[(size_t)(i >> 3)] |= (uint8_t)(1u << (i & 7));
+    } else if (ic.type.id == TypeId::Utf8) {
+      const int32_t* off = (const int32_t*)ic.data + ic.offset;
+      h.data.resize((size_t)(n + 1) * 4);
+      int32_t* po = (int32_t*)h.data.data();
+      for (int64_t i = 0; i <= n; i++) po[i] = off[i] - off[0];
+      if (n) h.extra.assign(ic.extra + off[0], ic.extra + off[n]);
+    } else {
+      const size_t w = (size_t)ic.type.width();
+      h.data.assign(ic.data + (size_t)ic.offset * w, ic.data + (size_t)(ic.offset + n) * w);
+    }
+    out.push_back(std::move(h));
+  }
+  return out;
+}
+
+static std::vector<uint8_t> read_whole_file(const std::string& path, uint64_t offset, uint64_t length) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw EngineError(B200_ERR_NOT_FOUND, "cannot open " + path);  // -> FetchFailed
+  fseek(f, 0, SEEK_END);
+  const uint64_t fsize = (uint64_t)ftell(f);
+  if (length == 0 && offset == 0) length = fsize;
+  if (offset + length > fsize) {
+    fclose(f);
+    throw EngineError(B200_ERR_INVALID, "byte range outside " + path);
+  }
+  fseek(f, (long)offset, SEEK_SET);
+  std::vector<uint8_t> buf((size_t)length);
+  const size_t got = length ? fread(buf.data(), 1, (size_t)length, f) : 0;
+  fclose(f);
+  if (got != length) throw EngineError(B200_ERR_INVALID, "short read on " + path);
+  return buf;
+}
+
+static void write_whole_file(const std::string& path, const std::vector<uint8_t>& bytes) {
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw EngineError(B200_ERR_INVALID, "cannot create " + path);
+  const size_t put = bytes.empty() ? 0 : fwrite(bytes.data(), 1, bytes.size(), f);
+  fclose(f);
+  if (put != bytes.size()) throw EngineError(B200_ERR_INVALID, "short write on " + path);
+}
+
+static void make_dirs(const std::string& path) {
+  std::string cur;
+  for (size_t i = 0; i <= path.size(); i++) {
+    if (i == path.size() || path[i] == '/') {
+      if (!cur.empty() && cur != "/") mkdir(cur.c_str(), 0777);
+    }
+    if (i < path.size()) cur.push_back(path[i]);
+  }
+}
+
+int b200_ipc_encode(struct ArrowArray* batch, struct ArrowSchema* schema, int compress, int64_t max_rows_per_message, uint8_t** out, uint64_t* out_len) {
+  return guard([&] {
+    if (!batch || !schema || !out || !out_len) throw EngineError(B200_ERR_INVALID, "null argument");
+    int64_t n = 0;
+    std::vector<HostCol> cols;
+    try {
+      cols = host_cols_from_arrow(batch, schema, &n);
+    } catch (const std::runtime_error& ex) {
+      throw EngineError(B200_ERR_INVALID, ex.what());
+    }
+    if (batch->release) batch->release(batch);
+    if (schema->release) schema->release(schema);
+    std::vector<uint8_t> bytes;
+    ipc::write_stream(bytes, cols, n, compress != 0, max_rows_per_message);
+    uint8_t* p = (uint8_t*)malloc(bytes.size() ? bytes.size() : 1);
+    if (!p) throw EngineError(B200_ERR_OOM, "host out of memory");
+    memcpy(p, bytes.data(), bytes.size());
+    *out = p;
+    *out_len = bytes.size();
+  });
+}
+
+void b200_ipc_free(uint8_t* p) { free(p); }
+
+int b200_ipc_decode(const uint8_t* buf, uint64_t len, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  return guard([&] {
+    if (!buf || !out || !out_schema) throw EngineError(B200_ERR_INVALID, "null argument");
+    std::vector<HostCol> cols;
+    int64_t n = 0;
+    try {
+      n = ipc::read_streams(buf, (size_t)len, cols);
+    } catch (const std::runtime_error& ex) {
+      throw EngineError(B200_ERR_INVALID, ex.what());
+    }
+    export_record_batch(std::move(cols), n, out, out_schema);
+  });
+}
+
+// Every piece this executor's map tasks produced for (job, stage), as files in the reference's layout below work_dir
+// (create_shuffle_path, execution_plans/mod.rs:66-99): what makes HBM-resident shuffle output survive the executor and
+// readable by the reference's own readers (a CPU executor's ShuffleReaderExec, the Flight service).
+int b200_shuffle_write_files(b200_engine* e, const char* job_id, int64_t stage_id, const char* work_dir, int n_out_partitions, int sort_layout,
+                             uint64_t* files_written, uint64_t* bytes_written) {
+  return guard([&] {
+    if (!e || !job_id || !work_dir) throw EngineError(B200_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    Exec x{e, nullptr, nullptr};
+    struct Item { int64_t part; Piece piece; };
+    std::vector<Item> items;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      for (auto& kv : e->shuffle)
+        if (kv.first.job == job_id && kv.first.stage == stage_id)
+          for (auto& pc : kv.second)
+            if (pc.src_rank == e->rank) items.push_back(Item{kv.first.part, pc});
+    }
+    const std::string base = std::string(work_dir) + "/" + job_id + "/" + std::to_string(stage_id);
+    uint64_t nfiles = 0, nbytes = 0;
+    const int64_t bs = e->batch_size;
+    if (!sort_layout) {
+      for (auto& it : items) {
+        std::vector<HostCol> cols = download_batch(x, *it.piece.batch, it.piece.r0, it.piece.r1);
+        std::vector<uint8_t> bytes;
+        ipc::write_stream(bytes, cols, it.piece.r1 - it.piece.r0, true, bs);
+        const std::string dir = base + "/" + std::to_string(it.part);
+        make_dirs(dir);
+        const std::string path = dir + (it.piece.file_id >= 0 ? "/data-" + std::to_string(it.piece.file_id) + ".arrow" : "/data.arrow");
+        write_whole_file(path, bytes);
+        nfiles++;
+        nbytes += bytes.size();
+      }
+    } else {
+      // one consolidated file per map task: [schema-only stream][partition 0 streams][partition 1 streams]... + index
+      std::map<int64_t, std::vector<Item*>> by_task;
+      for (auto& it : items) by_task[it.piece.file_id].push_back(&it);
+      for (auto& kv : by_task) {
+        if (kv.first < 0) throw EngineError(B200_ERR_INVALID, "sort-shuffle layout needs a file id (un-partitioned stage output)");
+        std::vector<uint8_t> bytes;
+        std::vector<int64_t> offsets((size_t)n_out_partitions + 1, 0);
+        bool header = false;
+        std::vector<std::vector<HostCol>> parts((size_t)n_out_partitions);
+        std::vector<int64_t> rows((size_t)n_out_partitions, 0);
+        for (Item* it : kv.second) {
+          if (it->part >= n_out_partitions) throw EngineError(B200_ERR_INVALID, "stored partition id beyond n_out_partitions");
+          parts[(size_t)it->part] = download_batch(x, *it->piece.batch, it->piece.r0, it->piece.r1);
+          rows[(size_t)it->part] = it->piece.r1 - it->piece.r0;
+          if (!header) {
+            ipc::write_schema(bytes, parts[(size_t)it->part]);
+            ipc::write_eos(bytes);
+            header = true;
+          }
+        }
+        for (int p = 0; p < n_out_partitions; p++) {
+          offsets[(size_t)p] = (int64_t)bytes.size();
+          if (rows[(size_t)p] > 0) ipc::write_stream(bytes, parts[(size_t)p], rows[(size_t)p], true, bs);
+        }
+        offsets[(size_t)n_out_partitions] = (int64_t)bytes.size();
+        const std::string dir = base + "/" + std::to_string(kv.first);
+        make_dirs(dir);
+        write_whole_file(dir + "/data.arrow", bytes);
+        std::vector<uint8_t> idx((size_t)(n_out_partitions + 1) * 8);
+        memcpy(idx.data(), offsets.data(), idx.size());
+        write_whole_file(dir + "/data.arrow.index", idx);
+        nfiles += 2;
+        nbytes += bytes.size() + idx.size();
+      }
+    }
+    if (files_written) *files_written = nfiles;
+    if (bytes_written) *bytes_written = nbytes;
+  });
+}
+
+// One reference-format shuffle file (or a byte range of it: a partition of a sort-shuffle data file) into the shuffle
+// store as a piece of (job, stage, out_partition) -- the local-read path of ShuffleReaderExec (shuffle_reader.rs:698-771,
+// sort_shuffle/reader.rs:51-84) with the decoded batches landing in HBM.  byte_length 0 with byte_offset 0 = whole file;
+// use_index != 0: `path` is a sort-shuffle data file, the range of `out_partition` is taken from `path` + ".index".
+int b200_shuffle_read_file(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition, int64_t file_id, const char* path, uint64_t byte_offset,
+                           uint64_t byte_length, int use_index) {
+  return guard([&] {
+    if (!e || !job_id || !path) throw EngineError(B200_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    std::vector<HostCol> cols;
+    int64_t n = 0;
+    try {
+      if (use_index) {
+        std::vector<uint8_t> idx = read_whole_file(std::string(path) + ".index", 0, 0);
+        if (idx.size() % 8 || idx.size() < 16) throw EngineError(B200_ERR_INVALID, "invalid shuffle index file");
+        const size_t entries = idx.size() / 8;
+        if ((size_t)out_partition + 1 >= entries) throw EngineError(B200_ERR_NOT_FOUND, "partition not found in the shuffle index");
+        int64_t o0, o1, first;
+        memcpy(&first, idx.data(), 8);
+        memcpy(&o0, idx.data() + 8 * (size_t)out_partition, 8);
+        memcpy(&o1, idx.data() + 8 * (size_t)out_partition + 8, 8);
+        if (o0 < 0 || o1 < o0 || first < 0) throw EngineError(B200_ERR_INVALID, "invalid partition byte range in the shuffle index");
+        // the leading schema-only stream, then the partition's own streams
+        if (first > 0) {
+          std::vector<uint8_t> head = read_whole_file(path, 0, (uint64_t)first);
+          ipc::read_streams(head.data(), head.size(), cols);
+        }
+        if (o1 > o0) {
+          std::vector<uint8_t> body = read_whole_file(path, (uint64_t)o0, (uint64_t)(o1 - o0));
+          n = ipc::read_streams(body.data(), body.size(), cols);
+        }
+      } else {
+        std::vector<uint8_t> body = read_whole_file(path, byte_offset, byte_length);
+        n = ipc::read_streams(body.data(), body.size(), cols);
+      }
+    } catch (const std::runtime_error& ex) {
+      throw EngineError(B200_ERR_INVALID, ex.what());
+    }
+    // host columns -> Arrow C structs -> the ordinary ingest path
+    ArrowArray arr;
+    ArrowSchema sch;
+    export_record_batch(std::move(cols), n, &arr, &sch);
+    DevBatchPtr b = import_batch(e, &arr, &sch);
+    std::vector<int64_t> sb;
+    for (auto& c : b->cols)
+      if (c.type.id == TypeId::Utf8) sb.push_back(c.chars_bytes);
+    std::lock_guard<std::mutex> g(e->mu);
+    auto& v = e->shuffle[ShuffleKey{job_id, stage_id, out_partition}];
+    v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == file_id && pc.src_rank == -1; }), v.end());
+    Piece pc;
+    pc.file_id = file_id;
+    pc.batch = b;
+    pc.r0 = 0;
+    pc.r1 = n;
+    pc.src_rank = -1;  // came from a file, not from one of the box's GPU executors
+    pc.str_bytes = sb;
+    v.push_back(pc);
   });
 }
 

@@ -77,6 +77,7 @@ EXPORTED_SYMBOLS = [
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
     "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_engine_kernel_stats",
+    "b200_ipc_encode", "b200_ipc_free", "b200_ipc_decode", "b200_shuffle_write_files", "b200_shuffle_read_file",
     "b200_version",
 ]
 
@@ -126,6 +127,12 @@ def load_library():
     L.b200_remove_stage_data.argtypes = [vp, cp, i64]
     L.b200_device_gather.argtypes = [vp, C.POINTER(DeviceBuffer), ci, vp, u64]
     L.b200_engine_kernel_stats.argtypes = [vp, C.POINTER(KernelStat), ci, C.POINTER(ci), ci]
+    L.b200_ipc_encode.argtypes = [vp, vp, ci, i64, C.POINTER(vp), C.POINTER(u64)]
+    L.b200_ipc_free.argtypes = [vp]
+    L.b200_ipc_free.restype = None
+    L.b200_ipc_decode.argtypes = [vp, u64, vp, vp]
+    L.b200_shuffle_write_files.argtypes = [vp, cp, i64, cp, ci, ci, C.POINTER(u64), C.POINTER(u64)]
+    L.b200_shuffle_read_file.argtypes = [vp, cp, i64, ci, i64, cp, u64, u64, ci]
     L.b200_comm_unique_id.argtypes = [vp, u64]
     L.b200_engine_comm_init.argtypes = [vp, vp, u64]
     L.b200_exchange_stage.argtypes = [vp, cp, i64, ci, ci, ci, cp, C.POINTER(ExchangeStats)]
@@ -152,6 +159,27 @@ class B200Error(RuntimeError):
 def _check(rc):
     if rc != 0:
         raise B200Error(rc, load_library().b200_last_error().decode(errors="replace"))
+
+
+def ipc_encode(batch: pa.RecordBatch, compress: bool = True, max_rows_per_message: int = 0) -> bytes:
+    """RecordBatch -> one Arrow IPC stream (schema, record batch message(s), end-of-stream) with LZ4_FRAME buffers: the byte
+    format of the reference's shuffle files (b200_ipc_encode; host only)."""
+    arr, sch = ArrowArray(), ArrowSchema()
+    batch._export_to_c(C.addressof(arr), C.addressof(sch))
+    out, n = C.c_void_p(), C.c_uint64(0)
+    _check(load_library().b200_ipc_encode(C.addressof(arr), C.addressof(sch), 1 if compress else 0, max_rows_per_message, C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out.value, n.value)
+    finally:
+        load_library().b200_ipc_free(out)
+
+
+def ipc_decode(data: bytes) -> pa.RecordBatch:
+    """One or several back-to-back Arrow IPC streams (optionally LZ4_FRAME compressed) -> one RecordBatch (b200_ipc_decode)."""
+    arr, sch = ArrowArray(), ArrowSchema()
+    buf = C.create_string_buffer(data, len(data))
+    _check(load_library().b200_ipc_decode(buf, len(data), C.addressof(arr), C.addressof(sch)))
+    return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
 
 
 def parquet_describe(path: str) -> dict:
@@ -357,6 +385,18 @@ class GpuExecutionEngine:
         sj = schema if isinstance(schema, str) else _json.dumps(schema)
         _check(load_library().b200_exchange_stage(self.h, job_id.encode(), stage_id, n_out_partitions, mode, root, sj.encode(), C.byref(st)))
         return {"sent_bytes": st.sent_bytes, "recv_bytes": st.recv_bytes}
+
+    # -- the reference's shuffle files ---------------------------------------------------------------------
+    def shuffle_write_files(self, job_id: str, stage_id: int, work_dir: str, n_out_partitions: int, sort_layout: bool) -> dict:
+        nf, nb = C.c_uint64(0), C.c_uint64(0)
+        _check(load_library().b200_shuffle_write_files(self.h, job_id.encode(), stage_id, work_dir.encode(), n_out_partitions, 1 if sort_layout else 0,
+                                                       C.byref(nf), C.byref(nb)))
+        return {"files": nf.value, "bytes": nb.value}
+
+    def shuffle_read_file(self, job_id: str, stage_id: int, out_partition: int, file_id: int, path: str, byte_offset: int = 0, byte_length: int = 0,
+                          use_index: bool = False) -> None:
+        _check(load_library().b200_shuffle_read_file(self.h, job_id.encode(), stage_id, out_partition, file_id, path.encode(), byte_offset, byte_length,
+                                                     1 if use_index else 0))
 
     def remove_job_data(self, job_id: str) -> None:
         _check(load_library().b200_remove_job_data(self.h, job_id.encode()))

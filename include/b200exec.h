@@ -194,6 +194,23 @@ int b200_engine_comm_init(b200_engine* e, const void* nccl_id, uint64_t id_bytes
 int b200_exchange_stage(b200_engine* e, const char* job_id, int64_t stage_id, int n_out_partitions, int mode, int root,
                         const char* schema_json, b200_exchange_stats* stats);
 
+/* ---- the reference's shuffle file format -----------------------------------
+ * Arrow IPC streams with LZ4_FRAME body compression, written the way ShuffleWriterExec / SortShuffleWriterExec write
+ * them (shuffle_writer.rs:317-328, sort_shuffle/writer.rs:419-513, index format sort_shuffle/index.rs:18-33) and read the
+ * way ShuffleReaderExec reads them (shuffle_reader.rs:698-771, sort_shuffle/reader.rs:51-84): GPU and CPU executors can
+ * consume each other's stage output, and HBM-resident partitions can be persisted under `work_dir` so that they survive
+ * the executor.  b200_ipc_encode / b200_ipc_decode are the host-only codec (no CUDA call). */
+int b200_ipc_encode(struct ArrowArray* batch, struct ArrowSchema* schema, int compress, int64_t max_rows_per_message,
+                    uint8_t** out, uint64_t* out_len);           /* releases batch / schema; free *out with b200_ipc_free */
+void b200_ipc_free(uint8_t* p);
+int b200_ipc_decode(const uint8_t* buf, uint64_t len, struct ArrowArray* out, struct ArrowSchema* out_schema);  /* one or several back-to-back streams */
+/* sort_layout 0: work_dir/job/stage/{out_part}/data-{file_id}.arrow (or data.arrow when the stage was un-partitioned);
+ * sort_layout 1: work_dir/job/stage/{file_id}/data.arrow + data.arrow.index with n_out_partitions + 1 offsets */
+int b200_shuffle_write_files(b200_engine* e, const char* job_id, int64_t stage_id, const char* work_dir, int n_out_partitions,
+                             int sort_layout, uint64_t* files_written, uint64_t* bytes_written);
+int b200_shuffle_read_file(b200_engine* e, const char* job_id, int64_t stage_id, int out_partition, int64_t file_id,
+                           const char* path, uint64_t byte_offset, uint64_t byte_length, int use_index);
+
 /* ---- pinned host staging (harness side of "RecordBatches are pinned and DMA'd") ------------- */
 void* b200_host_alloc_pinned(uint64_t bytes);
 void b200_host_free_pinned(void* p);
