@@ -72,66 +72,82 @@ __device__ __forceinline__ bool ff_cmp(int op, int c) {  // c: -1 / 0 / +1
   }
 }
 
-__device__ __forceinline__ bool ff_eval(const FastFilterSpec& S, int64_t i) {
-  unsigned long long regs = 0;
+// The predicate program for FF_R rows in lockstep: every instruction first loads its operands for all rows (independent
+// loads in flight together), then computes; rows are predicated, nothing branches on data.  Returns the pass bits.
+__device__ __forceinline__ uint32_t ff_eval_rows(const FastFilterSpec& S, const int64_t (&row)[FF_R], uint32_t live) {
+  unsigned long long regs[FF_R];
+#pragma unroll
+  for (int r = 0; r < FF_R; r++) regs[r] = 0;
+  uint32_t pass = live;
   for (int k = 0; k < S.n_ops; k++) {
     const FfOp op = S.ops[k];
-    bool r;
+    uint32_t res = 0;
     if (op.kind == FF_CMP) {
       if (op.vt == 2) {
-        const uint8_t *pa, *pb;
-        uint32_t la, lb;
-        if (op.a_imm) {
-          pa = (const uint8_t*)S.imms[op.a].lo;
-          la = (uint32_t)S.imms[op.a].hi;
-        } else {
-          ff_load_str(S.cols[op.a], i, pa, la);
+#pragma unroll
+        for (int r = 0; r < FF_R; r++) {
+          if (!(((op.filter ? pass : live) >> r) & 1)) continue;  // string compares walk bytes: skip rows that cannot matter
+          const uint8_t *pa, *pb;
+          uint32_t la, lb;
+          if (op.a_imm) {
+            pa = (const uint8_t*)S.imms[op.a].lo;
+            la = (uint32_t)S.imms[op.a].hi;
+          } else {
+            ff_load_str(S.cols[op.a], row[r], pa, la);
+          }
+          if (op.b_imm) {
+            pb = (const uint8_t*)S.imms[op.b].lo;
+            lb = (uint32_t)S.imms[op.b].hi;
+          } else {
+            ff_load_str(S.cols[op.b], row[r], pb, lb);
+          }
+          bool eq = la == lb;
+          for (uint32_t q = 0; eq && q < la; q++) eq = pa[q] == pb[q];
+          res |= (uint32_t)((op.cmp == 0) ? eq : !eq) << r;
         }
-        if (op.b_imm) {
-          pb = (const uint8_t*)S.imms[op.b].lo;
-          lb = (uint32_t)S.imms[op.b].hi;
-        } else {
-          ff_load_str(S.cols[op.b], i, pb, lb);
-        }
-        bool eq = la == lb;
-        for (uint32_t q = 0; eq && q < la; q++) eq = pa[q] == pb[q];
-        r = (op.cmp == 0) ? eq : !eq;
       } else {
-        int64_t alo, ahi, blo, bhi;
-        if (op.a_imm) {
-          alo = (int64_t)S.imms[op.a].lo;
-          ahi = (int64_t)S.imms[op.a].hi;
-        } else {
-          ff_load_int(S.cols[op.a], i, alo, ahi);
+        int64_t alo[FF_R], ahi[FF_R], blo[FF_R], bhi[FF_R];
+#pragma unroll
+        for (int r = 0; r < FF_R; r++) {
+          const int64_t i = ((live >> r) & 1) ? row[r] : row[0];
+          if (op.a_imm) {
+            alo[r] = (int64_t)S.imms[op.a].lo;
+            ahi[r] = (int64_t)S.imms[op.a].hi;
+          } else {
+            ff_load_int(S.cols[op.a], i, alo[r], ahi[r]);
+          }
+          if (op.b_imm) {
+            blo[r] = (int64_t)S.imms[op.b].lo;
+            bhi[r] = (int64_t)S.imms[op.b].hi;
+          } else {
+            ff_load_int(S.cols[op.b], i, blo[r], bhi[r]);
+          }
         }
-        if (op.b_imm) {
-          blo = (int64_t)S.imms[op.b].lo;
-          bhi = (int64_t)S.imms[op.b].hi;
-        } else {
-          ff_load_int(S.cols[op.b], i, blo, bhi);
+#pragma unroll
+        for (int r = 0; r < FF_R; r++) {
+          int c;
+          if (op.vt == 0) c = alo[r] < blo[r] ? -1 : (alo[r] > blo[r] ? 1 : 0);
+          else if (op.vt == 3) c = (uint64_t)alo[r] < (uint64_t)blo[r] ? -1 : ((uint64_t)alo[r] > (uint64_t)blo[r] ? 1 : 0);
+          else c = ahi[r] != bhi[r] ? (ahi[r] < bhi[r] ? -1 : 1) : ((uint64_t)alo[r] < (uint64_t)blo[r] ? -1 : ((uint64_t)alo[r] > (uint64_t)blo[r] ? 1 : 0));
+          res |= (uint32_t)ff_cmp(op.cmp, c) << r;
         }
-        int c;
-        if (op.vt == 0) c = alo < blo ? -1 : (alo > blo ? 1 : 0);
-        else if (op.vt == 3) c = (uint64_t)alo < (uint64_t)blo ? -1 : ((uint64_t)alo > (uint64_t)blo ? 1 : 0);
-        else c = ahi != bhi ? (ahi < bhi ? -1 : 1) : ((uint64_t)alo < (uint64_t)blo ? -1 : ((uint64_t)alo > (uint64_t)blo ? 1 : 0));
-        r = ff_cmp(op.cmp, c);
       }
-    } else if (op.kind == FF_AND) {
-      r = ((regs >> op.a) & 1) && ((regs >> op.b) & 1);
-    } else if (op.kind == FF_OR) {
-      r = ((regs >> op.a) & 1) || ((regs >> op.b) & 1);
-    } else if (op.kind == FF_NOT) {
-      r = !((regs >> op.a) & 1);
-    } else {  // FF_FILTER_REG
-      r = (regs >> op.a) & 1;
+    } else {
+#pragma unroll
+      for (int r = 0; r < FF_R; r++) {
+        const bool x = (regs[r] >> op.a) & 1, y = (regs[r] >> op.b) & 1;
+        const bool v = op.kind == FF_AND ? (x && y) : op.kind == FF_OR ? (x || y) : op.kind == FF_NOT ? !x : x;
+        res |= (uint32_t)v << r;
+      }
     }
     if (op.filter) {
-      if (!r) return false;
+      pass &= res;
     } else {
-      regs = (regs & ~(1ull << op.dst)) | ((unsigned long long)r << op.dst);
+#pragma unroll
+      for (int r = 0; r < FF_R; r++) regs[r] = (regs[r] & ~(1ull << op.dst)) | ((unsigned long long)((res >> r) & 1) << op.dst);
     }
   }
-  return true;
+  return pass;
 }
 
 __global__ void __launch_bounds__(FF_BLOCK, 4) fast_filter_kernel(const FastFilterSpec S) {
@@ -142,13 +158,17 @@ __global__ void __launch_bounds__(FF_BLOCK, 4) fast_filter_kernel(const FastFilt
   const int64_t n_tiles = (n + FF_TILE - 1) / FF_TILE;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const int64_t t0 = t * FF_TILE;
-    uint32_t pass = 0, lane_pre[FF_R];
+    uint32_t lane_pre[FF_R], live = 0;
+    int64_t row[FF_R];
 #pragma unroll
     for (int r = 0; r < FF_R; r++) {
-      const int64_t i = t0 + r * FF_BLOCK + tid;
-      const bool p = i < n && ff_eval(S, i);
-      pass |= (uint32_t)p << r;
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, p);
+      row[r] = t0 + r * FF_BLOCK + tid;
+      live |= (uint32_t)(row[r] < n) << r;
+    }
+    const uint32_t pass = live ? ff_eval_rows(S, row, live) : 0u;
+#pragma unroll
+    for (int r = 0; r < FF_R; r++) {
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, (pass >> r) & 1);
       lane_pre[r] = __popc(m & ((1u << lane) - 1u));
       if (lane == 0) warp_tot[r][warp] = __popc(m);
     }

@@ -270,6 +270,8 @@ struct PqPage {
   uint32_t def_off, def_len;  // definition-level section inside the payload; len 0 = required column / no levels
   uint32_t val_off, val_len;  // values section
   uint32_t encoding;        // 0 PLAIN, 1 dictionary indices, 2 RLE (BOOLEAN values)
+  uint32_t v1_levels;       // 1: data page V1 of a nullable column -- the payload starts with [u32 length][definition levels], values follow
+                            //    (the length sits inside the possibly compressed payload, so it is read on the device); val_len = payload bytes
   int64_t row0;             // first row of the page inside the column (dictionary pages: first entry in the dictionary array)
   int64_t dict_base;        // data pages: first entry of their chunk's dictionary
 };
@@ -280,6 +282,14 @@ struct PqColumn {
   int32_t _pad;
   void* dict;               // decoded dictionary entries (output type; byte arrays as 16-byte views)
 };
+struct PqDecompJob {
+  const uint8_t* src;   // compressed (or stored) bytes in HBM
+  uint8_t* dst;         // where the page payload is rebuilt
+  uint32_t src_len, dst_len;
+  uint32_t raw_copy;    // 1: plain copy (sections that are never compressed)
+  uint32_t _pad;
+};
+void launch_pq_snappy(const PqDecompJob* jobs, int n_jobs, unsigned int* error, cudaStream_t st);
 void launch_pq_levels(const PqPage* pages, int n_pages, uint8_t* valid, uint32_t* nonnull, unsigned long long* total_nonnull, cudaStream_t st);
 void launch_pq_page_scan(const uint32_t* nonnull, int n_pages, unsigned long long* dense_base, cudaStream_t st);
 void launch_pq_dict(const PqColumn& C, const PqPage* dict_pages, int n_dicts, cudaStream_t st);

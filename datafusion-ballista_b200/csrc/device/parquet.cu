@@ -60,6 +60,24 @@ __device__ __forceinline__ void pq_hybrid_decode(const uint8_t* p, const uint8_t
   }
 }
 
+// where the definition levels and the values of a page are (V1 pages of nullable columns carry the levels' length in-band)
+__device__ __forceinline__ void pq_sections(const PqPage& pg, uint32_t& def_off, uint32_t& def_len, uint32_t& val_off, uint32_t& val_len) {
+  if (pg.v1_levels) {
+    uint32_t len = 0;
+    for (int k = 0; k < 4; k++) len |= (uint32_t)pg.data[k] << (8 * k);
+    if (len > pg.val_len - 4) len = pg.val_len - 4;  // corrupt length: stay inside the page
+    def_off = 4;
+    def_len = len;
+    val_off = 4 + len;
+    val_len = pg.val_len - 4 - len;
+  } else {
+    def_off = pg.def_off;
+    def_len = pg.def_len;
+    val_off = pg.val_off;
+    val_len = pg.val_len;
+  }
+}
+
 // ---- definition levels -> validity bytes + non-null count per page ---------------------------------------------------------
 __global__ void __launch_bounds__(128) pq_levels_kernel(const PqPage* __restrict__ pages, int n_pages, uint8_t* __restrict__ valid, uint32_t* __restrict__ nonnull,
                                                         unsigned long long* __restrict__ total_nonnull) {
@@ -68,13 +86,15 @@ __global__ void __launch_bounds__(128) pq_levels_kernel(const PqPage* __restrict
   const PqPage pg = pages[warp];
   uint8_t* v = valid + pg.row0;
   uint32_t cnt = 0;
-  if (pg.def_len == 0) {
+  uint32_t def_off, def_len, val_off, val_len;
+  pq_sections(pg, def_off, def_len, val_off, val_len);
+  if (def_len == 0) {
     for (uint32_t k = lane; k < pg.n_values; k += 32) v[k] = 1;
     cnt = pg.n_values;
   } else {
-    const uint8_t* p = pg.data + pg.def_off;
+    const uint8_t* p = pg.data + def_off;
     uint32_t mine = 0;
-    pq_hybrid_decode(p, p + pg.def_len, 1, pg.n_values, lane, [&](uint32_t i, uint32_t lvl) {
+    pq_hybrid_decode(p, p + def_len, 1, pg.n_values, lane, [&](uint32_t i, uint32_t lvl) {
       v[i] = (uint8_t)(lvl & 1);
       mine += lvl & 1;
     });
@@ -219,8 +239,10 @@ __global__ void __launch_bounds__(128) pq_values_kernel(const PqColumn C, const 
   const PqPage pg = pages[warp];
   const uint64_t base = dense_base ? dense_base[warp] : (uint64_t)pg.row0;
   const uint32_t n = nonnull ? nonnull[warp] : pg.n_values;
-  const uint8_t* p = pg.data + pg.val_off;
-  const uint8_t* end = p + pg.val_len;
+  uint32_t def_off, def_len, val_off, val_len;
+  pq_sections(pg, def_off, def_len, val_off, val_len);
+  const uint8_t* p = pg.data + val_off;
+  const uint8_t* end = p + val_len;
   if (pg.encoding == 1) {  // [PLAIN|RLE]_DICTIONARY: one byte of bit width, then hybrid runs of dictionary indices
     if (p >= end) return;
     const int bw = *p++;
@@ -280,7 +302,93 @@ __global__ void __launch_bounds__(128) pq_expand_kernel(const PqPage* __restrict
   }
 }
 
+// ---- Snappy (raw format) page decompression: one warp per page -----------------------------------------------------------------
+// Format (google/snappy format_description.txt): varint uncompressed length, then elements tagged in their low two bits:
+// 00 literal (length in the upper six bits, 60..63 = 1..4 following length bytes), 01 copy with 11-bit offset and length
+// 4..11, 10 copy with 16-bit offset, 11 copy with 32-bit offset.  Lane 0 parses the element, all lanes move its bytes; a copy
+// whose offset is shorter than its length (a repeating pattern) is moved in offset-sized steps.
+__global__ void __launch_bounds__(128) pq_snappy_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, unsigned int* __restrict__ error) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_jobs) return;
+  const PqDecompJob J = jobs[warp];
+  if (J.raw_copy) {  // stored section (V2 levels, uncompressed V2 pages)
+    for (uint32_t k = lane; k < J.src_len; k += 32) J.dst[k] = J.src[k];
+    return;
+  }
+  const uint8_t* ip = J.src;
+  const uint8_t* iend = J.src + J.src_len;
+  uint8_t* out = J.dst;
+  // preamble
+  uint32_t ulen = 0;
+  for (int shift = 0; shift < 35 && ip < iend; shift += 7) {
+    const uint8_t b = *ip++;
+    ulen |= (uint32_t)(b & 0x7F) << shift;
+    if (!(b & 0x80)) break;
+  }
+  if (ulen != J.dst_len) {
+    if (lane == 0) atomicExch(error, 1u);
+    return;
+  }
+  uint32_t op = 0;
+  while (ip < iend && op < ulen) {
+    const uint8_t tag = *ip;  // every lane reads the same bytes: broadcast loads
+    uint32_t len, off = 0;
+    const uint8_t* lit = nullptr;
+    switch (tag & 3) {
+      case 0: {
+        uint32_t l = tag >> 2;
+        ip++;
+        if (l >= 60) {
+          const int nb = (int)l - 59;
+          l = 0;
+          for (int k = 0; k < nb; k++) l |= (uint32_t)ip[k] << (8 * k);
+          ip += nb;
+        }
+        len = l + 1;
+        lit = ip;
+        ip += len;
+        break;
+      }
+      case 1:
+        len = 4 + ((tag >> 2) & 7);
+        off = ((uint32_t)(tag >> 5) << 8) | ip[1];
+        ip += 2;
+        break;
+      case 2:
+        len = 1 + (tag >> 2);
+        off = (uint32_t)ip[1] | ((uint32_t)ip[2] << 8);
+        ip += 3;
+        break;
+      default:
+        len = 1 + (tag >> 2);
+        off = (uint32_t)ip[1] | ((uint32_t)ip[2] << 8) | ((uint32_t)ip[3] << 16) | ((uint32_t)ip[4] << 24);
+        ip += 5;
+        break;
+    }
+    if (op + len > ulen || (lit == nullptr && (off == 0 || off > op)) || (lit && lit + len > iend)) {
+      if (lane == 0) atomicExch(error, 1u);
+      return;
+    }
+    if (lit) {
+      for (uint32_t k = lane; k < len; k += 32) out[op + k] = lit[k];
+    } else {
+      // pattern copy: bytes further than `off` ahead depend on bytes this same copy writes
+      for (uint32_t done = 0; done < len; done += off) {
+        const uint32_t step = (len - done) < off ? (len - done) : off;
+        for (uint32_t k = lane; k < step; k += 32) out[op + done + k] = out[op + done + k - off];
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    op += len;
+  }
+  if (op != ulen && lane == 0) atomicExch(error, 1u);
+}
+
 static inline unsigned pq_grid(int n_warps) { return (unsigned)((n_warps * 32 + 127) / 128); }
+void launch_pq_snappy(const PqDecompJob* jobs, int n_jobs, unsigned int* error, cudaStream_t st) {
+  if (n_jobs > 0) pq_snappy_kernel<<<pq_grid(n_jobs), 128, 0, st>>>(jobs, n_jobs, error);
+}
 
 void launch_pq_levels(const PqPage* pages, int n_pages, uint8_t* valid, uint32_t* nonnull, unsigned long long* total_nonnull, cudaStream_t st) {
   if (n_pages > 0) pq_levels_kernel<<<pq_grid(n_pages), 128, 0, st>>>(pages, n_pages, valid, nonnull, total_nonnull);

@@ -2142,7 +2142,24 @@ struct Runner {
       }
       case PlanNode::Filter:
       case PlanNode::Projection: {
-        if (n.op == PlanNode::Filter && n.fetch >= 0) throw EngineError(B200_ERR_UNSUPPORTED, "FilterExec with fetch");
+        if (n.op == PlanNode::Filter && n.fetch >= 0) {
+          // FilterExec { fetch } (datafusion.proto:1027-1034): the first `fetch` rows that pass, in input order -- the
+          // materialising sinks keep the input order, so the prefix of the filtered batch is exactly that
+          std::vector<const PlanNode*> chain;
+          chain.push_back(&n);
+          const PlanNode* base = chain_base(*n.children[0], chain);
+          DevBatchPtr src = exec(*base, part);
+          for (auto* c : chain)
+            if (OpMetrics* m = x.m(c)) m->input_rows += (uint64_t)src->n;
+          PipelineBuilder pb(*src, x.st());
+          apply_chain(pb, chain);
+          DevBatchPtr all = run_materialize(x, pb, named_cols(pb, n.schema), src, met);
+          const int64_t keep = std::min<int64_t>(all->n, n.fetch);
+          out = std::make_shared<DevBatch>();
+          out->n = keep;
+          for (auto& c : all->cols) out->cols.push_back(slice_column(c, 0, keep));
+          break;
+        }
         out = with_chain(n, part, false, [&](const BuilderFactory& mk, DevBatchPtr& src) {
           auto pb = mk();
           return run_materialize(x, *pb, named_cols(*pb, n.schema), src, met);
@@ -3266,7 +3283,11 @@ struct PqHostColumn {
   bool optional = false;
   std::vector<PqPage> pages, dicts;
   int64_t rows = 0, dict_entries = 0;
-  DevPtr raw;  // the column's chunks, back to back
+  DevPtr raw;  // the column's chunks, back to back (as stored in the file: possibly compressed)
+  DevPtr dec;  // Snappy-compressed chunks: the pages' payloads rebuilt uncompressed
+  std::vector<PqDecompJob> jobs;
+  std::vector<uint8_t> page_in_dec, dict_in_dec;  // per page: its payload pointer is an offset into `dec` until `dec` exists
+  size_t dec_bytes = 0;
 };
 
 static DataType pq_arrow_type(const pq::SchemaElement& se, int* out_kind) {
@@ -3350,7 +3371,9 @@ DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vect
     size_t dpos = 0;
     for (auto& rg : fm.row_groups) {
       const pq::ColumnChunkMeta& cm = rg.columns[(size_t)c.leaf];
-      if (cm.codec != 0) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: column " + c.se.name + " is compressed (codec " + std::to_string(cm.codec) + "); the device scan reads UNCOMPRESSED pages");
+      if (cm.codec != 0 && cm.codec != 1)
+        throw EngineError(B200_ERR_UNSUPPORTED, "parquet: column " + c.se.name + " uses compression codec " + std::to_string(cm.codec) + " (the device scan reads UNCOMPRESSED and SNAPPY pages)");
+      const bool snappy = cm.codec == 1;
       int64_t start = cm.data_page_offset;
       if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
       if (start < 0 || (size_t)start + (size_t)cm.total_compressed > fsize) throw EngineError(B200_ERR_INVALID, "parquet: column chunk outside the file");
@@ -3368,37 +3391,64 @@ DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vect
         }
         const uint8_t* payload = hp + h.header_bytes;
         if (payload + h.compressed_size > hend) throw EngineError(B200_ERR_INVALID, "parquet: page overruns its chunk");
+        const uint8_t* dev_payload = dbase + (payload - (file.p + start));
         PqPage pg;
         memset(&pg, 0, sizeof pg);
-        pg.data = dbase + (payload - (file.p + start));
         pg.n_values = (uint32_t)h.num_values;
+        uint32_t plen = (uint32_t)h.compressed_size;   // bytes of the payload the decode kernels will see
+        const bool is_data = h.type == pq::P_DATA || h.type == pq::P_DATA_V2;
+        const uint32_t v2_levels = h.type == pq::P_DATA_V2 ? (uint32_t)(h.rep_bytes + h.def_bytes) : 0;
+        const bool in_dec = snappy && (h.type == pq::P_DICTIONARY || is_data);
+        if (in_dec) {
+          // the page payload is rebuilt, uncompressed, at c.dec + dec_bytes (the addresses are patched in once c.dec exists)
+          plen = (uint32_t)h.uncompressed_size;
+          if (v2_levels > (uint32_t)h.compressed_size || v2_levels > plen) throw EngineError(B200_ERR_INVALID, "parquet: level section overruns the page");
+          PqDecompJob lv, vj;
+          memset(&lv, 0, sizeof lv);
+          memset(&vj, 0, sizeof vj);
+          if (v2_levels) {  // V2: the levels are never compressed
+            lv.src = dev_payload;
+            lv.dst = (uint8_t*)c.dec_bytes;
+            lv.src_len = lv.dst_len = v2_levels;
+            lv.raw_copy = 1;
+            c.jobs.push_back(lv);
+          }
+          vj.src = dev_payload + v2_levels;
+          vj.dst = (uint8_t*)(c.dec_bytes + v2_levels);
+          vj.src_len = (uint32_t)h.compressed_size - v2_levels;
+          vj.dst_len = plen - v2_levels;
+          vj.raw_copy = (h.type == pq::P_DATA_V2 && !h.v2_compressed) ? 1 : 0;
+          c.jobs.push_back(vj);
+          pg.data = (const uint8_t*)c.dec_bytes;   // offset for now
+          c.dec_bytes += ((size_t)plen + 15) & ~(size_t)15;
+        } else {
+          pg.data = dev_payload;
+        }
         if (h.type == pq::P_DICTIONARY) {
           if (h.encoding != pq::E_PLAIN && h.encoding != pq::E_PLAIN_DICTIONARY) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: dictionary page encoding");
           pg.val_off = 0;
-          pg.val_len = (uint32_t)h.compressed_size;
+          pg.val_len = plen;
           pg.row0 = c.dict_entries;
           chunk_dict_base = c.dict_entries;
           c.dict_entries += h.num_values;
           c.dicts.push_back(pg);
-        } else if (h.type == pq::P_DATA || h.type == pq::P_DATA_V2) {
-          uint32_t off = 0;
+          c.dict_in_dec.push_back(in_dec ? 1 : 0);
+        } else if (is_data) {
           if (h.type == pq::P_DATA) {
             if (c.optional) {
               if (h.def_encoding != pq::E_RLE) throw EngineError(B200_ERR_UNSUPPORTED, "parquet: definition levels not RLE encoded");
-              uint32_t len;
-              memcpy(&len, payload, 4);
-              pg.def_off = 4;
-              pg.def_len = len;
-              off = 4 + len;
+              if (plen < 4) throw EngineError(B200_ERR_INVALID, "parquet: page too short for its level section");
+              pg.v1_levels = 1;   // [u32 length][levels][values]: resolved on the device
             }
+            pg.val_off = 0;
+            pg.val_len = plen;
           } else {
+            if (v2_levels > plen) throw EngineError(B200_ERR_INVALID, "parquet: level section overruns the page");
             pg.def_off = (uint32_t)h.rep_bytes;
             pg.def_len = c.optional ? (uint32_t)h.def_bytes : 0;
-            off = (uint32_t)(h.rep_bytes + h.def_bytes);
+            pg.val_off = v2_levels;
+            pg.val_len = plen - v2_levels;
           }
-          if (off > (uint32_t)h.compressed_size) throw EngineError(B200_ERR_INVALID, "parquet: level section overruns the page");
-          pg.val_off = off;
-          pg.val_len = (uint32_t)h.compressed_size - off;
           if (h.encoding == pq::E_PLAIN) pg.encoding = 0;
           else if (h.encoding == pq::E_PLAIN_DICTIONARY || h.encoding == pq::E_RLE_DICTIONARY) pg.encoding = 1;
           else if (h.encoding == pq::E_RLE && c.se.type == pq::T_BOOLEAN) pg.encoding = 2;
@@ -3408,12 +3458,37 @@ DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vect
           c.rows += h.num_values;
           chunk_values += h.num_values;
           c.pages.push_back(pg);
+          c.page_in_dec.push_back(in_dec ? 1 : 0);
         }  // index pages etc.: skipped
         hp = payload + h.compressed_size;
       }
       dpos += (size_t)cm.total_compressed;
     }
     if (c.rows != n_rows) throw EngineError(B200_ERR_INVALID, "parquet: column " + c.se.name + " has " + std::to_string(c.rows) + " values, the file " + std::to_string(n_rows) + " rows");
+    if (c.dec_bytes) {
+      // Snappy: rebuild every page payload uncompressed in HBM (one warp per page), then decode as usual
+      c.dec = dev_alloc(c.dec_bytes + 64, st);
+      uint8_t* base = (uint8_t*)c.dec->ptr;
+      for (auto& j : c.jobs) j.dst = base + (size_t)j.dst;
+      for (size_t i = 0; i < c.pages.size(); i++)
+        if (c.page_in_dec[i]) c.pages[i].data = base + (size_t)c.pages[i].data;
+      for (size_t i = 0; i < c.dicts.size(); i++)
+        if (c.dict_in_dec[i]) c.dicts[i].data = base + (size_t)c.dicts[i].data;
+      DevPtr dj = dev_alloc(c.jobs.size() * sizeof(PqDecompJob), st);
+      CUDA_CHECK(cudaMemcpyAsync(dj->ptr, c.jobs.data(), c.jobs.size() * sizeof(PqDecompJob), cudaMemcpyHostToDevice, st));
+      DevPtr err = dev_alloc(16, st);
+      CUDA_CHECK(cudaMemsetAsync(err->ptr, 0, 16, st));
+      {
+        KernelTimer kt(x, "parquet_snappy", (uint64_t)c.raw->bytes + (uint64_t)c.dec_bytes);
+        launch_pq_snappy((const PqDecompJob*)dj->ptr, (int)c.jobs.size(), (unsigned int*)err->ptr, st);
+        x.count();
+      }
+      const unsigned int* herr = x.fetch<unsigned int>(err->ptr);
+      const std::string cname = c.se.name;
+      x.defer([herr, cname, dj, err]() {
+        if (*herr) throw EngineError(B200_ERR_INVALID, "parquet: corrupt Snappy data in column " + cname);
+      });
+    }
   }
   // ---- decode ------------------------------------------------------------------------------------------------------------
   struct ColWork {
@@ -3496,6 +3571,7 @@ DevBatchPtr scan_parquet(const Exec& x, const std::string& path, const std::vect
       // registered tables use the canonical Arrow layout (offsets + contiguous characters): the views into the raw pages
       // are compacted once, here, and the raw pages are released
       col.keep.push_back(c.raw);
+      if (c.dec) col.keep.push_back(c.dec);
       if (w.dict) col.keep.push_back(w.dict);
       col = as_utf8(x, col);
     }

@@ -66,3 +66,20 @@ def test_shapes_outside_the_kernel_still_match(gpu, oracle, oracle_lib):
         want = driver.run_stages(oracle, st, "ff-vm")
         assert want.num_rows > 0
         assert_tables_equal(got, want, sort=False)
+
+
+def test_filter_with_fetch(gpu, oracle, oracle_lib):
+    """FilterExec { fetch }: the first rows that pass, in input order."""
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, 30, {"lineitem": COLS}, 1)
+    scan = tpch.table_scan("lineitem", COLS)
+    for fetch in (0, 7, 5000, 10**9):
+        f = P.filter_(PREDS["date_range"], scan, projection=[0, 3, 8])
+        f["fetch"] = fetch
+        st = [P.Stage(1, P.shuffle_writer(f, 1))]
+        got = driver.run_stages(gpu, st, f"ff-fetch{fetch}")
+        want = driver.run_stages(oracle, st, f"ff-fetch{fetch}")
+        if want is None or want.num_rows == 0:
+            assert got is None or got.num_rows == 0
+        else:
+            assert_tables_equal(got, want, sort=False)

@@ -102,9 +102,27 @@ def test_decoded_columns_match_pyarrow(gpu, tmp_path, kw, nulls):
 
 
 @pytest.mark.gpu
-def test_compressed_files_are_refused(gpu, tmp_path):
+@pytest.mark.parametrize("kw", VARIANTS)
+def test_snappy_pages(gpu, tmp_path, kw):
+    """pyarrow's default codec: the pages are decompressed on the device (one warp per page) before the decode."""
+    t = _table(30000, nulls=True, seed=21)
+    path = os.path.join(str(tmp_path), "s.parquet")
+    kw = dict(kw)
+    try:
+        pq.write_table(t, path, compression="snappy", **kw)
+    except TypeError:
+        kw.pop("store_decimal_as_integer", None)
+        pq.write_table(t, path, compression="snappy", **kw)
+    gpu.drop_table("pqs")
+    gpu.register_parquet("pqs", 0, path)
+    got = pa.Table.from_batches([gpu.export_table("pqs", 0)])
+    assert_tables_equal(got, pq.read_table(path), sort=False)
+
+
+@pytest.mark.gpu
+def test_other_codecs_are_refused(gpu, tmp_path):
     path = os.path.join(str(tmp_path), "z.parquet")
-    pq.write_table(_table(100), path, compression="snappy")
+    pq.write_table(_table(100), path, compression="zstd")
     with pytest.raises(bb.B200Error) as ei:
         gpu.register_parquet("pqz", 0, path)
     assert ei.value.code == -2
