@@ -138,7 +138,7 @@ cudaError_t launch_partition_hist(const PidSrc& pid, int64_t n, uint32_t P, uint
 // width-1 entries; only in/out/width are used); dest_out (optional): the destination row of every input row
 cudaError_t launch_partition_scatter(const PidSrc& pid, int64_t n, uint32_t P, const uint64_t* offsets, const GatherCols& cols, uint32_t* dest_out,
                                      cudaStream_t st);
-enum PackKind : int32_t { PK_COPY = 0, PK_STR_VIEWS = 1, PK_STR_UTF8 = 2, PK_BITMAP = 3 };
+enum PackKind : int32_t { PK_COPY = 0, PK_STR_VIEWS = 1, PK_STR_UTF8 = 2, PK_BITMAP = 3, PK_UTF8_VIEWS = 4 };
 struct PackJob {
   const void* src;        // bytes / views / int32 offsets (already positioned at the slice's first row)
   const uint8_t* valid;   // strings: validity bytes of the slice or nullptr

@@ -197,6 +197,17 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
     }
     return;
   }
+  if (J.kind == PK_UTF8_VIEWS) {
+    // Arrow offsets + characters -> 16-byte views {pointer, length} (the layout intermediate batches carry)
+    const int32_t* o = (const int32_t*)J.src;
+    unsigned long long* v = (unsigned long long*)J.dst;
+    for (int64_t i = tid; i < J.rows; i += 256) {
+      const int32_t o0 = o[i], o1 = o[i + 1];
+      v[2 * i] = (unsigned long long)(J.chars + o0);
+      v[2 * i + 1] = (unsigned long long)(uint32_t)(o1 - o0);
+    }
+    return;
+  }
   if (J.kind == PK_BITMAP) {
     // byte-per-value -> Arrow bitmap (+ number of zero values at dst2, if asked for)
     const uint8_t* s = (const uint8_t*)J.src;

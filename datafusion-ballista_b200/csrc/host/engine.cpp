@@ -304,6 +304,17 @@ struct PackList {
     j.rows = rows;
     jobs.push_back(j);
   }
+  // Arrow Utf8 slice -> views written at `views_out` (rows x 16 bytes)
+  void utf8_views(const DevColumn& c, void* views_out) {
+    PackJob j;
+    memset(&j, 0, sizeof j);
+    j.kind = PK_UTF8_VIEWS;
+    j.src = c.data;
+    j.chars = c.chars;
+    j.dst = views_out;
+    j.rows = c.n;
+    jobs.push_back(j);
+  }
   void strings(const DevColumn& c, void* offsets_out, void* chars_out, uint64_t chars_cap = ~0ull) {
     PackJob j;
     memset(&j, 0, sizeof j);
@@ -1995,6 +2006,17 @@ struct Runner {
         if (n == 0) continue;
         DevColumn sc = slice_column(p.first->cols[ci], r0, r1);
         if (sc.type != t) throw EngineError(B200_ERR_INVALID, "concat: type mismatch in column " + schema[ci].name);
+        if (batched && sc.phys == PH_UTF8) {
+          // offsets + characters -> views, straight into the concatenated column (no temporary, no extra launch)
+          pl.utf8_views(sc, (uint8_t*)oc.data + pos * oc.width());
+          if (any_valid) {
+            if (sc.valid) pl.copy(sc.valid, (uint8_t*)oc.valid + pos, (uint64_t)n);
+            else CUDA_CHECK(cudaMemsetAsync((uint8_t*)oc.valid + pos, 1, (size_t)n, x.st()));
+          }
+          for (auto& k : sc.keep) oc.keep.push_back(k);
+          pos += n;
+          continue;
+        }
         DevColumn v = as_views(x, sc);
         if (batched) pl.copy(v.data, (uint8_t*)oc.data + pos * oc.width(), (uint64_t)n * oc.width());
         else CUDA_CHECK(cudaMemcpyAsync((uint8_t*)oc.data + pos * oc.width(), v.data, (size_t)n * oc.width(), cudaMemcpyDeviceToDevice, x.st()));
