@@ -73,6 +73,7 @@ struct b200_engine {
   std::mutex mu;
   std::map<std::string, std::map<int, DevBatchPtr>> tables;
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
+  std::map<ShuffleKey, DevBatchPtr> packed_cache;  // b200_partition_device_buffers: exchange-layout copies handed out by pointer
   std::atomic<uint64_t> launches{0};
   std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0}, n_groupby{0}, n_fastfilter{0};  // pipelines per kernel family (b200_engine_counter)
   int64_t batch_size = 8192;
@@ -87,7 +88,10 @@ struct b200_engine {
     void* dev = nullptr;
     cudaEvent_t done = nullptr;
     bool used = false;
-  } nslot[2];
+    size_t bytes = 0;
+  } nslot[4];
+  int64_t ingest_chunk_rows = (int64_t)1 << 22;
+  int ingest_slots = 3;
   // per-kernel device timing (b200.metrics.kernel_timing = on): CUDA event pairs on the launching stream, resolved
   // when the statistics are read (b200_engine_kernel_stats)
   bool kernel_timing = false;
@@ -487,8 +491,9 @@ DevBatchPtr gather_batch(const Exec& x, const DevBatch& in, const int64_t* idx, 
 // `src` = n 16-byte values in host memory, `dst` = n 16-byte slots in HBM.  Chunks are narrowed by the
 // host pool into one of two pinned staging slots while the previous chunk is still on the bus; a chunk
 // whose values do not fit int32 is retried as int64 and finally copied as is.  Bit-exact by construction.
-static const int64_t NARROW_CHUNK_ROWS = (int64_t)1 << 22;  // 64 MiB of source per chunk
-static const int64_t NARROW_BLOCK_ROWS = (int64_t)1 << 16;  // one pool task
+static const int64_t NARROW_CHUNK_ROWS_DEFAULT = (int64_t)1 << 22;  // 64 MiB of source per chunk (b200.ingest.chunk_rows)
+static const int64_t NARROW_BLOCK_ROWS = (int64_t)1 << 16;          // one pool task
+static const int NARROW_SLOTS = 4;                                  // staging buffers in flight (b200.ingest.slots: 2..4)
 
 void ingest_decimal_narrowed(b200_engine* e, const uint8_t* src, uint8_t* dst, int64_t n, cudaStream_t st) {
   std::lock_guard<std::mutex> ingest_guard(e->ingest_mu);
@@ -511,15 +516,27 @@ void ingest_decimal_narrowed(b200_engine* e, const uint8_t* src, uint8_t* dst, i
     }
     e->pool.reset(new HostPool(std::min(want, 256)));
   }
-  for (auto& sl : e->nslot) {
+  const int64_t NARROW_CHUNK_ROWS = std::max<int64_t>(NARROW_BLOCK_ROWS, e->ingest_chunk_rows);
+  const int n_slots = std::min(NARROW_SLOTS, std::max(2, e->ingest_slots));
+  for (int si = 0; si < n_slots; si++) {
+    auto& sl = e->nslot[si];
+    const size_t need = (size_t)NARROW_CHUNK_ROWS * 8;
+    if (sl.pinned && sl.bytes < need) {
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      cudaFreeHost(sl.pinned);
+      cudaFree(sl.dev);
+      sl.pinned = sl.dev = nullptr;
+      sl.used = false;
+    }
     if (!sl.pinned) {
-      CUDA_CHECK(cudaHostAlloc(&sl.pinned, (size_t)NARROW_CHUNK_ROWS * 8, cudaHostAllocDefault));
-      CUDA_CHECK(cudaMalloc(&sl.dev, (size_t)NARROW_CHUNK_ROWS * 8));
-      CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+      CUDA_CHECK(cudaHostAlloc(&sl.pinned, need, cudaHostAllocDefault));
+      CUDA_CHECK(cudaMalloc(&sl.dev, need));
+      if (!sl.done) CUDA_CHECK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+      sl.bytes = need;
     }
   }
   int which = 0;
-  for (int64_t r0 = 0; r0 < n; r0 += NARROW_CHUNK_ROWS, which ^= 1) {
+  for (int64_t r0 = 0; r0 < n; r0 += NARROW_CHUNK_ROWS, which = (which + 1) % n_slots) {
     const int64_t rows = std::min(NARROW_CHUNK_ROWS, n - r0);
     b200_engine::NarrowSlot& sl = e->nslot[which];
     if (sl.used) CUDA_CHECK(cudaEventSynchronize(sl.done));  // its previous chunk has left the staging buffer
@@ -552,7 +569,22 @@ void ingest_decimal_narrowed(b200_engine* e, const uint8_t* src, uint8_t* dst, i
   }
 }
 
+DevBatchPtr import_batch_impl(b200_engine* e, ArrowArray* arr, ArrowSchema* sch);
+
+// Ownership of `arr` / `sch` moves to the engine on entry: they are released on success AND on failure (after the copies
+// already issued from their buffers have drained), as the Arrow C Data Interface asks of a consumer.
 DevBatchPtr import_batch(b200_engine* e, ArrowArray* arr, ArrowSchema* sch) {
+  try {
+    return import_batch_impl(e, arr, sch);
+  } catch (...) {
+    cudaStreamSynchronize(e->stream);
+    if (arr && arr->release) arr->release(arr);
+    if (sch && sch->release) sch->release(sch);
+    throw;
+  }
+}
+
+DevBatchPtr import_batch_impl(b200_engine* e, ArrowArray* arr, ArrowSchema* sch) {
   int64_t n = 0;
   std::vector<ImportedCol> ics = import_record_batch(arr, sch, &n);
   auto b = std::make_shared<DevBatch>();
@@ -3726,6 +3758,7 @@ void b200_engine_destroy(b200_engine* e) {
   cudaStreamSynchronize(e->stream);
   e->tables.clear();
   e->shuffle.clear();
+  e->packed_cache.clear();
   cudaStreamSynchronize(e->stream);
   for (auto& sl : e->nslot) {
     if (sl.pinned) cudaFreeHost(sl.pinned);
@@ -3767,6 +3800,9 @@ int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
     std::lock_guard<std::mutex> g(e->mu);
     e->config[key] = value;
     if (std::string(key) == "datafusion.execution.batch_size") e->batch_size = std::max<int64_t>(1, atoll(value));
+    if (std::string(key) == "b200.ingest.chunk_rows") e->ingest_chunk_rows = std::max<int64_t>(1 << 16, atoll(value));
+    if (std::string(key) == "b200.ingest.slots") e->ingest_slots = atoi(value);
+    if (std::string(key) == "b200.ingest.threads") e->pool.reset();  // re-created with the new size at the next ingest
     if (std::string(key) == "b200.agg.reset_hints") e->agg_hint.clear();  // forget which aggregate strategy each plan shape needed
     if (std::string(key) == "b200.metrics.kernel_timing") e->kernel_timing = std::string(value) == "on" || std::string(value) == "1" || std::string(value) == "true";
   });
@@ -4169,13 +4205,11 @@ int b200_partition_device_buffers(b200_engine* e, const char* job_id, int64_t st
       }
     }
     CUDA_CHECK(cudaStreamSynchronize(x.st()));
-    // keep the packed form alive as the partition's single piece
+    // the packed form stays alive next to the partition (until its stage / job data is removed); the stored pieces,
+    // their file ids and anything a concurrent map task adds are left alone: this is a read-style call
     {
       std::lock_guard<std::mutex> g(e->mu);
-      auto& v = e->shuffle[ShuffleKey{job_id, stage_id, out_partition}];
-      int64_t fid = v.empty() ? -1 : v[0].file_id;
-      v.clear();
-      v.push_back(Piece{fid, packed, 0, packed->n});
+      e->packed_cache[ShuffleKey{job_id, stage_id, out_partition}] = packed;
     }
     *n_out = k;
     *n_rows = packed->n;
@@ -4232,6 +4266,10 @@ int b200_remove_job_data(b200_engine* e, const char* job_id) {
       if (it->first.job == job_id) it = e->shuffle.erase(it);
       else ++it;
     }
+    for (auto it = e->packed_cache.begin(); it != e->packed_cache.end();) {
+      if (it->first.job == job_id) it = e->packed_cache.erase(it);
+      else ++it;
+    }
   });
 }
 
@@ -4254,6 +4292,10 @@ int b200_remove_stage_data(b200_engine* e, const char* job_id, int64_t stage_id)
     std::lock_guard<std::mutex> g(e->mu);
     for (auto it = e->shuffle.begin(); it != e->shuffle.end();) {
       if (it->first.job == job_id && it->first.stage == stage_id) it = e->shuffle.erase(it);
+      else ++it;
+    }
+    for (auto it = e->packed_cache.begin(); it != e->packed_cache.end();) {
+      if (it->first.job == job_id && it->first.stage == stage_id) it = e->packed_cache.erase(it);
       else ++it;
     }
   });

@@ -1,6 +1,7 @@
 // Host-side narrowing of Decimal128 values for ingest (see host_pool.hpp): plain C++ translation unit,
 // compiled by g++ (not nvcc) so that the AVX2 path can use intrinsics with a function-level target.
 #include <cstdint>
+#include <cstdlib>
 #include <immintrin.h>
 
 namespace b200 {
@@ -65,6 +66,48 @@ __attribute__((target("avx2"))) static bool narrow64_avx2(const int64_t* p, int6
 }
 #endif
 
+// AVX-512: 8 values (128 source bytes) per iteration -- two full-width loads, one two-source permute per word half, one
+// truncating down-convert; the checks fold into mask registers
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq"))) static bool narrow32_avx512(const int64_t* p, int64_t n, int32_t* out) {
+  const __m512i even = _mm512_setr_epi64(0, 2, 4, 6, 8, 10, 12, 14), odd = _mm512_setr_epi64(1, 3, 5, 7, 9, 11, 13, 15);
+  __mmask8 bad = 0;
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const __m512i v0 = _mm512_loadu_si512((const void*)(p + 2 * i));
+    const __m512i v1 = _mm512_loadu_si512((const void*)(p + 2 * i + 8));
+    const __m512i lo = _mm512_permutex2var_epi64(v0, even, v1);
+    const __m512i hi = _mm512_permutex2var_epi64(v0, odd, v1);
+    const __m256i t = _mm512_cvtepi64_epi32(lo);                                   // low dwords
+    bad |= _mm512_cmpneq_epi64_mask(hi, _mm512_srai_epi64(lo, 63));                  // high word == sign extension
+    bad |= _mm512_cmpneq_epi64_mask(lo, _mm512_cvtepi32_epi64(t));                   // value == its own 32-bit image
+    _mm256_storeu_si256((__m256i*)(out + i), t);
+  }
+  bool ok = bad == 0;
+  if (i < n) ok &= narrow32_scalar(p + 2 * i, n - i, out + i);
+  return ok;
+}
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512dq"))) static bool narrow64_avx512(const int64_t* p, int64_t n, int64_t* out) {
+  const __m512i even = _mm512_setr_epi64(0, 2, 4, 6, 8, 10, 12, 14), odd = _mm512_setr_epi64(1, 3, 5, 7, 9, 11, 13, 15);
+  __mmask8 bad = 0;
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const __m512i v0 = _mm512_loadu_si512((const void*)(p + 2 * i));
+    const __m512i v1 = _mm512_loadu_si512((const void*)(p + 2 * i + 8));
+    const __m512i lo = _mm512_permutex2var_epi64(v0, even, v1);
+    const __m512i hi = _mm512_permutex2var_epi64(v0, odd, v1);
+    bad |= _mm512_cmpneq_epi64_mask(hi, _mm512_srai_epi64(lo, 63));
+    _mm512_storeu_si512((void*)(out + i), lo);
+  }
+  bool ok = bad == 0;
+  if (i < n) ok &= narrow64_scalar(p + 2 * i, n - i, out + i);
+  return ok;
+}
+static bool have_avx512() {
+  static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+                        __builtin_cpu_supports("avx512dq") && !getenv("B200_NO_AVX512");
+  return v;
+}
+
 static bool have_avx2() {
 #if defined(__x86_64__)
   static const bool v = __builtin_cpu_supports("avx2");
@@ -78,12 +121,14 @@ static bool have_avx2() {
 // Return true on success; on failure `out` holds garbage and the caller falls back to the next width.
 bool narrow_i128_to_i32(const int64_t* p, int64_t n, int32_t* out) {
 #if defined(__x86_64__)
+  if (have_avx512()) return narrow32_avx512(p, n, out);
   if (have_avx2()) return narrow32_avx2(p, n, out);
 #endif
   return narrow32_scalar(p, n, out);
 }
 bool narrow_i128_to_i64(const int64_t* p, int64_t n, int64_t* out) {
 #if defined(__x86_64__)
+  if (have_avx512()) return narrow64_avx512(p, n, out);
   if (have_avx2()) return narrow64_avx2(p, n, out);
 #endif
   return narrow64_scalar(p, n, out);

@@ -96,7 +96,11 @@ def exchange_stage(engine, job_id: str, stage_id: int, n_out_partitions: int, sc
     total_send = int(sum(send_sizes))
     send = torch.empty(max(total_send, 1), dtype=torch.uint8, device=device)
     if is_cuda:
-        engine.device_gather(order, send.data_ptr(), total_send)  # enqueued on the engine's stream (== torch's current stream)
+        # the gather is enqueued on the ENGINE's stream, the collective below on torch's current stream: make the hand-over
+        # explicit instead of relying on the caller having made them the same stream
+        torch.cuda.current_stream(device).synchronize()   # `send` exists before the engine writes into it
+        engine.device_gather(order, send.data_ptr(), total_send)
+        engine.synchronize()                               # ... and is complete before NCCL reads it
     else:
         pos = 0
         for (ptr, nb) in order:

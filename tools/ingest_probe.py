@@ -30,12 +30,16 @@ for col in host.columns:
     arrays.append(pa.Array.from_buffers(col.type, len(col), bufs, null_count=0))
 batch = pa.RecordBatch.from_arrays(arrays, schema=host.schema)
 total = sum(b.size for a in arrays for b in a.buffers() if b is not None)
-for threads in [int(x) for x in os.environ.get("THREADS", "0,8,16,32,64,128").split(",")]:
+chunks = [int(x) for x in os.environ.get("CHUNKS", "4194304").split(",")]
+slots = [int(x) for x in os.environ.get("SLOTS", "3").split(",")]
+for threads, chunk, nsl in [(t, c, s) for t in [int(x) for x in os.environ.get("THREADS", "0,8,16,32,64,128").split(",")] for c in chunks for s in slots]:
     eng = bb.GpuExecutionEngine(0)
     if threads == 0:
         eng.set_config("b200.ingest.narrow_decimals", "off")
     else:
         eng.set_config("b200.ingest.threads", threads)
+        eng.set_config("b200.ingest.chunk_rows", chunk)
+        eng.set_config("b200.ingest.slots", nsl)
     ts = []
     for rep in range(4):
         eng.drop_table("t")
@@ -44,5 +48,5 @@ for threads in [int(x) for x in os.environ.get("THREADS", "0,8,16,32,64,128").sp
         ts.append(time.perf_counter() - t0)
     saved = eng.counter("ingest_bytes_saved") // 4
     best = min(ts[1:])
-    print(f"threads={threads:3d}  {best*1e3:7.2f} ms  {total/best/1e9:6.1f} GB/s of Arrow bytes  ({(total-saved)/1e9:.2f} GB over PCIe)", flush=True)
+    print(f"threads={threads:3d} chunk={chunk:9d} slots={nsl}  {best*1e3:7.2f} ms  {total/best/1e9:6.1f} GB/s of Arrow bytes  ({(total-saved)/1e9:.2f} GB over PCIe)", flush=True)
     eng.close()
