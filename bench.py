@@ -387,6 +387,7 @@ def run_b200(args):
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1)
     launches = eng.kernel_launches() - launches0
+    exch_timed = dict(exch)   # the e2e passes below go through the same step()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
@@ -455,8 +456,8 @@ def run_b200(args):
             "parity_checked": bool(parity.get("checked") and parity.get("equal")), "parity": parity,
         }
         if world > 1:
-            line["exchange"] = {"calls_per_step": exch["calls"] / args.steps, "sent_bytes_per_step_rank0": exch["sent"] / args.steps,
-                                "recv_bytes_per_step_rank0": exch["recv"] / args.steps}
+            line["exchange"] = {"calls_per_step": exch_timed["calls"] / args.steps, "sent_bytes_per_step_rank0": exch_timed["sent"] / args.steps,
+                                "recv_bytes_per_step_rank0": exch_timed["recv"] / args.steps}
         if e2e:
             line["e2e"] = e2e
         # CPU baseline beside it (rank 0): bounded sample of the same workload, on every CPU this process started with
