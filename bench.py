@@ -285,6 +285,13 @@ def setup_engine(args):
     stream = torch.cuda.Stream(device=device)
     eng.set_stream(stream.cuda_stream)
     if world > 1:
+        # fused shuffle (b200_stage_execute_exchange): a window of HBM per executor that the peers' partition scatter kernels
+        # store into directly; sized for the largest fixed-width shuffle of the workload
+        wgb = args.exchange_window_gb
+        if wgb < 0:
+            wgb = 0.0 if args.workload == "q1" else 16.0
+        if wgb > 0 and not args.no_fused_shuffle:
+            eng.set_config("b200.exchange.window_bytes", str(int(wgb * (1 << 30))))
         idt = torch.zeros(128, dtype=torch.uint8, device=device)
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(bb.GpuExecutionEngine.comm_unique_id()), dtype=torch.uint8))
@@ -489,6 +496,7 @@ def run_workload(args):
     torch, dist, bb, eng, stream, device, rank, world, local_rank = setup_engine(args)
     import pyarrow as pa
     from ballista_b200 import tpch, driver
+    fused = world > 1 and eng.counter("exchange_window_bytes") > 0
     names = sorted(tpch.QUERIES, key=lambda q: int(q[1:])) if args.workload == "all" else [args.workload]
     for nme in names:
         if nme not in tpch.QUERIES:
@@ -514,7 +522,7 @@ def run_workload(args):
         pmsf = min(msf, 1000)
         tabs, _ = load(pmsf)
         pl = plans(P)
-        got = {nme: driver.run_stages_distributed(eng, pl[nme], f"par-{nme}", rank, world) for nme in names}
+        got = {nme: driver.run_stages_distributed(eng, pl[nme], f"par-{nme}", rank, world, fused=fused) for nme in names}
         for nme in names:
             eng.remove_job_data(f"par-{nme}")
         if rank == 0:
@@ -560,7 +568,7 @@ def run_workload(args):
                 dist.barrier()
             torch.cuda.synchronize(device)
             t0 = time.perf_counter()
-            res[nme] = driver.run_stages_distributed(eng, pl[nme], f"{tag}-{nme}", rank, world, on_stage=on_stage(nme) if timed else None)
+            res[nme] = driver.run_stages_distributed(eng, pl[nme], f"{tag}-{nme}", rank, world, on_stage=on_stage(nme) if timed else None, fused=fused)
             eng.synchronize()
             dt = time.perf_counter() - t0
             eng.remove_job_data(f"{tag}-{nme}")
@@ -574,6 +582,7 @@ def run_workload(args):
     if rank == 0:
         sampler.start()
     launches0 = eng.kernel_launches()
+    fused0 = eng.counter("fused_exchanges")
     acc = {nme: 0.0 for nme in names}
     res = None
     for k in range(args.steps):
@@ -591,7 +600,7 @@ def run_workload(args):
     consistent = None
     if not args.no_parity:
         pl2 = plans(P * 2)
-        _, res2 = None, {nme: driver.run_stages_distributed(eng, pl2[nme], f"alt-{nme}", rank, world) for nme in names}
+        _, res2 = None, {nme: driver.run_stages_distributed(eng, pl2[nme], f"alt-{nme}", rank, world, fused=fused) for nme in names}
         if rank == 0:
             from util import canon
             consistent = all(tables_equal(canon(res[nme]), canon(res2[nme]), f64_rtol=1e-12) for nme in names)
@@ -620,6 +629,9 @@ def run_workload(args):
             "base_rows_scanned": rows,
             "exchange_rank0": {q: {"calls": e["calls"] / args.steps, "sent_gb": e["sent"] / args.steps / 1e9, "recv_gb": e["recv"] / args.steps / 1e9,
                                    "largest_stage_sent_gb": e["max_sent_stage"] / 1e9} for q, e in exch.items()},
+            "fused_shuffle": ({"window_gb": eng.counter("exchange_window_bytes") / (1 << 30), "exchanges_per_step": (eng.counter("fused_exchanges") - fused0) / args.steps,
+                               "what": "writer + hash exchange as one collective: the scatter kernel stores rows into the owner's HBM over NVLink (fixed-width shuffles)"}
+                              if fused else None),
             "kernels": kern,
             "roofline": ({"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom[1]["frac_of_hbm_peak"],
                           "traffic": None, "peak_source": peak_src, "note": "dominant kernel family by device time; algorithmic bytes per SURVEY.md 8(d)"} if dom[0] else None),
@@ -718,6 +730,8 @@ def main():
     ap.add_argument("--workload", default="q1", help="q1 (headline, weak scaling) | q5 | q17 | all | any TPC-H query name (strong scaling at --sf)")
     ap.add_argument("--sf", type=float, default=0.0, help="scale factor of the non-q1 workloads (default: chosen per workload and N)")
     ap.add_argument("--partitions-per-gpu", type=int, default=1)
+    ap.add_argument("--exchange-window-gb", type=float, default=-1.0, help="HBM per executor for the fused shuffle (N>1; default 16 for the non-q1 workloads)")
+    ap.add_argument("--no-fused-shuffle", action="store_true", help="N>1: always shuffle in two steps (writer, then NCCL exchange)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()

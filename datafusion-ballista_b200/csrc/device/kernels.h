@@ -73,6 +73,10 @@ struct GatherCol {
   uint8_t* valid_out;
   int width;
   int _pad;
+  // partition scatter only: when set, row `dst` of partition p is written to (byte address) part_base[p] + dst * width
+  // instead of out + dst * width -- the bases may point into ANOTHER GPU's memory (fused shuffle: the scatter kernel
+  // stores straight into the owning executor's window over NVLink)
+  const unsigned long long* part_base;
 };
 struct GatherCols {
   GatherCol c[GATHER_MAX_COLS];

@@ -74,13 +74,21 @@ __global__ void __launch_bounds__(PT_BLOCK) part_tile_hist_kernel(const PidSrc p
 }
 
 template <typename T>
-__device__ __forceinline__ void scatter_rows(const GatherCol& c, const int64_t (&row)[PT_ROUNDS], const uint32_t (&dst)[PT_ROUNDS], int64_t n) {
+__device__ __forceinline__ void scatter_rows(const GatherCol& c, const int64_t (&row)[PT_ROUNDS], const uint32_t (&dst)[PT_ROUNDS], const uint32_t (&p)[PT_ROUNDS],
+                                             int64_t n) {
   const T* __restrict__ in = (const T*)c.in;
   T* __restrict__ out = (T*)c.out;
   T v[PT_ROUNDS];
 #pragma unroll
   for (int r = 0; r < PT_ROUNDS; r++)
     if (row[r] < n) v[r] = in[row[r]];
+  if (c.part_base) {
+    // per-partition destination bases (possibly peer memory): generic stores, NVLink carries the remote ones
+#pragma unroll
+    for (int r = 0; r < PT_ROUNDS; r++)
+      if (row[r] < n) ((T*)c.part_base[p[r]])[dst[r]] = v[r];
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < PT_ROUNDS; r++)
     if (row[r] < n) out[dst[r]] = v[r];
@@ -137,11 +145,11 @@ __global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_kernel(const PidSr
   for (int c = 0; c < cols.n; c++) {
     const GatherCol& gc = cols.c[c];
     switch (gc.width) {
-      case 1: scatter_rows<uint8_t>(gc, row, dst, n); break;
-      case 2: scatter_rows<uint16_t>(gc, row, dst, n); break;
-      case 4: scatter_rows<uint32_t>(gc, row, dst, n); break;
-      case 8: scatter_rows<uint64_t>(gc, row, dst, n); break;
-      default: scatter_rows<ulonglong2>(gc, row, dst, n); break;
+      case 1: scatter_rows<uint8_t>(gc, row, dst, p, n); break;
+      case 2: scatter_rows<uint16_t>(gc, row, dst, p, n); break;
+      case 4: scatter_rows<uint32_t>(gc, row, dst, p, n); break;
+      case 8: scatter_rows<uint64_t>(gc, row, dst, p, n); break;
+      default: scatter_rows<ulonglong2>(gc, row, dst, p, n); break;
     }
   }
 }

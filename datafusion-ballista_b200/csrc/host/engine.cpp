@@ -102,6 +102,14 @@ struct b200_engine {
   ncclComm_t comm = nullptr;                 // exchange communicator (b200_engine_comm_init); nullptr = single executor
   std::mutex comm_mu;                        // one collective at a time
   uint64_t exch_sent_bytes = 0, exch_recv_bytes = 0;
+  // fused shuffle (b200_stage_execute_exchange): one window of HBM per executor, mapped into every peer process through
+  // CUDA IPC at b200_engine_comm_init, so the partition scatter kernel stores each row straight into the HBM of the executor
+  // that owns its output partition (NVLink / NVSwitch peer stores) -- no staging copy, no separate transfer
+  size_t win_config_bytes = 0;               // b200.exchange.window_bytes
+  uint8_t* win_local = nullptr;
+  size_t win_bytes = 0, win_used = 0;
+  std::vector<uint8_t*> win_peer;            // [rank] -> this process's mapping of that rank's window (own rank: win_local)
+  uint64_t fused_exchanges = 0;
   std::mutex export_mu;                      // small-result export arena (pinned), one export at a time
   uint8_t* export_arena = nullptr;
   std::atomic<uint64_t> narrowed_bytes_saved{0};         // PCIe bytes not sent thanks to narrowing (b200_engine_counter)
@@ -116,6 +124,15 @@ struct b200_stage {
   std::vector<OpMetrics> metrics;  // pre-order
   std::map<const PlanNode*, int> metric_index;
 };
+
+#define NCCL_CHECK(expr)                                                                                              \
+  do {                                                                                                                \
+    ncclResult_t _r = (expr);                                                                                         \
+    if (_r != 0) throw EngineError(B200_ERR_CUDA, std::string("NCCL error: ") + NcclApi::get().GetErrorString(_r) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+static void release_window(b200_engine* e);
+static void setup_window(b200_engine* e);
 
 namespace {
 
@@ -2761,7 +2778,219 @@ struct Runner {
     return out;
   }
 
-  std::vector<b200_shuffle_write_partition> execute_stage(const PlanNode& root, int input_partition) {
+  struct FusedExchange {
+    bool done = false;  // the rows were scattered into their owners' windows (nothing left to exchange)
+    uint64_t sent = 0, recvd = 0;
+  };
+
+  // ------------------------------------------------------------------------------------------------
+  // Fused shuffle writer + exchange (gang collective; ShuffleWriterExec's repartition, shuffle_writer.rs:214-330, and
+  // the readers' remote fetch, shuffle_reader.rs:522-602, as ONE kernel pass).  After the histogram every executor
+  // knows how many rows every map task holds for every output partition (one small NCCL all-gather), so every row has a
+  // known final address in the window of the executor that owns its partition: the scatter kernel stores it there
+  // directly -- local partitions through HBM, remote ones as peer stores over NVLink.  The reduce side finds its input
+  // already laid out partition by partition, map task by map task (the order sort_shuffle and the NCCL exchange produce).
+  // Returns false (nothing written) when some window cannot hold this exchange: the caller then takes the two-step path;
+  // the decision is taken from the all-gathered matrix, i.e. identically on every executor.
+  // ------------------------------------------------------------------------------------------------
+  bool scatter_to_owners(const PlanNode& root, int input_partition, const std::vector<DevColumn>& pay, const PidSrc& pid, int64_t n, uint32_t P,
+                         uint32_t n_tiles, const DevPtr& mat, const DevPtr& tile_hist, uint64_t row_bytes, FusedExchange* fx,
+                         std::vector<b200_shuffle_write_partition>& res, OpMetrics* met) {
+    b200_engine* e = x.e;
+    NcclApi& N = NcclApi::get();
+    const int W = e->world, me = e->rank;
+    const size_t mrow = (size_t)P + 3;
+    const size_t ncols = pay.size();
+    auto al = [](uint64_t v) { return (v + 255) & ~255ull; };
+    std::lock_guard<std::mutex> cg(e->comm_mu);
+    // my row of the matrix: the counts are already there (histogram); add validity mask, window fill, map task id
+    uint64_t* extra = (uint64_t*)x.stage_bytes(24);
+    extra[0] = 0;
+    for (size_t c = 0; c < ncols; c++)
+      if (pay[c].valid) extra[0] |= 1ull << c;
+    extra[1] = al(e->win_used);
+    extra[2] = (uint64_t)(int64_t)input_partition;
+    unsigned long long* mrows = (unsigned long long*)mat->ptr;
+    CUDA_CHECK(cudaMemcpyAsync(mrows + mrow * (size_t)me + P, extra, 24, cudaMemcpyHostToDevice, x.st()));
+    NCCL_CHECK(N.GroupStart());
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      NCCL_CHECK(N.Send(mrows + mrow * (size_t)me, mrow * 8, kNcclUint8, d, e->comm, x.st()));
+      NCCL_CHECK(N.Recv(mrows + mrow * (size_t)d, mrow * 8, kNcclUint8, d, e->comm, x.st()));
+    }
+    NCCL_CHECK(N.GroupEnd());
+    x.count(1);
+    // (the matrix and the base table below can exceed the task's pinned arena at large fan-outs: plain host vectors)
+    std::vector<unsigned long long> Mv(mrow * (size_t)W);
+    CUDA_CHECK(cudaMemcpyAsync(Mv.data(), mat->ptr, Mv.size() * 8, cudaMemcpyDeviceToHost, x.st()));
+    const unsigned long long* M = Mv.data();
+    // while the matrix travels: per-tile offsets of the local rows
+    const int64_t hn = (int64_t)P * n_tiles;
+    DevPtr offs = dev_alloc((size_t)(hn + 2) * 8, x.st());
+    DevPtr scratch = dev_alloc((size_t)(hn / 1024 + 4) * 8, x.st());
+    if (hn > 0) {
+      launch_scan_u32_to_u64((const uint32_t*)tile_hist->ptr, (uint64_t*)offs->ptr, hn, (uint64_t*)scratch->ptr, x.st());
+      x.count(3);
+    }
+    x.sync();
+    auto cnt = [&](int s, uint32_t p) { return (uint64_t)M[mrow * (size_t)s + p]; };
+    uint64_t any_valid = 0;
+    for (int s = 0; s < W; s++) any_valid |= M[mrow * (size_t)s + P];
+    // layout of every owner's window for this exchange: per owned partition, per column, all map tasks back to back
+    std::vector<uint64_t> tot(P, 0), before(P, 0);
+    for (uint32_t p = 0; p < P; p++)
+      for (int s = 0; s < W; s++) {
+        if (s < me) before[p] += cnt(s, p);
+        tot[p] += cnt(s, p);
+      }
+    const size_t nslots = ncols * 2;  // [c] data, [ncols + c] validity
+    std::vector<uint64_t> region(nslots * P, 0);
+    std::vector<uint64_t> cursor((size_t)W);
+    for (int r = 0; r < W; r++) cursor[(size_t)r] = M[mrow * (size_t)r + P + 1];
+    for (uint32_t p = 0; p < P; p++) {
+      uint64_t& cur = cursor[(size_t)(p % (uint32_t)W)];
+      for (size_t c = 0; c < ncols; c++) {
+        region[c * P + p] = cur;
+        cur += al(tot[p] * (uint64_t)pay[c].width());
+        if (any_valid >> c & 1) {
+          region[(ncols + c) * P + p] = cur;
+          cur += al(tot[p]);
+        }
+      }
+    }
+    for (int r = 0; r < W; r++)
+      if (cursor[(size_t)r] > e->win_bytes) return false;  // same verdict everywhere; nothing was written
+    // destination bases: byte address of row 0 of (column, partition) as the scatter kernel numbers the rows, i.e.
+    // shifted back by this task's prefix of the partition-contiguous order
+    std::vector<int64_t> bounds(P + 1, 0);
+    for (uint32_t p = 0; p < P; p++) bounds[p + 1] = bounds[p] + (int64_t)cnt(me, p);
+    std::vector<uint64_t> hbv(nslots * P);
+    uint64_t* hb = hbv.data();
+    for (size_t sl = 0; sl < nslots; sl++) {
+      const size_t c = sl % ncols;
+      const int64_t w = sl < ncols ? (int64_t)pay[c].width() : 1;
+      for (uint32_t p = 0; p < P; p++) {
+        const uint8_t* base = e->win_peer[(size_t)(p % (uint32_t)W)] + region[sl * P + p];
+        hb[sl * P + p] = (uint64_t)(base + ((int64_t)before[p] - bounds[p]) * w);
+      }
+    }
+    DevPtr bases = dev_alloc(nslots * P * 8 + 64, x.st());
+    CUDA_CHECK(cudaMemcpyAsync(bases->ptr, hb, nslots * P * 8, cudaMemcpyHostToDevice, x.st()));
+    std::vector<DevPtr> ones_keep;
+    {
+      GatherCols gc;
+      gc.n = 0;
+      auto flush = [&]() {
+        if (gc.n && n > 0) {
+          uint64_t b = 0;
+          for (int k = 0; k < gc.n; k++) b += (uint64_t)gc.c[k].width;
+          KernelTimer kt(x, "partition_scatter_peer", (uint64_t)n * (2 * b + 4));
+          CUDA_CHECK(launch_partition_scatter(pid, n, P, (const uint64_t*)offs->ptr, gc, nullptr, x.st()));
+          x.count();
+        }
+        gc.n = 0;
+      };
+      auto add = [&](const void* in, size_t slot, int width) {
+        GatherCol& g = gc.c[gc.n++];
+        memset(&g, 0, sizeof g);
+        g.in = in;
+        g.width = width;
+        g.part_base = (const unsigned long long*)bases->ptr + slot * P;
+        if (gc.n == GATHER_MAX_COLS) flush();
+      };
+      for (size_t c = 0; c < ncols; c++) {
+        add(pay[c].data, c, pay[c].width());
+        if (any_valid >> c & 1) {
+          const uint8_t* v = pay[c].valid;
+          if (!v && n > 0) {  // another map task has nulls in this column: this one contributes all-valid bytes
+            DevPtr ones = dev_alloc((size_t)n + 64, x.st());
+            CUDA_CHECK(cudaMemsetAsync(ones->ptr, 1, (size_t)n, x.st()));
+            ones_keep.push_back(ones);
+            v = (const uint8_t*)ones->ptr;
+          }
+          add(v, ncols + c, 1);
+        }
+      }
+      flush();
+    }
+    // every executor's stores must have landed before anyone reads its window: a zero-payload all-to-all on the same
+    // stream completes only after every peer's scatter kernel did
+    {
+      DevPtr bar = dev_alloc((size_t)W * 16 + 64, x.st());
+      NCCL_CHECK(N.GroupStart());
+      for (int d = 0; d < W; d++) {
+        if (d == me) continue;
+        NCCL_CHECK(N.Send((const uint8_t*)bar->ptr + 8 * (size_t)W, 8, kNcclUint8, d, e->comm, x.st()));
+        NCCL_CHECK(N.Recv((uint8_t*)bar->ptr + 8 * (size_t)d, 8, kNcclUint8, d, e->comm, x.st()));
+      }
+      NCCL_CHECK(N.GroupEnd());
+      x.count(1);
+    }
+    e->win_used = cursor[(size_t)me];
+    // the reduce side's view: one batch per owned partition, one piece per map task
+    const int64_t bs = e->batch_size;
+    uint64_t total_bytes = 0;
+    {
+      std::lock_guard<std::mutex> g(e->mu);
+      for (uint32_t p = 0; p < P; p++) {
+        const uint64_t rows = cnt(me, p);
+        if (rows) {
+          b200_shuffle_write_partition w{};
+          w.partition_id = p;
+          w.num_rows = rows;
+          w.num_batches = (rows + (uint64_t)bs - 1) / (uint64_t)bs;
+          w.num_bytes = rows * row_bytes;
+          w.file_id = input_partition;
+          w.is_sort_shuffle = root.sort_shuffle ? 1 : 0;
+          total_bytes += w.num_bytes;
+          res.push_back(w);
+          if ((int)(p % (uint32_t)W) != me) fx->sent += w.num_bytes;
+        }
+        if ((int)(p % (uint32_t)W) != me) continue;
+        auto& v = e->shuffle[ShuffleKey{job, root.stage_id, (int64_t)p}];
+        if (tot[p] == 0) {
+          if (v.empty()) e->shuffle.erase(ShuffleKey{job, root.stage_id, (int64_t)p});
+          continue;
+        }
+        auto b = std::make_shared<DevBatch>();
+        b->n = (int64_t)tot[p];
+        for (size_t c = 0; c < ncols; c++) {
+          DevColumn col;
+          col.name = root.schema[c].name;
+          col.type = pay[c].type;
+          col.phys = pay[c].phys;
+          col.n = b->n;
+          col.data = e->win_local + region[c * P + p];
+          col.nullable = (any_valid >> c & 1) != 0;
+          if (col.nullable) col.valid = e->win_local + region[(ncols + c) * P + p];
+          b->cols.push_back(col);
+        }
+        int64_t at = 0;
+        for (int s = 0; s < W; s++) {
+          const int64_t rs = (int64_t)cnt(s, p);
+          const int64_t fid = (int64_t)M[mrow * (size_t)s + P + 2];
+          if (rs) {
+            v.erase(std::remove_if(v.begin(), v.end(), [&](const Piece& pc) { return pc.file_id == fid && pc.src_rank == s; }), v.end());
+            v.push_back(Piece{fid, b, at, at + rs, s, {}});
+            if (s != me) fx->recvd += (uint64_t)rs * row_bytes;
+          }
+          at += rs;
+        }
+        std::stable_sort(v.begin(), v.end(), [](const Piece& a, const Piece& b2) { return a.src_rank != b2.src_rank ? a.src_rank < b2.src_rank : a.file_id < b2.file_id; });
+      }
+    }
+    x.sync();
+    if (met) {
+      met->output_rows += (uint64_t)n;
+      met->bytes_written += total_bytes;
+      met->bytes_read += total_bytes;
+    }
+    e->fused_exchanges++;
+    fx->done = true;
+    return true;
+  }
+
+  std::vector<b200_shuffle_write_partition> execute_stage(const PlanNode& root, int input_partition, FusedExchange* fx = nullptr) {
     if (root.op != PlanNode::ShuffleWriter) throw EngineError(B200_ERR_INVALID, "stage plan root must be a ShuffleWriterExec");
     OpMetrics* met = x.m(&root);
     const PlanNode& child = *root.children[0];
@@ -2885,8 +3114,14 @@ struct Runner {
     if ((size_t)P * (1 + sc.n) * 4 > 200 * 1024) throw EngineError(B200_ERR_UNSUPPORTED, "shuffle fan-out x string columns exceeds the histogram's shared memory");
     const uint32_t n_tiles = partition_n_tiles(n);
     const size_t acc_words = (size_t)P * (1 + sc.n);
-    DevPtr acc = dev_alloc(acc_words * 8, x.st());
-    CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, acc_words * 8, x.st()));
+    // fused shuffle: decided from the schema and the engine's configuration only, so that every executor of the gang
+    // takes the same branch
+    const int W = x.e->world, me = x.e->rank;
+    const bool fuse = fx && W > 1 && x.e->comm && x.e->win_local && sc.n == 0 && n_payload <= 60;
+    const size_t mrow = (size_t)P + 3;  // per executor: P row counts, validity mask, window fill, map task id
+    DevPtr acc = dev_alloc((fuse ? mrow * (size_t)W : acc_words) * 8, x.st());
+    CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, (fuse ? mrow * (size_t)W : acc_words) * 8, x.st()));
+    unsigned long long* const acc_ptr = (unsigned long long*)acc->ptr + (fuse ? mrow * (size_t)me : 0);
     DevPtr tile_hist = dev_alloc((size_t)std::max<uint64_t>((uint64_t)P * n_tiles, 1) * 4 + 64, x.st());
     uint64_t row_bytes = 0;
     for (auto& c : pay) row_bytes += (uint64_t)c.width() + (c.valid ? 1 : 0);
@@ -2894,10 +3129,14 @@ struct Runner {
       uint64_t kb = pid.pid ? 4 : 0;
       for (int k = 0; k < pid.n_keys; k++) kb += pid.keys[k].width;
       KernelTimer kt(x, "partition_hist", (uint64_t)n * kb);
-      CUDA_CHECK(launch_partition_hist(pid, n, P, (uint32_t*)tile_hist->ptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + P, x.st()));
+      CUDA_CHECK(launch_partition_hist(pid, n, P, (uint32_t*)tile_hist->ptr, acc_ptr, sc, acc_ptr + P, x.st()));
       x.count();
     }
-    const unsigned long long* hc = (const unsigned long long*)x.fetch_bytes(acc->ptr, acc_words * 8);
+    if (fuse) {
+      std::vector<b200_shuffle_write_partition> fr;
+      if (scatter_to_owners(root, input_partition, pay, pid, n, P, n_tiles, acc, tile_hist, row_bytes, fx, fr, met)) return fr;
+    }
+    const unsigned long long* hc = (const unsigned long long*)x.fetch_bytes(acc_ptr, acc_words * 8);
     // while the counts travel: scan the per-tile histogram and scatter
     const int64_t hn = (int64_t)P * n_tiles;
     DevPtr offs = dev_alloc((size_t)(hn + 2) * 8, x.st());
@@ -3001,12 +3240,6 @@ struct ExchEntry {
   int64_t partition, file_id, rows;
   std::vector<uint64_t> sizes;  // 3 per column: validity bytes, data bytes, chars bytes
 };
-
-#define NCCL_CHECK(expr)                                                                                              \
-  do {                                                                                                                \
-    ncclResult_t _r = (expr);                                                                                         \
-    if (_r != 0) throw EngineError(B200_ERR_CUDA, std::string("NCCL error: ") + NcclApi::get().GetErrorString(_r) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
-  } while (0)
 
 struct Exchange {
   Exec x;
@@ -3676,6 +3909,97 @@ int guard(F&& f) {
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// ---- exchange window (fused shuffle): allocate, publish through CUDA IPC, map every peer's ---------------------------------
+static void release_window(b200_engine* e) {
+  for (size_t d = 0; d < e->win_peer.size(); d++)
+    if (e->win_peer[d] && (int)d != e->rank) cudaIpcCloseMemHandle(e->win_peer[d]);
+  e->win_peer.clear();
+  if (e->win_local) cudaFree(e->win_local);
+  e->win_local = nullptr;
+  e->win_bytes = e->win_used = 0;
+}
+
+// all-gather of one fixed-size record per executor over the exchange communicator (setup path only)
+static void comm_allgather(b200_engine* e, const void* mine, void* all, size_t rec) {
+  NcclApi& N = NcclApi::get();
+  const int W = e->world, me = e->rank;
+  uint8_t* dev = nullptr;
+  CUDA_CHECK(cudaMalloc((void**)&dev, rec * (size_t)W));
+  try {
+    CUDA_CHECK(cudaMemcpyAsync(dev + rec * (size_t)me, mine, rec, cudaMemcpyHostToDevice, e->stream));
+    NCCL_CHECK(N.GroupStart());
+    for (int d = 0; d < W; d++) {
+      if (d == me) continue;
+      NCCL_CHECK(N.Send(dev + rec * (size_t)me, rec, kNcclUint8, d, e->comm, e->stream));
+      NCCL_CHECK(N.Recv(dev + rec * (size_t)d, rec, kNcclUint8, d, e->comm, e->stream));
+    }
+    NCCL_CHECK(N.GroupEnd());
+    CUDA_CHECK(cudaMemcpyAsync(all, dev, rec * (size_t)W, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  } catch (...) {
+    cudaFree(dev);
+    throw;
+  }
+  cudaFree(dev);
+}
+
+// Collective (called from b200_engine_comm_init on every executor).  Any executor that cannot provide or map a window
+// makes all of them run without one: the fused shuffle needs every peer, the two-step exchange none.
+static void setup_window(b200_engine* e) {
+  const int W = e->world, me = e->rank;
+  struct Rec {
+    cudaIpcMemHandle_t h;
+    uint64_t bytes, ok;
+  };
+  Rec mine;
+  memset(&mine, 0, sizeof mine);
+  const size_t want = (e->win_config_bytes + 4095) & ~(size_t)4095;
+  uint8_t* ptr = nullptr;
+  if (cudaMalloc((void**)&ptr, want) == cudaSuccess && cudaIpcGetMemHandle(&mine.h, ptr) == cudaSuccess) {
+    mine.bytes = want;
+    mine.ok = 1;
+  } else {
+    cudaGetLastError();
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+  }
+  std::vector<Rec> all((size_t)W);
+  comm_allgather(e, &mine, all.data(), sizeof(Rec));
+  bool ok = true;
+  for (auto& r : all) ok = ok && r.ok && r.bytes == want;
+  std::vector<uint8_t*> peer((size_t)W, nullptr);
+  if (ok) {
+    for (int d = 0; d < W && ok; d++) {
+      if (d == me) {
+        peer[(size_t)d] = ptr;
+        continue;
+      }
+      void* m = nullptr;
+      if (cudaIpcOpenMemHandle(&m, all[(size_t)d].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+      }
+      peer[(size_t)d] = (uint8_t*)m;
+    }
+  }
+  // second round: did everyone manage to map everyone?
+  uint64_t flag = ok ? 1 : 0;
+  std::vector<uint64_t> flags((size_t)W, 0);
+  comm_allgather(e, &flag, flags.data(), sizeof flag);
+  for (uint64_t f : flags) ok = ok && f;
+  if (!ok) {
+    for (int d = 0; d < W; d++)
+      if (d != me && peer[(size_t)d]) cudaIpcCloseMemHandle(peer[(size_t)d]);
+    if (ptr) cudaFree(ptr);
+    return;
+  }
+  e->win_local = ptr;
+  e->win_bytes = want;
+  e->win_used = 0;
+  e->win_peer = peer;
+}
+
+
 extern "C" {
 
 const char* b200_version(void) { return "b200exec 0.1 sm_100a"; }
@@ -3765,6 +4089,7 @@ void b200_engine_destroy(b200_engine* e) {
     if (sl.dev) cudaFree(sl.dev);
     if (sl.done) cudaEventDestroy(sl.done);
   }
+  release_window(e);
   if (e->comm && NcclApi::get().ok()) NcclApi::get().CommDestroy(e->comm);
   if (e->export_arena) cudaFreeHost(e->export_arena);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -3788,6 +4113,8 @@ uint64_t b200_engine_counter(b200_engine* e, const char* name) {
   const std::string n = name ? name : "";
   if (n == "fused") return e->n_fused;
   if (n == "fused_static") return e->n_fused_static;
+  if (n == "fused_exchanges") return e->fused_exchanges;
+  if (n == "exchange_window_bytes") return e->win_bytes;
   if (n == "vm") return e->n_vm;
   if (n == "groupby") return e->n_groupby;
   if (n == "fastfilter") return e->n_fastfilter;
@@ -3802,6 +4129,7 @@ int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
     if (std::string(key) == "datafusion.execution.batch_size") e->batch_size = std::max<int64_t>(1, atoll(value));
     if (std::string(key) == "b200.ingest.chunk_rows") e->ingest_chunk_rows = std::max<int64_t>(1 << 16, atoll(value));
     if (std::string(key) == "b200.ingest.slots") e->ingest_slots = atoi(value);
+    if (std::string(key) == "b200.exchange.window_bytes") e->win_config_bytes = (size_t)strtoull(value, nullptr, 10);  // read by b200_engine_comm_init
     if (std::string(key) == "b200.ingest.threads") e->pool.reset();  // re-created with the new size at the next ingest
     if (std::string(key) == "b200.agg.reset_hints") e->agg_hint.clear();  // forget which aggregate strategy each plan shape needed
     if (std::string(key) == "b200.metrics.kernel_timing") e->kernel_timing = std::string(value) == "on" || std::string(value) == "1" || std::string(value) == "true";
@@ -4092,6 +4420,47 @@ int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_
   });
 }
 
+int b200_stage_execute_exchange(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag, b200_shuffle_write_partition* out, int cap,
+                                int* n_out, b200_exchange_stats* stats) {
+  ScopeTimer tm("stage_execute_exchange");
+  return guard([&] {
+    if (!s || !n_out) throw EngineError(B200_ERR_INVALID, "null argument");
+    b200_engine* e = s->eng;
+    if (s->plan->op != PlanNode::ShuffleWriter || s->plan->n_out_partitions < 1)
+      throw EngineError(B200_ERR_INVALID, "b200_stage_execute_exchange needs a hash-partitioning ShuffleWriterExec");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    Exec x{e, s, cancel_flag};
+    Runner r{x, s->job_id};
+    Runner::FusedExchange fx;
+    std::vector<b200_shuffle_write_partition> res;
+    uint64_t sent = 0, recvd = 0;
+    try {
+      res = r.execute_stage(*s->plan, input_partition, &fx);
+      if (fx.done) {
+        sent = fx.sent;
+        recvd = fx.recvd;
+      } else if (e->world > 1) {
+        // two-step path (strings in the payload, no window, or a window too small for this exchange)
+        Exchange ex{x, Runner{x, s->job_id}, e, s->job_id, s->stage_id, s->plan->n_out_partitions, EXCH_HASH, 0, s->plan->schema, s->plan->schema.size()};
+        ex.run(&sent, &recvd);
+      }
+    } catch (...) {
+      cudaStreamSynchronize(e->stream);
+      Exec::abandon();
+      throw;
+    }
+    e->exch_sent_bytes += sent;
+    e->exch_recv_bytes += recvd;
+    if (stats) {
+      stats->sent_bytes = sent;
+      stats->recv_bytes = recvd;
+    }
+    if ((int)res.size() > cap) throw EngineError(B200_ERR_INVALID, "output array too small");
+    for (size_t i = 0; i < res.size(); i++) out[i] = res[i];
+    *n_out = (int)res.size();
+  });
+}
+
 int b200_stage_metrics(b200_stage* s, b200_operator_metrics* out, int cap, int* n_out) {
   return guard([&] {
     int n = (int)std::min<size_t>(s->metrics.size(), (size_t)cap);
@@ -4270,6 +4639,9 @@ int b200_remove_job_data(b200_engine* e, const char* job_id) {
       if (it->first.job == job_id) it = e->packed_cache.erase(it);
       else ++it;
     }
+    // partitions that arrived through the fused shuffle live in the exchange window: it is recycled as a whole once no
+    // stored partition can refer to it any more (peers write into it only inside a collective this executor takes part in)
+    if (e->shuffle.empty()) e->win_used = 0;
   });
 }
 
@@ -4334,6 +4706,7 @@ int b200_engine_kernel_stats(b200_engine* e, b200_kernel_stat* out, int cap, int
   });
 }
 
+
 int b200_comm_unique_id(void* out, uint64_t cap) {
   return guard([&] {
     if (!out || cap < sizeof(ncclUniqueId)) throw EngineError(B200_ERR_INVALID, "b200_comm_unique_id needs a 128-byte buffer");
@@ -4360,6 +4733,8 @@ int b200_engine_comm_init(b200_engine* e, const void* nccl_id, uint64_t id_bytes
     ncclUniqueId id;
     memcpy(&id, nccl_id, sizeof id);
     NCCL_CHECK(N.CommInitRank(&e->comm, e->world, id, e->rank));
+    release_window(e);
+    if (e->win_config_bytes) setup_window(e);
   });
 }
 

@@ -93,8 +93,12 @@ def _readers_of(node: dict, stage_id: int, under_merge: bool = False):
     return out
 
 
+def _fixed_width(schema) -> bool:
+    return all(str(f.get("type")).lower() not in ("utf8", "string") for f in schema)
+
+
 def run_stages_distributed(engine, stages: List[Stage], job_id: str, rank: int, world: int, collect: bool = True,
-                           on_stage=None) -> Optional[pa.Table]:
+                           on_stage=None, fused: bool = False) -> Optional[pa.Table]:
     """The same walk as run_stages with one executor per GPU: every rank runs the tasks whose input lives in its HBM,
     and after each stage the engines exchange the stage's output partitions (b200_exchange_stage) according to how
     the consuming stage reads them -- hash repartition (partition p -> rank p % world), merge / single-task consumer
@@ -122,10 +126,6 @@ def run_stages_distributed(engine, stages: List[Stage], job_id: str, rank: int, 
             else:
                 tasks = list(range(n_up)) if rank == 0 else []
             n_keys = n_up
-        qse = engine.create_query_stage_exec(job_id, st.stage_id, st.json(job_id))
-        for p in tasks:
-            qse.execute_query_stage(p)
-        qse.release()
         part = root.get("partitioning")
         n_out = part["n"] if part else n_keys
         out_parts[st.stage_id] = n_out
@@ -148,10 +148,29 @@ def run_stages_distributed(engine, stages: List[Stage], job_id: str, rank: int, 
                 mode, placement[st.stage_id] = EXCHANGE_HASH, "hash"
             else:
                 mode, placement[st.stage_id] = EXCHANGE_GATHER, "root"
-            if world > 1:
-                stats = engine.exchange_stage(job_id, st.stage_id, n_out, schema, mode, 0)
-                if on_stage is not None:
-                    on_stage(st.stage_id, mode, stats)
+        # fused = writer + hash exchange as one collective per map task (b200_stage_execute_exchange): needs the same number
+        # of map tasks on every executor -- true for partitioned tables loaded evenly and for hash-placed inputs whose
+        # partition count is a multiple of the executor count
+        symmetric = st.n_tasks != 1 and ((kind == "table" and what not in REPLICATED_TABLES) or
+                                         (kind != "table" and placement.get(what) == "hash" and out_parts[what] % world == 0))
+        fuse = fused and world > 1 and readers and mode == EXCHANGE_HASH and symmetric and _fixed_width(schema)
+        qse = engine.create_query_stage_exec(job_id, st.stage_id, st.json(job_id))
+        if fuse:
+            tot = {"sent_bytes": 0, "recv_bytes": 0, "fused": True}
+            for p in tasks:
+                _, xs = qse.execute_query_stage_exchange(p)
+                tot["sent_bytes"] += xs["sent_bytes"]
+                tot["recv_bytes"] += xs["recv_bytes"]
+            if on_stage is not None:
+                on_stage(st.stage_id, mode, tot)
+        else:
+            for p in tasks:
+                qse.execute_query_stage(p)
+        qse.release()
+        if readers and world > 1 and not fuse:
+            stats = engine.exchange_stage(job_id, st.stage_id, n_out, schema, mode, 0)
+            if on_stage is not None:
+                on_stage(st.stage_id, mode, stats)
     if not collect or rank != 0:
         return None
     last = stages[-1]

@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "b200_engine_export_table", "b200_tpch_table_rows", "b200_stage_prepare", "b200_stage_execute", "b200_stage_metrics",
     "b200_stage_release", "b200_partition_export", "b200_partition_rows", "b200_partition_device_buffers",
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
-    "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_engine_kernel_stats",
+    "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_stage_execute_exchange", "b200_engine_kernel_stats",
     "b200_ipc_encode", "b200_ipc_free", "b200_ipc_decode", "b200_shuffle_write_files", "b200_shuffle_read_file",
     "b200_version",
 ]
@@ -136,6 +136,7 @@ def load_library():
     L.b200_comm_unique_id.argtypes = [vp, u64]
     L.b200_engine_comm_init.argtypes = [vp, vp, u64]
     L.b200_exchange_stage.argtypes = [vp, cp, i64, ci, ci, ci, cp, C.POINTER(ExchangeStats)]
+    L.b200_stage_execute_exchange.argtypes = [vp, ci, vp, C.POINTER(ShuffleWritePartition), ci, C.POINTER(ci), C.POINTER(ExchangeStats)]
     L.b200_host_alloc_pinned.argtypes = [u64]
     L.b200_host_alloc_pinned.restype = vp
     L.b200_host_free_pinned.argtypes = [vp]
@@ -205,6 +206,16 @@ class QueryStageExecutor:
         _check(load_library().b200_stage_execute(self.h, input_partition, cf, out, cap, C.byref(n)))
         res = [ShuffleWritePartition.from_buffer_copy(out[i]) for i in range(n.value)]
         return res
+
+    def execute_query_stage_exchange(self, input_partition: int, cancel_flag=None):
+        """Collective: this map task plus the hash exchange of its output in one call (b200_stage_execute_exchange).
+        Returns (ShuffleWritePartition list, {"sent_bytes", "recv_bytes"})."""
+        n = C.c_int(0)
+        st = ExchangeStats()
+        cf = C.addressof(cancel_flag) if cancel_flag is not None else None
+        _check(load_library().b200_stage_execute_exchange(self.h, input_partition, cf, self._out, self._cap, C.byref(n), C.byref(st)))
+        res = [ShuffleWritePartition.from_buffer_copy(self._out[i]) for i in range(n.value)]
+        return res, {"sent_bytes": st.sent_bytes, "recv_bytes": st.recv_bytes}
 
     def collect_plan_metrics(self) -> List[dict]:
         cap = 256

@@ -193,6 +193,21 @@ int b200_comm_unique_id(void* out, uint64_t cap);
 int b200_engine_comm_init(b200_engine* e, const void* nccl_id, uint64_t id_bytes);
 int b200_exchange_stage(b200_engine* e, const char* job_id, int64_t stage_id, int n_out_partitions, int mode, int root,
                         const char* schema_json, b200_exchange_stats* stats);
+/* Fused shuffle writer + exchange: b200_stage_execute and the B200_EXCHANGE_HASH exchange of its output as ONE collective
+ * (ShuffleWriterExec::execute_shuffle_write, shuffle_writer.rs:214-330, together with the readers' fetch,
+ * shuffle_reader.rs:522-602).  Every executor of the communicator calls it for its map task of the same stage (executors
+ * that run several map tasks of the stage call it once per task, all in the same order).  When the engines were given an
+ * exchange window (configuration key "b200.exchange.window_bytes" set before b200_engine_comm_init: that many bytes of HBM
+ * per executor, published to the peers through CUDA IPC) and the stage's output holds no string column, the partition
+ * scatter kernel stores every row directly at its final place in the HBM of the executor that owns its output partition
+ * (partition p -> executor p % world; peer stores over NVLink), after one small all-gather of the per-partition row
+ * counts; nothing is staged and no separate transfer follows.  Otherwise (strings, no window, window too small for this
+ * exchange -- decided identically on every executor) it runs the two steps one after the other.  Either way the stored
+ * partitions afterwards are what b200_stage_execute + b200_exchange_stage leave.  `out` / `n_out` describe this map
+ * task's output as b200_stage_execute does; `stats` may be NULL.  Window memory is recycled when b200_remove_job_data
+ * leaves the engine without stored partitions.  Counters: "fused_exchanges", "exchange_window_bytes". */
+int b200_stage_execute_exchange(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag,
+                                b200_shuffle_write_partition* out, int cap, int* n_out, b200_exchange_stats* stats);
 
 /* ---- the reference's shuffle file format -----------------------------------
  * Arrow IPC streams with LZ4_FRAME body compression, written the way ShuffleWriterExec / SortShuffleWriterExec write

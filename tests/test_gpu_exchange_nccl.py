@@ -24,15 +24,19 @@ def _n_gpus():
         return 0
 
 
-def _worker(rank, world, nccl_id, case, q):
+def _worker(rank, world, nccl_id, case, q, window):
     try:
         import ballista_b200 as bb
         eng = bb.GpuExecutionEngine(rank, 0, rank, world)
+        if window:
+            eng.set_config("b200.exchange.window_bytes", str(window))
         eng.comm_init(nccl_id)
         name, tables, msf, parts, stages = case
         eng.tpch_load(tables, msf, rank, world, parts)
         stats = []
-        res = driver.run_stages_distributed(eng, stages, f"{name}-dist", rank, world, on_stage=lambda s, m, st: stats.append((s, m, st)))
+        res = driver.run_stages_distributed(eng, stages, f"{name}-dist", rank, world, on_stage=lambda s, m, st: stats.append((s, m, st)),
+                                            fused=bool(window))
+        stats.append((-1, -1, {"fused_exchanges": eng.counter("fused_exchanges"), "window": eng.counter("exchange_window_bytes")}))
         payload = None
         if rank == 0 and res is not None:
             sink = pa.BufferOutputStream()
@@ -46,12 +50,12 @@ def _worker(rank, world, nccl_id, case, q):
         q.put((rank, "error", traceback.format_exc(), None))
 
 
-def _run_case(case, world=2):
+def _run_case(case, world=2, window=0):
     import ballista_b200 as bb
     ctx = mp.get_context("spawn")
     nccl_id = bb.GpuExecutionEngine.comm_unique_id()
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, nccl_id, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, nccl_id, case, q, window)) for r in range(world)]
     for p in procs:
         p.start()
     got = {}
@@ -86,7 +90,7 @@ def test_q1_two_gpus(oracle, oracle_lib):
     got, stats = _run_case(case)
     want = _oracle(oracle, oracle_lib, case)
     assert_tables_equal(got, want, sort=False)
-    assert stats and all(st["sent_bytes"] < 16384 for _, _, st in stats)   # the inline path
+    assert stats and all(st["sent_bytes"] < 16384 for s, _, st in stats if s >= 0)   # the inline path
 
 
 @needs2
@@ -96,8 +100,52 @@ def test_q5_two_gpus(oracle, oracle_lib):
     want = _oracle(oracle, oracle_lib, case)
     assert want.num_rows > 0
     assert_tables_equal(got, want, sort=False)
-    assert any(st["sent_bytes"] > 16384 for _, _, st in stats)              # the lineitem shuffle took the direct path
+    assert any(st["sent_bytes"] > 16384 for s, _, st in stats if s >= 0)    # the lineitem shuffle took the direct path
     assert any(m == 2 for _, m, _ in stats)                                  # the broadcast build side
+
+
+@needs2
+@pytest.mark.parametrize("window", [256 << 20, 4096])
+def test_q5_two_gpus_fused_shuffle(oracle, oracle_lib, window):
+    """Writer + hash exchange as one collective (b200_stage_execute_exchange): the scatter kernel stores the rows of the
+    fixed-width shuffles (lineitem, orders, supplier keys) straight into the owning executor's window over NVLink.  With a
+    window too small for any exchange every executor falls back to the two-step path; same result either way."""
+    case = ("q5f", tpch.Q5_TABLES, 200, 2, tpch.q5(4))
+    got, stats = _run_case(case, window=window)
+    want = _oracle(oracle, oracle_lib, case)
+    assert want.num_rows > 0
+    assert_tables_equal(got, want, sort=False)
+    info = [st for s, _, st in stats if s == -1][0]
+    assert info["window"] >= window
+    assert any(st.get("fused") for s, _, st in stats if s >= 0)             # the driver took the collective entry point
+    if window > 4096:
+        assert info["fused_exchanges"] >= 3                                  # ... and the kernel wrote into the peers' windows
+        assert any(st.get("fused") and st["sent_bytes"] > 16384 for s, _, st in stats if s >= 0)
+    else:
+        assert info["fused_exchanges"] == 0
+
+
+@needs2
+def test_q17_q12_two_gpus_fused_shuffle(oracle, oracle_lib):
+    """Nullable / multi-task shapes through the fused shuffle: q12 and q17 at 2 map tasks per executor."""
+    for name, tables in (("q12", tpch.Q12_TABLES), ("q17", tpch.Q17_TABLES)):
+        msf = 100
+        if name == "q17":
+            for t, cols in tables.items():
+                n = oracle_lib.lib().oracle_tpch_table_rows(t.encode(), msf)
+                oracle.drop_table(t)
+                oracle.tpch_generate(t, msf, 0, 0, n, cols)
+            first = pa.Table.from_batches([oracle.export_table("part", 0)]).slice(0, 1).to_pylist()[0]
+            stages = tpch.q17(4, first["p_brand"], first["p_container"])
+        else:
+            stages = tpch.q12(4)
+        case = (name + "f", tables, msf, 2, stages)
+        got, stats = _run_case(case, window=256 << 20)
+        want = _oracle(oracle, oracle_lib, case)
+        assert_tables_equal(got, want, sort=False, f64_rtol=1e-12)
+        # q17 shuffles lineitem as (l_partkey, l_quantity, l_extendedprice): fixed width -> written into the peers' windows;
+        # both of q12's shuffles carry a string column and take the two-step path
+        assert ([st for s, _, st in stats if s == -1][0]["fused_exchanges"] >= 1) == (name == "q17")
 
 
 @needs2

@@ -1,15 +1,16 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/r02_gpu8.log; tail -8 gpurun_out/r02_gpu8.log
-THREADS=8,12,16,24 CHUNKS=1048576,4194304,16777216 SLOTS=3 python tools/ingest_probe.py 2>&1 | tail -14
-python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench5.json 2> gpurun_out/r02_bench5.err; tail -3 gpurun_out/r02_bench5.err; python - <<PY
-import json
-l=json.loads([x for x in open("gpurun_out/r02_bench5.json").read().splitlines() if x.startswith("{")][-1])
-print("q1", l["ms_per_step"], l["value"], "frac", l["roofline"]["frac"], "e2e", l["e2e"]["ms_per_step"], l["e2e"]["value"], l["parity_checked"], l.get("cpu_baseline",{}).get("value"))
-PY
-python bench.py --workload all --sf 10 --steps 2 --warmup 1 > gpurun_out/r02_alle.json 2> gpurun_out/r02_alle.err; tail -3 gpurun_out/r02_alle.err
+N=2
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+timeout 900 python -m pytest tests/test_gpu_exchange_nccl.py -x -q -m gpu 2>&1 | tail -25
+for MODE in fused twostep; do
+FLAG=""; [ $MODE = twostep ] && FLAG="--no-fused-shuffle"
+timeout 600 $TR bench.py --gpus $N --workload q5 --sf 50 --steps 3 --warmup 1 $FLAG > gpurun_out/r02_q5_n2_$MODE.json 2> gpurun_out/r02_q5_n2_$MODE.err; grep -E "Error|error|Traceback" -A3 gpurun_out/r02_q5_n2_$MODE.err | tail -8
 python - <<PY
 import json
-l=json.loads([x for x in open("gpurun_out/r02_alle.json").read().splitlines() if x.startswith("{")][-1])
-print("all", round(l["ms_per_step"],3), "ms", l["parity"].get("equal"), l["self_consistent_at_full_scale"], "qph", l["queries_per_hour"])
-for k,v in l["kernels"].items(): print("   ", k, round(v["ms_per_step"],3), round(v["launches_per_step"],1), round(v["achieved_gbs"]), round(v["frac_of_hbm_peak"],3))
+try:
+    l=json.loads([x for x in open("gpurun_out/r02_q5_n2_$MODE.json").read().splitlines() if x.startswith("{")][-1])
+    print("q5 N=2 $MODE", round(l["ms_per_step"],3), "ms", l["value"], l["parity"].get("equal"), l["self_consistent_at_full_scale"], l.get("fused_shuffle"))
+    print("   exchange", l["exchange_rank0"])
+    for k,v in l["kernels"].items(): print("   ", k, round(v["ms_per_step"],3), round(v["launches_per_step"],1), round(v["achieved_gbs"]), round(v["frac_of_hbm_peak"],3))
+except Exception as ex: print("no line", ex)
 PY
-python tools/op_probe.py parquet 2> gpurun_out/r02_probe_parquet.err | tr -d '\n ' ; echo; tail -2 gpurun_out/r02_probe_parquet.err
+done
