@@ -11,6 +11,7 @@
 //     every (destination, partition) into one contiguous message (exchange_pack_kernel).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../common/hash.hpp"
 #include "kernels.h"
@@ -154,6 +155,223 @@ __global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_kernel(const PidSr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staged variant (fan-out <= PT_STAGED_MAX_P): the tile's rows are first put in partition-major order in shared memory,
+// then written out by consecutive threads -- every (tile, partition) group leaves the SM as one contiguous run (full
+// 128-byte store instructions, whole sectors / maximum-size NVLink packets) instead of one 4..16-row fragment per
+// warp round.  Used for the fused shuffle, whose remote stores pay per packet, not per byte.
+// Shared memory: [PT_WARPS][P] warp bases | seed[P] (first output row of (p, tile) minus its first slot) | start[P + 1]
+// (first slot of p) | part[PT_TILE] (uint16 partition of every slot) | val[PT_TILE] x 16 bytes.
+// ------------------------------------------------------------------------------------------------
+static const uint32_t PT_STAGED_MAX_P = 256;
+
+template <typename T>
+__device__ __forceinline__ void staged_column(const GatherCol& c, const int64_t (&row)[PT_ROUNDS], const uint32_t (&slot)[PT_ROUNDS], int64_t n, int tile_rows,
+                                              const long long* seed, const unsigned short* part, T* val) {
+  const T* __restrict__ in = (const T*)c.in;
+  T v[PT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++)
+    if (row[r] < n) v[r] = in[row[r]];
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++)
+    if (row[r] < n) val[slot[r]] = v[r];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < PT_ROUNDS; k++) {
+    const int i = k * PT_BLOCK + (int)threadIdx.x;
+    if (i < tile_rows) {
+      const unsigned int q = part[i];
+      const long long d = seed[q] + i;  // output row of slot i inside partition q's numbering
+      T* o = c.part_base ? (T*)c.part_base[q] : (T*)c.out;
+      o[d] = val[i];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_staged_kernel(const PidSrc pid, int64_t n, uint32_t P, uint32_t n_tiles,
+                                                                           const uint64_t* __restrict__ offsets, GatherCols cols) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned int* sh = (unsigned int*)smem;                            // [PT_WARPS][P]
+  long long* seed = (long long*)(sh + (size_t)PT_WARPS * P + (((size_t)PT_WARPS * P) & 1));  // [P], 8-byte aligned
+  unsigned int* start = (unsigned int*)(seed + P);                   // [P + 1]
+  unsigned short* part = (unsigned short*)(start + P + 1 + ((P + 1) & 1));
+  unsigned char* val = (unsigned char*)(((uintptr_t)(part + PT_TILE) + 15) & ~(uintptr_t)15);
+  __shared__ unsigned int warp_tot[PT_WARPS];
+  for (uint32_t b = threadIdx.x; b < P * PT_WARPS; b += PT_BLOCK) sh[b] = 0;
+  __syncthreads();
+  const int64_t t0 = (int64_t)blockIdx.x * PT_TILE;
+  const int tile_rows = (int)min((int64_t)PT_TILE, n - t0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int* mine = sh + (size_t)warp * P;
+  uint32_t p[PT_ROUNDS];
+  int64_t row[PT_ROUNDS];
+  uint32_t rank[PT_ROUNDS];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++) {
+    row[r] = t0 + warp * (PT_TILE / PT_WARPS) + r * 32 + lane;
+    const bool live = row[r] < n;
+    p[r] = live ? pid_of(pid, row[r], P) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, p[r]);
+    uint32_t base = 0;
+    if (live) base = mine[p[r]];
+    __syncwarp();
+    rank[r] = base + __popc(peers & lt);
+    if (live && (peers & lt) == 0) mine[p[r]] = base + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per partition: rows of this tile, then an exclusive scan over the partitions (P <= 256: one value per thread)
+  unsigned int cnt = 0;
+  if (threadIdx.x < P) {
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; w++) {
+      const unsigned int c = sh[(size_t)w * P + threadIdx.x];
+      sh[(size_t)w * P + threadIdx.x] = cnt;  // warp w's first slot inside the partition's group
+      cnt += c;
+    }
+  }
+  unsigned int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned int before = 0;
+  for (int w = 0; w < warp; w++) before += warp_tot[w];
+  if (threadIdx.x < P) {
+    const unsigned int first = before + incl - cnt;  // first slot of this partition in the tile
+    start[threadIdx.x] = first;
+    seed[threadIdx.x] = (long long)offsets[(size_t)threadIdx.x * n_tiles + blockIdx.x] - (long long)first;
+  }
+  __syncthreads();
+  uint32_t slot[PT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++) {
+    slot[r] = row[r] < n ? start[p[r]] + mine[p[r]] + rank[r] : 0u;
+    if (row[r] < n) part[slot[r]] = (unsigned short)p[r];
+  }
+  __syncthreads();
+  for (int c = 0; c < cols.n; c++) {
+    const GatherCol& gc = cols.c[c];
+    switch (gc.width) {
+      case 1: staged_column<uint8_t>(gc, row, slot, n, tile_rows, seed, part, (uint8_t*)val); break;
+      case 2: staged_column<uint16_t>(gc, row, slot, n, tile_rows, seed, part, (uint16_t*)val); break;
+      case 4: staged_column<uint32_t>(gc, row, slot, n, tile_rows, seed, part, (uint32_t*)val); break;
+      case 8: staged_column<uint64_t>(gc, row, slot, n, tile_rows, seed, part, (uint64_t*)val); break;
+      default: staged_column<ulonglong2>(gc, row, slot, n, tile_rows, seed, part, (ulonglong2*)val); break;
+    }
+  }
+}
+
+// Warp-staged variant (fan-out <= 32): no CTA barrier in the column loop.  Every warp puts ITS 256 rows in partition-major
+// order in a private 4 KB slice of shared memory and writes them out with consecutive lanes: runs of 256 / P rows per
+// partition (P = 8: 32 rows = one full store instruction, 256..512 bytes) instead of 32 / P rows per warp round.
+// Lane q keeps partition q's numbers (first slot of the group, first output row of the group) and hands them out by shuffle.
+template <typename T>
+__device__ __forceinline__ void wstaged_column(const GatherCol& c, const int64_t (&row)[PT_ROUNDS], const uint32_t (&slot)[PT_ROUNDS], int64_t n, int warp_rows,
+                                               long long delta_mine, const unsigned char* part, T* val, int lane) {
+  const T* __restrict__ in = (const T*)c.in;
+  T v[PT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++)
+    if (row[r] < n) v[r] = in[row[r]];
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++)
+    if (row[r] < n) val[slot[r]] = v[r];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < PT_ROUNDS; k++) {
+    const int i = k * 32 + lane;
+    const unsigned int q = i < warp_rows ? part[i] : 0u;
+    const long long d = __shfl_sync(0xFFFFFFFFu, delta_mine, (int)q) + i;  // output row of slot i
+    if (i < warp_rows) {
+      T* o = c.part_base ? (T*)c.part_base[q] : (T*)c.out;
+      o[d] = val[i];
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(PT_BLOCK) part_tile_scatter_wstaged_kernel(const PidSrc pid, int64_t n, uint32_t P, uint32_t n_tiles,
+                                                                            const uint64_t* __restrict__ offsets, GatherCols cols) {
+  __shared__ unsigned int sh[PT_WARPS][32];                                  // per-warp counts -> per-warp first output rows
+  __shared__ unsigned long long gbase[PT_WARPS][32];
+  __shared__ unsigned char part_s[PT_WARPS][PT_TILE / PT_WARPS];
+  __shared__ __align__(16) unsigned char val_s[PT_WARPS][(PT_TILE / PT_WARPS) * 16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  sh[warp][lane] = 0;
+  __syncwarp();
+  const int64_t t0 = (int64_t)blockIdx.x * PT_TILE;
+  const int64_t w0 = t0 + warp * (PT_TILE / PT_WARPS);
+  const int warp_rows = (int)max((int64_t)0, min((int64_t)(PT_TILE / PT_WARPS), n - w0));
+  unsigned int* mine = sh[warp];
+  uint32_t p[PT_ROUNDS];
+  int64_t row[PT_ROUNDS];
+  uint32_t rank[PT_ROUNDS];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++) {
+    row[r] = w0 + r * 32 + lane;
+    const bool live = row[r] < n;
+    p[r] = live ? pid_of(pid, row[r], P) : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, p[r]);
+    uint32_t base = 0;
+    if (live) base = mine[p[r]];
+    __syncwarp();
+    rank[r] = base + __popc(peers & lt);
+    if (live && (peers & lt) == 0) mine[p[r]] = base + __popc(peers);
+    __syncwarp();
+  }
+  // lane q: this warp's rows of partition q, and the first slot of that group in the warp's partition-major order
+  const unsigned int cnt = mine[lane];
+  unsigned int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const unsigned int wstart = incl - cnt;
+  __syncthreads();
+  // first output row of (partition, tile, warp): the tile's offset plus the earlier warps' rows
+  if (threadIdx.x < P) {
+    unsigned long long run = offsets[(size_t)threadIdx.x * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; w++) {
+      gbase[w][threadIdx.x] = run;
+      run += sh[w][threadIdx.x];
+    }
+  }
+  __syncthreads();
+  const long long delta_mine = (uint32_t)lane < P ? (long long)gbase[warp][lane] - (long long)wstart : 0ll;
+  uint32_t slot[PT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < PT_ROUNDS; r++) {
+    const unsigned int ws = __shfl_sync(0xFFFFFFFFu, wstart, (int)(p[r] & 31u));
+    slot[r] = row[r] < n ? ws + rank[r] : 0u;
+    if (row[r] < n) part_s[warp][slot[r]] = (unsigned char)p[r];
+  }
+  __syncwarp();
+  for (int c = 0; c < cols.n; c++) {
+    const GatherCol& gc = cols.c[c];
+    switch (gc.width) {
+      case 1: wstaged_column<uint8_t>(gc, row, slot, n, warp_rows, delta_mine, part_s[warp], (uint8_t*)val_s[warp], lane); break;
+      case 2: wstaged_column<uint16_t>(gc, row, slot, n, warp_rows, delta_mine, part_s[warp], (uint16_t*)val_s[warp], lane); break;
+      case 4: wstaged_column<uint32_t>(gc, row, slot, n, warp_rows, delta_mine, part_s[warp], (uint32_t*)val_s[warp], lane); break;
+      case 8: wstaged_column<uint64_t>(gc, row, slot, n, warp_rows, delta_mine, part_s[warp], (uint64_t*)val_s[warp], lane); break;
+      default: wstaged_column<ulonglong2>(gc, row, slot, n, warp_rows, delta_mine, part_s[warp], (ulonglong2*)val_s[warp], lane); break;
+    }
+  }
+}
+
+static size_t partition_scatter_staged_smem(uint32_t P) {
+  return ((size_t)PT_WARPS * P + 1) * 4 + (size_t)P * 8 + ((size_t)P + 2) * 4 + (size_t)PT_TILE * 2 + 16 + (size_t)PT_TILE * 16;
+}
+
 size_t partition_scatter_smem(uint32_t P) { return (size_t)P * PT_WARPS * sizeof(unsigned int); }
 uint32_t partition_n_tiles(int64_t n) { return (uint32_t)((n + PT_TILE - 1) / PT_TILE); }
 
@@ -174,6 +392,24 @@ cudaError_t launch_partition_scatter(const PidSrc& pid, int64_t n, uint32_t P, c
                                      cudaStream_t st) {
   const uint32_t nt = partition_n_tiles(n);
   if (nt == 0) return cudaSuccess;
+  bool peer = false;
+  for (int c = 0; c < cols.n; c++) peer = peer || cols.c[c].part_base != nullptr;
+  static const int force_staged = getenv("B200_SCATTER_STAGED") ? atoi(getenv("B200_SCATTER_STAGED")) : -1;  // measurement switch
+  if (!dest_out && P <= 32 && (force_staged == 1 || (force_staged != 0 && peer))) {
+    part_tile_scatter_wstaged_kernel<<<nt, PT_BLOCK, 0, st>>>(pid, n, P, nt, offsets, cols);
+    return cudaGetLastError();
+  }
+  if (!dest_out && P <= PT_STAGED_MAX_P && (force_staged == 1 || (force_staged != 0 && peer))) {
+    const size_t sm = partition_scatter_staged_smem(P);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(part_tile_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_scatter_staged_smem(PT_STAGED_MAX_P));
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    part_tile_scatter_staged_kernel<<<nt, PT_BLOCK, sm, st>>>(pid, n, P, nt, offsets, cols);
+    return cudaGetLastError();
+  }
   const size_t sm = partition_scatter_smem(P);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(part_tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -58,7 +58,7 @@ if op == "join":
 elif op == "partition":
     cols = tpch.Q5_TABLES["lineitem"]
     load("lineitem", cols)
-    run([P.Stage(1, P.shuffle_writer(tpch.table_scan("lineitem", cols), 1, [c(0)], 8))], [1])
+    run([P.Stage(1, P.shuffle_writer(tpch.table_scan("lineitem", cols), 1, [c(0)], int(os.environ.get("FANOUT", "8"))))], [1])
 elif op in ("groupby", "groupby_small"):
     key = "l_partkey" if op == "groupby" else "l_suppkey"
     load("lineitem", [key, "l_quantity"])
