@@ -511,7 +511,11 @@ def run_workload(args):
         tpch.TABLE_LAYOUT.clear()
         if len(names) > 1:
             tpch.TABLE_LAYOUT.update(tabs)
-        return tabs, eng.tpch_load(tabs, m, rank, world, 1)
+        # input partitions per GPU: as asked, but never more than ~120 M lineitem rows in one (Arrow Utf8 offsets are int32:
+        # a partition's o_comment / l_comment characters must stay below 2 GiB)
+        li_rows = 6_000_000 * m // 1000 // world
+        in_parts = max(1, args.partitions_per_gpu, -(-li_rows // 120_000_000))
+        return tabs, eng.tpch_load(tabs, m, rank, world, in_parts)
 
     def plans(PP):
         return {nme: tpch.QUERIES[nme][1](PP) for nme in names}
@@ -522,8 +526,10 @@ def run_workload(args):
         pmsf = min(msf, 1000)
         tabs, _ = load(pmsf)
         pl = plans(P)
-        got = {nme: driver.run_stages_distributed(eng, pl[nme], f"par-{nme}", rank, world, fused=fused) for nme in names}
+        got = {}
         for nme in names:
+            got[nme] = driver.run_stages_distributed(eng, pl[nme], f"par-{nme}", rank, world, fused=fused)
+            eng.synchronize()
             eng.remove_job_data(f"par-{nme}")
         if rank == 0:
             import oracle_ffi
@@ -600,7 +606,11 @@ def run_workload(args):
     consistent = None
     if not args.no_parity:
         pl2 = plans(P * 2)
-        _, res2 = None, {nme: driver.run_stages_distributed(eng, pl2[nme], f"alt-{nme}", rank, world, fused=fused) for nme in names}
+        res2 = {}
+        for nme in names:
+            res2[nme] = driver.run_stages_distributed(eng, pl2[nme], f"alt-{nme}", rank, world, fused=fused)
+            eng.synchronize()
+            eng.remove_job_data(f"alt-{nme}")
         if rank == 0:
             from util import canon
             consistent = all(tables_equal(canon(res[nme]), canon(res2[nme]), f64_rtol=1e-12) for nme in names)
