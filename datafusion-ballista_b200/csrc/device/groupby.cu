@@ -63,11 +63,27 @@ __global__ void __launch_bounds__(GB_BLOCK) groupby_kernel(const GroupBySpec S) 
   if (threadIdx.x == 0) new_groups = 0;
   __syncthreads();
   const AggTable& T = S.table;
-  const unsigned long long mask = T.cap - 1;
-  const int64_t n = S.n_rows;
+  unsigned long long mask = T.cap - 1, slot_base = 0;
+  int64_t n = S.n_rows;
+  int64_t first = (int64_t)blockIdx.x * (GB_BLOCK * GB_R), stride = (int64_t)gridDim.x * (GB_BLOCK * GB_R);
+  if (S.pf_K > 0) {
+    // partition-first: which bucket does this CTA serve?  (largest b with cta_start[b] <= blockIdx.x)
+    int lo = 0, hi = S.pf_K;
+    if (blockIdx.x >= S.pf_cta_start[S.pf_K]) return;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (S.pf_cta_start[mid] <= blockIdx.x) lo = mid;
+      else hi = mid;
+    }
+    mask = S.pf_slots - 1;
+    slot_base = (unsigned long long)lo * S.pf_slots;
+    first = (int64_t)S.pf_row_start[lo] + (int64_t)(blockIdx.x - S.pf_cta_start[lo]) * (GB_BLOCK * GB_R);
+    n = (int64_t)S.pf_row_start[lo + 1];
+    stride = (int64_t)1 << 60;  // exactly one tile per CTA
+  }
   unsigned int inserted = 0;
   bool stop = false;
-  for (int64_t base = (int64_t)blockIdx.x * (GB_BLOCK * GB_R); base < n && !stop; base += (int64_t)gridDim.x * (GB_BLOCK * GB_R)) {
+  for (int64_t base = first; base < n && !stop; base += stride) {
     // another thread found the table full or met a row outside the pattern: the launch is void, leave early
     if (*(volatile unsigned int*)&S.status->overflow || *(volatile unsigned int*)&S.status->pack_overflow) break;
     unsigned long long slot[GB_R];
@@ -112,7 +128,7 @@ __global__ void __launch_bounds__(GB_BLOCK) groupby_kernel(const GroupBySpec S) 
         stop = true;
         continue;
       }
-      unsigned long long s = h & mask;
+      unsigned long long s = slot_base + (h & mask);
       bool found = false;
       for (int probe = 0; probe < GB_MAX_PROBE; probe++) {
         unsigned long long cur = *(volatile unsigned long long*)&T.hash[s];
@@ -144,7 +160,7 @@ __global__ void __launch_bounds__(GB_BLOCK) groupby_kernel(const GroupBySpec S) 
           found = true;
           break;
         }
-        s = (s + 1) & mask;
+        s = slot_base + ((s + 1) & mask);
       }
       if (!found) {
         atomicExch(&S.status->overflow, 1u);  // table (nearly) full: the host retries with a larger one
@@ -218,7 +234,53 @@ __global__ void __launch_bounds__(GB_BLOCK) groupby_kernel(const GroupBySpec S) 
   if (threadIdx.x == 0 && new_groups) atomicAdd(T.n_groups, new_groups);
 }
 
+// One warp: exclusive prefix sums of the bucket sizes (rows) and of the CTAs each bucket needs.
+__global__ void groupby_plan_kernel(const unsigned long long* __restrict__ counts, int K, unsigned long long* __restrict__ row_start,
+                                    unsigned int* __restrict__ cta_start) {
+  const int lane = threadIdx.x;
+  unsigned long long rows_run = 0;
+  unsigned int ctas_run = 0;
+  for (int b0 = 0; b0 < K; b0 += 32) {
+    const int b = b0 + lane;
+    const unsigned long long c = b < K ? counts[b] : 0ull;
+    const unsigned int t = (unsigned int)((c + GROUPBY_ROWS_PER_CTA - 1) / GROUPBY_ROWS_PER_CTA);
+    unsigned long long ri = c;
+    unsigned int ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long ro = __shfl_up_sync(0xFFFFFFFFu, ri, d);
+      const unsigned int to = __shfl_up_sync(0xFFFFFFFFu, ti, d);
+      if (lane >= d) {
+        ri += ro;
+        ti += to;
+      }
+    }
+    if (b < K) {
+      row_start[b] = rows_run + ri - c;
+      cta_start[b] = ctas_run + ti - t;
+    }
+    rows_run += __shfl_sync(0xFFFFFFFFu, ri, 31);
+    ctas_run += __shfl_sync(0xFFFFFFFFu, ti, 31);
+  }
+  if (lane == 0) {
+    row_start[K] = rows_run;
+    cta_start[K] = ctas_run;
+  }
+}
+
+cudaError_t launch_groupby_plan(const unsigned long long* counts, int K, unsigned long long* row_start, unsigned int* cta_start, cudaStream_t st) {
+  static_assert(GROUPBY_ROWS_PER_CTA == GB_BLOCK * GB_R, "one tile per CTA in partition-first mode");
+  groupby_plan_kernel<<<1, 32, 0, st>>>(counts, K, row_start, cta_start);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_groupby(const GroupBySpec& S, int sm_count, cudaStream_t st) {
+  if (S.pf_K > 0) {
+    // upper bound of sum_b ceil(rows_b / tile): the CTAs past cta_start[K] exit at once
+    const int64_t g = (S.n_rows + GROUPBY_ROWS_PER_CTA - 1) / GROUPBY_ROWS_PER_CTA + S.pf_K;
+    groupby_kernel<<<(unsigned)g, GB_BLOCK, 0, st>>>(S);
+    return cudaGetLastError();
+  }
   int64_t g = (S.n_rows + (int64_t)GB_BLOCK * GB_R - 1) / ((int64_t)GB_BLOCK * GB_R);
   if (g < 1) g = 1;
   if (g > (int64_t)sm_count * 8) g = (int64_t)sm_count * 8;  // 8 resident CTAs of 256 threads per SM

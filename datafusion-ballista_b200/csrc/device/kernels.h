@@ -216,8 +216,19 @@ struct GroupBySpec {
   int64_t n_rows;
   AggTable table;
   RunStatus* status;
+  // partition-first mode (pf_K > 0): the rows were radix-partitioned by hash(keys) % pf_K beforehand (shuffle.cu) and bucket
+  // b aggregates into its own region [b * pf_slots, (b + 1) * pf_slots) of the table, small enough to stay in L2 while the
+  // CTAs of that bucket run.  pf_row_start[b .. b+1] = the bucket's rows, pf_cta_start[b .. b+1] = the CTAs that process them
+  // (launch_groupby_plan fills both from the partition counts on the device: no host round trip).
+  int pf_K;
+  unsigned long long pf_slots;                 // power of two
+  const unsigned int* pf_cta_start;            // [pf_K + 1]
+  const unsigned long long* pf_row_start;      // [pf_K + 1]
 };
 cudaError_t launch_groupby(const GroupBySpec& S, int sm_count, cudaStream_t st);
+// counts[K] -> row_start[K + 1], cta_start[K + 1] (one CTA per GROUPBY_ROWS_PER_CTA rows of a bucket)
+static const int GROUPBY_ROWS_PER_CTA = 1024;
+cudaError_t launch_groupby_plan(const unsigned long long* counts, int K, unsigned long long* row_start, unsigned int* cta_start, cudaStream_t st);
 
 // ---- single-pass join (join.cu) -----------------------------------------------------------------
 struct JoinNode {   // one per build row

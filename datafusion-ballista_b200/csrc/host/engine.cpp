@@ -75,10 +75,13 @@ struct b200_engine {
   std::map<ShuffleKey, std::vector<Piece>> shuffle;
   std::map<ShuffleKey, DevBatchPtr> packed_cache;  // b200_partition_device_buffers: exchange-layout copies handed out by pointer
   std::atomic<uint64_t> launches{0};
-  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0}, n_groupby{0}, n_fastfilter{0};  // pipelines per kernel family (b200_engine_counter)
+  std::atomic<uint64_t> n_fused{0}, n_fused_static{0}, n_vm{0}, n_groupby{0}, n_groupby_pf{0}, n_fastfilter{0};  // pipelines per kernel family (b200_engine_counter)
   int64_t batch_size = 8192;
   std::map<std::string, std::string> config;
   std::map<std::string, int> agg_hint;       // plan fingerprint -> sink that worked (0 reg, >0 log2 cap)
+  uint64_t pf_bucket_slots = (uint64_t)1 << 19;  // partition-first aggregation: table slots per bucket (power of two; 0 = off)
+  int64_t pf_min_rows = (int64_t)1 << 22;
+  std::map<std::string, uint64_t> agg_groups;  // plan fingerprint -> most groups any task of that shape produced (sizes the table)
   void* pinned_stage = nullptr;              // small pinned buffer for status read-backs
   // ingest narrowing (import_batch): host pool + two pinned staging slots with their device mirrors
   std::unique_ptr<HostPool> pool;
@@ -877,6 +880,70 @@ static bool program_filters(const Program& P) {
 bool match_groupby(const Program& P, GroupBySpec& S);
 bool match_fast_filter(const Program& P, FastFilterSpec& S);
 
+// Partition-first aggregation (AggregateExec with more groups than the L2 can hold a table for): radix-partition the
+// referenced columns by hash(keys) % K with the shuffle writer's kernels, so that bucket b's groups live in their own
+// region of the table (cap / K slots, ~32 MB of touched cells) that stays in L2 while that bucket's CTAs run -- the
+// random accesses of the upsert become L2 hits instead of 32-byte DRAM sectors.  Bytes: one extra read + write of the
+// referenced columns (sequential) against three random sectors per row saved.  The bucket ranges are resolved on the
+// device (launch_groupby_plan): no host synchronisation between the partition and the aggregation.
+bool partition_for_groupby(const Exec& x, GroupBySpec& S, std::vector<DevPtr>& keep) {
+  // b200.agg.partition_first.bucket_slots (default 2^19 slots ~ 32 MB of touched cells; 0 = never partition),
+  // b200.agg.partition_first.min_rows (default 2^22)
+  const uint64_t GB_PF_BUCKET_SLOTS = x.e->pf_bucket_slots;
+  if (!GB_PF_BUCKET_SLOTS || S.n_keys < 1 || S.table.cap < GB_PF_BUCKET_SLOTS * 8 || S.n_rows < x.e->pf_min_rows || S.n_rows >= ((int64_t)1 << 32)) return false;
+  for (int k = 0; k < S.n_keys; k++) {
+    const uint32_t w = S.cols[S.key_col[k]].width;
+    if (w != 4 && w != 8) return false;
+  }
+  const uint32_t K = (uint32_t)std::min<uint64_t>(S.table.cap / GB_PF_BUCKET_SLOTS, PART_MAX_FANOUT);
+  const int64_t n = S.n_rows;
+  PidSrc ps;
+  memset(&ps, 0, sizeof ps);
+  for (int k = 0; k < S.n_keys; k++) {
+    const FusedCol& c = S.cols[S.key_col[k]];
+    ps.keys[ps.n_keys++] = KeyCol{c.data, nullptr, (uint8_t)(c.width == 4 ? PH_I32 : PH_I64), (uint8_t)c.width};
+  }
+  const uint32_t n_tiles = partition_n_tiles(n);
+  DevPtr acc = dev_alloc((size_t)K * 8 + 64, x.st());
+  CUDA_CHECK(cudaMemsetAsync(acc->ptr, 0, (size_t)K * 8, x.st()));
+  DevPtr tile_hist = dev_alloc((size_t)K * n_tiles * 4 + 64, x.st());
+  PartStrCols sc;
+  sc.n = 0;
+  CUDA_CHECK(launch_partition_hist(ps, n, K, (uint32_t*)tile_hist->ptr, (unsigned long long*)acc->ptr, sc, (unsigned long long*)acc->ptr + K, x.st()));
+  const int64_t hn = (int64_t)K * n_tiles;
+  DevPtr offs = dev_alloc((size_t)(hn + 2) * 8, x.st());
+  DevPtr scratch = dev_alloc((size_t)(hn / 1024 + 4) * 8, x.st());
+  launch_scan_u32_to_u64((const uint32_t*)tile_hist->ptr, (uint64_t*)offs->ptr, hn, (uint64_t*)scratch->ptr, x.st());
+  GatherCols gc;
+  gc.n = 0;
+  for (int c = 0; c < S.n_cols; c++) {
+    DevPtr out = dev_alloc((size_t)n * S.cols[c].width + 64, x.st());
+    GatherCol& g = gc.c[gc.n++];
+    memset(&g, 0, sizeof g);
+    g.in = S.cols[c].data;
+    g.out = out->ptr;
+    g.width = (int)S.cols[c].width;
+    S.cols[c].data = out->ptr;
+    keep.push_back(out);
+  }
+  CUDA_CHECK(launch_partition_scatter(ps, n, K, (const uint64_t*)offs->ptr, gc, nullptr, x.st()));
+  DevPtr row_start = dev_alloc((size_t)(K + 1) * 8 + 64, x.st()), cta_start = dev_alloc((size_t)(K + 1) * 4 + 64, x.st());
+  CUDA_CHECK(launch_groupby_plan((const unsigned long long*)acc->ptr, (int)K, (unsigned long long*)row_start->ptr, (unsigned int*)cta_start->ptr, x.st()));
+  x.count(6);
+  S.pf_K = (int)K;
+  S.pf_slots = S.table.cap / K;
+  S.pf_row_start = (const unsigned long long*)row_start->ptr;
+  S.pf_cta_start = (const unsigned int*)cta_start->ptr;
+  keep.push_back(row_start);
+  keep.push_back(cta_start);
+  keep.push_back(acc);
+  keep.push_back(tile_hist);
+  keep.push_back(offs);
+  keep.push_back(scratch);
+  x.e->n_groupby_pf++;
+  return true;
+}
+
 RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, const FusedPlan* fused = nullptr, bool wait = true, OpMetrics* met = nullptr,
                           const unsigned int* extra_fetch = nullptr, unsigned int* extra_out = nullptr, const GroupBySpec* gb = nullptr,
                           const FastFilterSpec* ff = nullptr) {
@@ -936,6 +1003,10 @@ RunOutcome launch_program(const Exec& x, PipelineBuilder& pb, int reg_groups, co
     GroupBySpec S = *gb;
     S.status = P.status;
     S.table = P.table;
+    const bool allow_pf = gb->pf_K != -1;
+    S.pf_K = 0;
+    std::vector<DevPtr> pf_keep;  // stream-ordered: released after the launch below is enqueued
+    if (allow_pf) partition_for_groupby(x, S, pf_keep);
     le = launch_groupby(S, x.e->sm_count, x.st());
     x.e->n_groupby++;
   } else if (fused) {
@@ -1810,6 +1881,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   const std::string hint_key = (x.s ? x.s->fingerprint : std::string("?")) + "#" + std::to_string(node_idx);
   int level = 0;
   bool had_hint = false;
+  uint64_t groups_hint = 0;
   {
     std::lock_guard<std::mutex> g(x.e->mu);
     auto it = x.e->agg_hint.find(hint_key);
@@ -1817,8 +1889,11 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       level = it->second / 4;
       pack_mode = std::min(pack_mode, it->second % 4);
       had_hint = true;
+      auto ig = x.e->agg_groups.find(hint_key);
+      if (ig != x.e->agg_groups.end()) groups_hint = ig->second;
     }
   }
+  const int hinted_level = had_hint ? level : -1;
   bool sampled = false;
   // strategy ladder: register sink (<= 4 groups) -> global table of growing capacity; packed keys -> plain keys
   std::unique_ptr<PipelineBuilder> pbp;
@@ -1826,7 +1901,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
   TableMem tm;
   RunOutcome ro;
   unsigned int n_groups = 0;
-  bool gb_bailed = false;
+  bool gb_bailed = false, pf_off = false;
   for (;;) {
     x.check_cancel();
     ScopeTimer t_iter("  agg: lower+alloc+launch+sync");
@@ -1864,6 +1939,10 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       P.sink = SINK_AGG_GLOBAL;
       if (!n_keys) cap = 2;
       else cap = std::min<uint64_t>(next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2), (uint64_t)1 << std::min(40, 12 + 4 * level));
+      // a plan shape seen before: size the table for the groups its tasks produced (x2.5: load factor <= 0.4 with room for a
+      // somewhat larger sibling task) instead of the whole class -- the classes are 16x apart, and every slot costs ~80 bytes
+      // of memset and of extraction scan.  An overflow falls back to the class size (level++ below leaves hinted_level).
+      if (groups_hint && level == hinted_level && n_keys) cap = std::min(cap, std::max<uint64_t>(next_pow2(groups_hint * 5 / 2), 4096));
       if (cap < 16) cap = 16;
     }
     {
@@ -1889,6 +1968,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       P.table = stm.T;
       if (match_groupby(P, probe)) {
         probe.n_rows = sample_rows;
+        probe.pf_K = -1;
         unsigned int seen = 0;
         RunOutcome so = launch_program(x, pb, 0, nullptr, true, nullptr, stm.T.n_groups, &seen, &probe);
         if (!so.status.pack_overflow && (so.status.overflow || seen > (unsigned)VM_REG_GROUPS)) {
@@ -1902,6 +1982,7 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     const bool use_fused = level == 0 && match_fused(P, fspec);
     GroupBySpec gspec;
     const bool use_gb = level > 0 && !gb_bailed && match_groupby(P, gspec);
+    gspec.pf_K = pf_off ? -1 : 0;
     {
       ScopeTimer t_l("    agg: launch_program (incl. sync)");
       ro = launch_program(x, pb, reg_groups, use_fused ? &fspec : nullptr, true, met, tm.T.n_groups, &n_groups, use_gb ? &gspec : nullptr);
@@ -1916,7 +1997,13 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
       continue;
     }
     if (!ro.status.overflow) break;
-    if (level > 0 && cap >= next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2)) throw EngineError(B200_ERR_EXECUTION, "aggregate hash table overflow");
+    if (level > 0 && cap >= next_pow2((uint64_t)std::max<int64_t>(src->n, 1) * 2)) {
+      if (use_gb && !pf_off) {
+        pf_off = true;  // a bucket's region of the partitioned table filled up (skewed buckets): same table, unpartitioned
+        continue;
+      }
+      throw EngineError(B200_ERR_EXECUTION, "aggregate hash table overflow");
+    }
     level++;
   }
   {
@@ -1929,6 +2016,8 @@ DevBatchPtr run_aggregate(const Exec& x, const BuilderFactory& make_pb, const Pl
     }
     std::lock_guard<std::mutex> g(x.e->mu);
     x.e->agg_hint[hint_key] = learnt * 4 + pack_mode;
+    uint64_t& gh = x.e->agg_groups[hint_key];
+    gh = std::max<uint64_t>(gh, n_groups);
   }
   PipelineBuilder& pb = *pbp;
   // extraction
@@ -4112,6 +4201,7 @@ uint64_t b200_engine_kernel_launches(b200_engine* e) { return e->launches; }
 uint64_t b200_engine_counter(b200_engine* e, const char* name) {
   const std::string n = name ? name : "";
   if (n == "fused") return e->n_fused;
+  if (n == "groupby_partition_first") return e->n_groupby_pf;
   if (n == "fused_static") return e->n_fused_static;
   if (n == "fused_exchanges") return e->fused_exchanges;
   if (n == "exchange_window_bytes") return e->win_bytes;
@@ -4131,7 +4221,15 @@ int b200_engine_set_config(b200_engine* e, const char* key, const char* value) {
     if (std::string(key) == "b200.ingest.slots") e->ingest_slots = atoi(value);
     if (std::string(key) == "b200.exchange.window_bytes") e->win_config_bytes = (size_t)strtoull(value, nullptr, 10);  // read by b200_engine_comm_init
     if (std::string(key) == "b200.ingest.threads") e->pool.reset();  // re-created with the new size at the next ingest
-    if (std::string(key) == "b200.agg.reset_hints") e->agg_hint.clear();  // forget which aggregate strategy each plan shape needed
+    if (std::string(key) == "b200.agg.partition_first.bucket_slots") {
+      const uint64_t v = strtoull(value, nullptr, 10);
+      e->pf_bucket_slots = v ? std::max<uint64_t>(next_pow2(v), 64) : 0;
+    }
+    if (std::string(key) == "b200.agg.partition_first.min_rows") e->pf_min_rows = std::max<int64_t>(1, atoll(value));
+    if (std::string(key) == "b200.agg.reset_hints") {
+      e->agg_hint.clear();
+      e->agg_groups.clear();
+    }  // forget which aggregate strategy each plan shape needed
     if (std::string(key) == "b200.metrics.kernel_timing") e->kernel_timing = std::string(value) == "on" || std::string(value) == "1" || std::string(value) == "true";
   });
 }
@@ -4441,7 +4539,7 @@ int b200_stage_execute_exchange(b200_stage* s, int input_partition, const volati
         recvd = fx.recvd;
       } else if (e->world > 1) {
         // two-step path (strings in the payload, no window, or a window too small for this exchange)
-        Exchange ex{x, Runner{x, s->job_id}, e, s->job_id, s->stage_id, s->plan->n_out_partitions, EXCH_HASH, 0, s->plan->schema, s->plan->schema.size()};
+        Exchange ex{x, Runner{x, s->job_id}, e, s->job_id, s->stage_id, (int)s->plan->n_out_partitions, EXCH_HASH, 0, s->plan->schema, s->plan->schema.size()};
         ex.run(&sent, &recvd);
       }
     } catch (...) {

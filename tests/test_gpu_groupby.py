@@ -57,6 +57,30 @@ def test_groupby_kernel_against_oracle(gpu, oracle, oracle_lib, name, msf, parts
     assert_tables_equal(got, want, sort=True)
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("bucket_slots", [64, 4096])
+def test_groupby_partition_first(gpu, oracle, oracle_lib, name, bucket_slots):
+    """The same aggregates with the rows radix-partitioned first and one table region per bucket (what tables larger than
+    the L2 get), forced here onto small inputs: many tiny buckets (up to the 4096-bucket limit) and a few larger ones; run
+    twice so that the second pass sizes the table from the learnt group count."""
+    cols, keys, aggs, states, filt = CASES[name]
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, 300, {"lineitem": cols}, 2)
+    gpu.set_config("b200.agg.partition_first.bucket_slots", str(bucket_slots))
+    gpu.set_config("b200.agg.partition_first.min_rows", "1000")
+    try:
+        st = _two_level(keys, aggs, tpch.table_scan("lineitem", cols), states, filt=filt)
+        want = driver.run_stages(oracle, st, f"gbpf-{name}")
+        p0 = gpu.counter("groupby_partition_first")
+        for rep in range(2):
+            got = driver.run_stages(gpu, st, f"gbpf-{name}-{rep}")
+            assert_tables_equal(got, want, sort=True)
+        assert gpu.counter("groupby_partition_first") >= p0 + 2
+    finally:
+        gpu.set_config("b200.agg.partition_first.bucket_slots", str(1 << 19))
+        gpu.set_config("b200.agg.partition_first.min_rows", str(1 << 22))
+
+
 def test_q15_shape_product_sum(gpu, oracle, oracle_lib):
     cols = tpch.Q15_TABLES["lineitem"]
     for e in (gpu, oracle):

@@ -25,6 +25,8 @@ msf = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 reps = int(os.environ.get("REPS", "2"))
 eng = bb.GpuExecutionEngine(0)
 eng.set_config("b200.metrics.kernel_timing", "on")
+if os.environ.get("PF_SLOTS"):
+    eng.set_config("b200.agg.partition_first.bucket_slots", os.environ["PF_SLOTS"])
 c = P.col
 D152 = P.dec(15, 2)
 
