@@ -131,7 +131,11 @@ struct PidSrc {
   const uint32_t* pid;
   KeyCol keys[VM_MAX_KEYS];
   int n_keys;
-  int _pad;
+  // 0: the shuffle's partition function, hash(keys) % P (what the reference computes).  != 0: the key hash is re-mixed with
+  // this salt first -- used when rows are partitioned for a purpose of the engine's own (partition-first aggregation) whose
+  // input may already be one shuffle partition: without the salt all of its keys agree on hash % P_shuffle and would pile
+  // up in the few buckets b with b % P_shuffle == p
+  int salt;
 };
 uint32_t partition_n_tiles(int64_t n);
 // tile_hist: [P][n_tiles] u32 (may be nullptr when only totals are wanted); counts: [P] u64, pre-zeroed;

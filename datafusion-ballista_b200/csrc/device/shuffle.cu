@@ -30,6 +30,7 @@ __device__ __forceinline__ uint32_t pid_of(const PidSrc& ps, int64_t i, uint32_t
   uint64_t h = jkey_valid(ps.keys[0], i) ? hash_i64((int64_t)jkey_image(ps.keys[0], i)) : 0ull;
   for (int k = 1; k < ps.n_keys; k++)
     if (jkey_valid(ps.keys[k], i)) h = combine_hashes(hash_i64((int64_t)jkey_image(ps.keys[k], i)), h);
+  if (ps.salt) h = mix64(h ^ ((uint64_t)(uint32_t)ps.salt * 0xD1B54A32D192ED03ull));
   return (uint32_t)(h % (uint64_t)P);
 }
 

@@ -899,6 +899,7 @@ bool partition_for_groupby(const Exec& x, GroupBySpec& S, std::vector<DevPtr>& k
   const int64_t n = S.n_rows;
   PidSrc ps;
   memset(&ps, 0, sizeof ps);
+  ps.salt = 0x5bd1e995;  // not the shuffle's partition function: the input may BE one shuffle partition of these very keys
   for (int k = 0; k < S.n_keys; k++) {
     const FusedCol& c = S.cols[S.key_col[k]];
     ps.keys[ps.n_keys++] = KeyCol{c.data, nullptr, (uint8_t)(c.width == 4 ? PH_I32 : PH_I64), (uint8_t)c.width};
