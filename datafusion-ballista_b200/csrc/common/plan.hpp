@@ -296,6 +296,16 @@ inline ExprPtr make_col(int idx, const Schema& in) {
   return e;
 }
 
+// rewrite every column reference k -> target[k] (in place)
+inline void remap_columns(const ExprPtr& e, const std::vector<int>& target) {
+  if (!e) return;
+  if (e->kind == Expr::Col) {
+    if (e->col < 0 || (size_t)e->col >= target.size()) throw std::runtime_error("plan IR: column index out of range in remap");
+    e->col = target[(size_t)e->col];
+  }
+  for (auto& a : e->args) remap_columns(a, target);
+}
+
 inline LitValue parse_lit_value(const DataType& t, const Json& v) {
   LitValue l;
   if (v.is_null()) {
@@ -706,8 +716,14 @@ inline PlanPtr parse_plan(const Json& j) {
         if (ae.fn == AggFn::Avg) {
           if (state_col + 1 >= c->schema.size()) throw std::runtime_error("Final aggregate: missing AVG state columns");
           ae.sum_type = c->schema[state_col + 1].type;
-          if (!a.has("input_type")) throw std::runtime_error("Final AVG needs \"input_type\"");
-          ae.input_type = parse_type(a.at("input_type"));
+          if (a.has("input_type")) {
+            ae.input_type = parse_type(a.at("input_type"));
+          } else if (j.has("input_schema") && a.has("args") && a.at("args").size() > 0) {
+            // the protobuf form (AggregateExecNode.input_schema = 7 + the original argument expression): typed here
+            ae.input_type = parse_expr(a.at("args").at(0), parse_schema(j.at("input_schema")))->type;
+          } else {
+            throw std::runtime_error("Final AVG needs \"input_type\" (or the original argument and \"input_schema\")");
+          }
           ae.result_type = avg_result_type(ae.input_type);
         } else {
           if (state_col >= c->schema.size()) throw std::runtime_error("Final aggregate: missing state column");
@@ -786,7 +802,24 @@ inline PlanPtr parse_plan(const Json& j) {
     bool rnull = n->join_type == JoinType::Left || n->join_type == JoinType::Full;
     Schema cat = l->schema;
     cat.insert(cat.end(), r->schema.begin(), r->schema.end());
-    if (j.has("filter")) n->join_filter = parse_expr(j.at("filter"), cat);
+    if (j.has("filter") && j.has("filter_columns")) {
+      // the protobuf form (JoinFilter, datafusion.proto:1343-1352): the expression indexes an intermediate schema whose k-th
+      // column is (side, index) of an input; rewritten here onto the left ++ right schema the engines evaluate it on
+      const Json& fc = j.at("filter_columns");
+      Schema inter;
+      std::vector<int> target;
+      for (size_t k = 0; k < fc.size(); k++) {
+        const int side = (int)fc.at(k).at(0).as_int(), idx = (int)fc.at(k).at(1).as_int();
+        const Schema& src = side == 0 ? l->schema : r->schema;
+        if (side < 0 || side > 1 || idx < 0 || (size_t)idx >= src.size()) throw std::runtime_error("join filter column out of range");
+        inter.push_back(src[idx]);
+        target.push_back(side == 0 ? idx : (int)l->schema.size() + idx);
+      }
+      n->join_filter = parse_expr(j.at("filter"), inter);
+      remap_columns(n->join_filter, target);
+    } else if (j.has("filter")) {
+      n->join_filter = parse_expr(j.at("filter"), cat);
+    }
     switch (n->join_type) {
       case JoinType::LeftSemi:
       case JoinType::LeftAnti: both = l->schema; break;

@@ -30,6 +30,8 @@
 #include "host_pool.hpp"
 #include "lower.hpp"
 #include "nccl_dyn.hpp"
+#include "../common/plan_proto.hpp"
+#include "../common/plan_dump.hpp"
 #include "parquet_meta.hpp"
 #include "arrow_ipc.hpp"
 
@@ -4480,6 +4482,52 @@ int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, con
     s->plan = std::move(plan);
     *out = s;
   });
+}
+
+// The task's plan as the scheduler ships it (TaskDefinition.plan: protobuf datafusion.PhysicalPlanNode): decoded to the IR
+// by csrc/common/plan_proto.hpp, then prepared like any other stage plan.  Pure host code, no CUDA call.
+int b200_plan_proto_to_json(const void* plan_bytes, uint64_t n_bytes, const char* job_id, char** out_json) {
+  return guard([&] {
+    if (!plan_bytes || !out_json) throw EngineError(B200_ERR_INVALID, "null argument");
+    std::string js;
+    try {
+      js = pbp::plan_proto_to_json(plan_bytes, (size_t)n_bytes, job_id ? std::string(job_id) : std::string());
+    } catch (const pbp::Unsupported& u) {
+      throw EngineError(B200_ERR_UNSUPPORTED, u.what());
+    } catch (const std::runtime_error& r) {
+      throw EngineError(B200_ERR_INVALID, r.what());
+    }
+    char* m = (char*)malloc(js.size() + 1);
+    if (!m) throw EngineError(B200_ERR_OOM, "plan JSON");
+    memcpy(m, js.c_str(), js.size() + 1);
+    *out_json = m;
+  });
+}
+
+void b200_string_free(char* s) { free(s); }
+
+// EXPLAIN-style diagnostic: the typed plan the engine derived from a stage-plan IR text (column references resolved to
+// indices, expression / aggregate result types, every node's output schema), as canonical JSON.  Host only.
+int b200_plan_typed_json(const char* plan_json, uint64_t plan_len, char** out_json) {
+  return guard([&] {
+    if (!plan_json || !out_json) throw EngineError(B200_ERR_INVALID, "null argument");
+    Json j = parse_json(plan_json, plan_len ? (size_t)plan_len : strlen(plan_json));
+    PlanPtr plan = parse_plan(j);
+    const std::string js = dump_plan(*plan);
+    char* m = (char*)malloc(js.size() + 1);
+    if (!m) throw EngineError(B200_ERR_OOM, "plan JSON");
+    memcpy(m, js.c_str(), js.size() + 1);
+    *out_json = m;
+  });
+}
+
+int b200_stage_prepare_proto(b200_engine* e, const char* job_id, int64_t stage_id, const void* plan_bytes, uint64_t n_bytes, b200_stage** out) {
+  char* js = nullptr;
+  int rc = b200_plan_proto_to_json(plan_bytes, n_bytes, job_id, &js);
+  if (rc != 0) return rc;
+  rc = b200_stage_prepare(e, job_id, stage_id, js, 0, out);
+  free(js);
+  return rc;
 }
 
 int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag, b200_shuffle_write_partition* out, int cap, int* n_out) {

@@ -78,6 +78,7 @@ EXPORTED_SYMBOLS = [
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
     "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_stage_execute_exchange", "b200_engine_kernel_stats",
     "b200_ipc_encode", "b200_ipc_free", "b200_ipc_decode", "b200_shuffle_write_files", "b200_shuffle_read_file",
+    "b200_stage_prepare_proto", "b200_plan_proto_to_json", "b200_string_free", "b200_plan_typed_json",
     "b200_version",
 ]
 
@@ -115,6 +116,11 @@ def load_library():
     L.b200_tpch_table_rows.restype = i64
     L.b200_stage_prepare.argtypes = [vp, cp, i64, cp, u64, C.POINTER(vp)]
     L.b200_stage_execute.argtypes = [vp, ci, vp, C.POINTER(ShuffleWritePartition), ci, C.POINTER(ci)]
+    L.b200_stage_prepare_proto.argtypes = [vp, cp, i64, vp, u64, C.POINTER(vp)]
+    L.b200_plan_proto_to_json.argtypes = [vp, u64, cp, C.POINTER(vp)]
+    L.b200_plan_typed_json.argtypes = [cp, u64, C.POINTER(vp)]
+    L.b200_string_free.argtypes = [vp]
+    L.b200_string_free.restype = None
     L.b200_stage_metrics.argtypes = [vp, C.POINTER(OperatorMetrics), ci, C.POINTER(ci)]
     L.b200_stage_release.argtypes = [vp]
     L.b200_stage_release.restype = None
@@ -233,6 +239,30 @@ class QueryStageExecutor:
             self.h = None
 
 
+def plan_proto_to_json(plan_bytes: bytes, job_id: Optional[str] = None) -> str:
+    """Decode a protobuf datafusion.PhysicalPlanNode (a Ballista task's plan bytes) into the stage-plan IR (JSON text).
+    Host-only (b200_plan_proto_to_json): needs the library, not a GPU."""
+    L = load_library()
+    out = C.c_void_p()
+    buf = C.create_string_buffer(plan_bytes, len(plan_bytes))
+    _check(L.b200_plan_proto_to_json(C.cast(buf, C.c_void_p), len(plan_bytes), job_id.encode() if job_id else None, C.byref(out)))
+    try:
+        return C.string_at(out.value).decode()
+    finally:
+        L.b200_string_free(out)
+
+
+def plan_typed_json(plan_json: str) -> str:
+    """The typed plan the engine derives from an IR text (b200_plan_typed_json): canonical JSON, host-only."""
+    L = load_library()
+    out = C.c_void_p()
+    _check(L.b200_plan_typed_json(plan_json.encode(), 0, C.byref(out)))
+    try:
+        return C.string_at(out.value).decode()
+    finally:
+        L.b200_string_free(out)
+
+
 class GpuExecutionEngine:
     """One per executor process == one per GPU (SURVEY.md 8(b) "Threading")."""
 
@@ -338,6 +368,13 @@ class GpuExecutionEngine:
         h = C.c_void_p()
         pj = plan_json.encode()
         _check(load_library().b200_stage_prepare(self.h, job_id.encode(), stage_id, pj, len(pj), C.byref(h)))
+        return QueryStageExecutor(self, h, job_id, stage_id)
+
+    def create_query_stage_exec_proto(self, job_id: str, stage_id: int, plan_bytes: bytes) -> QueryStageExecutor:
+        """The same from the protobuf plan bytes of a Ballista task (b200_stage_prepare_proto)."""
+        h = C.c_void_p()
+        buf = C.create_string_buffer(plan_bytes, len(plan_bytes))
+        _check(load_library().b200_stage_prepare_proto(self.h, job_id.encode(), stage_id, C.cast(buf, C.c_void_p), len(plan_bytes), C.byref(h)))
         return QueryStageExecutor(self, h, job_id, stage_id)
 
     # -- shuffle partitions ----------------------------------------------------------------------

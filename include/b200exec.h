@@ -123,6 +123,23 @@ int b200_engine_export_table(b200_engine* e, const char* table, int partition,
  * writer, like DefaultExecutionEngine (execution_engine.rs:164-167). */
 int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, const char* plan_json,
                        uint64_t plan_len, b200_stage** out);
+/* The same from the bytes the scheduler ships: `TaskDefinition.plan` / `MultiTaskDefinition.plan`
+ * (ballista/core/proto/ballista.proto:518-529,551-560) = a protobuf datafusion.PhysicalPlanNode
+ * (ballista/core/proto/datafusion.proto:716-757) whose shuffle writer / reader nodes travel as PhysicalExtensionNode
+ * (BallistaPhysicalExtensionCodec, ballista/core/src/serde/mod.rs:322-640).  The executor can pass `task.plan` through as it
+ * arrived (execution_engine.rs:106-169 decodes the same bytes into an ExecutionPlan first).  Nodes, expressions or types the
+ * device engine does not implement return B200_ERR_UNSUPPORTED with the offending variant named, malformed bytes
+ * B200_ERR_INVALID.  `job_id` (may be NULL) replaces the job id stored inside the shuffle writer node.
+ * b200_plan_proto_to_json is the decoder alone (host only, no GPU needed): *out_json is a NUL-terminated malloc'd string,
+ * release it with b200_string_free. */
+int b200_stage_prepare_proto(b200_engine* e, const char* job_id, int64_t stage_id, const void* plan_bytes,
+                             uint64_t n_bytes, b200_stage** out);
+int b200_plan_proto_to_json(const void* plan_bytes, uint64_t n_bytes, const char* job_id, char** out_json);
+void b200_string_free(char* s);
+/* EXPLAIN-style diagnostic (host only): the typed plan derived from a stage-plan IR text -- column references resolved to
+ * indices, expression and aggregate types, every node's output schema (what ExecutionPlan::schema() reports per node) -- as
+ * canonical JSON; two IR texts describe the same plan exactly when these texts are equal. */
+int b200_plan_typed_json(const char* plan_json, uint64_t plan_len, char** out_json);
 /* ---- QueryStageExecutor::execute_query_stage (execution_engine.rs:73-77) ------------------- */
 /* Runs input partition `input_partition`; writes up to `cap` entries to `out`, count to *n_out.
  * `cancel_flag` (may be NULL) is polled between kernels: non-zero => B200_ERR_CANCELLED and all
