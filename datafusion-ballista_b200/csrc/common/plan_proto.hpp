@@ -611,5 +611,62 @@ inline std::string plan_proto_to_json(const void* bytes, size_t n, const std::st
   return plan_json(Msg(s), override_job);
 }
 
+// ---- ballista.protobuf.TaskDefinition / MultiTaskDefinition (ballista.proto:518-542) ------------------------------------------
+// What an executor receives for a task (LaunchTask / LaunchMultiTask / PollWork): identity, session properties and the plan
+// bytes.  Decoded to {"job_id","stage_id","stage_attempt_num","session_id","launch_time","tasks":[{"task_id",
+// "task_attempt_num","partition_id"}],"props":{..}}; *plan receives the embedded PhysicalPlanNode bytes.
+struct TaskInfo {
+  std::string job_id, session_id;
+  uint64_t stage_id = 0, stage_attempt = 0, launch_time = 0;
+  struct Task {
+    uint64_t task_id, attempt, partition;
+  };
+  std::vector<Task> tasks;
+  std::vector<std::pair<std::string, std::string>> props;  // KeyValuePair { key = 1, optional value = 2 } (:203-206)
+  Slice plan;
+};
+
+inline TaskInfo decode_task_definition(const void* bytes, size_t n, bool multi) {
+  Slice s;
+  s.p = (const uint8_t*)bytes;
+  s.n = n;
+  const Msg m(s);
+  TaskInfo t;
+  std::vector<Msg> props;
+  if (multi) {  // MultiTaskDefinition { task_ids = 1, job_id = 2, stage_id = 3, stage_attempt_num = 4, plan = 5, session_id = 7, launch_time = 8, props = 9 }
+    for (auto& id : m.subs(1)) t.tasks.push_back(TaskInfo::Task{id.u64(1), id.u64(2), id.u64(3)});  // TaskId (:266-270)
+    t.job_id = m.str(2);
+    t.stage_id = m.u64(3);
+    t.stage_attempt = m.u64(4);
+    t.plan = m.bytes(5);
+    t.session_id = m.str(7);
+    t.launch_time = m.u64(8);
+    props = m.subs(9);
+  } else {  // TaskDefinition { task_id = 1, task_attempt_num = 2, job_id = 3, stage_id = 4, stage_attempt_num = 5, partition_id = 6, plan = 7, session_id = 9, launch_time = 10, props = 11 }
+    t.tasks.push_back(TaskInfo::Task{m.u64(1), m.u64(2), m.u64(6)});
+    t.job_id = m.str(3);
+    t.stage_id = m.u64(4);
+    t.stage_attempt = m.u64(5);
+    t.plan = m.bytes(7);
+    t.session_id = m.str(9);
+    t.launch_time = m.u64(10);
+    props = m.subs(11);
+  }
+  for (auto& kv : props) t.props.push_back({kv.str(1), kv.str(2)});
+  if (t.plan.n == 0) throw std::runtime_error("task definition without plan bytes");
+  return t;
+}
+
+inline std::string task_info_json(const TaskInfo& t) {
+  std::string o = "{\"job_id\":" + jstr(t.job_id) + ",\"stage_id\":" + std::to_string(t.stage_id) + ",\"stage_attempt_num\":" + std::to_string(t.stage_attempt) +
+                  ",\"session_id\":" + jstr(t.session_id) + ",\"launch_time\":" + std::to_string(t.launch_time) + ",\"tasks\":[";
+  for (size_t i = 0; i < t.tasks.size(); i++)
+    o += std::string(i ? "," : "") + "{\"task_id\":" + std::to_string(t.tasks[i].task_id) + ",\"task_attempt_num\":" + std::to_string(t.tasks[i].attempt) +
+         ",\"partition_id\":" + std::to_string(t.tasks[i].partition) + "}";
+  o += "],\"props\":{";
+  for (size_t i = 0; i < t.props.size(); i++) o += std::string(i ? "," : "") + jstr(t.props[i].first) + ":" + jstr(t.props[i].second);
+  return o + "}}";
+}
+
 }  // namespace pbp
 }  // namespace b200

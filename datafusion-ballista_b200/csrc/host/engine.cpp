@@ -4530,6 +4530,42 @@ int b200_stage_prepare_proto(b200_engine* e, const char* job_id, int64_t stage_i
   return rc;
 }
 
+// A whole task as the executor received it (TaskDefinition / MultiTaskDefinition bytes, ballista.proto:518-542): the session
+// properties are applied like b200_engine_set_config (TaskDefinition.props -> SessionConfig, executor_server.rs), the embedded
+// plan is prepared, and the task identities come back as JSON ({"job_id","stage_id","tasks":[{"task_id","partition_id",..}],..}):
+// the caller then runs b200_stage_execute(stage, partition_id) per task.  e == NULL: decode only (*out_stage untouched).
+int b200_stage_prepare_task(b200_engine* e, const void* task_bytes, uint64_t n_bytes, int multi, b200_stage** out_stage, char** out_task_json) {
+  std::string job;
+  int64_t stage_id = 0;
+  pbp::Slice plan;
+  int rc = guard([&] {
+    if (!task_bytes || !out_task_json || (e && !out_stage)) throw EngineError(B200_ERR_INVALID, "null argument");
+    pbp::TaskInfo t;
+    try {
+      t = pbp::decode_task_definition(task_bytes, (size_t)n_bytes, multi != 0);
+    } catch (const std::runtime_error& r) {
+      throw EngineError(B200_ERR_INVALID, r.what());
+    }
+    const std::string js = pbp::task_info_json(t);
+    char* m = (char*)malloc(js.size() + 1);
+    if (!m) throw EngineError(B200_ERR_OOM, "task JSON");
+    memcpy(m, js.c_str(), js.size() + 1);
+    *out_task_json = m;
+    job = t.job_id;
+    stage_id = (int64_t)t.stage_id;
+    plan = t.plan;
+    if (e)
+      for (auto& kv : t.props) b200_engine_set_config(e, kv.first.c_str(), kv.second.c_str());
+  });
+  if (rc != 0 || !e) return rc;
+  rc = b200_stage_prepare_proto(e, job.c_str(), stage_id, plan.p, plan.n, out_stage);
+  if (rc != 0) {
+    free(*out_task_json);
+    *out_task_json = nullptr;
+  }
+  return rc;
+}
+
 int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag, b200_shuffle_write_partition* out, int cap, int* n_out) {
   ScopeTimer tm("stage_execute");
   return guard([&] {

@@ -78,7 +78,7 @@ EXPORTED_SYMBOLS = [
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
     "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_stage_execute_exchange", "b200_engine_kernel_stats",
     "b200_ipc_encode", "b200_ipc_free", "b200_ipc_decode", "b200_shuffle_write_files", "b200_shuffle_read_file",
-    "b200_stage_prepare_proto", "b200_plan_proto_to_json", "b200_string_free", "b200_plan_typed_json",
+    "b200_stage_prepare_proto", "b200_stage_prepare_task", "b200_plan_proto_to_json", "b200_string_free", "b200_plan_typed_json",
     "b200_version",
 ]
 
@@ -119,6 +119,7 @@ def load_library():
     L.b200_stage_prepare_proto.argtypes = [vp, cp, i64, vp, u64, C.POINTER(vp)]
     L.b200_plan_proto_to_json.argtypes = [vp, u64, cp, C.POINTER(vp)]
     L.b200_plan_typed_json.argtypes = [cp, u64, C.POINTER(vp)]
+    L.b200_stage_prepare_task.argtypes = [vp, vp, u64, ci, C.POINTER(vp), C.POINTER(vp)]
     L.b200_string_free.argtypes = [vp]
     L.b200_string_free.restype = None
     L.b200_stage_metrics.argtypes = [vp, C.POINTER(OperatorMetrics), ci, C.POINTER(ci)]
@@ -252,6 +253,19 @@ def plan_proto_to_json(plan_bytes: bytes, job_id: Optional[str] = None) -> str:
         L.b200_string_free(out)
 
 
+def task_definition_decode(task_bytes: bytes, multi: bool = False) -> dict:
+    """Decode a ballista.protobuf.TaskDefinition / MultiTaskDefinition (identities + props; host only)."""
+    import json as _json
+    L = load_library()
+    out = C.c_void_p()
+    buf = C.create_string_buffer(task_bytes, len(task_bytes))
+    _check(L.b200_stage_prepare_task(None, C.cast(buf, C.c_void_p), len(task_bytes), 1 if multi else 0, None, C.byref(out)))
+    try:
+        return _json.loads(C.string_at(out.value).decode())
+    finally:
+        L.b200_string_free(out)
+
+
 def plan_typed_json(plan_json: str) -> str:
     """The typed plan the engine derives from an IR text (b200_plan_typed_json): canonical JSON, host-only."""
     L = load_library()
@@ -376,6 +390,18 @@ class GpuExecutionEngine:
         buf = C.create_string_buffer(plan_bytes, len(plan_bytes))
         _check(load_library().b200_stage_prepare_proto(self.h, job_id.encode(), stage_id, C.cast(buf, C.c_void_p), len(plan_bytes), C.byref(h)))
         return QueryStageExecutor(self, h, job_id, stage_id)
+
+    def create_query_stage_exec_task(self, task_bytes: bytes, multi: bool = False):
+        """From a whole TaskDefinition / MultiTaskDefinition (b200_stage_prepare_task): (QueryStageExecutor, task info dict)."""
+        import json as _json
+        h, out = C.c_void_p(), C.c_void_p()
+        buf = C.create_string_buffer(task_bytes, len(task_bytes))
+        _check(load_library().b200_stage_prepare_task(self.h, C.cast(buf, C.c_void_p), len(task_bytes), 1 if multi else 0, C.byref(h), C.byref(out)))
+        try:
+            info = _json.loads(C.string_at(out.value).decode())
+        finally:
+            load_library().b200_string_free(out)
+        return QueryStageExecutor(self, h, info["job_id"], info["stage_id"]), info
 
     # -- shuffle partitions ----------------------------------------------------------------------
     def partition_export(self, job_id: str, stage_id: int, out_partition: int) -> pa.RecordBatch:

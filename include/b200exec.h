@@ -135,6 +135,15 @@ int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, con
 int b200_stage_prepare_proto(b200_engine* e, const char* job_id, int64_t stage_id, const void* plan_bytes,
                              uint64_t n_bytes, b200_stage** out);
 int b200_plan_proto_to_json(const void* plan_bytes, uint64_t n_bytes, const char* job_id, char** out_json);
+/* A whole task as the executor received it: `TaskDefinition` (multi == 0; LaunchTask / PollWorkResult.tasks) or
+ * `MultiTaskDefinition` (multi != 0; LaunchMultiTask) bytes, ballista.proto:518-542.  Applies `props` as
+ * b200_engine_set_config does (TaskDefinition.props is how session settings reach an executor), prepares the embedded plan
+ * (as b200_stage_prepare_proto, job and stage id taken from the task) and returns the task identities as JSON in
+ * *out_task_json (release with b200_string_free): {"job_id","stage_id","stage_attempt_num","session_id","launch_time",
+ * "tasks":[{"task_id","task_attempt_num","partition_id"}],"props":{...}} -- run b200_stage_execute(stage, partition_id) per
+ * task.  With e == NULL only the decoding happens (host only). */
+int b200_stage_prepare_task(b200_engine* e, const void* task_bytes, uint64_t n_bytes, int multi, b200_stage** out_stage,
+                            char** out_task_json);
 void b200_string_free(char* s);
 /* EXPLAIN-style diagnostic (host only): the typed plan derived from a stage-plan IR text -- column references resolved to
  * indices, expression and aggregate types, every node's output schema (what ExecutionPlan::schema() reports per node) -- as

@@ -362,9 +362,36 @@ def main():
         p = dict(plan)
         ir = json.dumps(p, separators=(",", ":"))
         cases.append({"name": f"extra/{name}", "ir": ir, "proto_b64": base64.b64encode(encode(ir)).decode()})
+    # whole tasks as an executor receives them (ballista.proto:518-542), wrapping the q5 lineitem shuffle stage
+    plan = base64.b64decode([c for c in cases if c["name"] == "q5/stage5"][0]["proto_b64"])
+    td = C("ballista.protobuf.TaskDefinition")()
+    td.task_id, td.task_attempt_num, td.job_id, td.stage_id, td.stage_attempt_num, td.partition_id = 17, 1, "job-a1b2", 5, 0, 3
+    td.plan, td.session_id, td.launch_time = plan, "sess-9", 1726000000123
+    for k, v in (("datafusion.execution.batch_size", "4096"), ("ballista.job.name", "tpch q5")):
+        kv = td.props.add()
+        kv.key, kv.value = k, v
+    td.props.add().key = "flag.without.value"
+    mt = C("ballista.protobuf.MultiTaskDefinition")()
+    for tid, part in ((40, 0), (41, 1), (42, 2)):
+        t = mt.task_ids.add()
+        t.task_id, t.task_attempt_num, t.partition_id = tid, 0, part
+    mt.job_id, mt.stage_id, mt.stage_attempt_num, mt.plan, mt.session_id, mt.launch_time = "job-a1b2", 5, 2, plan, "sess-9", 1726000000456
+    kv = mt.props.add()
+    kv.key, kv.value = "datafusion.execution.batch_size", "1024"
+    tasks = {
+        "single_b64": base64.b64encode(td.SerializeToString()).decode(),
+        "single": {"job_id": "job-a1b2", "stage_id": 5, "stage_attempt_num": 0, "session_id": "sess-9", "launch_time": 1726000000123,
+                   "tasks": [{"task_id": 17, "task_attempt_num": 1, "partition_id": 3}],
+                   "props": {"datafusion.execution.batch_size": "4096", "ballista.job.name": "tpch q5", "flag.without.value": ""}},
+        "multi_b64": base64.b64encode(mt.SerializeToString()).decode(),
+        "multi": {"job_id": "job-a1b2", "stage_id": 5, "stage_attempt_num": 2, "session_id": "sess-9", "launch_time": 1726000000456,
+                  "tasks": [{"task_id": 40, "task_attempt_num": 0, "partition_id": 0}, {"task_id": 41, "task_attempt_num": 0, "partition_id": 1},
+                            {"task_id": 42, "task_attempt_num": 0, "partition_id": 2}],
+                  "props": {"datafusion.execution.batch_size": "1024"}},
+    }
     with open(os.path.join(HERE, "proto_plans.json"), "w") as fh:
         json.dump({"generated_by": "tests/golden/make_proto_plans.py", "proto_files": "ballista/core/proto/{datafusion_common,datafusion,ballista}.proto",
-                   "cases": cases}, fh, indent=0)
+                   "cases": cases, "tasks": tasks}, fh, indent=0)
     print(len(cases), "plans,", sum(len(c["proto_b64"]) for c in cases) * 3 // 4, "proto bytes")
 
 

@@ -42,3 +42,28 @@ def test_query_from_plan_bytes(gpu, oracle, oracle_lib, q, tables, ordered):
     want = driver.run_stages(oracle, stages, f"{q}-proto")
     assert want is not None and want.num_rows > 0
     assert_tables_equal(got, want, sort=not ordered, f64_rtol=1e-12)
+
+
+def test_stage_from_task_definition(gpu, oracle, oracle_lib):
+    """b200_stage_prepare_task: the whole MultiTaskDefinition as received -- props applied, plan prepared, one execute per task id."""
+    with open(os.path.join(HERE, "golden", "proto_plans.json")) as fh:
+        t = json.load(fh)["tasks"]
+    for e in (gpu, oracle):
+        load_tables(e, oracle_lib, 30, {"lineitem": tpch.Q5_TABLES["lineitem"]}, 3)
+    try:
+        qse, info = gpu.create_query_stage_exec_task(base64.b64decode(t["multi_b64"]), multi=True)   # props: batch_size = 1024
+        assert info == t["multi"]
+        stage5 = [s for s in tpch.q5(4) if s.stage_id == 5][0]
+        ref = oracle.create_query_stage_exec(info["job_id"], 5, stage5.json(info["job_id"]))
+        for task in info["tasks"]:
+            got = qse.execute_query_stage(task["partition_id"])
+            want = ref.execute_query_stage(task["partition_id"])
+            assert [(w.partition_id, w.num_rows) for w in got] == [(w.partition_id, w.num_rows) for w in want]
+            assert sum(w.num_rows for w in got) > 0
+            assert all(w.num_batches == -(-w.num_rows // 1024) for w in got)                          # the task's props were applied
+        qse.release()
+        ref.release()
+        for p in range(4):
+            assert_tables_equal(gpu.partition_export(info["job_id"], 5, p), oracle.partition_export(info["job_id"], 5, p), sort=False)
+    finally:
+        gpu.set_config("datafusion.execution.batch_size", "8192")

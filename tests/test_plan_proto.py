@@ -122,3 +122,12 @@ def test_decoded_plans_execute_like_their_source(oracle, oracle_lib, q):
     assert (want is None) == (got is None)
     if want is not None:
         assert_tables_equal(got, want, sort=False)
+
+
+def test_task_definitions_decode():
+    """TaskDefinition / MultiTaskDefinition bytes (what LaunchTask / LaunchMultiTask / PollWork deliver): identities, props."""
+    t = FIX["tasks"]
+    assert engine.task_definition_decode(base64.b64decode(t["single_b64"]), multi=False) == t["single"]
+    assert engine.task_definition_decode(base64.b64decode(t["multi_b64"]), multi=True) == t["multi"]
+    with pytest.raises(engine.B200Error):
+        engine.task_definition_decode(b"\x08\x01", multi=False)     # a task without plan bytes
