@@ -557,6 +557,11 @@ inline std::string plan_json(const Msg& n, const std::string& override_job) {
       return o + "}";
     }
     case 13: return "{\"op\":\"CoalescePartitionsExec\",\"input\":" + in(1) + "}";  // CoalescePartitionsExecNode { input = 1 } (:1315-1318)
+    case 14: {  // RepartitionExecNode { input = 1, partitioning = 5 } (:1325-1333): inside a stage only the row-preserving kinds
+      const Msg part = m.sub(5);  // Partitioning { round_robin = 1, hash = 2, unknown = 3 } (:1335-1341)
+      if (part.has(2)) throw Unsupported("hash RepartitionExec inside a stage (the distributed planner cuts stages there)");
+      return "{\"op\":\"RepartitionExec\",\"input\":" + in(1) + "}";
+    }
     case 32: return in(1);                                                             // CooperativeExecNode: a scheduling wrapper (:1125-1127)
     case 18: {  // PhysicalExtensionNode { node = 1, inputs = 2 } (:845-848) -> BallistaPhysicalPlanNode (ballista.proto:47-54)
       const Msg b(m.bytes(1));

@@ -286,6 +286,9 @@ def set_plan(msg, t, o):
         msg.coalesce_batches.target_batch_size = 8192
     elif op == "CoalescePartitionsExec":
         set_plan(msg.merge.input, t["input"], o["input"])
+    elif op == "RepartitionExec":
+        set_plan(msg.repartition.input, t["input"], o["input"])
+        msg.repartition.partitioning.round_robin = 8
     elif op in ("GlobalLimitExec", "LocalLimitExec"):
         if op == "GlobalLimitExec":
             set_plan(msg.global_limit.input, t["input"], o["input"])
@@ -345,7 +348,7 @@ def extra_cases():
     l = P.scan("l", [P.field("a", "i64"), P.field("b", "utf8", True)])
     r = P.scan("r", [P.field("c", "i64"), P.field("d", P.dec(10, 2), True)])
     smj = P.sort_merge_join(l, r, [[c(0), c(0)]], "Left", filter=P.binop(">", c(3), P.lit_dec(100, 10, 2)))
-    out["smj_limits"] = P.shuffle_writer(P.limit(P.coalesce_partitions(P.coalesce_batches(smj)), 5, 2), 3, sort_shuffle=False)
+    out["smj_limits"] = P.shuffle_writer(P.limit(P.coalesce_partitions(P.coalesce_batches({"op": "RepartitionExec", "input": smj})), 5, 2), 3, sort_shuffle=False)
     full = P.hash_join(l, r, [[c(0), c(0)]], "Full", "Partitioned", filter=P.binop("<>", c(1), P.lit_utf8("z")), projection=[3, 1])
     out["full_join"] = P.shuffle_writer(P.sort_preserving_merge([P.sort_key(c(1))], P.limit(full, 7, global_=False), fetch=3), 4, [c(0)], 3, sort_shuffle=False)
     return out
