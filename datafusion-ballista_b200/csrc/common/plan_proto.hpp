@@ -39,6 +39,24 @@ struct Entry {
   Slice b;         // wire 2
 };
 
+// protobuf `string` fields are UTF-8 by contract; bytes off the network are checked before they end up in JSON text
+inline void require_utf8(const uint8_t* p, size_t n) {
+  size_t i = 0;
+  while (i < n) {
+    const uint8_t c = p[i];
+    size_t len = c < 0x80 ? 1 : (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xe ? 3 : (c >> 3) == 0x1e ? 4 : 0;
+    if (len == 0 || i + len > n) throw std::runtime_error("plan proto: string field is not valid UTF-8");
+    for (size_t k = 1; k < len; k++)
+      if ((p[i + k] & 0xc0) != 0x80) throw std::runtime_error("plan proto: string field is not valid UTF-8");
+    if (len == 2 && c < 0xc2) throw std::runtime_error("plan proto: string field is not valid UTF-8");                       // overlong
+    if (len == 3 && c == 0xe0 && p[i + 1] < 0xa0) throw std::runtime_error("plan proto: string field is not valid UTF-8");   // overlong
+    if (len == 3 && c == 0xed && p[i + 1] >= 0xa0) throw std::runtime_error("plan proto: string field is not valid UTF-8");  // surrogates
+    if (len == 4 && (c > 0xf4 || (c == 0xf0 && p[i + 1] < 0x90) || (c == 0xf4 && p[i + 1] >= 0x90)))
+      throw std::runtime_error("plan proto: string field is not valid UTF-8");
+    i += len;
+  }
+}
+
 struct Msg {
   std::vector<Entry> e;
   Msg() {}
@@ -109,7 +127,9 @@ struct Msg {
   bool boolean(uint32_t f) const { return u64(f) != 0; }
   std::string str(uint32_t f) const {
     const Entry* x = last(f);
-    return x ? std::string((const char*)x->b.p, x->b.n) : std::string();
+    if (!x) return std::string();
+    require_utf8(x->b.p, x->b.n);
+    return std::string((const char*)x->b.p, x->b.n);
   }
   Slice bytes(uint32_t f) const {
     const Entry* x = last(f);
@@ -125,7 +145,10 @@ struct Msg {
   std::vector<std::string> strs(uint32_t f) const {
     std::vector<std::string> r;
     for (auto& x : e)
-      if (x.field == f && x.wire == 2) r.push_back(std::string((const char*)x.b.p, x.b.n));
+      if (x.field == f && x.wire == 2) {
+        require_utf8(x.b.p, x.b.n);
+        r.push_back(std::string((const char*)x.b.p, x.b.n));
+      }
     return r;
   }
   // repeated scalar: packed (wire 2) or one entry per element
@@ -190,6 +213,21 @@ struct Unsupported : std::runtime_error {
   explicit Unsupported(const std::string& m) : std::runtime_error(m) {}
 };
 
+// plan bytes come off the network: bound the recursion (a legitimate plan nests a few dozen levels)
+struct DepthGuard {
+  static int& depth() {
+    static thread_local int d = 0;
+    return d;
+  }
+  DepthGuard() {
+    if (++depth() > 512) {
+      --depth();
+      throw std::runtime_error("plan proto: nesting deeper than 512 levels");
+    }
+  }
+  ~DepthGuard() { --depth(); }
+};
+
 // ---- datafusion_common.ArrowType (datafusion_common.proto:365-410) ---------------------------------------------------------
 inline std::string type_json(const Msg& t) {
   const Entry* x = t.oneof({1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 40, 41, 42});
@@ -241,7 +279,9 @@ inline std::string literal_json(const Msg& v) {
     case 33: return lit(type_json(Msg(x->b)), "null");
     case 1: return lit("\"bool\"", x->v ? "true" : "false");
     case 2:
-    case 23: return lit("\"utf8\"", jstr(std::string((const char*)x->b.p, x->b.n)));
+    case 23:
+      require_utf8(x->b.p, x->b.n);
+      return lit("\"utf8\"", jstr(std::string((const char*)x->b.p, x->b.n)));
     case 4: return lit("\"i8\"", std::to_string((int32_t)x->v));
     case 5: return lit("\"i16\"", std::to_string((int32_t)x->v));
     case 6: return lit("\"i32\"", std::to_string((int32_t)x->v));
@@ -303,11 +343,13 @@ inline bool literal_utf8(const Msg& e, std::string& out) {
   const Msg v(x->b);
   const Entry* s = v.oneof({2, 3, 23});
   if (!s) return false;
+  require_utf8(s->b.p, s->b.n);
   out.assign((const char*)s->b.p, s->b.n);
   return true;
 }
 
 inline std::string expr_json(const Msg& e) {
+  DepthGuard dg;
   const Entry* x = e.oneof({1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 18, 19, 20, 21});
   if (!x) throw std::runtime_error("plan proto: PhysicalExprNode without ExprType");
   const Msg m(x->b);
@@ -449,6 +491,7 @@ inline std::string join_common_json(const Msg& m, uint32_t f_on, uint32_t f_type
 }
 
 inline std::string plan_json(const Msg& n, const std::string& override_job) {
+  DepthGuard dg;
   const Entry* x = n.oneof({1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38});
   if (!x) throw std::runtime_error("plan proto: PhysicalPlanNode without PhysicalPlanType");
   const Msg m(x->b);

@@ -131,3 +131,47 @@ def test_task_definitions_decode():
     assert engine.task_definition_decode(base64.b64decode(t["multi_b64"]), multi=True) == t["multi"]
     with pytest.raises(engine.B200Error):
         engine.task_definition_decode(b"\x08\x01", multi=False)     # a task without plan bytes
+
+
+def test_decoder_survives_damaged_bytes():
+    """Plan bytes arrive over the network: truncations, bit flips and absurd nesting must produce an error or a plan, never a
+    crash or a hang (bounds-checked wire reader, recursion limit)."""
+    import random
+    rnd = random.Random(20260923)
+    protos = [base64.b64decode(c["proto_b64"]) for c in CASES if c["name"] in ("q5/stage8", "q21/stage9", "extra/expressions", "extra/agg_partial_final")]
+    assert len(protos) == 4
+    outcomes = {"ok": 0, "error": 0}
+    for raw in protos:
+        for _ in range(300):
+            b = bytearray(raw)
+            kind = rnd.randrange(3)
+            if kind == 0:
+                b = b[:rnd.randrange(len(b))]
+            elif kind == 1:
+                for _k in range(rnd.randrange(1, 4)):
+                    b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            else:
+                at = rnd.randrange(len(b))
+                b[at:at] = bytes(rnd.randrange(256) for _k in range(rnd.randrange(1, 9)))
+            try:
+                json.loads(engine.plan_proto_to_json(bytes(b)))
+                outcomes["ok"] += 1
+            except engine.B200Error:
+                outcomes["error"] += 1
+    assert outcomes["error"] > 100
+    # a filter nested 100 000 deep: FilterExecNode (field 12) { input = 1 } wrapped around itself
+    inner = b""
+    for _ in range(2000):
+        inner = bytes([0x62]) + _varint(len(inner) + 1 + len(_varint(len(inner)))) + bytes([0x0a]) + _varint(len(inner)) + inner
+    with pytest.raises(engine.B200Error):
+        engine.plan_proto_to_json(inner)
+
+
+def _varint(v):
+    out = bytearray()
+    while True:
+        c = v & 0x7f
+        v >>= 7
+        out.append(c | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
