@@ -457,7 +457,7 @@ def run_b200(args):
                        "exchange": "in-library NCCL send/recv (b200_exchange_stage): hash repartition + gather to the merge task" if world > 1 else "none (1 executor)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "fused_kernel<G=4,R=4,BT=256,shape=q1> (stage 1: scan+filter+project+partial aggregate)",
+                         "kernel": "fused_kernel<G=4,R=4,BT=256,shape=q1 with pre-packed key images> (stage 1: scan+filter+project+partial aggregate)",
                          "peak_source": peak_src, "kernel_ms": kern_s * 1e3, "algorithmic_bytes": alg_bytes},
             "gpu_launches": launches, "clocks": clocks,
             "parity_checked": bool(parity.get("checked") and parity.get("equal")), "parity": parity,
