@@ -624,9 +624,34 @@ inline std::string plan_json(const Msg& n, const std::string& override_job) {
           }
           return o + "}";
         }
-        case 2:  // ShuffleReaderExecNode { schema = 2, stage_id = 3, broadcast = 5 } (ballista.proto:83-92)
+        case 2: {  // ShuffleReaderExecNode { partition = 1, schema = 2, stage_id = 3, broadcast = 5 } (ballista.proto:83-92)
+          // "locations": per output partition, where its map outputs live -- PartitionLocation { map_partition_id = 1,
+          // partition_id = 2 { job_id = 1, stage_id = 2, partition_id = 4 }, executor_meta = 3 { id = 1, host = 2, port = 3 },
+          // partition_stats = 4 { num_rows = 1, num_batches = 2, num_bytes = 3 }, file_id = 6, is_sort_shuffle = 7 }
+          // (ballista.proto:244-264,272-277,339-346).  The engine reads what sits in its shuffle store; the host side uses
+          // this list to fetch the pieces that live elsewhere (b200_shuffle_read_file / the exchange).
+          std::string loc = "[";
+          bool fp = true;
+          for (auto& part : w.subs(1)) {
+            loc += std::string(fp ? "" : ",") + "[";
+            fp = false;
+            bool fl = true;
+            for (auto& l : part.subs(1)) {
+              const Msg pid = l.sub(2), ex = l.sub(3), st = l.sub(4);
+              loc += std::string(fl ? "" : ",") + "{\"map_partition_id\":" + std::to_string(l.u64(1)) + ",\"job_id\":" + jstr(pid.str(1)) + ",\"stage_id\":" +
+                     std::to_string(pid.u64(2)) + ",\"partition_id\":" + std::to_string(pid.u64(4)) + ",\"executor_id\":" + jstr(ex.str(1)) + ",\"host\":" +
+                     jstr(ex.str(2)) + ",\"port\":" + std::to_string(ex.u64(3)) + ",\"num_rows\":" + std::to_string(st.i64(1)) + ",\"num_bytes\":" +
+                     std::to_string(st.i64(3)) + ",\"is_sort_shuffle\":" + (l.boolean(7) ? "true" : "false");
+              if (l.has(6)) loc += ",\"file_id\":" + std::to_string(l.u64(6));
+              loc += "}";
+              fl = false;
+            }
+            loc += "]";
+          }
+          loc += "]";
           return "{\"op\":\"ShuffleReaderExec\",\"stage_id\":" + std::to_string(w.u64(3)) + ",\"schema\":" + schema_json(w.sub(2)) + ",\"broadcast\":" +
-                 (w.boolean(5) ? "true" : "false") + "}";
+                 (w.boolean(5) ? "true" : "false") + ",\"locations\":" + loc + "}";
+        }
         default:  // UnresolvedShuffleExecNode { stage_id = 1, schema = 2, broadcast = 6 } (ballista.proto:75-81)
           return "{\"op\":\"UnresolvedShuffleExec\",\"stage_id\":" + std::to_string(w.u64(1)) + ",\"schema\":" + schema_json(w.sub(2)) + ",\"broadcast\":" +
                  (w.boolean(6) ? "true" : "false") + "}";

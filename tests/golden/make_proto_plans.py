@@ -205,8 +205,20 @@ def set_plan(msg, t, o):
         if op == "ShuffleReaderExec":
             r = b.shuffle_reader
             r.stage_id = t["stage_id"]
-            r.partition.add()
-            r.upstream_partition_count = 1
+            # two output partitions, each with the map outputs of two executors (what the scheduler resolves an
+            # UnresolvedShuffleExec into, execution_graph / execution_stage)
+            for out_p in range(2):
+                part = r.partition.add()
+                for m in range(2):
+                    loc = part.location.add()
+                    loc.map_partition_id = m
+                    loc.partition_id.job_id, loc.partition_id.stage_id, loc.partition_id.partition_id = "job", t["stage_id"], out_p
+                    loc.executor_meta.id, loc.executor_meta.host, loc.executor_meta.port = f"exec-{m}", f"10.0.0.{m + 1}", 50050 + m
+                    loc.partition_stats.num_rows, loc.partition_stats.num_batches, loc.partition_stats.num_bytes = 1000 + out_p, 1, 16000 + m
+                    if m == 1:
+                        loc.file_id = 7
+                    loc.is_sort_shuffle = bool(m)
+            r.upstream_partition_count = 2
         else:
             r = b.unresolved_shuffle
             r.stage_id = t["stage_id"]

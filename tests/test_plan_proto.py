@@ -175,3 +175,24 @@ def _varint(v):
         out.append(c | (0x80 if v else 0))
         if not v:
             return bytes(out)
+
+
+def test_shuffle_reader_locations_pass_through():
+    """A resolved ShuffleReaderExec names where every map output lives (PartitionLocation): the decoder hands that to the host."""
+    case = [c for c in CASES if c["name"] == "q5/stage6"][0]
+    ir = json.loads(engine.plan_proto_to_json(base64.b64decode(case["proto_b64"])))
+
+    def readers(n):
+        out = [n] if n.get("op") == "ShuffleReaderExec" else []
+        for k in ("input", "left", "right"):
+            if k in n:
+                out += readers(n[k])
+        return out
+    rs = readers(ir)
+    assert rs, "q5 stage 6 reads shuffles"
+    for r in rs:
+        assert len(r["locations"]) == 2 and all(len(p) == 2 for p in r["locations"])
+        l0, l1 = r["locations"][1]
+        assert l0 == {"map_partition_id": 0, "job_id": "job", "stage_id": r["stage_id"], "partition_id": 1, "executor_id": "exec-0",
+                      "host": "10.0.0.1", "port": 50050, "num_rows": 1001, "num_bytes": 16000, "is_sort_shuffle": False}
+        assert l1["file_id"] == 7 and l1["is_sort_shuffle"] is True and l1["executor_id"] == "exec-1"
