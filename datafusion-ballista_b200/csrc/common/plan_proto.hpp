@@ -741,5 +741,40 @@ inline std::string task_info_json(const TaskInfo& t) {
   return o + "}}";
 }
 
+// ---- protobuf writer (for the way back: TaskStatus) ------------------------------------------------------------------------
+struct Writer {
+  std::string out;
+  void varint(uint64_t v) {
+    while (v >= 0x80) {
+      out.push_back((char)(v | 0x80));
+      v >>= 7;
+    }
+    out.push_back((char)v);
+  }
+  void key(uint32_t field, uint32_t wire) { varint(((uint64_t)field << 3) | wire); }
+  // proto3: scalar fields at their default value are not written
+  void u64(uint32_t field, uint64_t v) {
+    if (!v) return;
+    key(field, 0);
+    varint(v);
+  }
+  void u64_always(uint32_t field, uint64_t v) {  // members of a oneof / optional fields are written even when zero
+    key(field, 0);
+    varint(v);
+  }
+  void boolean(uint32_t field, bool v) { u64(field, v ? 1 : 0); }
+  void str(uint32_t field, const std::string& v) {
+    if (v.empty()) return;
+    key(field, 2);
+    varint(v.size());
+    out += v;
+  }
+  void msg(uint32_t field, const Writer& m) {  // sub-messages are written even when empty (presence)
+    key(field, 2);
+    varint(m.out.size());
+    out += m.out;
+  }
+};
+
 }  // namespace pbp
 }  // namespace b200

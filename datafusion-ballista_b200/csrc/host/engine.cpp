@@ -4566,6 +4566,85 @@ int b200_stage_prepare_task(b200_engine* e, const void* task_bytes, uint64_t n_b
   return rc;
 }
 
+// TaskStatus (ballista.proto:494-509) for a finished task; rules of executor/src/lib.rs:101-152 and core/src/error.rs:205-256.
+int b200_task_status_encode(const char* job_id, const char* executor_id, const b200_task_result* r, const b200_shuffle_write_partition* parts, int n_parts,
+                            const b200_operator_metrics* metrics, int n_metrics, char** out_bytes, uint64_t* out_len) {
+  return guard([&] {
+    if (!job_id || !r || !out_bytes || !out_len || (n_parts > 0 && !parts) || (n_metrics > 0 && !metrics)) throw EngineError(B200_ERR_INVALID, "null argument");
+    pbp::Writer w;
+    w.u64(1, r->task_id);
+    w.str(2, job_id);
+    w.u64(3, r->stage_id);
+    w.u64(4, r->stage_attempt_num);
+    w.u64(5, r->partition_id);
+    w.u64(6, r->launch_time);
+    w.u64(7, r->start_exec_time);
+    w.u64(8, r->end_exec_time);
+    if (r->status == B200_OK) {
+      pbp::Writer ok;  // SuccessfulTask { executor_id = 1, partitions = 2 } (:453-458)
+      ok.str(1, executor_id ? executor_id : "");
+      for (int i = 0; i < n_parts; i++) {
+        pbp::Writer p;  // ShuffleWritePartition { partition_id = 1, num_batches = 3, num_rows = 4, num_bytes = 5, optional file_id = 6, is_sort_shuffle = 7 } (:481-492)
+        p.u64(1, parts[i].partition_id);
+        p.u64(3, parts[i].num_batches);
+        p.u64(4, parts[i].num_rows);
+        p.u64(5, parts[i].num_bytes);
+        if (parts[i].file_id >= 0) p.u64_always(6, (uint64_t)parts[i].file_id);
+        p.boolean(7, parts[i].is_sort_shuffle != 0);
+        ok.msg(2, p);
+      }
+      w.msg(11, ok);
+    } else {
+      pbp::Writer f;  // FailedTask { error = 1, retryable = 2, count_to_failures = 3, failed_reason 4..9 } (:437-451)
+      const std::string msg = r->error_message ? r->error_message : "";
+      if (r->status == B200_ERR_NOT_FOUND) {
+        f.str(1, msg);
+        pbp::Writer fe;  // FetchPartitionError { executor_id = 1, map_stage_id = 2, map_partition_id = 3 } (:463-467)
+        fe.str(1, r->fetch_executor_id ? r->fetch_executor_id : "");
+        fe.u64(2, r->fetch_map_stage_id);
+        fe.u64(3, r->fetch_map_partition_id);
+        f.msg(5, fe);
+      } else if (r->status == B200_ERR_CANCELLED) {
+        f.str(1, msg.empty() ? std::string("Task killed") : msg);
+        f.msg(9, pbp::Writer());  // TaskKilled {}
+      } else {
+        f.str(1, "Task failed due to runtime execution error: " + msg);
+        f.msg(4, pbp::Writer());  // ExecutionError {}
+      }
+      w.msg(10, f);
+    }
+    for (int i = 0; i < n_metrics; i++) {
+      pbp::Writer set;  // OperatorMetricsSet { metrics = 1 } (:286-288); OperatorMetric oneof (:318-336)
+      auto one = [&](uint32_t field, uint64_t v) {
+        pbp::Writer m;
+        m.u64_always(field, v);
+        set.msg(1, m);
+      };
+      auto named = [&](const char* name, uint64_t v) {
+        pbp::Writer nc;  // NamedCount { name = 1, value = 2 } (:291-294)
+        nc.str(1, name);
+        nc.u64(2, v);
+        pbp::Writer m;
+        m.msg(6, nc);
+        set.msg(1, m);
+      };
+      one(1, metrics[i].output_rows);
+      one(2, metrics[i].elapsed_compute_ns);
+      one(12, metrics[i].bytes_written);
+      named("input_rows", metrics[i].input_rows);
+      named("bytes_read", metrics[i].bytes_read);
+      named("kernel_launches", metrics[i].kernel_launches);
+      w.msg(12, set);
+    }
+    char* m = (char*)malloc(w.out.size() + 1);
+    if (!m) throw EngineError(B200_ERR_OOM, "task status");
+    memcpy(m, w.out.data(), w.out.size());
+    m[w.out.size()] = 0;
+    *out_bytes = m;
+    *out_len = w.out.size();
+  });
+}
+
 int b200_stage_execute(b200_stage* s, int input_partition, const volatile int32_t* cancel_flag, b200_shuffle_write_partition* out, int cap, int* n_out) {
   ScopeTimer tm("stage_execute");
   return guard([&] {

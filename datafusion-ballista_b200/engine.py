@@ -78,7 +78,7 @@ EXPORTED_SYMBOLS = [
     "b200_partition_import_device", "b200_device_gather", "b200_remove_job_data", "b200_remove_stage_data", "b200_host_alloc_pinned", "b200_host_free_pinned",
     "b200_comm_unique_id", "b200_engine_comm_init", "b200_exchange_stage", "b200_stage_execute_exchange", "b200_engine_kernel_stats",
     "b200_ipc_encode", "b200_ipc_free", "b200_ipc_decode", "b200_shuffle_write_files", "b200_shuffle_read_file",
-    "b200_stage_prepare_proto", "b200_stage_prepare_task", "b200_plan_proto_to_json", "b200_string_free", "b200_plan_typed_json",
+    "b200_stage_prepare_proto", "b200_stage_prepare_task", "b200_task_status_encode", "b200_plan_proto_to_json", "b200_string_free", "b200_plan_typed_json",
     "b200_version",
 ]
 
@@ -119,6 +119,8 @@ def load_library():
     L.b200_stage_prepare_proto.argtypes = [vp, cp, i64, vp, u64, C.POINTER(vp)]
     L.b200_plan_proto_to_json.argtypes = [vp, u64, cp, C.POINTER(vp)]
     L.b200_plan_typed_json.argtypes = [cp, u64, C.POINTER(vp)]
+    L.b200_task_status_encode.argtypes = [cp, cp, C.POINTER(TaskResult), C.POINTER(ShuffleWritePartition), ci, C.POINTER(OperatorMetrics), ci,
+                                          C.POINTER(vp), C.POINTER(u64)]
     L.b200_stage_prepare_task.argtypes = [vp, vp, u64, ci, C.POINTER(vp), C.POINTER(vp)]
     L.b200_string_free.argtypes = [vp]
     L.b200_string_free.restype = None
@@ -249,6 +251,29 @@ def plan_proto_to_json(plan_bytes: bytes, job_id: Optional[str] = None) -> str:
     _check(L.b200_plan_proto_to_json(C.cast(buf, C.c_void_p), len(plan_bytes), job_id.encode() if job_id else None, C.byref(out)))
     try:
         return C.string_at(out.value).decode()
+    finally:
+        L.b200_string_free(out)
+
+
+class TaskResult(C.Structure):
+    """b200_task_result (include/b200exec.h)."""
+    _fields_ = [("task_id", C.c_uint32), ("stage_id", C.c_uint32), ("stage_attempt_num", C.c_uint32), ("partition_id", C.c_uint32),
+                ("launch_time", C.c_uint64), ("start_exec_time", C.c_uint64), ("end_exec_time", C.c_uint64), ("status", C.c_int32),
+                ("fetch_map_stage_id", C.c_uint32), ("fetch_map_partition_id", C.c_uint32), ("fetch_executor_id", C.c_char_p),
+                ("error_message", C.c_char_p)]
+
+
+def task_status_encode(job_id: str, executor_id: str, result: "TaskResult", partitions=(), metrics=()) -> bytes:
+    """ballista.protobuf.TaskStatus bytes for a finished task (b200_task_status_encode; host only).
+    partitions: ShuffleWritePartition structs (b200_stage_execute's output); metrics: OperatorMetrics structs."""
+    L = load_library()
+    parts = (ShuffleWritePartition * max(len(partitions), 1))(*partitions)
+    mets = (OperatorMetrics * max(len(metrics), 1))(*metrics)
+    out, n = C.c_void_p(), C.c_uint64(0)
+    _check(L.b200_task_status_encode(job_id.encode(), executor_id.encode(), C.byref(result), parts, len(partitions), mets, len(metrics),
+                                     C.byref(out), C.byref(n)))
+    try:
+        return C.string_at(out.value, n.value)
     finally:
         L.b200_string_free(out)
 

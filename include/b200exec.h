@@ -134,6 +134,25 @@ int b200_stage_prepare(b200_engine* e, const char* job_id, int64_t stage_id, con
  * release it with b200_string_free. */
 int b200_stage_prepare_proto(b200_engine* e, const char* job_id, int64_t stage_id, const void* plan_bytes,
                              uint64_t n_bytes, b200_stage** out);
+/* ... and the way back: the `TaskStatus` message (ballista.proto:494-509) an executor reports for a finished task, built the
+ * way ballista/executor/src/lib.rs:101-152 (`as_task_status`) and ballista/core/src/error.rs:205-256 (`FailedTask::from`)
+ * build it.  status == B200_OK: `successful { executor_id, partitions }` from b200_stage_execute's output.  B200_ERR_NOT_FOUND:
+ * `failed { error, retryable = false, count_to_failures = false, fetch_partition_error { fetch_* } }` (the scheduler re-runs the
+ * map stage).  B200_ERR_CANCELLED: `failed { task_killed }`.  Anything else: `failed { error = "Task failed due to runtime
+ * execution error: <message>", execution_error }`.  `metrics`: one OperatorMetricsSet per operator (b200_stage_metrics order)
+ * with output_rows, elapse_time (device ns), output_bytes and the named counts input_rows / bytes_read / kernel_launches.
+ * *out_bytes is malloc'd (b200_string_free releases it).  Host only. */
+typedef struct b200_task_result {
+  uint32_t task_id, stage_id, stage_attempt_num, partition_id;
+  uint64_t launch_time, start_exec_time, end_exec_time; /* ms since the epoch, as TaskExecutionTimes */
+  int32_t status;                                        /* what b200_stage_execute returned */
+  uint32_t fetch_map_stage_id, fetch_map_partition_id;   /* B200_ERR_NOT_FOUND only */
+  const char* fetch_executor_id;                         /* B200_ERR_NOT_FOUND only (may be NULL) */
+  const char* error_message;                             /* failed tasks: b200_last_error() (may be NULL) */
+} b200_task_result;
+int b200_task_status_encode(const char* job_id, const char* executor_id, const b200_task_result* r,
+                            const b200_shuffle_write_partition* parts, int n_parts, const b200_operator_metrics* metrics,
+                            int n_metrics, char** out_bytes, uint64_t* out_len);
 int b200_plan_proto_to_json(const void* plan_bytes, uint64_t n_bytes, const char* job_id, char** out_json);
 /* A whole task as the executor received it: `TaskDefinition` (multi == 0; LaunchTask / PollWorkResult.tasks) or
  * `MultiTaskDefinition` (multi != 0; LaunchMultiTask) bytes, ballista.proto:518-542.  Applies `props` as

@@ -404,9 +404,53 @@ def main():
                             {"task_id": 42, "task_attempt_num": 0, "partition_id": 2}],
                   "props": {"datafusion.execution.batch_size": "1024"}},
     }
+    # the way back: TaskStatus messages as ballista/executor/src/lib.rs:101-152 + ballista/core/src/error.rs:205-256 build them
+    statuses = []
+    parts = [dict(partition_id=0, num_batches=2, num_rows=10000, num_bytes=480000, file_id=3, is_sort_shuffle=1),
+             dict(partition_id=3, num_batches=1, num_rows=17, num_bytes=816, file_id=-1, is_sort_shuffle=0)]
+    mets = [dict(name="SortShuffleWriterExec", output_rows=10017, input_rows=10017, elapsed_compute_ns=123456, bytes_read=480816, bytes_written=480816, kernel_launches=4),
+            dict(name="FilterExec", output_rows=10017, input_rows=60000, elapsed_compute_ns=0, bytes_read=2880000, bytes_written=0, kernel_launches=1)]
+    base = dict(task_id=17, stage_id=5, stage_attempt_num=1, partition_id=3, launch_time=1726000000123, start_exec_time=1726000000200, end_exec_time=1726000000950)
+    for name, status, extra in (("successful", 0, {}), ("fetch_failed", -5, dict(fetch_executor_id="exec-7", fetch_map_stage_id=4, fetch_map_partition_id=9,
+                                                                              error_message="partition 9 of stage 4 is gone")),
+                                ("killed", -6, dict(error_message="task cancelled")), ("execution_error", -3, dict(error_message="Execution: Arithmetic overflow")),
+                                ("zero_ids", 0, dict(task_id=0, partition_id=0, stage_attempt_num=0))):
+        r = dict(base, status=status, **extra)
+        ts = C("ballista.protobuf.TaskStatus")()
+        ts.task_id, ts.job_id, ts.stage_id, ts.stage_attempt_num, ts.partition_id = r["task_id"], "job-a1b2", r["stage_id"], r["stage_attempt_num"], r["partition_id"]
+        ts.launch_time, ts.start_exec_time, ts.end_exec_time = r["launch_time"], r["start_exec_time"], r["end_exec_time"]
+        use_parts = parts if status == 0 else []
+        if status == 0:
+            ts.successful.executor_id = "exec-1"
+            for p in use_parts:
+                sp = ts.successful.partitions.add()
+                sp.partition_id, sp.num_batches, sp.num_rows, sp.num_bytes = p["partition_id"], p["num_batches"], p["num_rows"], p["num_bytes"]
+                if p["file_id"] >= 0:
+                    sp.file_id = p["file_id"]
+                sp.is_sort_shuffle = bool(p["is_sort_shuffle"])
+        elif status == -5:
+            ts.failed.error = r["error_message"]
+            fe = ts.failed.fetch_partition_error
+            fe.executor_id, fe.map_stage_id, fe.map_partition_id = r["fetch_executor_id"], r["fetch_map_stage_id"], r["fetch_map_partition_id"]
+        elif status == -6:
+            ts.failed.error = r["error_message"]
+            ts.failed.task_killed.SetInParent()
+        else:
+            ts.failed.error = "Task failed due to runtime execution error: " + r["error_message"]
+            ts.failed.execution_error.SetInParent()
+        for m in mets:
+            ms = ts.metrics.add()
+            ms.metrics.add().output_rows = m["output_rows"]
+            ms.metrics.add().elapse_time = m["elapsed_compute_ns"]
+            ms.metrics.add().output_bytes = m["bytes_written"]
+            for nm in ("input_rows", "bytes_read", "kernel_launches"):
+                c = ms.metrics.add().count
+                c.name, c.value = nm, m[nm]
+        statuses.append({"name": name, "result": r, "partitions": use_parts, "metrics": mets, "executor_id": "exec-1", "job_id": "job-a1b2",
+                         "expected_b64": base64.b64encode(ts.SerializeToString()).decode()})
     with open(os.path.join(HERE, "proto_plans.json"), "w") as fh:
         json.dump({"generated_by": "tests/golden/make_proto_plans.py", "proto_files": "ballista/core/proto/{datafusion_common,datafusion,ballista}.proto",
-                   "cases": cases, "tasks": tasks}, fh, indent=0)
+                   "cases": cases, "tasks": tasks, "statuses": statuses}, fh, indent=0)
     print(len(cases), "plans,", sum(len(c["proto_b64"]) for c in cases) * 3 // 4, "proto bytes")
 
 

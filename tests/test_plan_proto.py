@@ -196,3 +196,21 @@ def test_shuffle_reader_locations_pass_through():
         assert l0 == {"map_partition_id": 0, "job_id": "job", "stage_id": r["stage_id"], "partition_id": 1, "executor_id": "exec-0",
                       "host": "10.0.0.1", "port": 50050, "num_rows": 1001, "num_bytes": 16000, "is_sort_shuffle": False}
         assert l1["file_id"] == 7 and l1["is_sort_shuffle"] is True and l1["executor_id"] == "exec-1"
+
+
+@pytest.mark.parametrize("case", FIX["statuses"], ids=[c["name"] for c in FIX["statuses"]])
+def test_task_status_bytes(case):
+    """b200_task_status_encode writes, byte for byte, the TaskStatus google.protobuf serialises from the reference's message
+    definitions for the same outcome (successful / fetch failed / killed / execution error, with operator metrics)."""
+    r = case["result"]
+    tr = engine.TaskResult(task_id=r["task_id"], stage_id=r["stage_id"], stage_attempt_num=r["stage_attempt_num"], partition_id=r["partition_id"],
+                           launch_time=r["launch_time"], start_exec_time=r["start_exec_time"], end_exec_time=r["end_exec_time"], status=r["status"],
+                           fetch_map_stage_id=r.get("fetch_map_stage_id", 0), fetch_map_partition_id=r.get("fetch_map_partition_id", 0),
+                           fetch_executor_id=r["fetch_executor_id"].encode() if "fetch_executor_id" in r else None,
+                           error_message=r["error_message"].encode() if "error_message" in r else None)
+    parts = [engine.ShuffleWritePartition(partition_id=p["partition_id"], num_batches=p["num_batches"], num_rows=p["num_rows"], num_bytes=p["num_bytes"],
+                                          file_id=p["file_id"], is_sort_shuffle=p["is_sort_shuffle"]) for p in case["partitions"]]
+    mets = [engine.OperatorMetrics(name=m["name"].encode(), output_rows=m["output_rows"], input_rows=m["input_rows"], elapsed_compute_ns=m["elapsed_compute_ns"],
+                                   bytes_read=m["bytes_read"], bytes_written=m["bytes_written"], kernel_launches=m["kernel_launches"]) for m in case["metrics"]]
+    got = engine.task_status_encode(case["job_id"], case["executor_id"], tr, parts, mets)
+    assert got == base64.b64decode(case["expected_b64"])
