@@ -106,6 +106,8 @@ def run_stages_distributed(engine, stages: List[Stage], job_id: str, rank: int, 
     from .engine import EXCHANGE_BROADCAST, EXCHANGE_GATHER, EXCHANGE_HASH
     out_parts: Dict[int, int] = {}
     placement: Dict[int, str] = {}   # stage id -> "hash" | "root" | "all"
+    # tables every executor holds in full (the engine's loader says which; tiny tables are replicated whatever their name)
+    REPLICATED_TABLES = set(globals()["REPLICATED_TABLES"]) | set(getattr(engine, "replicated_tables", ()))
     for si, st in enumerate(stages):
         root = st.plan
         kind, what = _probe_side_leaf(root["input"])

@@ -381,12 +381,16 @@ class GpuExecutionEngine:
         table, split into `parts` input partitions; the small dimension tables are replicated in full.
         Returns {table: global row count}."""
         rows = {}
+        if not hasattr(self, "replicated_tables"):
+            self.replicated_tables = set()   # consulted by driver.run_stages_distributed: scanned on one executor only
         for t, cols in tables.items():
             n = self.tpch_table_rows(t, msf)
             rows[t] = n
             self.drop_table(t)
+            self.replicated_tables.discard(t)
             if t in replicated or n < 1000:
                 self.tpch_generate(t, msf, 0, 0, n, cols)
+                self.replicated_tables.add(t)
                 continue
             lo, hi = n * rank // world, n * (rank + 1) // world
             step = (hi - lo + parts - 1) // parts

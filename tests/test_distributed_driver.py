@@ -148,3 +148,19 @@ def test_task_placement_q5():
             assert sorted(seen) == list(range(P)) and set(seen.values()) == {1}
     # the broadcast build side and the final gather are there
     assert EXCHANGE_BROADCAST in modes.values() and EXCHANGE_GATHER in modes.values()
+
+
+def test_tables_the_loader_replicated_are_scanned_once():
+    """A table the engine's loader put on every executor in full (tiny tables at small scale factors) must be scanned by one
+    executor only, whatever its name -- otherwise every rank contributes the same rows."""
+    world = 4
+    stages = tpch.q5(2 * world)
+    leaf = {st.stage_id: driver._probe_side_leaf(st.plan["input"]) for st in stages}
+    supplier_stages = [sid for sid, (kind, what) in leaf.items() if kind == "table" and what == "supplier"]
+    assert supplier_stages
+    for rank in range(world):
+        e = RecordingEngine(2)
+        e.replicated_tables = {"supplier"}
+        driver.run_stages_distributed(e, stages, "job", rank, world, collect=False)
+        ran = {ev[1] for ev in e.log if ev[0] == "task"}
+        assert (set(supplier_stages) <= ran) == (rank == 0)
