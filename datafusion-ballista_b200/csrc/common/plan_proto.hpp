@@ -309,10 +309,12 @@ inline std::string literal_json(const Msg& v) {
     case 20: {  // Decimal128 { value = 1 (i128, big-endian two's complement), p = 2, s = 3 } (datafusion_common.proto:352-356)
       const Msg d(x->b);
       const Slice b = d.bytes(1);
-      if (b.n == 0 || b.n > 16) throw std::runtime_error("plan proto: Decimal128 literal needs 1..16 value bytes");
+      const std::string dt = "{\"dec\":[" + std::to_string(d.i64(2)) + "," + std::to_string(d.i64(3)) + "]}";
+      if (b.n == 0) return lit(dt, "null");  // no value bytes: a NULL of that decimal type
+      if (b.n > 16) throw std::runtime_error("plan proto: Decimal128 literal with more than 16 value bytes");
       __int128 val = (b.p[0] & 0x80) ? -1 : 0;
       for (size_t i = 0; i < b.n; i++) val = (__int128)(((unsigned __int128)val << 8) | b.p[i]);
-      return lit("{\"dec\":[" + std::to_string(d.i64(2)) + "," + std::to_string(d.i64(3)) + "]}", "\"" + i128_to_string(val) + "\"");
+      return lit(dt, "\"" + i128_to_string(val) + "\"");
     }
     default: throw Unsupported("literal: scalar value variant " + std::to_string(x->field) + " not supported");
   }
