@@ -178,13 +178,23 @@ def usable_cpus() -> int:
 
 
 def host_mem_available() -> int:
+    """Bytes this process may still allocate: MemAvailable, capped by what the container's memory cgroup (v2 or v1) leaves."""
+    avail = 0
     try:
         for ln in open("/proc/meminfo"):
             if ln.startswith("MemAvailable:"):
-                return int(ln.split()[1]) * 1024
+                avail = int(ln.split()[1]) * 1024
     except Exception:
         pass
-    return 0
+    for mx, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                    ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            limit = open(mx).read().strip()
+            if limit and limit != "max" and int(limit) < (1 << 60):
+                avail = min(avail, max(0, int(limit) - int(open(cur).read().strip()))) if avail else max(0, int(limit) - int(open(cur).read().strip()))
+        except Exception:
+            pass
+    return avail
 
 
 def cpu_q1(msf: int, row_begin: int, row_end: int, threads: int, steps: int, warmup: int):
