@@ -107,7 +107,7 @@ class _DecodedPlans:
         return self._e.create_query_stage_exec(job_id, stage_id, engine.plan_proto_to_json(proto, job_id=job_id))
 
 
-@pytest.mark.parametrize("q", ["q1", "q3", "q4", "q5", "q10", "q12", "q13", "q16", "q18", "q21", "q22"])
+@pytest.mark.parametrize("q", [f"q{i}" for i in range(1, 23)])
 def test_decoded_plans_execute_like_their_source(oracle, oracle_lib, q):
     """End to end on the CPU oracle (same plan front end as the device engine): a query whose every stage is decoded from plan
     bytes returns the table the IR text returns -- join filters through column_indices, Final aggregates typed from
