@@ -47,3 +47,31 @@ def test_engine_requires_a_gpu_no_cpu_fallback():
         assert e.code == -4
     else:
         raise AssertionError("engine creation must fail without a GPU")
+
+
+def test_header_is_plain_c_and_usable_without_python(tmp_path):
+    """include/b200exec.h compiles as C99 with -Wall -Werror, and a C program linked against the library decodes a protobuf
+    plan, types it and encodes a TaskStatus (host-only entry points: no GPU needed)."""
+    import base64
+    import ctypes as C
+    import json
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    assert cc, "no C compiler"
+    lib_dir = os.path.dirname(bb.engine.LIB_PATH)
+    exe = str(tmp_path / "c_consumer")
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "native", "c_consumer.c"), "-o", exe, "-L", lib_dir, "-lb200exec", f"-Wl,-rpath,{lib_dir}"])
+    with open(os.path.join(ROOT, "tests", "golden", "proto_plans.json")) as fh:
+        case = [c for c in json.load(fh)["cases"] if c["name"] == "q3/stage5"][0]
+    plan = tmp_path / "plan.pb"
+    plan.write_bytes(base64.b64decode(case["proto_b64"]))
+    out = subprocess.run([exe, str(plan)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    kv = dict(tok.split("=", 1) for line in out.stdout.splitlines() for tok in line.split() if "=" in tok)
+    assert "sm_100a" in out.stdout
+    assert int(kv["sizeof_task_result"]) == C.sizeof(bb.engine.TaskResult)
+    assert int(kv["sizeof_swp"]) == C.sizeof(bb.engine.ShuffleWritePartition) and int(kv["sizeof_metrics"]) == C.sizeof(bb.engine.OperatorMetrics)
+    assert kv["has_job"] == "1" and int(kv["ir_bytes"]) > 100 and int(kv["typed_bytes"]) > 100
+    assert kv["malformed_rc"] == "-1" and kv["status_rc"] == "0" and int(kv["status_len"]) > 20
